@@ -1,0 +1,179 @@
+/*
+ * ss_b200.h -- C ABI of libss_b200.so: the B200 (sm_100a) implementation of the
+ * SmartStartContinuous hot path (start-state selection + MPC navigation).
+ *
+ * The reference (darren-huang/SmartStartContinuous) is pure Python; the "FFI" a
+ * maintainer would bind is ctypes (see INTEGRATION.md for the stub).  Every entry
+ * point below names the reference code it replaces (file:line, relative to the
+ * reference root).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative SS_E* code; a human readable
+ *     message for the last failure on a context is returned by ss_last_error().
+ *   - all matrices are C-contiguous (row-major); `double` on the host side because the
+ *     reference works in float64 numpy end to end.
+ *   - the caller owns every buffer it passes; the library copies inputs in during the
+ *     call, owns all device memory inside the context, and writes results into the
+ *     caller's output buffers before returning (calls are synchronous, exactly like
+ *     the scipy / sess.run calls they replace).
+ *   - `*_dev` variants take DEVICE pointers for the bulk inputs (zero-copy from torch
+ *     tensors); their small outputs are still written to host memory.
+ *   - a context is bound to one GPU and is not thread-safe (one agent per process in
+ *     the reference; multi-GPU = one process and one context per GPU).
+ *   - there is no CPU fallback anywhere behind this interface.
+ */
+#ifndef SS_B200_H_
+#define SS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ss_ctx ss_ctx;
+
+enum {
+    SS_OK = 0,
+    SS_EINVAL = -1,      /* bad argument (maps to ValueError)                         */
+    SS_ECUDA = -2,       /* CUDA runtime failure (maps to RuntimeError)               */
+    SS_ESINGULAR = -3,   /* covariance not positive definite (numpy.linalg.LinAlgError,
+                            as scipy.stats.gaussian_kde raises)                       */
+    SS_ESTATE = -4,      /* call order: model / plan not set                          */
+    SS_EUNSUPPORTED = -5 /* shape outside what the kernels were built for             */
+};
+
+/* penalty_mode of the MPC scorer */
+enum {
+    SS_PENALTY_REFERENCE = 0,  /* numerical.py:89-93: one projection coefficient per time step,
+                                  global over all K samples (reference-exact; two-phase)     */
+    SS_PENALTY_PER_SAMPLE = 1  /* per-sample projection; fully fused, no HBM round trip      */
+};
+
+/* precision of the dynamics-MLP rollout */
+enum {
+    SS_PRECISION_FP32 = 0,     /* FP32 FFMA everywhere (SIMT kernel; parity mode)            */
+    SS_PRECISION_BF16_TC = 1,  /* hidden x hidden layers on tcgen05 (BF16 in, FP32 accumulate
+                                  in TMEM); first/last layer, state and scoring in FP32      */
+    SS_PRECISION_AUTO = 2      /* BF16_TC when the shape is supported, else FP32             */
+};
+
+/* ---- context --------------------------------------------------------------------- */
+int ss_create(ss_ctx** out, int device);
+int ss_destroy(ss_ctx* ctx);
+const char* ss_last_error(ss_ctx* ctx);          /* ctx may be NULL: last create() error */
+/* run all work of this context on an existing CUDA stream (e.g. torch's current one) */
+int ss_set_stream(ss_ctx* ctx, void* cuda_stream);
+/* sm_count, cc_major, cc_minor, max SM clock (kHz) */
+int ss_device_info(ss_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int* sm_clock_khz);
+/* device time (ms, CUDA events on the context's stream) of the most recent call, split in
+ * up to 8 named phases; returns the number of phases written */
+int ss_last_timings(ss_ctx* ctx, float* ms, const char** names, int max_phases);
+/* number of kernel launches issued by this context since creation */
+int64_t ss_launch_count(ss_ctx* ctx);
+/* pinned host memory for end-to-end callers (bench e2e leg) */
+void* ss_host_alloc(int64_t bytes);
+void ss_host_free(void* p);
+void* ss_device_alloc(int64_t bytes);
+void ss_device_free(void* p);
+int ss_memcpy_h2d(ss_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes);
+
+/* ---- stage 1: Gaussian KDE + UCB + argmax --------------------------------------------
+ * Replaces smartexplorationcontinuous.py:260 (scipy.stats.gaussian_kde(all_states.T,
+ * bw_method='scott')), :275 (kernel(possible_ss_states.T) * one_radii_volume),
+ * :276-279 (C_hat, UCB) and :280 (np.argmax).
+ *
+ *   data     [n_pts, d]   all_states (every s in the buffer + the newest s2)
+ *   queries  [m, d]       candidate smart-start states (s2 of the sampled steps)
+ *   values   [m]          float32 state values from agent.get_state_value (:274)
+ *   n_transitions         len(replay_buffer)  (|D| in the UCB term; n_pts - 1 in the reference)
+ *   volume                one-step hyper-ellipsoid volume (:262-268), 1 when radii is None
+ *   alpha, beta           exploitation_param, exploration_param
+ *   out_density [m] / out_ucb [m]   optional (may be NULL): kernel(q) (before * volume) and ucb
+ *   out_best_j            first index of the maximum ucb (np.argmax semantics: NaN wins, first wins)
+ * Errors: SS_EINVAL for d > n_pts or empty inputs (scipy raises ValueError),
+ *         SS_ESINGULAR when the data covariance is not positive definite.
+ */
+int ss_kde_ucb_argmax(ss_ctx* ctx, const double* data, int64_t n_pts, int d,
+                      const double* queries, int64_t m, const float* values,
+                      int64_t n_transitions, double volume, double alpha, double beta,
+                      double* out_density, double* out_ucb,
+                      int64_t* out_best_j, double* out_best_ucb);
+/* same, bulk inputs already resident in device memory (outputs: host; out_density/out_ucb: device) */
+int ss_kde_ucb_argmax_dev(ss_ctx* ctx, const double* data_dev, int64_t n_pts, int d,
+                          const double* queries_dev, int64_t m, const float* values_dev,
+                          int64_t n_transitions, double volume, double alpha, double beta,
+                          double* out_density_dev, double* out_ucb_dev,
+                          int64_t* out_best_j, double* out_best_ucb);
+
+/* ---- stage 2: NND_MB random-shooting MPC ---------------------------------------------
+ * ss_mpc_set_model: the weights Dyn_Model holds (dynamics_model.py:36-37,
+ * feedforward_network.py:3-23) and the normalisation statistics of NND_MB_agent.py:302-315.
+ * Call after construction and after every train_dynamics_model (NND_MB_agent.py:437-480).
+ *   weights[l] [in_l, out_l] (y = x W + b), l = 0..num_fc_layers (hidden layers use ReLU,
+ *   the last layer is linear); in_0 = d + da, out_last = d.
+ */
+int ss_mpc_set_model(ss_ctx* ctx, int d, int da, int num_fc_layers, int depth_fc_layers,
+                     const double* const* weights, const double* const* biases,
+                     const double* mean_x, const double* std_x,
+                     const double* mean_y, const double* std_y,
+                     const double* mean_z, const double* std_z);
+
+/* ss_mpc_set_plan: what start_new_episode_plan leaves on the agent (NND_MB_agent.py:375-418):
+ * desired_states [W, d], distances_left [W], radii [d] (all > 0, numerical.py:112-113).  W >= 2. */
+int ss_mpc_set_plan(ss_ctx* ctx, const double* desired_states, int W,
+                    const double* distances_left, const double* radii, int d);
+
+/* ss_mpc_plan: get_best_sim_actions (NND_MB_agent.py:498-520) = sample (:500-501) +
+ * Dyn_Model.do_forward_sim (dynamics_model.py:204-240) + generate_scores_add_delta
+ * (NND_MB_agent.py:566-628) + argmax/selection (:516-518).
+ *
+ *   state [d]           current state;  wp_index = current_desired_state_index
+ *   K_local sequences are evaluated by this context; they are sequences
+ *   [k_offset, k_offset + K_local) of a global batch of K_global (multi-GPU sharding;
+ *   single GPU: k_offset = 0, K_global = K_local).
+ *   actions             host [K_local, H, da] float64 action samples (parity mode), or NULL:
+ *                       sampled on the device with Philox4x32-10(seed) indexed by the GLOBAL
+ *                       sequence number, uniform in [act_low, act_high) like npr.uniform.
+ *   out_best_k          GLOBAL index of the first maximum score on this shard
+ *   out_best_sequence   [H, da], out_best_path [H+1, d] (rolled out in FP32), out_scores [K_local]
+ *                       (nullable)
+ * In SS_PENALTY_REFERENCE mode with K_global != K_local use the three-call form below so the
+ * per-time-step projection sums can be all-reduced across GPUs.
+ */
+int ss_mpc_plan(ss_ctx* ctx, const double* state, int wp_index,
+                int64_t K_local, int64_t k_offset, int64_t K_global, int H,
+                const double* actions, uint64_t seed,
+                const double* act_low, const double* act_high,
+                double gamma, double horizontal_penalty_factor,
+                int penalty_mode, int precision,
+                int64_t* out_best_k, double* out_best_score,
+                double* out_best_sequence, double* out_best_path, double* out_scores);
+
+/* three-call form: rollout (phase A) -> [all-reduce the 2*(H+1) doubles at *sums_dev] -> finish */
+int ss_mpc_rollout(ss_ctx* ctx, const double* state, int wp_index,
+                   int64_t K_local, int64_t k_offset, int64_t K_global, int H,
+                   const double* actions, uint64_t seed,
+                   const double* act_low, const double* act_high,
+                   double gamma, double horizontal_penalty_factor,
+                   int penalty_mode, int precision);
+int ss_mpc_projection_sums(ss_ctx* ctx, double** sums_dev, int* count);
+int ss_mpc_finish(ss_ctx* ctx, int64_t* out_best_k, double* out_best_score, double* out_scores);
+/* roll out ONE sequence of the last ss_mpc_rollout batch again (the global winner) in FP32 and
+ * return its actions [H, da] and predicted path [H+1, d] (NND_MB_agent.py:516-518) */
+int ss_mpc_replay(ss_ctx* ctx, int64_t k_global, double* out_sequence, double* out_path);
+/* trajectories of the last ss_mpc_rollout made in SS_PENALTY_REFERENCE mode (they are kept for
+ * the second scoring pass): out_states [H+1, K_local, d], as do_forward_sim returns them
+ * (dynamics_model.py:199-240). */
+int ss_mpc_get_states(ss_ctx* ctx, double* out_states);
+/* the device sampler alone: actions [K_local, H, da] for sequences k_offset.. (tests / oracle) */
+int ss_mpc_sample_actions(ss_ctx* ctx, int64_t K_local, int64_t k_offset, int H, int da,
+                          uint64_t seed, const double* act_low, const double* act_high,
+                          double* out_actions);
+/* 1 when ss_mpc_set_model's shape can run on the tcgen05 kernel */
+int ss_mpc_tc_supported(ss_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SS_B200_H_ */

@@ -1,0 +1,200 @@
+// capi.cu -- context management and the stage-1 entry points of the C ABI (include/ss_b200.h).
+#include <cstring>
+
+#include "common.cuh"
+
+int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double* queries_dev,
+            long long m, const float* values_dev, long long n_transitions, double volume,
+            double alpha, double beta, double* density_dev, double* ucb_dev, int64_t* out_best_j,
+            double* out_best_ucb);
+
+static std::string g_create_error;
+
+extern "C" int ss_create(ss_ctx** out, int device) {
+    if (!out) return SS_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return SS_ECUDA;
+    }
+    if (device < 0 || device >= count) {
+        g_create_error = "device index out of range";
+        return SS_EINVAL;
+    }
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess ||
+        (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        return SS_ECUDA;
+    }
+    if (prop.major != 10) {
+        g_create_error = "libss_b200 is built for sm_100a (B200) only; found compute capability " +
+                         std::to_string(prop.major) + "." + std::to_string(prop.minor);
+        return SS_EUNSUPPORTED;
+    }
+    ss_ctx* c = new ss_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->cc_major = prop.major;
+    c->cc_minor = prop.minor;
+    c->clock_khz = prop.clockRate;
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        delete c;
+        return SS_ECUDA;
+    }
+    c->own_stream = true;
+    *out = c;
+    return SS_OK;
+}
+
+extern "C" int ss_destroy(ss_ctx* c) {
+    if (!c) return SS_EINVAL;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->kde_data64, &c->kde_q64, &c->kde_vals, &c->kde_pts, &c->kde_qw,
+                      &c->kde_partial, &c->kde_fit, &c->kde_moments, &c->kde_density, &c->kde_ucb,
+                      &c->kde_block_best, &c->kde_result, &c->tc_w1, &c->tc_w2, &c->tc_w3,
+                      &c->tc_misc, &c->plan_ds, &c->plan_dl, &c->mpc_actions64, &c->mpc_states,
+                      &c->mpc_scores, &c->mpc_partial_sums, &c->mpc_sums, &c->mpc_block_best,
+                      &c->mpc_result, &c->mpc_replay, &c->mpc_sampled};
+    for (DevBuf* b : bufs) b->release();
+    for (auto& b : c->w32) b.release();
+    for (auto& b : c->b32) b.release();
+    if (c->timer.created)
+        for (int i = 0; i <= SS_MAX_PHASES; ++i) cudaEventDestroy(c->timer.ev[i]);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SS_OK;
+}
+
+extern "C" const char* ss_last_error(ss_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int ss_set_stream(ss_ctx* c, void* stream) {
+    if (!c) return SS_EINVAL;
+    if (c->own_stream) {
+        cudaStreamSynchronize(c->stream);
+        cudaStreamDestroy(c->stream);
+        c->own_stream = false;
+    }
+    c->stream = reinterpret_cast<cudaStream_t>(stream);
+    return SS_OK;
+}
+
+extern "C" int ss_device_info(ss_ctx* c, int* sm_count, int* cc_major, int* cc_minor, int* clock_khz) {
+    if (!c) return SS_EINVAL;
+    if (sm_count) *sm_count = c->sm_count;
+    if (cc_major) *cc_major = c->cc_major;
+    if (cc_minor) *cc_minor = c->cc_minor;
+    if (clock_khz) *clock_khz = c->clock_khz;
+    return SS_OK;
+}
+
+extern "C" int ss_last_timings(ss_ctx* c, float* ms, const char** names, int max_phases) {
+    if (!c || !c->timer.created) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    int n = c->timer.n < max_phases ? c->timer.n : max_phases;
+    for (int i = 0; i < n; ++i) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, c->timer.ev[i], c->timer.ev[i + 1]) != cudaSuccess) t = -1.f;
+        if (ms) ms[i] = t;
+        if (names) names[i] = c->timer.names[i];
+    }
+    return n;
+}
+
+extern "C" int64_t ss_launch_count(ss_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" void* ss_host_alloc(int64_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, (size_t)bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void ss_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+extern "C" void* ss_device_alloc(int64_t bytes) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void ss_device_free(void* p) {
+    if (p) cudaFree(p);
+}
+extern "C" int ss_memcpy_h2d(ss_ctx* c, void* dst, const void* src, int64_t bytes) {
+    if (!c) return SS_EINVAL;
+    SS_CUDA_CHECK(c, cudaSetDevice(c->device));
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, c->stream));
+    SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return SS_OK;
+}
+
+static int kde_check(ss_ctx* c, const void* data, int64_t n_pts, int d, const void* queries, int64_t m,
+                     const void* values, int64_t n_transitions, int64_t* out_best_j, double* out_best_ucb) {
+    if (!data || !queries || !values || !out_best_j || !out_best_ucb)
+        SS_FAIL(c, SS_EINVAL, "kde: null pointer");
+    if (d < 1 || d > SS_MAX_D) SS_FAIL(c, SS_EUNSUPPORTED, "kde: need 1 <= d <= 32");
+    if (m < 1) SS_FAIL(c, SS_EINVAL, "kde: no candidate queries");
+    if (n_transitions < 1) SS_FAIL(c, SS_EINVAL, "kde: empty replay buffer");
+    // scipy: "data appears to lie in a lower-dimensional subspace" / needs n > d
+    if (n_pts <= d)
+        SS_FAIL(c, SS_EINVAL, "kde: number of data points must exceed the state dimension (scipy ValueError)");
+    return SS_OK;
+}
+
+extern "C" int ss_kde_ucb_argmax_dev(ss_ctx* c, const double* data_dev, int64_t n_pts, int d,
+                                     const double* queries_dev, int64_t m, const float* values_dev,
+                                     int64_t n_transitions, double volume, double alpha, double beta,
+                                     double* out_density_dev, double* out_ucb_dev, int64_t* out_best_j,
+                                     double* out_best_ucb) {
+    if (!c) return SS_EINVAL;
+    int rc = kde_check(c, data_dev, n_pts, d, queries_dev, m, values_dev, n_transitions, out_best_j, out_best_ucb);
+    if (rc) return rc;
+    SS_CUDA_CHECK(c, cudaSetDevice(c->device));
+    timer_begin(c);
+    return kde_run(c, data_dev, n_pts, d, queries_dev, m, values_dev, n_transitions, volume, alpha, beta,
+                   out_density_dev, out_ucb_dev, out_best_j, out_best_ucb);
+}
+
+extern "C" int ss_kde_ucb_argmax(ss_ctx* c, const double* data, int64_t n_pts, int d,
+                                 const double* queries, int64_t m, const float* values,
+                                 int64_t n_transitions, double volume, double alpha, double beta,
+                                 double* out_density, double* out_ucb, int64_t* out_best_j,
+                                 double* out_best_ucb) {
+    if (!c) return SS_EINVAL;
+    int rc = kde_check(c, data, n_pts, d, queries, m, values, n_transitions, out_best_j, out_best_ucb);
+    if (rc) return rc;
+    SS_CUDA_CHECK(c, cudaSetDevice(c->device));
+    timer_begin(c);
+    const size_t nd = (size_t)n_pts * d * 8, nq = (size_t)m * d * 8;
+    SS_CUDA_CHECK(c, c->kde_data64.ensure(nd));
+    SS_CUDA_CHECK(c, c->kde_q64.ensure(nq));
+    SS_CUDA_CHECK(c, c->kde_vals.ensure((size_t)m * 4));
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(c->kde_data64.p, data, nd, cudaMemcpyHostToDevice, c->stream));
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(c->kde_q64.p, queries, nq, cudaMemcpyHostToDevice, c->stream));
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(c->kde_vals.p, values, (size_t)m * 4, cudaMemcpyHostToDevice, c->stream));
+    double* dens_dev = nullptr;
+    double* ucb_dev = nullptr;
+    if (out_density) {
+        SS_CUDA_CHECK(c, c->kde_density.ensure((size_t)m * 8));
+        dens_dev = c->kde_density.as<double>();
+    }
+    if (out_ucb) {
+        SS_CUDA_CHECK(c, c->kde_ucb.ensure((size_t)m * 8));
+        ucb_dev = c->kde_ucb.as<double>();
+    }
+    timer_mark(c, "kde_h2d");
+    rc = kde_run(c, c->kde_data64.as<double>(), n_pts, d, c->kde_q64.as<double>(), m,
+                 c->kde_vals.as<float>(), n_transitions, volume, alpha, beta, dens_dev, ucb_dev,
+                 out_best_j, out_best_ucb);
+    if (rc) return rc;
+    if (out_density)
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(out_density, dens_dev, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (out_ucb)
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(out_ucb, ucb_dev, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return SS_OK;
+}

@@ -1,0 +1,214 @@
+// common.cuh -- context, device buffers and small device helpers shared by the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/ss_b200.h"
+
+#define SS_CUDA_CHECK(ctx, expr)                                                        \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);            \
+            return SS_ECUDA;                                                            \
+        }                                                                               \
+    } while (0)
+
+#define SS_FAIL(ctx, code, msg)                                                         \
+    do {                                                                                \
+        (ctx)->err = (msg);                                                             \
+        return (code);                                                                  \
+    } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+constexpr int SS_MAX_D = 32;    // state dimension the MPC kernels accept
+constexpr int SS_MAX_DA = 8;    // action dimension
+constexpr int SS_MAX_LAYERS = 8;
+constexpr int SS_MAX_PHASES = 8;
+
+// normalisation statistics + action bounds, passed to kernels by value
+struct MpcNorm {
+    float mean_x[SS_MAX_D], inv_std_x[SS_MAX_D];
+    float mean_y[SS_MAX_DA], inv_std_y[SS_MAX_DA];
+    float mean_z[SS_MAX_D], std_z[SS_MAX_D];
+};
+
+struct ActionSource {
+    const double* host_actions;  // device copy of host-provided [K_local, H, da] doubles, or null
+    uint64_t seed;
+    double low[SS_MAX_DA], range[SS_MAX_DA];
+    int da, H;
+};
+
+struct PhaseTimer {
+    cudaEvent_t ev[SS_MAX_PHASES + 1];
+    const char* names[SS_MAX_PHASES];
+    int n = 0;
+    bool created = false;
+};
+
+struct ss_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 0, cc_major = 0, cc_minor = 0, clock_khz = 0;
+    std::string err;
+    int64_t launches = 0;
+    PhaseTimer timer;
+
+    // ---- KDE scratch
+    DevBuf kde_data64, kde_q64, kde_vals, kde_pts, kde_qw, kde_partial, kde_fit, kde_moments;
+    DevBuf kde_density, kde_ucb, kde_block_best, kde_result;
+
+    // ---- MPC model
+    bool model_set = false;
+    int d = 0, da = 0, L = 0, h = 0;
+    int din_pad = 0, h_pad = 0;
+    std::vector<DevBuf> w32, b32;      // padded fp32 weights [in_pad][out_pad], biases [out_pad]
+    MpcNorm norm;
+    // tcgen05 images (built lazily by mpc_tc.cu)
+    DevBuf tc_w1, tc_w2, tc_w3, tc_misc;
+    bool tc_ready = false;
+    // ---- MPC plan
+    bool plan_set = false;
+    int W = 0;
+    DevBuf plan_ds, plan_dl;           // fp32 [W][d], [W]
+    float inv_radii[SS_MAX_D];
+    // ---- MPC run state
+    DevBuf mpc_actions64, mpc_states, mpc_scores, mpc_partial_sums, mpc_sums, mpc_block_best,
+        mpc_result, mpc_replay, mpc_sampled;
+    struct {
+        bool valid = false;
+        int64_t K_local = 0, k_offset = 0, K_global = 0;
+        int H = 0, wp_index = 0, penalty_mode = 0, precision = 0;
+        double gamma = 0, hpf = 0;
+        float state[SS_MAX_D];
+        ActionSource act;
+        bool states_stored = false;
+        int sum_blocks = 0;
+    } run;
+};
+
+// ---- phase timing helpers (CUDA events on the context stream) -------------------------
+static inline void timer_begin(ss_ctx* c) {
+    PhaseTimer& t = c->timer;
+    if (!t.created) {
+        for (int i = 0; i <= SS_MAX_PHASES; ++i) cudaEventCreate(&t.ev[i]);
+        t.created = true;
+    }
+    t.n = 0;
+    cudaEventRecord(t.ev[0], c->stream);
+}
+static inline void timer_mark(ss_ctx* c, const char* name) {
+    PhaseTimer& t = c->timer;
+    if (t.n >= SS_MAX_PHASES) return;
+    t.names[t.n] = name;
+    t.n++;
+    cudaEventRecord(t.ev[t.n], c->stream);
+}
+
+// ---- device helpers --------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// np.argmax ordering on (value, index): NaN beats everything, then larger value, then lower index
+__device__ __forceinline__ bool argmax_better(double va, long long ia, double vb, long long ib) {
+    if (ia < 0) return false;
+    if (ib < 0) return true;
+    bool na = va != va, nb = vb != vb;
+    if (na || nb) {
+        if (na && nb) return ia < ib;
+        return na;
+    }
+    if (va > vb) return true;
+    if (va < vb) return false;
+    return ia < ib;
+}
+
+// block-wide argmax (blockDim.x <= 1024); result valid in thread 0
+__device__ __forceinline__ void block_argmax(double& v, long long& i, double* s_v, long long* s_i) {
+    for (int off = 16; off > 0; off >>= 1) {
+        double ov = __shfl_down_sync(0xffffffffu, v, off);
+        long long oi = __shfl_down_sync(0xffffffffu, i, off);
+        if (argmax_better(ov, oi, v, i)) { v = ov; i = oi; }
+    }
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { s_v[warp] = v; s_i[warp] = i; }
+    __syncthreads();
+    if (warp == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        v = lane < nw ? s_v[lane] : 0.0;
+        i = lane < nw ? s_i[lane] : -1;
+        for (int off = 16; off > 0; off >>= 1) {
+            double ov = __shfl_down_sync(0xffffffffu, v, off);
+            long long oi = __shfl_down_sync(0xffffffffu, i, off);
+            if (argmax_better(ov, oi, v, i)) { v = ov; i = oi; }
+        }
+    }
+    __syncthreads();
+}
+
+// Philox4x32-10 (Salmon et al., SC'11); counter-based so the sample of sequence k at step t
+// does not depend on how sequences are sharded over GPUs.
+__device__ __host__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                       uint32_t c3, uint32_t k0, uint32_t k1,
+                                                       uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// action a[k_global][t][j]: host-provided double or Philox uniform in [low, high)
+__device__ __forceinline__ float fetch_action(const ActionSource& src, long long k_local,
+                                              long long k_global, int t, int j) {
+    if (src.host_actions) {
+        return (float)src.host_actions[((size_t)k_local * src.H + t) * src.da + j];
+    }
+    uint32_t e = (uint32_t)(t * src.da + j);
+    uint32_t r[4];
+    philox4x32_10((uint32_t)k_global, (uint32_t)((uint64_t)k_global >> 32), e >> 2, 0u,
+                  (uint32_t)src.seed, (uint32_t)(src.seed >> 32), r);
+    double u = (double)(r[e & 3] >> 8) * (1.0 / 16777216.0);
+    return (float)(src.low[j] + u * src.range[j]);
+}

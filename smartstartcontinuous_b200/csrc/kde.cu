@@ -1,0 +1,521 @@
+// kde.cu -- SmartStart stage 1 on sm_100a: Gaussian KDE (Scott bandwidth) over the replay
+// buffer, UCB score and arg-max, replacing scipy.stats.gaussian_kde + numpy at
+// smartexplorationcontinuous.py:260-280.
+//
+// Pipeline (all on the context stream):
+//   1. kde_moments_kernel    fp64 shifted first/second moments of the data set (per-block partials)
+//   2. kde_fit_kernel        fp64: mean, covariance (ddof=1), Scott factor, Cholesky, whitening
+//                            matrix  Wm = sqrt(log2(e)/2) * L^-1  and the normalisation constant
+//   3. kde_whiten_kernel     fp64 -> fp32: y = Wm (x - mean); points stored negated and duplicated
+//                            ([-y0,-y0,-y1,-y1,...]) so the pair kernel can use packed FADD2/FFMA2
+//   4. kde_pairs_kernel      the hot loop: sum_i exp2(-|y_q - y_i|^2) for a tile of queries x a
+//                            slice of points; points streamed through shared memory with bulk
+//                            async copies (TMA, UBLKCP) + mbarriers, two queries per packed
+//                            f32x2 instruction, MUFU.EX2 for the exponential
+//   5. kde_finish_kernel     fp64: reduce point-slices, rescue underflowed queries in fp64, density,
+//                            UCB and the np.argmax-ordered arg-max (single pass, last block reduces)
+//
+// Roofline: SFU bound -- one MUFU.EX2 per kernel evaluation (16 / clk / SM); see DESIGN.md.
+#include "common.cuh"
+
+namespace {
+
+constexpr int KDE_THREADS = 128;      // threads per CTA in the pair kernel
+constexpr int KDE_TILE_FLOATS = 4096;  // 16 KB of points per shared-memory stage
+constexpr int KDE_STAGES = 3;
+constexpr double KDE_RESCUE_BELOW = 7.8886090522101181e-31;  // 2^-100
+
+struct KdeFit {
+    double mean[SS_MAX_D];
+    double wm[SS_MAX_D * SS_MAX_D];   // whitening matrix (lower triangular), row-major d x d
+    double norm;                      // N * (2 pi)^(d/2) * prod diag(L)
+    int status;                       // 0 ok, 1 not positive definite
+};
+
+__host__ __device__ constexpr int kde_point_stride(int D) { return ((2 * D + 3) / 4) * 4; }
+__host__ __device__ constexpr int kde_tile_pts(int D) { return (KDE_TILE_FLOATS / kde_point_stride(D)) / 4 * 4; }
+__host__ __device__ constexpr int kde_queries_per_thread(int D) {
+    return D <= 4 ? 8 : (D <= 8 ? 4 : 2);
+}
+
+// ---- 1. moments ------------------------------------------------------------------------
+// partial[b] = { sum (x - x0) [d], sum (x - x0)(x - x0)^T lower-tri [d(d+1)/2] }, x0 = data[0]
+// (shifted by the first data point so the fp64 one-pass covariance does not cancel)
+template <int DM>
+__global__ void __launch_bounds__(256)
+kde_moments_kernel(const double* __restrict__ data, long long n, int d, double* __restrict__ partial) {
+    __shared__ double sm[8];
+    constexpr int NM = DM + DM * (DM + 1) / 2;
+    const int nm = d + d * (d + 1) / 2;
+    double loc[NM];
+#pragma unroll
+    for (int i = 0; i < NM; ++i) loc[i] = 0.0;
+    double x0[DM], v[DM];
+#pragma unroll
+    for (int j = 0; j < DM; ++j) x0[j] = j < d ? data[j] : 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int j = 0; j < DM; ++j) v[j] = j < d ? data[i * d + j] - x0[j] : 0.0;
+        // moments laid out for the *runtime* d: index p advances only over j,k < d
+        int p = d;
+#pragma unroll
+        for (int j = 0; j < DM; ++j) {
+            if (j < d) {
+                loc[j] += v[j];
+#pragma unroll
+                for (int k = 0; k <= j; ++k) loc[p + k] += v[j] * v[k];
+                p += j + 1;
+            }
+        }
+    }
+    for (int q = 0; q < nm; ++q) {
+        double s = loc[q];
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sm[w];
+            partial[(size_t)blockIdx.x * nm + q] = t;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- 2. fit ----------------------------------------------------------------------------
+__global__ void kde_fit_kernel(const double* __restrict__ data, long long n, int d,
+                               const double* __restrict__ partial, int nblocks,
+                               KdeFit* __restrict__ fit) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int nm = d + d * (d + 1) / 2;
+    double mom[SS_MAX_D + SS_MAX_D * (SS_MAX_D + 1) / 2];
+    for (int q = 0; q < nm; ++q) {
+        double s = 0.0;
+        for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * nm + q];
+        mom[q] = s;
+    }
+    const double N = (double)n;
+    const double factor = pow(N, -1.0 / (d + 4));          // scotts_factor
+    double cov[SS_MAX_D * SS_MAX_D];
+    int p = d;
+    for (int j = 0; j < d; ++j) {
+        fit->mean[j] = data[j] + mom[j] / N;
+        for (int k = 0; k <= j; ++k) {
+            double c = (mom[p++] - mom[j] * mom[k] / N) / (N - 1.0);   // ddof = 1
+            cov[j * d + k] = c * factor * factor;
+            cov[k * d + j] = cov[j * d + k];
+        }
+    }
+    // Cholesky (lower), in place in l[]
+    double l[SS_MAX_D * SS_MAX_D];
+    int status = 0;
+    for (int j = 0; j < d; ++j) {
+        for (int k = 0; k <= j; ++k) {
+            double s = cov[j * d + k];
+            for (int q = 0; q < k; ++q) s -= l[j * d + q] * l[k * d + q];
+            if (j == k) {
+                if (!(s > 0.0)) { status = 1; s = 1.0; }
+                l[j * d + j] = sqrt(s);
+            } else {
+                l[j * d + k] = s / l[k * d + k];
+            }
+        }
+        for (int k = j + 1; k < d; ++k) l[j * d + k] = 0.0;
+    }
+    // inverse of the lower-triangular factor
+    double inv[SS_MAX_D * SS_MAX_D];
+    for (int j = 0; j < d * d; ++j) inv[j] = 0.0;
+    for (int c = 0; c < d; ++c) {
+        inv[c * d + c] = 1.0 / l[c * d + c];
+        for (int r = c + 1; r < d; ++r) {
+            double s = 0.0;
+            for (int q = c; q < r; ++q) s -= l[r * d + q] * inv[q * d + c];
+            inv[r * d + c] = s / l[r * d + r];
+        }
+    }
+    // exp(-e/2) = exp2(-(sqrt(log2(e)/2) |L^-1 (q-x)|)^2)
+    const double scale = sqrt(0.5 * 1.4426950408889634074);
+    double det = 1.0;
+    for (int j = 0; j < d; ++j) det *= l[j * d + j];
+    for (int j = 0; j < d * d; ++j) fit->wm[j] = inv[j] * scale;
+    fit->norm = N * pow(2.0 * 3.14159265358979323846, 0.5 * d) * det;
+    fit->status = status;
+}
+
+// ---- 3. whitening ----------------------------------------------------------------------
+// points:  out[i][2j], out[i][2j+1] = -y_j (duplicated, negated); padding rows = far away
+// queries: out[i][j] = y_j
+template <bool POINTS>
+__global__ void kde_whiten_kernel(const double* __restrict__ x, long long n, long long n_pad, int d,
+                                  int D, const KdeFit* __restrict__ fit, float* __restrict__ out) {
+    const int stride = POINTS ? kde_point_stride(D) : D;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    float* o = out + (size_t)i * stride;
+    if (i >= n) {
+        for (int j = 0; j < stride; ++j) o[j] = 0.f;
+        if (POINTS) { o[0] = -1e18f; o[1] = -1e18f; }   // exp2(-1e36) == 0
+        return;
+    }
+    double c[SS_MAX_D];
+    for (int j = 0; j < d; ++j) c[j] = x[i * d + j] - fit->mean[j];
+    for (int j = 0; j < D; ++j) {
+        double y = 0.0;
+        if (j < d)
+            for (int k = 0; k <= j; ++k) y += fit->wm[j * d + k] * c[k];
+        if (POINTS) {
+            o[2 * j] = (float)(-y);
+            o[2 * j + 1] = (float)(-y);
+        } else {
+            o[j] = (float)y;
+        }
+    }
+    if (POINTS)
+        for (int j = 2 * D; j < stride; ++j) o[j] = 0.f;
+}
+
+// ---- 4. the pair kernel ----------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA engine; SASS: UBLKCP), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// grid: (query tiles, point slices).  partial[slice][q] = sum over the slice's points.
+template <int D>
+__global__ void __launch_bounds__(KDE_THREADS)
+kde_pairs_kernel(const float* __restrict__ pts, long long n_tiles, const float* __restrict__ qw,
+                 long long m_pad, float* __restrict__ partial) {
+    constexpr int PS = kde_point_stride(D);           // floats per point in smem/global
+    constexpr int Q = kde_queries_per_thread(D);      // queries per thread (Q/2 packed pairs)
+    constexpr int TILE_PTS = kde_tile_pts(D);
+    constexpr int TILE_FLOATS = TILE_PTS * PS;
+    constexpr uint32_t TILE_BYTES = TILE_FLOATS * 4;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float* tiles = reinterpret_cast<float*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)KDE_STAGES * TILE_BYTES);
+
+    const int tid = threadIdx.x;
+    // this CTA's slice of point tiles
+    const long long per = (n_tiles + gridDim.y - 1) / gridDim.y;
+    const long long t0 = blockIdx.y * per;
+    const long long t1 = t0 + per < n_tiles ? t0 + per : n_tiles;
+    const long long nt = t1 > t0 ? t1 - t0 : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < KDE_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int s = 0; s < KDE_STAGES && s < nt; ++s) {
+            mbar_expect_tx(&full[s], TILE_BYTES);
+            bulk_g2s(tiles + (size_t)s * TILE_FLOATS, pts + (size_t)(t0 + s) * TILE_FLOATS, TILE_BYTES,
+                     &full[s]);
+        }
+    }
+
+    // queries of this thread: q = (blockIdx.x * KDE_THREADS + tid) * Q + [0, Q)
+    const long long qbase = ((long long)blockIdx.x * KDE_THREADS + tid) * Q;
+    float2 qv[Q / 2][D];
+#pragma unroll
+    for (int p = 0; p < Q / 2; ++p)
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+            qv[p][j] = make_float2(qw[(qbase + 2 * p) * D + j], qw[(qbase + 2 * p + 1) * D + j]);
+
+    float2 total[Q / 2];
+#pragma unroll
+    for (int p = 0; p < Q / 2; ++p) total[p] = make_float2(0.f, 0.f);
+
+    for (long long it = 0; it < nt; ++it) {
+        const int s = (int)(it % KDE_STAGES);
+        mbar_wait(&full[s], (uint32_t)((it / KDE_STAGES) & 1));
+        const float* tp = tiles + (size_t)s * TILE_FLOATS;
+        float2 acc[Q / 2];
+#pragma unroll
+        for (int p = 0; p < Q / 2; ++p) acc[p] = make_float2(0.f, 0.f);
+#pragma unroll 2
+        for (int i = 0; i < TILE_PTS; ++i) {
+            // broadcast loads: every lane reads the same point
+            float xs[PS];
+#pragma unroll
+            for (int v = 0; v < PS / 4; ++v) {
+                float4 f = *reinterpret_cast<const float4*>(tp + i * PS + 4 * v);
+                xs[4 * v] = f.x; xs[4 * v + 1] = f.y; xs[4 * v + 2] = f.z; xs[4 * v + 3] = f.w;
+            }
+#pragma unroll
+            for (int p = 0; p < Q / 2; ++p) {
+                float2 dlt = __fadd2_rn(qv[p][0], make_float2(xs[0], xs[1]));
+                float2 e = __fmul2_rn(dlt, dlt);
+#pragma unroll
+                for (int j = 1; j < D; ++j) {
+                    dlt = __fadd2_rn(qv[p][j], make_float2(xs[2 * j], xs[2 * j + 1]));
+                    e = __ffma2_rn(dlt, dlt, e);
+                }
+                acc[p] = __fadd2_rn(acc[p], make_float2(ex2_approx(-e.x), ex2_approx(-e.y)));
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < Q / 2; ++p) total[p] = __fadd2_rn(total[p], acc[p]);
+        __syncthreads();                                   // everyone is done with stage s
+        if (tid == 0 && it + KDE_STAGES < nt) {
+            mbar_expect_tx(&full[s], TILE_BYTES);
+            bulk_g2s(tiles + (size_t)s * TILE_FLOATS,
+                     pts + (size_t)(t0 + it + KDE_STAGES) * TILE_FLOATS, TILE_BYTES, &full[s]);
+        }
+    }
+    float* out = partial + (size_t)blockIdx.y * m_pad + qbase;
+#pragma unroll
+    for (int p = 0; p < Q / 2; ++p) {
+        out[2 * p] = total[p].x;
+        out[2 * p + 1] = total[p].y;
+    }
+}
+
+// ---- 5. finish: slice reduction, fp64 rescue, density, UCB, arg-max --------------------
+struct KdeResult {
+    double best_ucb;
+    long long best_j;
+    unsigned int blocks_done;
+    int n_rescued;
+};
+
+__global__ void __launch_bounds__(256)
+kde_finish_kernel(const float* __restrict__ partial, int n_slices, long long m, long long m_pad,
+                  const double* __restrict__ data, long long n, int d,
+                  const double* __restrict__ queries, const float* __restrict__ values,
+                  const KdeFit* __restrict__ fit, double n_transitions, double volume, double alpha,
+                  double beta, double* __restrict__ density, double* __restrict__ ucb_out,
+                  double* __restrict__ block_v, long long* __restrict__ block_i,
+                  KdeResult* __restrict__ result) {
+    __shared__ double s_v[32];
+    __shared__ long long s_i[32];
+    __shared__ int s_list[256];
+    __shared__ int s_nlist;
+    __shared__ double s_red[8];
+    __shared__ bool s_last;
+    if (threadIdx.x == 0) s_nlist = 0;
+    __syncthreads();
+
+    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    double sum = 0.0;
+    if (j < m) {
+        for (int s = 0; s < n_slices; ++s) sum += (double)partial[(size_t)s * m_pad + j];
+        if (!(sum >= KDE_RESCUE_BELOW)) s_list[atomicAdd(&s_nlist, 1)] = threadIdx.x;
+    }
+    __syncthreads();
+    // fp64 rescue of queries whose fp32 sum underflowed (far from every data point):
+    // the whole block recomputes sum_i exp(-|L^-1 (q - x_i)|^2 / 2) exactly as scipy does.
+    const int nres = s_nlist;
+    for (int r = 0; r < nres; ++r) {
+        const int owner = s_list[r];
+        const long long jq = blockIdx.x * (long long)blockDim.x + owner;
+        double yq[SS_MAX_D];
+        for (int a = 0; a < d; ++a) {
+            double y = 0.0;
+            for (int k = 0; k <= a; ++k) y += fit->wm[a * d + k] * (queries[jq * d + k] - fit->mean[k]);
+            yq[a] = y;
+        }
+        double part = 0.0;
+        for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+            double e = 0.0;
+            for (int a = 0; a < d; ++a) {
+                double y = 0.0;
+                for (int k = 0; k <= a; ++k) y += fit->wm[a * d + k] * (data[i * d + k] - fit->mean[k]);
+                double df = yq[a] - y;
+                e += df * df;
+            }
+            part += exp2(-e);
+        }
+        for (int off = 16; off > 0; off >>= 1) part += __shfl_down_sync(0xffffffffu, part, off);
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+        __syncthreads();
+        if (threadIdx.x == owner) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += s_red[w];
+            sum = t;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && nres) atomicAdd(&result->n_rescued, nres);
+
+    double u = 0.0;
+    long long idx = -1;
+    if (j < m) {
+        const double dens = sum / fit->norm;
+        const double c_hat = n_transitions * (dens * volume);
+        u = alpha * (double)values[j] + sqrt((beta * log(n_transitions)) / c_hat);
+        idx = j;
+        if (density) density[j] = dens;
+        if (ucb_out) ucb_out[j] = u;
+    }
+    block_argmax(u, idx, s_v, s_i);
+    if (threadIdx.x == 0) {
+        block_v[blockIdx.x] = u;
+        block_i[blockIdx.x] = idx;
+        __threadfence();
+        unsigned int done = atomicAdd(&result->blocks_done, 1u);
+        s_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        double v = 0.0;
+        long long bi = -1;
+        for (int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+            double ov = block_v[b];
+            long long oi = block_i[b];
+            if (argmax_better(ov, oi, v, bi)) { v = ov; bi = oi; }
+        }
+        block_argmax(v, bi, s_v, s_i);
+        if (threadIdx.x == 0) {
+            result->best_ucb = v;
+            result->best_j = bi;
+            result->blocks_done = 0;
+        }
+    }
+}
+
+template <int D>
+cudaError_t launch_pairs(ss_ctx* c, const float* pts, long long n_tiles, const float* qw,
+                         long long m_pad, int slices, float* partial) {
+    constexpr int Q = kde_queries_per_thread(D);
+    const size_t smem = (size_t)KDE_STAGES * kde_tile_pts(D) * kde_point_stride(D) * 4 + KDE_STAGES * 8;
+    cudaError_t e = cudaFuncSetAttribute(kde_pairs_kernel<D>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)(m_pad / (KDE_THREADS * Q)), (unsigned)slices);
+    kde_pairs_kernel<D><<<grid, KDE_THREADS, smem, c->stream>>>(pts, n_tiles, qw, m_pad, partial);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+int pad_dim(int d) {
+    const int opts[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
+    for (int o : opts)
+        if (d <= o) return o;
+    return -1;
+}
+
+}  // namespace
+
+int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double* queries_dev,
+            long long m, const float* values_dev, long long n_transitions, double volume,
+            double alpha, double beta, double* density_dev, double* ucb_dev, int64_t* out_best_j,
+            double* out_best_ucb) {
+    const int D = pad_dim(d);
+    if (D < 0) SS_FAIL(c, SS_EUNSUPPORTED, "kde: state dimension > 32 is not supported");
+    const int Q = kde_queries_per_thread(D);
+    const int PS = kde_point_stride(D);
+    const int tile_pts = kde_tile_pts(D);
+    const long long n_tiles = (n + tile_pts - 1) / tile_pts;
+    const long long n_pad = n_tiles * tile_pts;
+    const long long qtile = (long long)KDE_THREADS * Q;
+    const long long m_pad = (m + qtile - 1) / qtile * qtile;
+    const long long q_tiles = m_pad / qtile;
+    // fill the GPU: ~4 CTAs per SM
+    long long want = (long long)c->sm_count * 4;
+    long long slices = (want + q_tiles - 1) / q_tiles;
+    if (slices > n_tiles) slices = n_tiles;
+    if (slices < 1) slices = 1;
+    // drop empty trailing slices
+    {
+        long long per = (n_tiles + slices - 1) / slices;
+        slices = (n_tiles + per - 1) / per;
+    }
+    const int mom_blocks = (int)std::min<long long>(c->sm_count * 2, (n + 255) / 256);
+    const int nm = d + d * (d + 1) / 2;
+    const int fin_blocks = (int)((m + 255) / 256);
+
+    SS_CUDA_CHECK(c, c->kde_moments.ensure((size_t)mom_blocks * nm * 8));
+    SS_CUDA_CHECK(c, c->kde_fit.ensure(sizeof(KdeFit)));
+    SS_CUDA_CHECK(c, c->kde_pts.ensure((size_t)n_pad * PS * 4));
+    SS_CUDA_CHECK(c, c->kde_qw.ensure((size_t)m_pad * D * 4));
+    SS_CUDA_CHECK(c, c->kde_partial.ensure((size_t)slices * m_pad * 4));
+    SS_CUDA_CHECK(c, c->kde_block_best.ensure((size_t)fin_blocks * 16));
+    SS_CUDA_CHECK(c, c->kde_result.ensure(sizeof(KdeResult)));
+    KdeFit* fit = c->kde_fit.as<KdeFit>();
+    KdeResult* res = c->kde_result.as<KdeResult>();
+
+    SS_CUDA_CHECK(c, cudaMemsetAsync(res, 0, sizeof(KdeResult), c->stream));
+    if (d <= 8)
+        kde_moments_kernel<8><<<mom_blocks, 256, 0, c->stream>>>(data_dev, n, d,
+                                                                 c->kde_moments.as<double>());
+    else
+        kde_moments_kernel<SS_MAX_D><<<mom_blocks, 256, 0, c->stream>>>(data_dev, n, d,
+                                                                        c->kde_moments.as<double>());
+    kde_fit_kernel<<<1, 32, 0, c->stream>>>(data_dev, n, d, c->kde_moments.as<double>(), mom_blocks,
+                                            fit);
+    kde_whiten_kernel<true><<<(unsigned)((n_pad + 255) / 256), 256, 0, c->stream>>>(
+        data_dev, n, n_pad, d, D, fit, c->kde_pts.as<float>());
+    kde_whiten_kernel<false><<<(unsigned)((m_pad + 255) / 256), 256, 0, c->stream>>>(
+        queries_dev, m, m_pad, d, D, fit, c->kde_qw.as<float>());
+    c->launches += 4;
+    SS_CUDA_CHECK(c, cudaGetLastError());
+    timer_mark(c, "kde_fit_whiten");
+
+    cudaError_t e = cudaSuccess;
+    const float* pts = c->kde_pts.as<float>();
+    const float* qw = c->kde_qw.as<float>();
+    float* partial = c->kde_partial.as<float>();
+    switch (D) {
+#define KDE_CASE(DD) \
+    case DD: e = launch_pairs<DD>(c, pts, n_tiles, qw, m_pad, (int)slices, partial); break;
+        KDE_CASE(1) KDE_CASE(2) KDE_CASE(3) KDE_CASE(4) KDE_CASE(6) KDE_CASE(8)
+        KDE_CASE(12) KDE_CASE(16) KDE_CASE(24) KDE_CASE(32)
+#undef KDE_CASE
+    }
+    SS_CUDA_CHECK(c, e);
+    timer_mark(c, "kde_pairs");
+
+    double* bv = c->kde_block_best.as<double>();
+    long long* bi = reinterpret_cast<long long*>(bv + fin_blocks);
+    kde_finish_kernel<<<fin_blocks, 256, 0, c->stream>>>(
+        partial, (int)slices, m, m_pad, data_dev, n, d, queries_dev, values_dev, fit,
+        (double)n_transitions, volume, alpha, beta, density_dev, ucb_dev, bv, bi, res);
+    c->launches++;
+    SS_CUDA_CHECK(c, cudaGetLastError());
+    timer_mark(c, "kde_finish");
+
+    KdeResult hres;
+    KdeFit hfit_status;
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(&hres, res, sizeof(KdeResult), cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(&hfit_status.status, &fit->status, sizeof(int),
+                                     cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (hfit_status.status != 0)
+        SS_FAIL(c, SS_ESINGULAR, "kde: data covariance is not positive definite (singular matrix)");
+    *out_best_j = hres.best_j;
+    *out_best_ucb = hres.best_ucb;
+    return SS_OK;
+}

@@ -1,0 +1,385 @@
+// mpc_host.cu -- host side of the MPC planner: model / plan upload, phase orchestration.
+//
+//   ss_mpc_set_model  <- Dyn_Model weights + NND_MB_agent.py:302-315 statistics
+//   ss_mpc_set_plan   <- NND_MB_agent.start_new_episode_plan (NND_MB_agent.py:375-418)
+//   ss_mpc_rollout    phase A: sample/fetch actions, roll the MLP for H steps, score
+//   ss_mpc_finish     phase B (reference penalty) + arg-max
+//   ss_mpc_replay     re-roll the winner for best_sequence / best_path (NND_MB_agent.py:516-518)
+#include <cstring>
+
+#include "mpc_kernels.cuh"
+
+namespace {
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+__global__ void sample_actions_kernel(ActionSource src, long long K, long long k_offset,
+                                      double* __restrict__ out) {
+    const long long n = K * src.H * src.da;
+    for (long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x; o < n;
+         o += (long long)gridDim.x * blockDim.x) {
+        const long long k = o / (src.H * src.da);
+        const int rem = (int)(o - k * (src.H * src.da));
+        const int t = rem / src.da, j = rem - t * src.da;
+        out[o] = (double)fetch_action(src, k, k_offset + k, t, j);
+    }
+}
+
+int fill_action_source(ss_ctx* c, ActionSource& s, int H, int da, uint64_t seed, const double* low,
+                       const double* high) {
+    s.host_actions = nullptr;
+    s.seed = seed;
+    s.da = da;
+    s.H = H;
+    for (int j = 0; j < SS_MAX_DA; ++j) { s.low[j] = 0.0; s.range[j] = 0.0; }
+    if (low && high)
+        for (int j = 0; j < da; ++j) { s.low[j] = low[j]; s.range[j] = high[j] - low[j]; }
+    else if (!low != !high)
+        SS_FAIL(c, SS_EINVAL, "mpc: act_low and act_high must both be given");
+    return SS_OK;
+}
+
+PlanView make_plan_view(ss_ctx* c, const float* gpow, double gamma, double hpf) {
+    PlanView p;
+    p.ds = c->plan_ds.as<float>();
+    p.dl = c->plan_dl.as<float>();
+    p.gpow = gpow;
+    p.W = c->W;
+    p.d = c->d;
+    for (int j = 0; j < SS_MAX_D; ++j) p.inv_r[j] = c->inv_radii[j];
+    p.pen_scale = (float)(hpf * gamma);
+    return p;
+}
+
+void fill_model_args(ss_ctx* c, RolloutArgs& a) {
+    for (int l = 0; l <= c->L; ++l) {
+        a.w[l] = c->w32[l].as<float>();
+        a.b[l] = c->b32[l].as<float>();
+    }
+    a.d = c->d; a.da = c->da; a.L = c->L; a.h = c->h;
+    a.din_pad = c->din_pad; a.h_pad = c->h_pad; a.dout_pad = round_up(c->d, 8);
+    a.norm = c->norm;
+}
+
+}  // namespace
+
+extern "C" int ss_mpc_set_model(ss_ctx* c, int d, int da, int num_fc_layers, int depth,
+                                const double* const* weights, const double* const* biases,
+                                const double* mean_x, const double* std_x, const double* mean_y,
+                                const double* std_y, const double* mean_z, const double* std_z) {
+    if (!c) return SS_EINVAL;
+    if (d < 1 || d > SS_MAX_D || da < 1 || da > SS_MAX_DA)
+        SS_FAIL(c, SS_EUNSUPPORTED, "mpc: need 1 <= d <= 32 and 1 <= da <= 8");
+    if (num_fc_layers < 1 || num_fc_layers > SS_MAX_LAYERS || depth < 1)
+        SS_FAIL(c, SS_EUNSUPPORTED, "mpc: need 1 <= num_fc_layers <= 8 and depth_fc_layers >= 1");
+    if (!weights || !biases || !mean_x || !std_x || !mean_y || !std_y || !mean_z || !std_z)
+        SS_FAIL(c, SS_EINVAL, "mpc: null model pointer");
+    SS_CUDA_CHECK(c, cudaSetDevice(c->device));
+    if (d != c->d) c->plan_set = false;   // a plan refers to the state dimension
+    c->d = d; c->da = da; c->L = num_fc_layers; c->h = depth;
+    c->din_pad = round_up(d + da, 16);
+    c->h_pad = round_up(depth, 16);
+    c->w32.resize(num_fc_layers + 1);
+    c->b32.resize(num_fc_layers + 1);
+    for (int l = 0; l <= num_fc_layers; ++l) {
+        const int in = l == 0 ? d + da : depth, out = l == num_fc_layers ? d : depth;
+        const int in_pad = l == 0 ? c->din_pad : c->h_pad;
+        const int out_pad = l == num_fc_layers ? round_up(d, 8) : c->h_pad;
+        std::vector<float> w((size_t)in_pad * out_pad, 0.f), b(out_pad, 0.f);
+        for (int i = 0; i < in; ++i)
+            for (int o = 0; o < out; ++o) w[(size_t)i * out_pad + o] = (float)weights[l][(size_t)i * out + o];
+        for (int o = 0; o < out; ++o) b[o] = (float)biases[l][o];
+        SS_CUDA_CHECK(c, c->w32[l].ensure(w.size() * 4));
+        SS_CUDA_CHECK(c, c->b32[l].ensure(b.size() * 4));
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(c->w32[l].p, w.data(), w.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(c->b32[l].p, b.data(), b.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));   // w, b are stack-local staging
+    }
+    // Q4: the reference evaluates nan_to_num((x - mean) / std); for std == 0 that is 0
+    // when x == mean and +-1.8e308 otherwise.  A zero-variance feature carries no information, so
+    // the kernels use 0 for it (documented deviation).
+    std::memset(&c->norm, 0, sizeof(c->norm));
+    for (int j = 0; j < d; ++j) {
+        c->norm.mean_x[j] = (float)mean_x[j];
+        c->norm.inv_std_x[j] = std_x[j] != 0.0 ? (float)(1.0 / std_x[j]) : 0.f;
+        c->norm.mean_z[j] = (float)mean_z[j];
+        c->norm.std_z[j] = (float)std_z[j];
+    }
+    for (int j = 0; j < da; ++j) {
+        c->norm.mean_y[j] = (float)mean_y[j];
+        c->norm.inv_std_y[j] = std_y[j] != 0.0 ? (float)(1.0 / std_y[j]) : 0.f;
+    }
+    c->model_set = true;
+    c->run.valid = false;
+    c->tc_ready = false;
+    if (mpc_tc_shape_supported(c)) {
+        int rc = mpc_tc_prepare(c);
+        if (rc != SS_OK) return rc;
+    }
+    return SS_OK;
+}
+
+extern "C" int ss_mpc_tc_supported(ss_ctx* c) { return c && c->model_set && c->tc_ready ? 1 : 0; }
+
+extern "C" int ss_mpc_set_plan(ss_ctx* c, const double* desired_states, int W,
+                               const double* distances_left, const double* radii, int d) {
+    if (!c) return SS_EINVAL;
+    if (!c->model_set) SS_FAIL(c, SS_ESTATE, "mpc: set the model before the plan");
+    if (d != c->d) SS_FAIL(c, SS_EINVAL, "mpc: plan state dimension differs from the model's");
+    if (W < 2) SS_FAIL(c, SS_EINVAL, "mpc: a plan needs at least two desired states");
+    if (!desired_states || !distances_left || !radii) SS_FAIL(c, SS_EINVAL, "mpc: null plan pointer");
+    for (int j = 0; j < d; ++j)
+        if (!(radii[j] > 0.0)) SS_FAIL(c, SS_EINVAL, "mpc: radii must be > 0 (AssertionError in the reference)");
+    SS_CUDA_CHECK(c, cudaSetDevice(c->device));
+    std::vector<float> ds((size_t)W * d), dl(W);
+    for (size_t i = 0; i < ds.size(); ++i) ds[i] = (float)desired_states[i];
+    for (int i = 0; i < W; ++i) dl[i] = (float)distances_left[i];
+    SS_CUDA_CHECK(c, c->plan_ds.ensure(ds.size() * 4));
+    SS_CUDA_CHECK(c, c->plan_dl.ensure(dl.size() * 4));
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(c->plan_ds.p, ds.data(), ds.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(c->plan_dl.p, dl.data(), dl.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    for (int j = 0; j < SS_MAX_D; ++j) c->inv_radii[j] = j < d ? (float)(1.0 / radii[j]) : 0.f;
+    c->W = W;
+    c->plan_set = true;
+    c->run.valid = false;
+    return SS_OK;
+}
+
+extern "C" int ss_mpc_sample_actions(ss_ctx* c, int64_t K_local, int64_t k_offset, int H, int da,
+                                     uint64_t seed, const double* act_low, const double* act_high,
+                                     double* out_actions) {
+    if (!c) return SS_EINVAL;
+    if (K_local < 1 || H < 1 || da < 1 || da > SS_MAX_DA || !act_low || !act_high || !out_actions)
+        SS_FAIL(c, SS_EINVAL, "mpc: bad sample_actions arguments");
+    SS_CUDA_CHECK(c, cudaSetDevice(c->device));
+    ActionSource src;
+    int rc = fill_action_source(c, src, H, da, seed, act_low, act_high);
+    if (rc) return rc;
+    const size_t n = (size_t)K_local * H * da;
+    SS_CUDA_CHECK(c, c->mpc_sampled.ensure(n * 8));
+    sample_actions_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(src, K_local, k_offset,
+                                                                   c->mpc_sampled.as<double>());
+    c->launches++;
+    SS_CUDA_CHECK(c, cudaGetLastError());
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(out_actions, c->mpc_sampled.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return SS_OK;
+}
+
+extern "C" int ss_mpc_rollout(ss_ctx* c, const double* state, int wp_index, int64_t K_local,
+                              int64_t k_offset, int64_t K_global, int H, const double* actions,
+                              uint64_t seed, const double* act_low, const double* act_high,
+                              double gamma, double hpf, int penalty_mode, int precision) {
+    if (!c) return SS_EINVAL;
+    if (!c->model_set || !c->plan_set) SS_FAIL(c, SS_ESTATE, "mpc: model and plan must be set before planning");
+    if (!state || K_local < 1 || H < 1 || k_offset < 0 || K_global < k_offset + K_local)
+        SS_FAIL(c, SS_EINVAL, "mpc: bad K / H / state arguments");
+    if (wp_index < 0 || wp_index >= c->W) SS_FAIL(c, SS_EINVAL, "mpc: wp_index outside the plan");
+    if (penalty_mode != SS_PENALTY_REFERENCE && penalty_mode != SS_PENALTY_PER_SAMPLE)
+        SS_FAIL(c, SS_EINVAL, "mpc: unknown penalty_mode");
+    if (!actions && (!act_low || !act_high))
+        SS_FAIL(c, SS_EINVAL, "mpc: device sampling needs act_low / act_high");
+    if (precision == SS_PRECISION_AUTO) precision = c->tc_ready ? SS_PRECISION_BF16_TC : SS_PRECISION_FP32;
+    if (precision == SS_PRECISION_BF16_TC && !c->tc_ready)
+        SS_FAIL(c, SS_EUNSUPPORTED, "mpc: this model shape has no tcgen05 kernel (use precision FP32 or AUTO)");
+    if (precision != SS_PRECISION_FP32 && precision != SS_PRECISION_BF16_TC)
+        SS_FAIL(c, SS_EINVAL, "mpc: unknown precision");
+    SS_CUDA_CHECK(c, cudaSetDevice(c->device));
+    timer_begin(c);
+
+    auto& r = c->run;
+    r.valid = false;
+    r.K_local = K_local; r.k_offset = k_offset; r.K_global = K_global; r.H = H;
+    r.wp_index = wp_index; r.penalty_mode = penalty_mode; r.precision = precision;
+    r.gamma = gamma; r.hpf = hpf;
+    for (int j = 0; j < SS_MAX_D; ++j) r.state[j] = j < c->d ? (float)state[j] : 0.f;
+    int rc = fill_action_source(c, r.act, H, c->da, seed, act_low, act_high);
+    if (rc) return rc;
+    const int T = H + 1;
+    if (actions) {
+        const size_t n = (size_t)K_local * H * c->da;
+        SS_CUDA_CHECK(c, c->mpc_actions64.ensure(n * 8));
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(c->mpc_actions64.p, actions, n * 8, cudaMemcpyHostToDevice, c->stream));
+        r.act.host_actions = c->mpc_actions64.as<double>();
+    }
+    // gamma^t table (float64 pow, rounded once) + state0 for the second pass
+    {
+        std::vector<float> misc(T + SS_MAX_D);
+        for (int t = 0; t < T; ++t) misc[t] = (float)std::pow(gamma, (double)t);
+        for (int j = 0; j < SS_MAX_D; ++j) misc[T + j] = r.state[j];
+        SS_CUDA_CHECK(c, c->mpc_replay.ensure((size_t)(T + SS_MAX_D) * 4 + (size_t)T * SS_MAX_D * 4));
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(c->mpc_replay.p, misc.data(), misc.size() * 4, cudaMemcpyHostToDevice, c->stream));
+        SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    }
+    const float* gpow = c->mpc_replay.as<float>();
+
+    RolloutArgs a;
+    std::memset(&a, 0, sizeof(a));
+    fill_model_args(c, a);
+    a.act = r.act;
+    a.plan = make_plan_view(c, gpow, gamma, hpf);
+    for (int j = 0; j < SS_MAX_D; ++j) a.state0[j] = r.state[j];
+    a.wp_index = wp_index; a.H = H; a.K_local = K_local; a.k_offset = k_offset;
+    a.per_sample = penalty_mode == SS_PENALTY_PER_SAMPLE;
+    SS_CUDA_CHECK(c, c->mpc_scores.ensure((size_t)K_local * 4));
+    a.scores_out = c->mpc_scores.as<float>();
+    const bool ref = penalty_mode == SS_PENALTY_REFERENCE;
+    const int blocks = precision == SS_PRECISION_BF16_TC ? mpc_tc_grid(c, a) : mpc_simt_grid(a);
+    r.states_stored = ref;
+    if (ref) {
+        SS_CUDA_CHECK(c, c->mpc_states.ensure((size_t)T * K_local * c->d * 4));
+        SS_CUDA_CHECK(c, c->mpc_partial_sums.ensure((size_t)blocks * T * 2 * 8));
+        SS_CUDA_CHECK(c, c->mpc_sums.ensure((size_t)T * 2 * 8));
+        a.states_out = c->mpc_states.as<float>();
+        a.partial_sums = c->mpc_partial_sums.as<double>();
+    }
+    timer_mark(c, "mpc_setup");
+    int grid = 0;
+    rc = precision == SS_PRECISION_BF16_TC ? mpc_tc_launch(c, a, &grid) : mpc_simt_launch(c, a, &grid);
+    if (rc) return rc;
+    timer_mark(c, "mpc_rollout");
+    if (ref) {
+        rc = mpc_reduce_sums(c, c->mpc_partial_sums.as<double>(), grid, T, c->mpc_sums.as<double>());
+        if (rc) return rc;
+        r.sum_blocks = grid;
+    }
+    r.valid = true;
+    return SS_OK;
+}
+
+extern "C" int ss_mpc_projection_sums(ss_ctx* c, double** sums_dev, int* count) {
+    if (!c) return SS_EINVAL;
+    if (!c->run.valid) SS_FAIL(c, SS_ESTATE, "mpc: no rollout to take projection sums from");
+    if (c->run.penalty_mode != SS_PENALTY_REFERENCE) {
+        if (sums_dev) *sums_dev = nullptr;
+        if (count) *count = 0;
+        return SS_OK;
+    }
+    if (sums_dev) *sums_dev = c->mpc_sums.as<double>();
+    if (count) *count = 2 * (c->run.H + 1);
+    return SS_OK;
+}
+
+extern "C" int ss_mpc_finish(ss_ctx* c, int64_t* out_best_k, double* out_best_score, double* out_scores) {
+    if (!c) return SS_EINVAL;
+    auto& r = c->run;
+    if (!r.valid) SS_FAIL(c, SS_ESTATE, "mpc: ss_mpc_finish without ss_mpc_rollout");
+    SS_CUDA_CHECK(c, cudaSetDevice(c->device));
+    const int T = r.H + 1;
+    const float* gpow = c->mpc_replay.as<float>();
+    int rc;
+    if (r.penalty_mode == SS_PENALTY_REFERENCE) {
+        PlanView p = make_plan_view(c, gpow, r.gamma, r.hpf);
+        rc = mpc_score_reference(c, p, r.wp_index, gpow + T, c->mpc_states.as<float>(), r.K_local, T,
+                                 c->mpc_sums.as<double>(), c->mpc_scores.as<float>());
+        if (rc) return rc;
+        timer_mark(c, "mpc_score_pass2");
+    }
+    SS_CUDA_CHECK(c, c->mpc_block_best.ensure(1024 * 16));
+    if (!c->mpc_result.p) {
+        SS_CUDA_CHECK(c, c->mpc_result.ensure(sizeof(MpcResult)));
+        SS_CUDA_CHECK(c, cudaMemsetAsync(c->mpc_result.p, 0, sizeof(MpcResult), c->stream));
+    }
+    double* bv = c->mpc_block_best.as<double>();
+    rc = mpc_argmax(c, c->mpc_scores.as<float>(), r.K_local, r.k_offset, bv,
+                    reinterpret_cast<long long*>(bv + 1024), c->mpc_result.p);
+    if (rc) return rc;
+    timer_mark(c, "mpc_argmax");
+    MpcResult h;
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(&h, c->mpc_result.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    std::vector<float> sc;
+    if (out_scores) {
+        sc.resize(r.K_local);
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(sc.data(), c->mpc_scores.p, (size_t)r.K_local * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (out_scores)
+        for (int64_t k = 0; k < r.K_local; ++k) out_scores[k] = (double)sc[k];
+    if (out_best_k) *out_best_k = h.best_k;
+    if (out_best_score) *out_best_score = h.best_score;
+    return SS_OK;
+}
+
+extern "C" int ss_mpc_get_states(ss_ctx* c, double* out_states) {
+    if (!c) return SS_EINVAL;
+    auto& r = c->run;
+    if (!r.valid || !r.states_stored)
+        SS_FAIL(c, SS_ESTATE, "mpc: no stored trajectories (roll out in reference penalty mode first)");
+    if (!out_states) SS_FAIL(c, SS_EINVAL, "mpc: null output");
+    SS_CUDA_CHECK(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)(r.H + 1) * r.K_local * c->d;
+    std::vector<float> tmp(n);
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(tmp.data(), c->mpc_states.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n; ++i) out_states[i] = (double)tmp[i];
+    return SS_OK;
+}
+
+extern "C" int ss_mpc_replay(ss_ctx* c, int64_t k_global, double* out_sequence, double* out_path) {
+    if (!c) return SS_EINVAL;
+    auto& r = c->run;
+    if (!r.valid) SS_FAIL(c, SS_ESTATE, "mpc: ss_mpc_replay without ss_mpc_rollout");
+    if (k_global < 0 || k_global >= r.K_global) SS_FAIL(c, SS_EINVAL, "mpc: replay index outside the batch");
+    SS_CUDA_CHECK(c, cudaSetDevice(c->device));
+    const int T = r.H + 1, d = c->d, da = c->da;
+    const int64_t k_local = k_global - r.k_offset;
+    const bool mine = k_local >= 0 && k_local < r.K_local;
+    if (r.act.host_actions && !mine)
+        SS_FAIL(c, SS_EINVAL, "mpc: host-provided actions of another shard cannot be replayed here");
+    const float* gpow = c->mpc_replay.as<float>();
+    float* path_dev = c->mpc_replay.as<float>() + T + SS_MAX_D;
+
+    RolloutArgs a;
+    std::memset(&a, 0, sizeof(a));
+    fill_model_args(c, a);
+    a.act = r.act;
+    if (a.act.host_actions) a.act.host_actions += (size_t)k_local * r.H * da;
+    a.plan = make_plan_view(c, gpow, r.gamma, r.hpf);
+    for (int j = 0; j < SS_MAX_D; ++j) a.state0[j] = r.state[j];
+    a.wp_index = r.wp_index; a.H = r.H; a.K_local = 1; a.k_offset = k_global;
+    a.per_sample = 1;
+    a.states_out = path_dev;
+    int rc = mpc_simt_launch(c, a, nullptr);
+    if (rc) return rc;
+    std::vector<float> path((size_t)T * d);
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(path.data(), path_dev, path.size() * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (out_sequence) {
+        const size_t n = (size_t)r.H * da;
+        SS_CUDA_CHECK(c, c->mpc_block_best.ensure(1024 * 16 + n * 8));
+        double* seq_dev = reinterpret_cast<double*>(c->mpc_block_best.as<char>() + 1024 * 16);
+        sample_actions_kernel<<<1, 128, 0, c->stream>>>(a.act, 1, k_global, seq_dev);
+        c->launches++;
+        SS_CUDA_CHECK(c, cudaGetLastError());
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(out_sequence, seq_dev, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (out_path)
+        for (size_t i = 0; i < path.size(); ++i) out_path[i] = (double)path[i];
+    timer_mark(c, "mpc_replay");
+    return SS_OK;
+}
+
+extern "C" int ss_mpc_plan(ss_ctx* c, const double* state, int wp_index, int64_t K_local,
+                           int64_t k_offset, int64_t K_global, int H, const double* actions,
+                           uint64_t seed, const double* act_low, const double* act_high, double gamma,
+                           double hpf, int penalty_mode, int precision, int64_t* out_best_k,
+                           double* out_best_score, double* out_best_sequence, double* out_best_path,
+                           double* out_scores) {
+    if (!c) return SS_EINVAL;
+    if (penalty_mode == SS_PENALTY_REFERENCE && K_global != K_local)
+        SS_FAIL(c, SS_EINVAL,
+                "mpc: reference penalty over a sharded batch needs ss_mpc_rollout / all-reduce / ss_mpc_finish");
+    int rc = ss_mpc_rollout(c, state, wp_index, K_local, k_offset, K_global, H, actions, seed, act_low,
+                            act_high, gamma, hpf, penalty_mode, precision);
+    if (rc) return rc;
+    int64_t best = -1;
+    rc = ss_mpc_finish(c, &best, out_best_score, out_scores);
+    if (rc) return rc;
+    if (out_best_k) *out_best_k = best;
+    if (out_best_sequence || out_best_path) {
+        rc = ss_mpc_replay(c, best, out_best_sequence, out_best_path);
+        if (rc) return rc;
+    }
+    return SS_OK;
+}

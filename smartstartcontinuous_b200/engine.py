@@ -1,0 +1,262 @@
+"""Python host side of the C ABI: one ``Engine`` = one ``ss_ctx`` = one GPU.
+
+The two seams of the reference map to two methods:
+
+  Engine.select_start(...)  -> smartexplorationcontinuous.py:260-280 (KDE + UCB + argmax)
+  Engine.plan(...)          -> NND_MB_agent.get_best_sim_actions, NND_MB_agent.py:498-520
+
+Error codes of the library are mapped to the exception classes the reference raises
+(ValueError / numpy.linalg.LinAlgError / AssertionError-like ValueError); a missing
+library or GPU raises -- nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import (PENALTY_PER_SAMPLE, PENALTY_REFERENCE, PRECISION_AUTO, PRECISION_BF16_TC,
+                   PRECISION_FP32)
+
+_PENALTY = {"reference": PENALTY_REFERENCE, "per_sample": PENALTY_PER_SAMPLE,
+            PENALTY_REFERENCE: PENALTY_REFERENCE, PENALTY_PER_SAMPLE: PENALTY_PER_SAMPLE}
+_PRECISION = {"fp32": PRECISION_FP32, "bf16_tc": PRECISION_BF16_TC, "auto": PRECISION_AUTO,
+              PRECISION_FP32: PRECISION_FP32, PRECISION_BF16_TC: PRECISION_BF16_TC,
+              PRECISION_AUTO: PRECISION_AUTO}
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        h = C.c_void_p()
+        rc = self._lib.ss_create(C.byref(h), int(device))
+        if rc != 0:
+            msg = self._lib.ss_last_error(None).decode()
+            raise RuntimeError("ss_create(device=%d) failed (%d): %s" % (device, rc, msg))
+        self._h = h
+        self.device = int(device)
+        self._model_shape = None
+        self._keepalive = []
+
+    # ------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ss_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc == 0:
+            return
+        msg = self._lib.ss_last_error(self._h).decode()
+        if rc == _lib.SS_ESINGULAR:
+            raise np.linalg.LinAlgError(msg)
+        if rc in (_lib.SS_EINVAL, _lib.SS_EUNSUPPORTED):
+            raise ValueError(msg)
+        raise RuntimeError("libss_b200 error %d: %s" % (rc, msg))
+
+    def set_stream(self, cuda_stream_handle):
+        self._check(self._lib.ss_set_stream(self._h, C.c_void_p(int(cuda_stream_handle))))
+
+    def device_info(self):
+        v = [C.c_int() for _ in range(4)]
+        self._check(self._lib.ss_device_info(self._h, *[C.byref(x) for x in v]))
+        return dict(sm_count=v[0].value, cc=(v[1].value, v[2].value), sm_clock_khz=v[3].value)
+
+    def last_timings(self):
+        ms = (C.c_float * 8)()
+        names = (C.c_char_p * 8)()
+        n = self._lib.ss_last_timings(self._h, ms, names, 8)
+        return [(names[i].decode(), float(ms[i])) for i in range(n)]
+
+    def launch_count(self):
+        return int(self._lib.ss_launch_count(self._h))
+
+    # ------------------------------------------------------------------ stage 1
+    def select_start(self, all_states, queries, values, n_transitions, volume=1.0, alpha=1.0,
+                     beta=2.0, want_density=False, want_ucb=False):
+        """KDE + UCB + argmax.  Returns (best_j, best_ucb, densities | None, ucb | None)."""
+        data = _f64(all_states)
+        q = _f64(queries)
+        if data.ndim != 2 or q.ndim != 2 or data.shape[1] != q.shape[1]:
+            raise ValueError("all_states [n+1, d] and queries [m, d] must be 2-D with the same d")
+        v = np.ascontiguousarray(np.asarray(values).reshape(-1), dtype=np.float32)
+        if v.shape[0] != q.shape[0]:
+            raise ValueError("values must have one entry per query")
+        dens = np.empty(q.shape[0]) if want_density else None
+        ucb = np.empty(q.shape[0]) if want_ucb else None
+        best = C.c_int64(-1)
+        best_ucb = C.c_double(0.0)
+        self._check(self._lib.ss_kde_ucb_argmax(
+            self._h, _ptr(data), data.shape[0], data.shape[1], _ptr(q), q.shape[0], _ptr(v),
+            int(n_transitions), float(volume), float(alpha), float(beta), _ptr(dens), _ptr(ucb),
+            C.byref(best), C.byref(best_ucb)))
+        return int(best.value), float(best_ucb.value), dens, ucb
+
+    def select_start_dev(self, data_ptr, n_pts, d, queries_ptr, m, values_ptr, n_transitions,
+                         volume=1.0, alpha=1.0, beta=2.0, density_ptr=None, ucb_ptr=None):
+        """Same with device pointers (e.g. torch tensors' data_ptr()); returns (best_j, best_ucb)."""
+        best = C.c_int64(-1)
+        best_ucb = C.c_double(0.0)
+        self._check(self._lib.ss_kde_ucb_argmax_dev(
+            self._h, C.c_void_p(data_ptr), int(n_pts), int(d), C.c_void_p(queries_ptr), int(m),
+            C.c_void_p(values_ptr), int(n_transitions), float(volume), float(alpha), float(beta),
+            C.c_void_p(density_ptr) if density_ptr else None,
+            C.c_void_p(ucb_ptr) if ucb_ptr else None, C.byref(best), C.byref(best_ucb)))
+        return int(best.value), float(best_ucb.value)
+
+    # ------------------------------------------------------------------ stage 2
+    def set_model(self, weights, biases, norm):
+        """weights[l] [in, out] (y = x W + b), biases[l] [out]; norm: dict mean_x std_x mean_y
+        std_y mean_z std_z (NND_MB_agent.py:302-315)."""
+        ws = [_f64(w) for w in weights]
+        bs = [_f64(b).reshape(-1) for b in biases]
+        L = len(ws) - 1
+        if L < 1 or len(bs) != len(ws):
+            raise ValueError("need num_fc_layers + 1 weight matrices and as many biases")
+        d = ws[-1].shape[1]
+        da = ws[0].shape[0] - d
+        h = ws[0].shape[1]
+        for l, (w, b) in enumerate(zip(ws, bs)):
+            exp_in = d + da if l == 0 else h
+            exp_out = d if l == L else h
+            if w.shape != (exp_in, exp_out) or b.shape != (exp_out,):
+                raise ValueError("layer %d has shape %s / %s, expected (%d, %d)"
+                                 % (l, w.shape, b.shape, exp_in, exp_out))
+        n = {k: _f64(np.asarray(norm[k]).reshape(-1)) for k in
+             ("mean_x", "std_x", "mean_y", "std_y", "mean_z", "std_z")}
+        if n["mean_x"].size != d or n["mean_y"].size != da or n["mean_z"].size != d:
+            raise ValueError("normalisation statistics do not match the model's d / da")
+        wp = (C.c_void_p * len(ws))(*[w.ctypes.data for w in ws])
+        bp = (C.c_void_p * len(bs))(*[b.ctypes.data for b in bs])
+        self._check(self._lib.ss_mpc_set_model(
+            self._h, d, da, L, h, wp, bp, _ptr(n["mean_x"]), _ptr(n["std_x"]), _ptr(n["mean_y"]),
+            _ptr(n["std_y"]), _ptr(n["mean_z"]), _ptr(n["std_z"])))
+        if self._model_shape is not None and self._model_shape[0] != d:
+            self._plan_set = False
+        self._model_shape = (d, da, L, h)
+
+    def tc_supported(self):
+        return bool(self._lib.ss_mpc_tc_supported(self._h))
+
+    def set_plan(self, desired_states, distances_left, radii):
+        ds = _f64(desired_states)
+        dl = _f64(distances_left).reshape(-1)
+        r = _f64(radii).reshape(-1)
+        if ds.ndim != 2 or dl.shape[0] != ds.shape[0] or r.shape[0] != ds.shape[1]:
+            raise ValueError("desired_states [W, d], distances_left [W], radii [d] expected")
+        self._check(self._lib.ss_mpc_set_plan(self._h, _ptr(ds), ds.shape[0], _ptr(dl), _ptr(r),
+                                              ds.shape[1]))
+        self._plan_set = True
+
+    def _plan_args(self, state, actions, K, H, act_low, act_high):
+        d, da, _, _ = self._model_shape
+        st = _f64(state).reshape(-1)
+        if st.size != d:
+            raise ValueError("state has %d entries, model expects %d" % (st.size, d))
+        if actions is not None:
+            actions = _f64(actions)
+            if actions.ndim != 3 or actions.shape[2] != da:
+                raise ValueError("actions must be [K, H, da]")
+            K, H = actions.shape[0], actions.shape[1]
+        lo = None if act_low is None else _f64(np.broadcast_to(np.asarray(act_low, dtype=np.float64), (da,)))
+        hi = None if act_high is None else _f64(np.broadcast_to(np.asarray(act_high, dtype=np.float64), (da,)))
+        return st, actions, int(K), int(H), lo, hi
+
+    def plan(self, state, wp_index, *, actions=None, K=None, H=None, seed=0, act_low=None,
+             act_high=None, gamma=.75, horizontal_penalty_factor=.5, penalty_mode="reference",
+             precision="auto", want_scores=False, want_path=True, k_offset=0, K_global=None):
+        """One MPC decision on this GPU.  Returns dict(best_k, best_score, best_sequence [H,da],
+        best_path [H+1,d], scores [K] | None)."""
+        if self._model_shape is None:
+            raise RuntimeError("set_model() first")
+        d, da, _, _ = self._model_shape
+        st, actions, K, H, lo, hi = self._plan_args(state, actions, K, H, act_low, act_high)
+        K_global = K if K_global is None else int(K_global)
+        scores = np.empty(K) if want_scores else None
+        seq = np.empty((H, da)) if want_path else None
+        path = np.empty((H + 1, d)) if want_path else None
+        best = C.c_int64(-1)
+        best_score = C.c_double(0.0)
+        self._last = (K, H)
+        self._check(self._lib.ss_mpc_plan(
+            self._h, _ptr(st), int(wp_index), K, int(k_offset), K_global, H, _ptr(actions),
+            C.c_uint64(int(seed)), _ptr(lo), _ptr(hi), float(gamma),
+            float(horizontal_penalty_factor), _PENALTY[penalty_mode], _PRECISION[precision],
+            C.byref(best), C.byref(best_score), _ptr(seq), _ptr(path), _ptr(scores)))
+        return dict(best_k=int(best.value), best_score=float(best_score.value), best_sequence=seq,
+                    best_path=path, scores=scores)
+
+    # three-call form (multi-GPU reference penalty): rollout -> all-reduce sums -> finish
+    def rollout(self, state, wp_index, *, actions=None, K=None, H=None, seed=0, act_low=None,
+                act_high=None, gamma=.75, horizontal_penalty_factor=.5, penalty_mode="reference",
+                precision="auto", k_offset=0, K_global=None):
+        st, actions, K, H, lo, hi = self._plan_args(state, actions, K, H, act_low, act_high)
+        K_global = K if K_global is None else int(K_global)
+        self._check(self._lib.ss_mpc_rollout(
+            self._h, _ptr(st), int(wp_index), K, int(k_offset), K_global, H, _ptr(actions),
+            C.c_uint64(int(seed)), _ptr(lo), _ptr(hi), float(gamma),
+            float(horizontal_penalty_factor), _PENALTY[penalty_mode], _PRECISION[precision]))
+        self._last = (K, H)
+
+    def projection_sums_ptr(self):
+        """(device pointer, count) of the float64 per-time-step sums to all-reduce, or (0, 0)."""
+        p = C.c_void_p()
+        n = C.c_int()
+        self._check(self._lib.ss_mpc_projection_sums(self._h, C.byref(p), C.byref(n)))
+        return (p.value or 0), n.value
+
+    def finish(self, want_scores=False):
+        K, _ = self._last
+        scores = np.empty(K) if want_scores else None
+        best = C.c_int64(-1)
+        best_score = C.c_double(0.0)
+        self._check(self._lib.ss_mpc_finish(self._h, C.byref(best), C.byref(best_score), _ptr(scores)))
+        return int(best.value), float(best_score.value), scores
+
+    def get_states(self):
+        """[H+1, K, d] trajectories of the last reference-mode rollout."""
+        d = self._model_shape[0]
+        K, H = self._last
+        out = np.empty((H + 1, K, d))
+        self._check(self._lib.ss_mpc_get_states(self._h, _ptr(out)))
+        return out
+
+    def forward_sim(self, state, actions, precision="fp32"):
+        """Dyn_Model.do_forward_sim(many_in_parallel=True) on the GPU: [H+1, K, d]."""
+        if not getattr(self, "_plan_set", False):
+            d = self._model_shape[0]
+            self.set_plan(np.stack([np.zeros(d), np.ones(d)]), [1.0, 0.0], np.ones(d))
+        self.rollout(state, 0, actions=actions, penalty_mode="reference", precision=precision)
+        return self.get_states()
+
+    def replay(self, k_global):
+        d, da, _, _ = self._model_shape
+        _, H = self._last
+        seq = np.empty((H, da))
+        path = np.empty((H + 1, d))
+        self._check(self._lib.ss_mpc_replay(self._h, int(k_global), _ptr(seq), _ptr(path)))
+        return seq, path
+
+    def sample_actions(self, K, H, da, seed, act_low, act_high, k_offset=0):
+        lo = _f64(np.broadcast_to(np.asarray(act_low, dtype=np.float64), (da,)))
+        hi = _f64(np.broadcast_to(np.asarray(act_high, dtype=np.float64), (da,)))
+        out = np.empty((K, H, da))
+        self._check(self._lib.ss_mpc_sample_actions(self._h, int(K), int(k_offset), int(H), int(da),
+                                                    C.c_uint64(int(seed)), _ptr(lo), _ptr(hi),
+                                                    _ptr(out)))
+        return out

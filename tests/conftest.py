@@ -1,0 +1,38 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+def load_golden(name):
+    with np.load(os.path.join(GOLDEN, name)) as z:
+        return {k: z[k] for k in z.files}
+
+
+def golden_model(g):
+    L = int(g["in_num_layers"])
+    weights = [g["in_w%d" % i] for i in range(L + 1)]
+    biases = [g["in_b%d" % i] for i in range(L + 1)]
+    norm = {k: g["in_" + k] for k in ("mean_x", "std_x", "mean_y", "std_y", "mean_z", "std_z")}
+    return weights, biases, norm
+
+
+@pytest.fixture(scope="session")
+def engine():
+    """One libss_b200 context on cuda:0 (GPU tests only).  No fallback: a missing library or
+    GPU is an error, not a skip."""
+    from smartstartcontinuous_b200.engine import Engine
+    eng = Engine(0)
+    yield eng
+    eng.close()

@@ -1,0 +1,127 @@
+"""Replay buffer semantics: the reference's tests (tests/RLAgents/test_replayBuffer.py:5-100)
+restated, plus the contiguous mirror used to feed the KDE kernel."""
+import random
+
+import numpy as np
+import pytest
+
+from smartstartcontinuous_b200.replay_buffer import ReplayBuffer
+
+
+def test_add_and_sample():
+    rb = ReplayBuffer(0, 1)
+    rb.add(0, 1, 1, 1, True, 1)
+    s, a, r, t, s2 = rb.sample_batch(1)
+    assert s[0] == 1 and a[0] == 1 and r[0] == 1 and t[0] == True and s2[0] == 1  # noqa: E712
+    assert rb.size() == 1
+
+
+def test_other_agents_cannot_add():
+    rb = ReplayBuffer("main", 4)
+    rb.add("other", 1, 1, 1, False, 2)
+    rb.start_new_episode("other")
+    assert len(rb) == 0 and len(rb.episode_starting_indices) == 0
+
+
+def test_fifo_replacement():
+    rb = ReplayBuffer(0, 1)
+    rb.add(0, 2, 2, 2, False, 2)
+    rb.add(0, 1, 1, 1, True, 1)
+    assert rb.size() == 1
+    s, a, r, t, s2 = rb.sample_batch(1)
+    assert s[0] == 1 and t[0] == True  # noqa: E712
+
+
+def test_episode_markers():
+    rb = ReplayBuffer(0, 1)
+    rb.start_new_episode(0)
+    rb.add(0, 2, 2, 2, False, 2)
+    assert rb.next_episode_number == 1
+    assert rb.episode_starting_indices[0] == 0 and len(rb.episode_starting_indices) == 1
+    for i in range(1, 21):
+        rb = ReplayBuffer(0, i)
+        for _ in range(i):
+            rb.start_new_episode(0)
+            rb.add(0, 2, 2, 2, False, 2)
+        assert rb.next_episode_number == i
+        assert list(rb.episode_starting_indices) == list(range(i))
+
+
+def test_episode_removal_and_reindexing():
+    rb = ReplayBuffer(0, 1)
+    rb.start_new_episode(0)
+    rb.add(0, 2, 2, 2, False, 2)
+    rb.add(0, 2, 2, 2, False, 2)
+    assert rb.next_episode_number == 1 and len(rb.episode_starting_indices) == 0
+    rb = ReplayBuffer(0, 2)
+    rb.start_new_episode(0)
+    rb.add(0, 2, 2, 2, False, 2)
+    rb.start_new_episode(0)
+    rb.add(0, 2, 2, 2, False, 2)
+    rb.add(0, 2, 2, 2, False, 2)
+    assert rb.next_episode_number == 2
+    assert list(rb.episode_starting_indices) == [0]
+
+
+def test_double_start_is_ignored(capsys):
+    rb = ReplayBuffer(0, 1)
+    rb.start_new_episode(0)
+    rb.start_new_episode(0)
+    assert list(rb.episode_starting_indices) == [0]
+    rb = ReplayBuffer(0, 2)
+    rb.start_new_episode(0)
+    rb.add(0, 2, 2, 2, False, 2)
+    rb.start_new_episode(0)
+    assert list(rb.episode_starting_indices) == [0, 1]
+
+
+def test_episode_number_to_buffer_index():
+    rb = ReplayBuffer(0, 10)
+    for i in range(20):
+        rb.start_new_episode(0)
+        rb.add(0, i, i, i, False, i)
+        for j in range(len(rb.episode_starting_indices)):
+            e = rb.episode_starting_indices[-(j + 1)]
+            assert (i - j, i - j, i - j, False, i - j) == rb.buffer[rb.episode_number_to_buffer_index(e)]
+
+
+def _fill(rb, main, episodes, steps, d, rng):
+    for _ in range(episodes):
+        rb.start_new_episode(main)
+        s = rng.normal(size=d)
+        for t in range(steps):
+            s2 = s + rng.normal(size=d) * 0.1
+            rb.add(main, s.copy(), rng.normal(size=1), 0.0, t == steps - 1, s2.copy())
+            s = s2
+
+
+@pytest.mark.parametrize("cap", [1000, 137])
+def test_mirror_matches_deque(cap):
+    """get_all_states / states_s2 / episodic paths from the contiguous ring equal the
+    reference's list-comprehension definitions (replay_buffer.py:102,154-176,205)."""
+    rng = np.random.default_rng(0)
+    main = object()
+    rb = ReplayBuffer(main, cap)
+    _fill(rb, main, 9, 40, 3, rng)
+    ref_all = np.array([st[0] for st in rb.buffer] + [rb.buffer[-1][4]])
+    np.testing.assert_array_equal(rb.get_all_states(), ref_all)
+    random.seed(3)
+    idx = rb.get_possible_smart_start_indices(50)
+    first = rb.episode_number_to_buffer_index(rb.episode_starting_indices[0])
+    assert idx.min() >= first and len(set(idx.tolist())) == len(idx)
+    np.testing.assert_array_equal(rb.states_s2(idx), np.array([rb.buffer[int(i)][4] for i in idx]))
+    for i in idx[:10]:
+        path = rb.get_episodic_path_to_buffer_index(int(i))
+        assert np.array_equal(path[-1], rb.buffer[int(i)][4])
+        # consecutive states of one episode: each s2 is the next s
+        k = int(i) - (len(path) - 2)
+        assert np.array_equal(path[0], rb.buffer[k][0])
+        assert k == first or rb.buffer[k - 1][3] or rb.buffer_index_to_episode_number(k) in rb.episode_starting_indices
+
+
+def test_no_episode_errors():
+    rb = ReplayBuffer(0, 5)
+    assert rb.get_possible_smart_start_indices(3) is None
+    rb.add(0, 1.0, 0.0, 0.0, False, 2.0)
+    with pytest.raises(ValueError):
+        rb.get_episodic_path_to_buffer_index(0)
