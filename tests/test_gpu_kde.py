@@ -1,0 +1,123 @@
+"""Stage 1 on the B200 through the C ABI vs the oracle / the reference's golden vectors."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import kde_oracle
+from smartstartcontinuous_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4      # north-star tolerance for the fp32 path (densities, ucb)
+
+
+def _ucb_close(ucb, oucb, values, alpha=1.0):
+    """ucb = alpha * V + bonus: each term is good to RTOL, so the sum is good to
+    RTOL * (|alpha V| + bonus) -- not to RTOL * |ucb| when the two terms cancel."""
+    bonus = oucb - alpha * values.astype(np.float64)
+    bound = RTOL * (np.abs(alpha * values) + np.abs(bonus))
+    finite = np.isfinite(oucb)
+    assert np.all(np.abs(ucb[finite] - oucb[finite]) <= bound[finite])
+    assert np.array_equal(ucb[~finite], oucb[~finite], equal_nan=True)
+
+
+def _check_choice(best_j, ucb_oracle, rtol=RTOL):
+    """Index must match wherever the oracle's top-2 gap exceeds the tolerance."""
+    order = np.argsort(-ucb_oracle, kind="stable")
+    top, second = ucb_oracle[order[0]], ucb_oracle[order[1]] if len(order) > 1 else -np.inf
+    if top - second > 2 * rtol * abs(top):
+        assert best_j == int(np.argmax(ucb_oracle))
+    else:
+        assert ucb_oracle[best_j] >= top - 2 * rtol * abs(top)
+
+
+@pytest.mark.parametrize("name", ["kde_pendulum.npz", "kde_mountaincar.npz"])
+def test_golden_selection(engine, name):
+    g = load_golden(name)
+    best, best_ucb, dens, ucb = engine.select_start(
+        g["in_all_states"], g["in_queries"], g["in_values"], int(g["in_n_transitions"]),
+        float(g["in_volume"]), float(g["in_alpha"]), float(g["in_beta"]), want_density=True, want_ucb=True)
+    np.testing.assert_allclose(dens, g["out_density"], rtol=RTOL)
+    _ucb_close(ucb, g["out_ucb"], g["in_values"])
+    _check_choice(best, g["out_ucb"])
+    assert best_ucb == pytest.approx(ucb[best], rel=1e-12)
+
+
+@pytest.mark.parametrize("d,n,m", [(1, 700, 33), (2, 5000, 1000), (3, 20001, 2049), (4, 3000, 257),
+                                   (6, 4000, 100), (8, 2500, 64), (11, 3000, 50), (17, 2000, 40)])
+def test_random_dims_vs_oracle(engine, d, n, m):
+    rng = np.random.default_rng(d * 1000 + n)
+    A = rng.normal(size=(d, d)) + 2 * np.eye(d)
+    data = rng.normal(size=(n, d)) @ A + rng.normal(size=d) * 5
+    q = data[rng.choice(n, m, replace=False)] + 0.05 * rng.normal(size=(m, d))
+    vals = rng.normal(size=m).astype(np.float32)
+    best, _, dens, ucb = engine.select_start(data, q, vals, n - 1, 0.37, 1.0, 2.0, want_density=True,
+                                             want_ucb=True)
+    obest, odens, oucb = kde_oracle.select_start(data, q, vals, n - 1, 0.37, 1.0, 2.0)
+    np.testing.assert_allclose(dens, odens, rtol=RTOL)
+    _ucb_close(ucb, oucb, vals)
+    _check_choice(best, oucb)
+
+
+def test_far_queries_are_rescued_in_fp64(engine):
+    """Queries far from every data point underflow the fp32 sum; the kernel recomputes them in
+    fp64 exactly like scipy so the (huge) exploration bonus still ranks them correctly."""
+    rng = np.random.default_rng(5)
+    data = rng.normal(size=(4000, 3))
+    q = np.concatenate([data[:30], np.array([[40.0, 0, 0], [0, 45.0, 0], [30.0, 30.0, 0.0]])])
+    vals = np.zeros(len(q), dtype=np.float32)
+    best, _, dens, ucb = engine.select_start(data, q, vals, 3999, 1.0, 1.0, 2.0, want_density=True,
+                                             want_ucb=True)
+    obest, odens, oucb = kde_oracle.select_start(data, q, vals, 3999, 1.0, 1.0, 2.0,
+                                                 density_fn=kde_oracle.kde_density_direct)
+    ok = odens > 0
+    np.testing.assert_allclose(dens[ok], odens[ok], rtol=1e-4)
+    assert np.all(dens[~ok] == 0) and np.all(np.isinf(ucb[~ok]))
+    assert best == obest
+
+
+def test_first_max_and_nan_semantics(engine):
+    """np.argmax: first maximum wins; a NaN counts as the maximum."""
+    rng = np.random.default_rng(6)
+    data = rng.normal(size=(1000, 2))
+    q = np.repeat(data[10:11], 300, axis=0)          # identical queries -> identical ucb
+    vals = np.zeros(300, dtype=np.float32)
+    best, _, _, ucb = engine.select_start(data, q, vals, 999, 1.0, 1.0, 2.0, want_ucb=True)
+    assert np.all(ucb == ucb[0]) and best == 0
+    vals[137] = np.nan
+    vals[250] = np.nan
+    best, best_ucb, _, _ = engine.select_start(data, q, vals, 999, 1.0, 1.0, 2.0)
+    assert best == 137 and np.isnan(best_ucb)
+
+
+def test_errors(engine):
+    rng = np.random.default_rng(7)
+    data = rng.normal(size=(100, 3))
+    with pytest.raises(ValueError):
+        engine.select_start(data[:3], data[:2], np.zeros(2, np.float32), 2)          # n <= d
+    with pytest.raises(np.linalg.LinAlgError):
+        flat = data.copy(); flat[:, 2] = flat[:, 0]                                   # singular covariance
+        engine.select_start(flat, flat[:5], np.zeros(5, np.float32), 99)
+    with pytest.raises(ValueError):
+        engine.select_start(data, data[:5, :2], np.zeros(5, np.float32), 99)          # d mismatch
+
+
+def test_full_size_c2_properties(engine):
+    """BASELINE config 2 size (100 001 x 16 384, d=3): checked against the oracle on a query
+    subset plus size-independent properties (permutation invariance of the data set)."""
+    all_states, s2, _ = syn.pendulum_buffer(100_000, seed=0)
+    rng = np.random.default_rng(0)
+    idx = rng.choice(100_000, 16_384, replace=False)
+    q = s2[idx]
+    vals = syn.critic_like_values(q)
+    best, best_ucb, dens, ucb = engine.select_start(all_states, q, vals, 100_000, 1e-3, 1.0, 2.0,
+                                                    want_density=True, want_ucb=True)
+    sub = rng.choice(16_384, 256, replace=False)
+    odens = kde_oracle.kde_density(all_states, q[sub])
+    np.testing.assert_allclose(dens[sub], odens, rtol=RTOL)
+    assert best == int(np.argmax(ucb)) and best_ucb == ucb[best]
+    perm = rng.permutation(len(all_states))
+    best2, _, dens2, _ = engine.select_start(all_states[perm], q, vals, 100_000, 1e-3, 1.0, 2.0,
+                                             want_density=True)
+    np.testing.assert_allclose(dens2, dens, rtol=2e-5)
+    _check_choice(best2, ucb)
