@@ -97,6 +97,8 @@ struct ss_ctx {
     // tcgen05 images (built lazily by mpc_tc.cu)
     DevBuf tc_w1, tc_w2, tc_w3, tc_misc;
     bool tc_ready = false;
+    int tc_hp = 0;
+    std::vector<std::vector<double>> hw, hb;   // host copies of the float64 parameters
     // ---- MPC plan
     bool plan_set = false;
     int W = 0;

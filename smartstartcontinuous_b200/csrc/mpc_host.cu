@@ -81,8 +81,12 @@ extern "C" int ss_mpc_set_model(ss_ctx* c, int d, int da, int num_fc_layers, int
     c->h_pad = round_up(depth, 16);
     c->w32.resize(num_fc_layers + 1);
     c->b32.resize(num_fc_layers + 1);
+    c->hw.assign(num_fc_layers + 1, {});
+    c->hb.assign(num_fc_layers + 1, {});
     for (int l = 0; l <= num_fc_layers; ++l) {
         const int in = l == 0 ? d + da : depth, out = l == num_fc_layers ? d : depth;
+        c->hw[l].assign(weights[l], weights[l] + (size_t)in * out);
+        c->hb[l].assign(biases[l], biases[l] + out);
         const int in_pad = l == 0 ? c->din_pad : c->h_pad;
         const int out_pad = l == num_fc_layers ? round_up(d, 8) : c->h_pad;
         std::vector<float> w((size_t)in_pad * out_pad, 0.f), b(out_pad, 0.f);

@@ -1,9 +1,536 @@
-// mpc_tc.cu -- tcgen05 rollout kernel (placeholder until the kernel lands in this round).
+// mpc_tc.cu -- tcgen05 / TMEM rollout kernel for the random-shooting MPC (sm_100a only).
+//
+// Replaces the H sess.run float64 GEMM round trips of Dyn_Model.do_forward_sim
+// (dynamics_model.py:204-240) + the numpy scoring of generate_scores_add_delta
+// (NND_MB_agent.py:566-628) for the 2-hidden-layer dynamics MLP (the 2x500 network of the
+// BASELINE configs).  One persistent CTA per SM owns tiles of 128 sequences ("rows" = TMEM
+// lanes) and walks them through all H steps without touching HBM for activations:
+//
+//   layer 1   [128 x 32] x [32 x HP]   tcgen05.mma, A = split-bf16 input in TMEM, B = W1 image
+//             (input, weights and bias are hi/lo bf16 splits packed along K, so the layer is
+//             FP32-accurate although it runs on the tensor pipe)
+//   relu+cvt  TMEM accumulator chunk -> registers -> bf16x2 -> TMEM (becomes the A operand)
+//   layer 2   [128 x HP] x [HP x HP]   tcgen05.mma kind::f16 (BF16 in, FP32 accumulate in TMEM),
+//             A from TMEM, B = W2 streamed from L2 by the TMA engine (cp.async.bulk, 16 KB
+//             pre-packed core-matrix blocks) through a 6-stage mbarrier ring; bias folded in via
+//             two constant-one hidden units (hi/lo split)
+//   layer 3   fused into the layer-2 epilogue: relu, FP32 FFMA dot with W3 from shared memory
+//   update    state += z * std_z + mean_z, waypoint logic + progress/penalty score (score.cuh),
+//             all in FP32 registers of the row's thread
+//
+// Warp roles: warps 0-7 = row warps (two threads per row, each takes half the columns of every
+// accumulator chunk), warp 8 = MMA issuer (one elected lane), warp 9 = TMA producer.
+// TMEM (512 columns): [0,256) H1 as bf16 A operand, [256,448) 3-deep ring of 128x64 FP32
+// accumulator chunks, [448,464) layer-1 A operand.
+#include <cuda_bf16.h>
+
+#include <cstring>
+
 #include "mpc_kernels.cuh"
 
-bool mpc_tc_shape_supported(const ss_ctx*) { return false; }
-int mpc_tc_prepare(ss_ctx*) { return SS_OK; }
-int mpc_tc_grid(const ss_ctx*, const RolloutArgs&) { return 1; }
-int mpc_tc_launch(ss_ctx* c, const RolloutArgs&, int*) {
-    SS_FAIL(c, SS_EUNSUPPORTED, "mpc: tcgen05 kernel not available");
+namespace tc {
+
+constexpr int TM = 128;                 // rows per tile
+constexpr int NC = 64;                  // units per accumulator chunk (MMA N)
+constexpr int KSLAB = 128;              // K elements per W2 stage
+constexpr int STAGE_BYTES = NC * KSLAB * 2;   // 16 KB
+constexpr int NSTAGE = 6;
+constexpr int K1 = 32;                  // K slots of the layer-1 MMA
+constexpr int ACC_SLOTS = 3;
+constexpr int ROW_WARPS = 8;
+constexpr int ROW_THREADS = ROW_WARPS * 32;
+constexpr int THREADS = ROW_THREADS + 64;
+constexpr int HP_MAX = 512;
+constexpr int MAX_DIN = 10;             // 3 * din + 2 <= K1
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t COL_H1 = 0, COL_ACC = 256, COL_A1 = 448;
+constexpr int SPIN_LIMIT = 1 << 28;
+
+struct Params {
+    const __nv_bfloat16* w1_img;        // [HP/64][4][64][8]
+    const __nv_bfloat16* w2_img;        // [HP/64][HP/128][16][64][8]
+    const float* w3;                    // [HP][DTW]
+    float b3[SS_MAX_D];
+    int hp;                             // padded hidden width (multiple of 128)
+    int din;
+    long long n_tiles;
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    uint32_t done = 0;
+    int spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(smem_u32(b)), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > SPIN_LIMIT) asm volatile("trap;");   // never hang the GPU on a protocol bug
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                     "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* b) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(b))
+                 : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major, no swizzle: core matrices of 8 rows x 16 B; LBO = stride between the two K halves of
+// one MMA (here: NC * 16 B), SBO = stride between 8-row groups (128 B); version 1 (Blackwell)
+__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((NC * 16) >> 4) << 16) |
+           ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+}
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) |
+                           ((uint32_t)(TM >> 4) << 24);   // D f32, A/B bf16, K-major, N=64, M=128
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+        "%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::
+            "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// pack two floats to bf16x2 (lo -> bits [0,16), hi -> bits [16,32)), optionally with relu
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+struct Smem {
+    // dynamic shared memory carve-up (offsets in bytes from a 128-byte aligned base)
+    static constexpr size_t W2_RING = 0;
+    static constexpr size_t W1 = W2_RING + (size_t)NSTAGE * STAGE_BYTES;
+    static constexpr size_t W3 = W1 + (size_t)(HP_MAX / NC) * 4096;
+    static constexpr size_t ZX = W3 + (size_t)HP_MAX * 8 * 4;
+    static constexpr size_t BARS = ZX + (size_t)TM * 8 * 4;
+    static constexpr int N_BARS = 2 * NSTAGE + 2 * ACC_SLOTS + HP_MAX / NC + 2;
+    static constexpr size_t TMEM_PTR = BARS + (size_t)N_BARS * 8;
+    static constexpr size_t SUMS = TMEM_PTR + 16;      // double [4][T][2]
+};
+
+template <int DT>
+__global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const RolloutArgs a, const Params p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* w2_ring = smem + Smem::W2_RING;
+    unsigned char* w1s = smem + Smem::W1;
+    float* w3s = reinterpret_cast<float*>(smem + Smem::W3);
+    float* zx = reinterpret_cast<float*>(smem + Smem::ZX);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::BARS);
+    uint64_t* w2_full = bars;
+    uint64_t* w2_empty = w2_full + NSTAGE;
+    uint64_t* acc_full = w2_empty + NSTAGE;
+    uint64_t* acc_free = acc_full + ACC_SLOTS;
+    uint64_t* h1_ready = acc_free + ACC_SLOTS;          // [HP_MAX / NC]
+    uint64_t* x_ready = h1_ready + HP_MAX / NC;
+    uint64_t* w1_full = x_ready + 1;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Smem::TMEM_PTR);
+    double* sums = reinterpret_cast<double*>(smem + Smem::SUMS);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T = a.H + 1;
+    const int nch = p.hp / NC;          // accumulator chunks per layer
+    const int nslab = p.hp / KSLAB;     // W2 stages per chunk
+    constexpr int DTW = DT <= 4 ? 4 : 8;
+
+    // ---- one-time setup ----------------------------------------------------------------
+    if (tid == 0) {
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&w2_full[s], 1); mbar_init(&w2_empty[s], 1); }
+        for (int s = 0; s < ACC_SLOTS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], ROW_WARPS); }
+        for (int c = 0; c < HP_MAX / NC; ++c) mbar_init(&h1_ready[c], ROW_WARPS);
+        mbar_init(x_ready, 4);
+        mbar_init(w1_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                     "n"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (int i = tid; i < p.hp * DTW; i += THREADS) w3s[i] = p.w3[i];
+    for (int i = tid; i < 4 * T * 2; i += THREADS) sums[i] = 0.0;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+
+    if (warp < ROW_WARPS) {
+        // =============================== ROW WARPS ========================================
+        const int q = warp & 3, ch = warp >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+        uint32_t acc_it = 0, step_it = 0;
+        for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const long long k_local = tile * TM + row;
+            const bool live = k_local < a.K_local;
+            float x[DT];
+            ScoreAcc sc;
+#pragma unroll
+            for (int j = 0; j < DT; ++j) x[j] = j < a.d ? a.state0[j] : 0.f;
+            if (ch == 0) score_init<DT>(a.plan, a.wp_index, x, sc);
+            for (int t = 0; t < T; ++t) {
+                if (ch == 0) {
+                    float ab = 0.f, bb = 0.f;
+                    score_point<DT>(a.plan, t, x, sc, a.per_sample != 0, ab, bb);
+                    if (a.states_out && live)
+                        for (int j = 0; j < a.d; ++j)
+                            a.states_out[((size_t)t * a.K_local + k_local) * a.d + j] = x[j];
+                    if (a.partial_sums) {
+                        double dab = live ? (double)ab : 0.0, dbb = live ? (double)bb : 0.0;
+                        for (int off = 16; off > 0; off >>= 1) {
+                            dab += __shfl_down_sync(0xffffffffu, dab, off);
+                            dbb += __shfl_down_sync(0xffffffffu, dbb, off);
+                        }
+                        if (lane == 0) {
+                            sums[((size_t)q * T + t) * 2] += dab;
+                            sums[((size_t)q * T + t) * 2 + 1] += dbb;
+                        }
+                    }
+                }
+                if (t == a.H) break;
+                // ---- layer-1 A operand: hi/lo split of the normalised (state, action) -------
+                if (ch == 0) {
+                    float xin[MAX_DIN];
+#pragma unroll
+                    for (int j = 0; j < MAX_DIN; ++j) xin[j] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < DT; ++j)
+                        if (j < a.d) xin[j] = (x[j] - a.norm.mean_x[j]) * a.norm.inv_std_x[j];
+                    for (int j = 0; j < a.da; ++j) {
+                        float act = live ? fetch_action(a.act, k_local, a.k_offset + k_local, t, j) : 0.f;
+                        float v = (act - a.norm.mean_y[j]) * a.norm.inv_std_y[j];
+#pragma unroll
+                        for (int jj = 0; jj < MAX_DIN; ++jj)
+                            if (jj == a.d + j) xin[jj] = v;
+                    }
+                    float slot[K1];
+#pragma unroll
+                    for (int s = 0; s < K1; ++s) slot[s] = 0.f;
+#pragma unroll
+                    for (int j = 0; j < MAX_DIN; ++j) {
+                        const float hi = bf16_round(xin[j]);
+                        const float lo = xin[j] - hi;
+                        slot[3 * j] = hi;          // x_hi * W_hi
+                        slot[3 * j + 1] = hi;      // x_hi * W_lo
+                        slot[3 * j + 2] = lo;      // x_lo * W_hi
+                    }
+                    // bias slots (b_hi, b_lo) sit right after the 3*din input slots
+#pragma unroll
+                    for (int s = 0; s < K1; ++s)
+                        if (s == 3 * p.din || s == 3 * p.din + 1) slot[s] = 1.f;
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int c2 = 0; c2 < 16; ++c2) pk[c2] = pack_bf16(slot[2 * c2], slot[2 * c2 + 1]);
+                    tmem_st16(lane_addr + COL_A1, pk);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(x_ready);
+                }
+                // ---- layer-1 epilogue: relu, bf16, becomes the layer-2 A operand -------------
+                for (int c = 0; c < nch; ++c, ++acc_it) {
+                    const uint32_t slot_i = acc_it % ACC_SLOTS;
+                    mbar_wait(&acc_full[slot_i], (acc_it / ACC_SLOTS) & 1);
+                    tc_fence_after();
+                    uint32_t v[32];
+                    tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * 32, v);
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int c2 = 0; c2 < 16; ++c2)
+                        pk[c2] = pack_bf16_relu(__uint_as_float(v[2 * c2]), __uint_as_float(v[2 * c2 + 1]));
+                    tmem_st16(lane_addr + COL_H1 + c * (NC / 2) + ch * 16, pk);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive(&acc_free[slot_i]); mbar_arrive(&h1_ready[c]); }
+                }
+                // ---- layer-2 epilogue fused with layer 3 --------------------------------------
+                float z[DT];
+#pragma unroll
+                for (int j = 0; j < DT; ++j) z[j] = 0.f;
+                for (int n = 0; n < nch; ++n, ++acc_it) {
+                    const uint32_t slot_i = acc_it % ACC_SLOTS;
+                    mbar_wait(&acc_full[slot_i], (acc_it / ACC_SLOTS) & 1);
+                    tc_fence_after();
+                    uint32_t v[32];
+                    tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * 32, v);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&acc_free[slot_i]);
+                    const float* wrow = w3s + (size_t)(n * NC + ch * 32) * DTW;
+#pragma unroll
+                    for (int j2 = 0; j2 < 32; ++j2) {
+                        const float hval = fmaxf(__uint_as_float(v[j2]), 0.f);
+                        const float4 w0 = *reinterpret_cast<const float4*>(wrow + j2 * DTW);
+                        z[0] = fmaf(hval, w0.x, z[0]);
+                        if (DT > 1) z[1] = fmaf(hval, w0.y, z[1]);
+                        if (DT > 2) z[2] = fmaf(hval, w0.z, z[2]);
+                        if (DT > 3) z[3] = fmaf(hval, w0.w, z[3]);
+                        if (DT > 4) {
+                            const float4 w1 = *reinterpret_cast<const float4*>(wrow + j2 * DTW + 4);
+                            z[4] = fmaf(hval, w1.x, z[4]);
+                            if (DT > 5) z[5] = fmaf(hval, w1.y, z[5]);
+                            if (DT > 6) z[6] = fmaf(hval, w1.z, z[6]);
+                            if (DT > 7) z[7] = fmaf(hval, w1.w, z[7]);
+                        }
+                    }
+                }
+                // ---- combine the two column halves, update the state ---------------------------
+                if (ch == 1) {
+#pragma unroll
+                    for (int j = 0; j < DT; ++j) zx[row * 8 + j] = z[j];
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");
+                if (ch == 0) {
+#pragma unroll
+                    for (int j = 0; j < DT; ++j)
+                        if (j < a.d) {
+                            const float zz = z[j] + zx[row * 8 + j] + p.b3[j];
+                            x[j] += fmaf(zz, a.norm.std_z[j], a.norm.mean_z[j]);
+                        }
+                }
+                ++step_it;
+            }
+            if (ch == 0 && live && a.scores_out) a.scores_out[k_local] = sc.score;
+        }
+        (void)step_it;
+    } else if (warp == ROW_WARPS) {
+        // =============================== MMA ISSUER =======================================
+        if (lane == 0) {
+            uint32_t acc_it = 0, w2_it = 0, step_it = 0;
+            mbar_wait(w1_full, 0);
+            for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                for (int t = 0; t < a.H; ++t, ++step_it) {
+                    mbar_wait(x_ready, step_it & 1);
+                    tc_fence_after();
+                    // layer 1: acc chunk c = A1 [128 x 32] * W1img[c] [64 x 32]^T
+                    for (int c = 0; c < nch; ++c, ++acc_it) {
+                        const uint32_t slot_i = acc_it % ACC_SLOTS;
+                        mbar_wait(&acc_free[slot_i], ((acc_it / ACC_SLOTS) & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem + COL_ACC + slot_i * NC;
+                        const uint32_t b_addr = smem_u32(w1s) + c * 4096;
+#pragma unroll
+                        for (int ks = 0; ks < K1 / 16; ++ks)
+                            umma_ts(d_tmem, tmem + COL_A1 + ks * 8, make_b_desc(b_addr + ks * 2 * (NC * 16)), IDESC, ks);
+                        tc_commit(&acc_full[slot_i]);
+                    }
+                    // layer 2: acc chunk n = H1 [128 x HP] * W2img[n] [64 x HP]^T, K streamed in slabs
+                    for (int n = 0; n < nch; ++n, ++acc_it) {
+                        const uint32_t slot_i = acc_it % ACC_SLOTS;
+                        mbar_wait(&acc_free[slot_i], ((acc_it / ACC_SLOTS) & 1) ^ 1);
+                        tc_fence_after();
+                        const uint32_t d_tmem = tmem + COL_ACC + slot_i * NC;
+                        for (int ksl = 0; ksl < nslab; ++ksl, ++w2_it) {
+                            const uint32_t st = w2_it % NSTAGE;
+                            if (n == 0) {
+                                mbar_wait(&h1_ready[2 * ksl], step_it & 1);
+                                mbar_wait(&h1_ready[2 * ksl + 1], step_it & 1);
+                            }
+                            mbar_wait(&w2_full[st], (w2_it / NSTAGE) & 1);
+                            tc_fence_after();
+                            const uint32_t b_addr = smem_u32(w2_ring) + st * STAGE_BYTES;
+#pragma unroll
+                            for (int ks = 0; ks < KSLAB / 16; ++ks)
+                                umma_ts(d_tmem, tmem + COL_H1 + ksl * (KSLAB / 2) + ks * 8,
+                                        make_b_desc(b_addr + ks * 2 * (NC * 16)), IDESC, (ksl | ks) != 0);
+                            tc_commit(&w2_empty[st]);
+                        }
+                        tc_commit(&acc_full[slot_i]);
+                    }
+                }
+            }
+        }
+    } else {
+        // =============================== TMA PRODUCER =====================================
+        if (lane == 0) {
+            mbar_expect_tx(w1_full, (uint32_t)(nch * 4096));
+            bulk_g2s(w1s, p.w1_img, (uint32_t)(nch * 4096), w1_full);
+            uint32_t w2_it = 0;
+            for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+                for (int t = 0; t < a.H; ++t)
+                    for (int n = 0; n < nch; ++n)
+                        for (int ksl = 0; ksl < nslab; ++ksl, ++w2_it) {
+                            const uint32_t st = w2_it % NSTAGE;
+                            mbar_wait(&w2_empty[st], ((w2_it / NSTAGE) & 1) ^ 1);
+                            mbar_expect_tx(&w2_full[st], STAGE_BYTES);
+                            bulk_g2s(w2_ring + (size_t)st * STAGE_BYTES,
+                                     reinterpret_cast<const unsigned char*>(p.w2_img) +
+                                         ((size_t)n * nslab + ksl) * STAGE_BYTES,
+                                     STAGE_BYTES, &w2_full[st]);
+                        }
+        }
+    }
+    // ---- teardown ---------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (a.partial_sums)
+        for (int o = tid; o < 2 * T; o += THREADS)
+            a.partial_sums[(size_t)blockIdx.x * 2 * T + o] =
+                sums[o] + sums[2 * T + o] + sums[4 * T + o] + sums[6 * T + o];
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
+}
+
+// ---- host side ---------------------------------------------------------------------------
+static uint16_t bf16_bits(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static float bf16_val(uint16_t b) {
+    uint32_t u = (uint32_t)b << 16;
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+
+static size_t smem_bytes(int T) { return Smem::SUMS + (size_t)4 * T * 2 * 8 + 128; }
+
+}  // namespace tc
+
+bool mpc_tc_shape_supported(const ss_ctx* c) {
+    // two hidden layers, hidden width + the two constant-one bias units within 512, small I/O dims
+    return c->L == 2 && c->h >= 64 && c->h + 2 <= tc::HP_MAX && c->d <= 8 && c->d + c->da <= tc::MAX_DIN;
+}
+
+int mpc_tc_prepare(ss_ctx* c) {
+    using namespace tc;
+    const int h = c->h, d = c->d, din = c->d + c->da;
+    const int hp = (h + 2 + KSLAB - 1) / KSLAB * KSLAB;
+    const int nch = hp / NC, nslab = hp / KSLAB;
+    const std::vector<double>&W1 = c->hw[0], &W2 = c->hw[1], &W3 = c->hw[2];
+    const std::vector<double>&B1 = c->hb[0], &B2 = c->hb[1];
+    // layer-1 image: K slots (3j, 3j+1, 3j+2) = (W_hi, W_lo, W_hi) of input j; then (b_hi, b_lo)
+    std::vector<uint16_t> w1((size_t)nch * 2048, 0);
+    auto w1_at = [&](int slot, int u) -> uint16_t& {
+        const int cidx = u / NC, nn = u % NC;
+        return w1[(size_t)cidx * 2048 + (slot / 8) * (NC * 8) + nn * 8 + (slot % 8)];
+    };
+    for (int u = 0; u < h; ++u) {
+        for (int j = 0; j < din; ++j) {
+            const float w = (float)W1[(size_t)j * h + u];
+            const uint16_t hi = bf16_bits(w), lo = bf16_bits(w - bf16_val(hi));
+            w1_at(3 * j, u) = hi;
+            w1_at(3 * j + 1, u) = lo;
+            w1_at(3 * j + 2, u) = hi;
+        }
+        const float b = (float)B1[u];
+        const uint16_t hi = bf16_bits(b), lo = bf16_bits(b - bf16_val(hi));
+        w1_at(3 * din, u) = hi;
+        w1_at(3 * din + 1, u) = lo;
+    }
+    // constant-one hidden units h and h+1 (carry the layer-2 bias through the GEMM)
+    w1_at(3 * din, h) = bf16_bits(1.f);
+    w1_at(3 * din, h + 1) = bf16_bits(1.f);
+    // layer-2 image: blocks (n, kslab) of [16 k-chunks][64 units][8 k]
+    std::vector<uint16_t> w2((size_t)nch * nslab * (STAGE_BYTES / 2), 0);
+    auto w2_at = [&](int k, int u) -> uint16_t& {
+        const int n = u / NC, nn = u % NC, ksl = k / KSLAB, kk = k % KSLAB;
+        return w2[((size_t)n * nslab + ksl) * (STAGE_BYTES / 2) + (kk / 8) * (NC * 8) + nn * 8 + (kk % 8)];
+    };
+    for (int u = 0; u < h; ++u) {
+        for (int k = 0; k < h; ++k) w2_at(k, u) = bf16_bits((float)W2[(size_t)k * h + u]);
+        const float b = (float)B2[u];
+        const uint16_t hi = bf16_bits(b), lo = bf16_bits(b - bf16_val(hi));
+        w2_at(h, u) = hi;
+        w2_at(h + 1, u) = lo;
+    }
+    // layer 3 (FP32, in shared memory): [hp][DTW]
+    const int dtw = d <= 4 ? 4 : 8;
+    std::vector<float> w3((size_t)hp * dtw, 0.f);
+    for (int u = 0; u < h; ++u)
+        for (int j = 0; j < d; ++j) w3[(size_t)u * dtw + j] = (float)W3[(size_t)u * d + j];
+    SS_CUDA_CHECK(c, c->tc_w1.ensure(w1.size() * 2));
+    SS_CUDA_CHECK(c, c->tc_w2.ensure(w2.size() * 2));
+    SS_CUDA_CHECK(c, c->tc_w3.ensure(w3.size() * 4));
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(c->tc_w1.p, w1.data(), w1.size() * 2, cudaMemcpyHostToDevice, c->stream));
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(c->tc_w2.p, w2.data(), w2.size() * 2, cudaMemcpyHostToDevice, c->stream));
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(c->tc_w3.p, w3.data(), w3.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    c->tc_hp = hp;
+    c->tc_ready = true;
+    return SS_OK;
+}
+
+int mpc_tc_grid(const ss_ctx* c, const RolloutArgs& a) {
+    const long long tiles = (a.K_local + tc::TM - 1) / tc::TM;
+    return (int)(tiles < c->sm_count ? tiles : c->sm_count);
+}
+
+int mpc_tc_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out) {
+    using namespace tc;
+    if (!c->tc_ready) SS_FAIL(c, SS_EUNSUPPORTED, "mpc: tcgen05 kernel not prepared for this model");
+    if (a.H + 1 > 1024) SS_FAIL(c, SS_EUNSUPPORTED, "mpc: horizon too long for the tcgen05 kernel");
+    Params p;
+    std::memset(&p, 0, sizeof(p));
+    p.w1_img = c->tc_w1.as<__nv_bfloat16>();
+    p.w2_img = c->tc_w2.as<__nv_bfloat16>();
+    p.w3 = c->tc_w3.as<float>();
+    for (int j = 0; j < c->d; ++j) p.b3[j] = (float)c->hb[2][j];
+    p.hp = c->tc_hp;
+    p.din = c->d + c->da;
+    p.n_tiles = (a.K_local + TM - 1) / TM;
+    const int grid = mpc_tc_grid(c, a);
+    if (grid_blocks_out) *grid_blocks_out = grid;
+    const size_t smem = smem_bytes(a.H + 1);
+    cudaError_t e;
+    if (a.d <= 4) {
+        e = cudaFuncSetAttribute(mpc_rollout_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) mpc_rollout_tc_kernel<4><<<grid, THREADS, smem, c->stream>>>(a, p);
+    } else {
+        e = cudaFuncSetAttribute(mpc_rollout_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) mpc_rollout_tc_kernel<8><<<grid, THREADS, smem, c->stream>>>(a, p);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    c->launches++;
+    SS_CUDA_CHECK(c, e);
+    return SS_OK;
 }
