@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SmartStart hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One JSON line on stdout (rank 0).  Headline metric: NND-MPC rollout-steps/s; the second half of
+BASELINE.json's metric, KDE kernel-evals/s, is reported in the same line under "kde".
+
+  step      one MPC decision (NND_MB_agent.get_best_sim_actions): K action sequences rolled H steps
+            through the 2x500 dynamics MLP, scored against the waypoint plan, arg-best
+            (reference-exact penalty mode).  Workload per GPU: Pendulum d=3, da=1, K=131072
+            (= BASELINE config 4's K=1M / 8), H=50 -- at N=8 this is exactly config 4.
+  value     K_total * H / device time, inputs resident (actions sampled on the device, Philox)
+  e2e       same decision through the C ABI with HOST buffers: action samples [K,H,da] float64 in
+            pinned host memory -> H2D inside the call -> rollout -> score -> D2H of the result
+  kde       BASELINE config 2: 100 001 Pendulum states x 16 384 candidate queries per GPU
+  roofline  tensor pipe for the rollout kernel (achieved = 507 000 FLOP x K*H / kernel time, against
+            the measured sustained bf16 peak), SFU pipe for the KDE pair kernel
+  --impl reference: the oracle port of the reference's CPU path (numpy float64, BLAS on all host
+            cores; scipy gaussian_kde for the KDE), timed on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_STEP = {2: 505_000, 3: 507_000}      # 2*[(d+da)h + h^2 + h d], h=500
+K_PER_GPU = 131_072
+HORIZON = 50
+KDE_N = 100_000
+KDE_M = 16_384
+SFU_PER_CLK_PER_SM = 16                        # MUFU.EX2 lanes per SM per clock (sm_100)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return dict(hbm_gbs=p["hbm_gbs"], bf16_sustained=p["bf16_tflops_sustained"], bf16_burst=p["bf16_tflops"],
+                    sm_max_mhz=p.get("sm_max_mhz", 1965.0), source="MEASURED_PEAKS.json")
+    return dict(hbm_gbs=6650.0, bf16_sustained=1400.0, bf16_burst=1590.0, sm_max_mhz=1965.0,
+                source="fallback (B200_PROFILING.md)")
+
+
+def make_workload(seed=0):
+    """Seeded synthetic inputs of the benchmark shapes."""
+    from smartstartcontinuous_b200 import synthetic as syn
+    from smartstartcontinuous_b200.nnd_mb_agent import plan_from_path
+    rng = np.random.default_rng(seed)
+    obs, act = syn.pendulum_rollouts(rng, 25, 333)          # 25 x 333 random-policy transitions
+    norm = syn.normalisation_stats(np.concatenate(list(obs)),
+                                   np.concatenate([np.concatenate([a, a[-1:]]) for a in act]))
+    w, b = syn.xavier_mlp(rng, 3, 1, 2, 500, scale=0.5)
+    plan = plan_from_path(list(obs[0][:80]), mean_per_stepsize=1, std_per_stepsize=1,
+                          stepsizes_in_waypoint_radii=1, path_shortcutting=True, theta=1, steps_per_waypoint=1)
+    return dict(w=w, b=b, norm=norm, plan=plan, state=obs[0][0].copy(), low=[-2.0], high=[2.0])
+
+
+def kde_workload(seed=0, n=KDE_N, m=KDE_M):
+    from smartstartcontinuous_b200 import synthetic as syn
+    all_states, s2, _ = syn.pendulum_buffer(n, seed=seed)
+    rng = np.random.default_rng(seed)
+    q = np.ascontiguousarray(s2[rng.choice(n, m, replace=False)])
+    return dict(all_states=all_states, queries=q, values=syn.critic_like_values(q), n=n, volume=1e-3)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except OSError:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        busy = [v for v in sm if v > 0]
+        return dict(sm_mhz=float(np.median(busy)) if busy else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_reference_mpc(wl, K, H, seed):
+    """The reference's CPU planner (oracle port): npr.uniform sampling + float64 numpy rollout +
+    scoring.  Returns seconds."""
+    from oracle import mpc_oracle
+    rs = np.random.RandomState(seed)
+    t0 = time.perf_counter()
+    acts = rs.uniform(wl["low"], wl["high"], (K, H, 1))
+    mpc_oracle.plan(wl["state"], acts, wl["w"], wl["b"], wl["norm"], wl["plan"]["desired_states"],
+                    wl["plan"]["distances_left"], wl["plan"]["radii"], 0, .75, .5)
+    return time.perf_counter() - t0
+
+
+def cpu_reference_kde(kw, m):
+    from oracle import kde_oracle
+    t0 = time.perf_counter()
+    kde_oracle.select_start(kw["all_states"], kw["queries"][:m], kw["values"][:m], kw["n"], kw["volume"], 1.0, 2.0,
+                            density_fn=kde_oracle.scipy_density)
+    return time.perf_counter() - t0
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    """--impl reference: rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = make_workload()
+    kw = kde_workload()
+    K_s, m_s = 2048, 256          # bounded samples: ~1 s and ~0.5 s per step on a server CPU
+    for _ in range(args.warmup):
+        cpu_reference_mpc(wl, 256, HORIZON, 0)
+    t_mpc = [cpu_reference_mpc(wl, K_s, HORIZON, i) for i in range(args.steps)]
+    t_kde = [cpu_reference_kde(kw, m_s) for _ in range(max(1, min(args.steps, 5)))]
+    v = K_s * HORIZON / float(np.mean(t_mpc))
+    kv = m_s * (kw["n"] + 1) / float(np.mean(t_kde))
+    cores = blas_threads()
+    sample = "K=%d of %d sequences per step, H=%d (rate is K-independent: GEMM-bound)" % (K_s, K_PER_GPU, HORIZON)
+    print(json.dumps({
+        "impl": "reference", "metric": "mpc_rollout_steps_per_s", "value": v, "unit": "rollout-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * float(np.mean(t_mpc)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "NND_MB MPC, Pendulum d=3 da=1, MLP 2x500, H=50 (BASELINE config 4 shard)",
+                   "note": "oracle port of the reference's numpy/TF-CPU path; TensorFlow 1.5 is not installable, "
+                           "its float64 GEMMs run in numpy/BLAS"},
+        "cpu_baseline": {"value": v, "unit": "rollout-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "rollout-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "kde": {"metric": "kde_kernel_evals_per_s", "value": kv, "unit": "kernel-evals/s", "cores": 1,
+                "kind": "reference-library (scipy.stats.gaussian_kde, single thread)",
+                "sample": "%d of %d queries x %d points" % (m_s, KDE_M, kw["n"] + 1)},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from smartstartcontinuous_b200.distributed import ShardedPlanner, ShardedSelector
+    from smartstartcontinuous_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    eng = Engine(local_rank)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    wl = make_workload()
+    eng.set_model(wl["w"], wl["b"], wl["norm"])
+    eng.set_plan(wl["plan"]["desired_states"], wl["plan"]["distances_left"], wl["plan"]["radii"])
+    planner = ShardedPlanner(eng, device=dev)
+    selector = ShardedSelector(eng, device=dev)
+    K_total = K_PER_GPU * world
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        """Per-step CUDA-event times on the launching stream; L2 flushed between steps (outside
+        the events).  Returns (sum of per-step ms, max over ranks)."""
+        for _ in range(warmup):
+            fn(0)
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for i in range(steps):
+            flush.zero_()
+            ev[i][0].record(stream)
+            fn(i + 1)
+            ev[i][1].record(stream)
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    precision = "bf16_tc" if eng.tc_supported() else "fp32"
+    rollout_ms = []
+
+    def mpc_step(i):
+        planner.plan(wl["state"], 0, K=K_total, H=HORIZON, seed=1000 + i, act_low=wl["low"], act_high=wl["high"],
+                     penalty_mode="reference", precision=precision, want_path=True)
+        if i > 0:
+            rollout_ms.append(dict(eng.last_timings()).get("mpc_rollout", 0.0))
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = eng.launch_count()
+    ms_total = timed(mpc_step, args.steps, args.warmup)
+    launches = eng.launch_count() - launches0
+    ms_per_step = ms_total / args.steps
+    value = K_total * HORIZON / (ms_per_step * 1e-3)
+
+    # ---- e2e: host action samples in pinned memory through the C ABI -------------------------
+    n_act = K_PER_GPU * HORIZON
+    pinned = torch.empty(n_act, dtype=torch.float64).pin_memory()
+    host_actions = pinned.numpy().reshape(K_PER_GPU, HORIZON, 1)
+    k_off = rank * K_PER_GPU
+    host_actions[:] = np.random.RandomState(rank).uniform(wl["low"], wl["high"], (K_PER_GPU, HORIZON, 1))
+
+    def e2e_step(i):
+        # every rank plans on its own K_PER_GPU host samples; merge as in ShardedPlanner
+        eng.rollout(wl["state"], 0, actions=host_actions, penalty_mode="reference", precision=precision,
+                    k_offset=k_off, K_global=K_total)
+        if world > 1:
+            ptr, n = eng.projection_sums_ptr()
+            from smartstartcontinuous_b200.distributed import _DevView
+            dist.all_reduce(torch.as_tensor(_DevView(ptr, n), device=dev))
+        bk, bs, _ = eng.finish()
+        if world > 1:
+            mine = torch.tensor([bs, float(bk)], dtype=torch.float64, device=dev)
+            g = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(g, mine)
+        if k_off <= bk < k_off + K_PER_GPU:
+            eng.replay(bk)
+
+    e2e_ms = timed(e2e_step, max(3, args.steps // 2), 2) / max(3, args.steps // 2)
+    e2e_value = K_total * HORIZON / (e2e_ms * 1e-3)
+
+    # ---- KDE (BASELINE config 2 per GPU) -----------------------------------------------------
+    kw = kde_workload()
+    d_data = torch.as_tensor(kw["all_states"], device=dev)
+    d_q = torch.as_tensor(kw["queries"], device=dev)
+    d_v = torch.as_tensor(kw["values"], device=dev)
+    pairs_ms = []
+
+    def kde_step(i):
+        eng.select_start_dev(d_data.data_ptr(), d_data.shape[0], 3, d_q.data_ptr(), d_q.shape[0], d_v.data_ptr(),
+                             kw["n"], kw["volume"], 1.0, 2.0)
+        if i > 0:
+            pairs_ms.append(dict(eng.last_timings()).get("kde_pairs", 0.0))
+
+    kde_ms = timed(kde_step, args.steps, args.warmup) / args.steps
+    evals = KDE_M * (KDE_N + 1) * world
+    kde_value = evals / (kde_ms * 1e-3)
+
+    def kde_e2e_step(i):
+        eng.select_start(kw["all_states"], kw["queries"], kw["values"], kw["n"], kw["volume"], 1.0, 2.0)
+
+    kde_e2e_ms = timed(kde_e2e_step, max(3, args.steps // 2), 2) / max(3, args.steps // 2)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    info = eng.device_info()
+    k_ms = float(np.mean(rollout_ms)) if rollout_ms else ms_per_step
+    achieved_tf = FLOP_PER_STEP[3] * K_PER_GPU * HORIZON / (k_ms * 1e-3) / 1e12
+    p_ms = float(np.mean(pairs_ms)) if pairs_ms else kde_ms
+    sfu_peak = SFU_PER_CLK_PER_SM * info["sm_count"] * peaks["sm_max_mhz"] * 1e6
+    kde_achieved = KDE_M * (KDE_N + 1) / (p_ms * 1e-3)
+    kde_bytes = 4 * 3 * (KDE_N + 1 + KDE_M) + 4 * KDE_M + 8
+    out = {
+        "metric": "mpc_rollout_steps_per_s", "value": value, "unit": "rollout-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16 (tcgen05, fp32 accumulate; first/last layer, state, scoring fp32)" if precision == "bf16_tc" else "f32",
+        "data": "synthetic",
+        "config": {"workload": "NND_MB random-shooting MPC, Pendulum-v0 d=3 da=1, K=%d per GPU (BASELINE config 4 "
+                               "= K=1M over 8 GPUs), H=%d, MLP 2x500, reference-exact penalty" % (K_PER_GPU, HORIZON),
+                   "K_total": K_total, "H": HORIZON, "mlp": "2x500", "actions": "device Philox4x32-10",
+                   "l2": "flushed between timed steps (256 MiB memset, outside the event-timed region)",
+                   "parallelism": "K sharded over %d GPU(s); all-reduce of %d float64 + all-gather of (score,k)"
+                                  % (world, 2 * (HORIZON + 1))},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "rollout-steps/s", "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": int(n_act * 8 + 3 * 8), "d2h_bytes_per_step": int(16 + HORIZON * 8 + (HORIZON + 1) * 3 * 8),
+                "path": "ss_mpc_rollout/ss_mpc_finish/ss_mpc_replay with host float64 action samples (pinned)"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
+                     "frac": achieved_tf / peaks["bf16_sustained"], "traffic": None,
+                     "kernel": "mpc_rollout_tc_kernel" if precision == "bf16_tc" else "mpc_rollout_simt_kernel",
+                     "kernel_ms": k_ms, "peak_source": peaks["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
+                     "algorithmic_flop_per_rollout_step": FLOP_PER_STEP[3]},
+        "kde": {"metric": "kde_kernel_evals_per_s", "value": kde_value, "unit": "kernel-evals/s", "ms_per_step": kde_ms,
+                "config": {"workload": "KDE+UCB+argmax, %d Pendulum states (d=3) x %d queries per GPU (BASELINE config 2)"
+                                       % (KDE_N + 1, KDE_M)},
+                "e2e": {"value": evals / (kde_e2e_ms * 1e-3), "unit": "kernel-evals/s", "ms_per_step": kde_e2e_ms,
+                        "h2d_bytes_per_step": int(8 * 3 * (KDE_N + 1 + KDE_M) + 4 * KDE_M), "d2h_bytes_per_step": 16},
+                "roofline": {"bound": "sfu", "achieved": kde_achieved, "peak": sfu_peak, "unit": "kernel-evals/s",
+                             "frac": kde_achieved / sfu_peak, "kernel": "kde_pairs_kernel<3>", "kernel_ms": p_ms,
+                             "peak_source": "16 MUFU.EX2/clk/SM x %d SMs x %.0f MHz (max SM clock)" % (info["sm_count"], peaks["sm_max_mhz"]),
+                             "hbm_achieved_gbs": kde_bytes / (p_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
+                             "traffic": None}},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        K_s = 1024
+        cpu_reference_mpc(wl, 128, HORIZON, 0)
+        ts = [cpu_reference_mpc(wl, K_s, HORIZON, i) for i in range(5)]
+        out["cpu_baseline"] = {"value": K_s * HORIZON / float(np.mean(ts)), "unit": "rollout-steps/s",
+                               "cores": blas_threads(), "kind": "port",
+                               "sample": "5 plans of K=%d (of %d) sequences, H=%d, float64 numpy/BLAS" % (K_s, K_PER_GPU, HORIZON)}
+        tk = [cpu_reference_kde(kw, 128) for _ in range(3)]
+        out["kde"]["cpu_baseline"] = {"value": 128 * (KDE_N + 1) / float(np.mean(tk)), "unit": "kernel-evals/s", "cores": 1,
+                                      "kind": "reference-library (scipy.stats.gaussian_kde)",
+                                      "sample": "3 x 128 (of %d) queries x %d points" % (KDE_M, KDE_N + 1)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -25,6 +25,12 @@ __global__ void sample_actions_kernel(ActionSource src, long long K, long long k
     }
 }
 
+__global__ void gather_path_kernel(const float* __restrict__ states, long long K, long long k, int T,
+                                   int d, float* __restrict__ out) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o < T * d) out[o] = states[((size_t)(o / d) * K + k) * d + (o % d)];
+}
+
 int fill_action_source(ss_ctx* c, ActionSource& s, int H, int da, uint64_t seed, const double* low,
                        const double* high) {
     s.host_actions = nullptr;
@@ -344,8 +350,17 @@ extern "C" int ss_mpc_replay(ss_ctx* c, int64_t k_global, double* out_sequence, 
     a.wp_index = r.wp_index; a.H = r.H; a.K_local = 1; a.k_offset = k_global;
     a.per_sample = 1;
     a.states_out = path_dev;
-    int rc = mpc_simt_launch(c, a, nullptr);
-    if (rc) return rc;
+    int rc = SS_OK;
+    if (r.states_stored && mine) {
+        // the trajectories of this batch are still resident (reference mode): just gather the row
+        gather_path_kernel<<<(T * d + 127) / 128, 128, 0, c->stream>>>(c->mpc_states.as<float>(), r.K_local,
+                                                                       k_local, T, d, path_dev);
+        c->launches++;
+        SS_CUDA_CHECK(c, cudaGetLastError());
+    } else {
+        rc = mpc_simt_launch(c, a, nullptr);
+        if (rc) return rc;
+    }
     std::vector<float> path((size_t)T * d);
     SS_CUDA_CHECK(c, cudaMemcpyAsync(path.data(), path_dev, path.size() * 4, cudaMemcpyDeviceToHost, c->stream));
     if (out_sequence) {

@@ -1,0 +1,158 @@
+"""One process per GPU: shard the K action sequences / the KDE queries over the ranks.
+
+The reference has no multi-device path; the north star adds exactly one
+strategy: data-parallel sharding with replicated weights / plan / buffer and tiny merges:
+
+  MPC   rank g rolls out sequences [g*K/G, (g+1)*K/G) (device Philox is indexed by the GLOBAL
+        sequence number, so the samples do not depend on G); reference-exact penalty needs the
+        per-time-step projection sums of ALL sequences (numerical.py:89-93) -> one all-reduce of
+        2*(H+1) float64; then one all-gather of (score, k) and an np.argmax-ordered pick; the
+        owner of the winner replays it and broadcasts (best_sequence, best_path).
+  KDE   rank g scores queries [g*m/G, (g+1)*m/G) against the full (replicated) buffer; one
+        all-gather of (ucb, j).
+
+Collectives go through torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests).
+There is no data-path collective beyond those few bytes.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(total, world, rank):
+    """Contiguous, balanced split of range(total): (offset, count) of `rank`."""
+    base, rem = divmod(int(total), int(world))
+    count = base + (1 if rank < rem else 0)
+    offset = rank * base + min(rank, rem)
+    return offset, count
+
+
+def argmax_pick(values, indices):
+    """np.argmax ordering over (value, global index) pairs: NaN beats everything, then the
+    larger value, ties -> the lower global index (first occurrence).  Entries with index < 0
+    are ignored."""
+    best = -1
+    for i, (v, k) in enumerate(zip(values, indices)):
+        if k < 0:
+            continue
+        if best < 0:
+            best = i
+            continue
+        bv, bk = values[best], indices[best]
+        v_nan, b_nan = v != v, bv != bv
+        if v_nan or b_nan:
+            better = (v_nan and b_nan and k < bk) or (v_nan and not b_nan)
+        else:
+            better = v > bv or (v == bv and k < bk)
+        if better:
+            best = i
+    return best
+
+
+class _DevView:
+    """Zero-copy torch view of library-owned device memory (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr, n, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+class ShardedPlanner:
+    """MPC over all ranks of a torch.distributed group; every rank returns the same result."""
+
+    def __init__(self, engine, device=None, group=None):
+        dist = _dist()
+        self.engine = engine
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = device          # torch device for the merge tensors ("cuda:N" or "cpu")
+
+    def _sums_tensor(self):
+        import torch
+        if hasattr(self.engine, "projection_sums_tensor"):        # CPU test double
+            return self.engine.projection_sums_tensor()
+        ptr, n = self.engine.projection_sums_ptr()
+        if n == 0:
+            return None
+        return torch.as_tensor(_DevView(ptr, n), device=self.device)
+
+    def plan(self, state, wp_index, *, K, H, seed=0, act_low=None, act_high=None, actions=None,
+             gamma=.75, horizontal_penalty_factor=.5, penalty_mode="reference", precision="auto",
+             want_path=True):
+        import torch
+        dist = _dist()
+        k_offset, k_local = shard_bounds(K, self.world, self.rank)
+        local_actions = None if actions is None else actions[k_offset:k_offset + k_local]
+        self.engine.rollout(state, wp_index, actions=local_actions, K=k_local, H=H, seed=seed,
+                            act_low=act_low, act_high=act_high, gamma=gamma,
+                            horizontal_penalty_factor=horizontal_penalty_factor,
+                            penalty_mode=penalty_mode, precision=precision, k_offset=k_offset,
+                            K_global=K)
+        if self.world > 1 and penalty_mode in ("reference", 0):
+            sums = self._sums_tensor()
+            if sums is not None:
+                dist.all_reduce(sums, group=self.group)      # 2*(H+1) float64
+        best_k, best_score, _ = self.engine.finish()
+        if self.world > 1:
+            mine = torch.tensor([best_score, float(best_k)], dtype=torch.float64, device=self.device)
+            gathered = [torch.empty_like(mine) for _ in range(self.world)]
+            dist.all_gather(gathered, mine, group=self.group)
+            pairs = torch.stack(gathered).cpu().numpy()
+            w = argmax_pick(pairs[:, 0].tolist(), [int(v) for v in pairs[:, 1]])
+            best_score, best_k = float(pairs[w, 0]), int(pairs[w, 1])
+        else:
+            w = 0
+        seq = path = None
+        if want_path:
+            if self.world == 1 or actions is None:
+                seq, path = self.engine.replay(best_k)           # Philox replay works on any rank
+            else:
+                d, da = self.engine._model_shape[0], self.engine._model_shape[1]
+                buf = torch.zeros(H * da + (H + 1) * d, dtype=torch.float64, device=self.device)
+                if self.rank == w:
+                    s, p = self.engine.replay(best_k)
+                    buf.copy_(torch.as_tensor(np.concatenate([s.reshape(-1), p.reshape(-1)])))
+                dist.broadcast(buf, src=dist.get_global_rank(self.group, w) if self.group else w,
+                               group=self.group)
+                flat = buf.cpu().numpy()
+                seq, path = flat[:H * da].reshape(H, da), flat[H * da:].reshape(H + 1, d)
+        return dict(best_k=best_k, best_score=best_score, best_sequence=seq, best_path=path,
+                    owner=w, k_offset=k_offset, k_local=k_local)
+
+
+class ShardedSelector:
+    """KDE + UCB + argmax with the queries sharded over the ranks (buffer replicated)."""
+
+    def __init__(self, engine, device=None, group=None):
+        dist = _dist()
+        self.engine = engine
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.device = device
+
+    def select_start(self, all_states, queries, values, n_transitions, volume=1.0, alpha=1.0, beta=2.0):
+        import torch
+        dist = _dist()
+        off, cnt = shard_bounds(len(queries), self.world, self.rank)
+        if cnt > 0:
+            j, ucb, _, _ = self.engine.select_start(all_states, queries[off:off + cnt],
+                                                    np.asarray(values).reshape(-1)[off:off + cnt],
+                                                    n_transitions, volume, alpha, beta)
+            j += off
+        else:
+            j, ucb = -1, 0.0
+        if self.world == 1:
+            return j, ucb
+        mine = torch.tensor([ucb, float(j)], dtype=torch.float64, device=self.device)
+        gathered = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine, group=self.group)
+        pairs = torch.stack(gathered).cpu().numpy()
+        w = argmax_pick(pairs[:, 0].tolist(), [int(v) for v in pairs[:, 1]])
+        return int(pairs[w, 1]), float(pairs[w, 0])
