@@ -1,0 +1,25 @@
+"""Short, fixed workload for ncu: 2 MPC decisions on the BASELINE config-4 shard + 2 KDE
+selections on config 2 (same code path as bench.py, no timing)."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from smartstartcontinuous_b200.engine import Engine
+
+eng = Engine(0)
+wl = bench.make_workload()
+eng.set_model(wl["w"], wl["b"], wl["norm"])
+eng.set_plan(wl["plan"]["desired_states"], wl["plan"]["distances_left"], wl["plan"]["radii"])
+prec = "bf16_tc" if eng.tc_supported() else "fp32"
+K = int(os.environ.get("SS_PROFILE_K", bench.K_PER_GPU))
+for i in range(2):
+    r = eng.plan(wl["state"], 0, K=K, H=bench.HORIZON, seed=i, act_low=wl["low"], act_high=wl["high"],
+                 penalty_mode="reference", precision=prec)
+print("mpc", r["best_k"], r["best_score"], eng.last_timings())
+kw = bench.kde_workload()
+for i in range(2):
+    j, u, _, _ = eng.select_start(kw["all_states"], kw["queries"], kw["values"], kw["n"], kw["volume"])
+print("kde", j, u, eng.last_timings())

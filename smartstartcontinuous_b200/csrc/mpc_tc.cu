@@ -6,22 +6,23 @@
 // BASELINE configs).  One persistent CTA per SM owns tiles of 128 sequences ("rows" = TMEM
 // lanes) and walks them through all H steps without touching HBM for activations:
 //
-//   layer 1   [128 x 32] x [32 x HP]   tcgen05.mma, A = split-bf16 input in TMEM, B = W1 image
+//   layer 1   [128 x 32] x [32 x HP]   tcgen05.mma, A = split-bf16 input in smem, B = W1 image
 //             (input, weights and bias are hi/lo bf16 splits packed along K, so the layer is
 //             FP32-accurate although it runs on the tensor pipe)
 //   relu+cvt  TMEM accumulator chunk -> registers -> bf16x2 -> TMEM (becomes the A operand)
 //   layer 2   [128 x HP] x [HP x HP]   tcgen05.mma kind::f16 (BF16 in, FP32 accumulate in TMEM),
-//             A from TMEM, B = W2 streamed from L2 by the TMA engine (cp.async.bulk, 16 KB
-//             pre-packed core-matrix blocks) through a 6-stage mbarrier ring; bias folded in via
+//             A from TMEM, B = W2 streamed from L2 by the TMA engine (cp.async.bulk, 32 KB
+//             pre-packed core-matrix blocks) through a 4-stage mbarrier ring; bias folded in via
 //             two constant-one hidden units (hi/lo split)
 //   layer 3   fused into the layer-2 epilogue: relu, FP32 FFMA dot with W3 from shared memory
 //   update    state += z * std_z + mean_z, waypoint logic + progress/penalty score (score.cuh),
 //             all in FP32 registers of the row's thread
 //
 // Warp roles: warps 0-7 = row warps (two threads per row, each takes half the columns of every
-// accumulator chunk), warp 8 = MMA issuer (one elected lane), warp 9 = TMA producer.
-// TMEM (512 columns): [0,256) H1 as bf16 A operand, [256,448) 3-deep ring of 128x64 FP32
-// accumulator chunks, [448,464) layer-1 A operand.
+// accumulator chunk), warp 8 = MMA issuer (warp-uniform loop, one elected lane issues so the
+// UTCHMMA stream stays back to back), warp 9 = TMA producer.
+// TMEM (512 columns): [0,256) H1 as bf16 A operand, [256,512) 2-deep ring of 128x128 FP32
+// accumulator chunks.  The layer-1 A operand (128 x 32 bf16) lives in shared memory.
 #include <cuda_bf16.h>
 
 #include <cstring>
@@ -31,24 +32,26 @@
 namespace tc {
 
 constexpr int TM = 128;                 // rows per tile
-constexpr int NC = 64;                  // units per accumulator chunk (MMA N)
+constexpr int NC = 128;                 // units per accumulator chunk (MMA N)
 constexpr int KSLAB = 128;              // K elements per W2 stage
-constexpr int STAGE_BYTES = NC * KSLAB * 2;   // 16 KB
-constexpr int NSTAGE = 6;
+constexpr int STAGE_BYTES = NC * KSLAB * 2;   // 32 KB
+constexpr int NSTAGE = 4;
 constexpr int K1 = 32;                  // K slots of the layer-1 MMA
-constexpr int ACC_SLOTS = 3;
+constexpr int ACC_SLOTS = 2;
+constexpr int W1_CHUNK_BYTES = NC * K1 * 2;   // 8 KB
+constexpr int A1_BYTES = TM * K1 * 2;         // 8 KB
 constexpr int ROW_WARPS = 8;
 constexpr int ROW_THREADS = ROW_WARPS * 32;
 constexpr int THREADS = ROW_THREADS + 64;
 constexpr int HP_MAX = 512;
 constexpr int MAX_DIN = 10;             // 3 * din + 2 <= K1
 constexpr uint32_t TMEM_COLS = 512;
-constexpr uint32_t COL_H1 = 0, COL_ACC = 256, COL_A1 = 448;
+constexpr uint32_t COL_H1 = 0, COL_ACC = 256;
 constexpr int SPIN_LIMIT = 1 << 28;
 
 struct Params {
-    const __nv_bfloat16* w1_img;        // [HP/64][4][64][8]
-    const __nv_bfloat16* w2_img;        // [HP/64][HP/128][16][64][8]
+    const __nv_bfloat16* w1_img;        // [HP/128][4][128][8]
+    const __nv_bfloat16* w2_img;        // [HP/128][HP/128][16][128][8]
     const float* w3;                    // [HP][DTW]
     float b3[SS_MAX_D];
     int hp;                             // padded hidden width (multiple of 128)
@@ -100,14 +103,29 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                        uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
+}
 // K-major, no swizzle: core matrices of 8 rows x 16 B; LBO = stride between the two K halves of
-// one MMA (here: NC * 16 B), SBO = stride between 8-row groups (128 B); version 1 (Blackwell)
-__device__ __forceinline__ uint64_t make_b_desc(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((NC * 16) >> 4) << 16) |
+// one MMA (rows * 16 B for a [k/8][row][8] image), SBO = stride between 8-row groups (128 B);
+// version 1 (Blackwell)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t rows) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((rows * 16) >> 4) << 16) |
            ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
 }
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) |
-                           ((uint32_t)(TM >> 4) << 24);   // D f32, A/B bf16, K-major, N=64, M=128
+                           ((uint32_t)(TM >> 4) << 24);   // D f32, A/B bf16, K-major, N=128, M=128
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -147,7 +165,8 @@ struct Smem {
     // dynamic shared memory carve-up (offsets in bytes from a 128-byte aligned base)
     static constexpr size_t W2_RING = 0;
     static constexpr size_t W1 = W2_RING + (size_t)NSTAGE * STAGE_BYTES;
-    static constexpr size_t W3 = W1 + (size_t)(HP_MAX / NC) * 4096;
+    static constexpr size_t A1 = W1 + (size_t)(HP_MAX / NC) * W1_CHUNK_BYTES;
+    static constexpr size_t W3 = A1 + (size_t)A1_BYTES;
     static constexpr size_t ZX = W3 + (size_t)HP_MAX * 8 * 4;
     static constexpr size_t BARS = ZX + (size_t)TM * 8 * 4;
     static constexpr int N_BARS = 2 * NSTAGE + 2 * ACC_SLOTS + HP_MAX / NC + 2;
@@ -160,6 +179,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* w2_ring = smem + Smem::W2_RING;
     unsigned char* w1s = smem + Smem::W1;
+    unsigned char* a1s = smem + Smem::A1;
     float* w3s = reinterpret_cast<float*>(smem + Smem::W3);
     float* zx = reinterpret_cast<float*>(smem + Smem::ZX);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::BARS);
@@ -175,8 +195,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = a.H + 1;
-    const int nch = p.hp / NC;          // accumulator chunks per layer
-    const int nslab = p.hp / KSLAB;     // W2 stages per chunk
+    const int nch = p.hp / NC;          // accumulator chunks per layer == W2 K-slabs per chunk
     constexpr int DTW = DT <= 4 ? 4 : 8;
 
     // ---- one-time setup ----------------------------------------------------------------
@@ -205,7 +224,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
         const int q = warp & 3, ch = warp >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-        uint32_t acc_it = 0, step_it = 0;
+        uint32_t acc_it = 0;
         for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
             const long long k_local = tile * TM + row;
             const bool live = k_local < a.K_local;
@@ -264,11 +283,17 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
 #pragma unroll
                     for (int s = 0; s < K1; ++s)
                         if (s == 3 * p.din || s == 3 * p.din + 1) slot[s] = 1.f;
-                    uint32_t pk[16];
+                    // smem image [k/8][row][8] (K-major core matrices): 4 x 16 B per row
 #pragma unroll
-                    for (int c2 = 0; c2 < 16; ++c2) pk[c2] = pack_bf16(slot[2 * c2], slot[2 * c2 + 1]);
-                    tmem_st16(lane_addr + COL_A1, pk);
-                    tc_fence_before();
+                    for (int kc = 0; kc < K1 / 8; ++kc) {
+                        uint4 v;
+                        v.x = pack_bf16(slot[8 * kc], slot[8 * kc + 1]);
+                        v.y = pack_bf16(slot[8 * kc + 2], slot[8 * kc + 3]);
+                        v.z = pack_bf16(slot[8 * kc + 4], slot[8 * kc + 5]);
+                        v.w = pack_bf16(slot[8 * kc + 6], slot[8 * kc + 7]);
+                        *reinterpret_cast<uint4*>(a1s + kc * (TM * 16) + row * 16) = v;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
                     __syncwarp();
                     if (lane == 0) mbar_arrive(x_ready);
                 }
@@ -277,13 +302,16 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                     const uint32_t slot_i = acc_it % ACC_SLOTS;
                     mbar_wait(&acc_full[slot_i], (acc_it / ACC_SLOTS) & 1);
                     tc_fence_after();
-                    uint32_t v[32];
-                    tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * 32, v);
-                    uint32_t pk[16];
 #pragma unroll
-                    for (int c2 = 0; c2 < 16; ++c2)
-                        pk[c2] = pack_bf16_relu(__uint_as_float(v[2 * c2]), __uint_as_float(v[2 * c2 + 1]));
-                    tmem_st16(lane_addr + COL_H1 + c * (NC / 2) + ch * 16, pk);
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t v[32];
+                        tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * 64 + half * 32, v);
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int c2 = 0; c2 < 16; ++c2)
+                            pk[c2] = pack_bf16_relu(__uint_as_float(v[2 * c2]), __uint_as_float(v[2 * c2 + 1]));
+                        tmem_st16(lane_addr + COL_H1 + c * (NC / 2) + ch * 32 + half * 16, pk);
+                    }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { mbar_arrive(&acc_free[slot_i]); mbar_arrive(&h1_ready[c]); }
@@ -296,15 +324,16 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                     const uint32_t slot_i = acc_it % ACC_SLOTS;
                     mbar_wait(&acc_full[slot_i], (acc_it / ACC_SLOTS) & 1);
                     tc_fence_after();
-                    uint32_t v[32];
-                    tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * 32, v);
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * 64, v0);
+                    tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * 64 + 32, v1);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_free[slot_i]);
-                    const float* wrow = w3s + (size_t)(n * NC + ch * 32) * DTW;
+                    const float* wrow = w3s + (size_t)(n * NC + ch * 64) * DTW;
 #pragma unroll
-                    for (int j2 = 0; j2 < 32; ++j2) {
-                        const float hval = fmaxf(__uint_as_float(v[j2]), 0.f);
+                    for (int j2 = 0; j2 < 64; ++j2) {
+                        const float hval = fmaxf(__uint_as_float(j2 < 32 ? v0[j2 & 31] : v1[j2 & 31]), 0.f);
                         const float4 w0 = *reinterpret_cast<const float4*>(wrow + j2 * DTW);
                         z[0] = fmaf(hval, w0.x, z[0]);
                         if (DT > 1) z[1] = fmaf(hval, w0.y, z[1]);
@@ -333,54 +362,55 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                             x[j] += fmaf(zz, a.norm.std_z[j], a.norm.mean_z[j]);
                         }
                 }
-                ++step_it;
             }
             if (ch == 0 && live && a.scores_out) a.scores_out[k_local] = sc.score;
         }
-        (void)step_it;
     } else if (warp == ROW_WARPS) {
         // =============================== MMA ISSUER =======================================
-        if (lane == 0) {
-            uint32_t acc_it = 0, w2_it = 0, step_it = 0;
-            mbar_wait(w1_full, 0);
-            for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                for (int t = 0; t < a.H; ++t, ++step_it) {
-                    mbar_wait(x_ready, step_it & 1);
+        // the whole warp walks the loop (warp-uniform control flow); one elected lane issues
+        uint32_t acc_it = 0, w2_it = 0, step_it = 0;
+        mbar_wait(w1_full, 0);
+        const uint32_t a1_addr = smem_u32(a1s), w1_addr = smem_u32(w1s), ring_addr = smem_u32(w2_ring);
+        for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (int t = 0; t < a.H; ++t, ++step_it) {
+                mbar_wait(x_ready, step_it & 1);
+                tc_fence_after();
+                // layer 1: acc chunk c = A1 [128 x 32] * W1img[c] [128 x 32]^T
+                for (int c = 0; c < nch; ++c, ++acc_it) {
+                    const uint32_t slot_i = acc_it % ACC_SLOTS;
+                    mbar_wait(&acc_free[slot_i], ((acc_it / ACC_SLOTS) & 1) ^ 1);
                     tc_fence_after();
-                    // layer 1: acc chunk c = A1 [128 x 32] * W1img[c] [64 x 32]^T
-                    for (int c = 0; c < nch; ++c, ++acc_it) {
-                        const uint32_t slot_i = acc_it % ACC_SLOTS;
-                        mbar_wait(&acc_free[slot_i], ((acc_it / ACC_SLOTS) & 1) ^ 1);
-                        tc_fence_after();
+                    if (elect_one()) {
                         const uint32_t d_tmem = tmem + COL_ACC + slot_i * NC;
-                        const uint32_t b_addr = smem_u32(w1s) + c * 4096;
 #pragma unroll
                         for (int ks = 0; ks < K1 / 16; ++ks)
-                            umma_ts(d_tmem, tmem + COL_A1 + ks * 8, make_b_desc(b_addr + ks * 2 * (NC * 16)), IDESC, ks);
+                            umma_ss(d_tmem, make_desc(a1_addr + ks * 2 * (TM * 16), TM),
+                                    make_desc(w1_addr + c * W1_CHUNK_BYTES + ks * 2 * (NC * 16), NC), IDESC, ks);
                         tc_commit(&acc_full[slot_i]);
                     }
-                    // layer 2: acc chunk n = H1 [128 x HP] * W2img[n] [64 x HP]^T, K streamed in slabs
-                    for (int n = 0; n < nch; ++n, ++acc_it) {
-                        const uint32_t slot_i = acc_it % ACC_SLOTS;
-                        mbar_wait(&acc_free[slot_i], ((acc_it / ACC_SLOTS) & 1) ^ 1);
+                    __syncwarp();
+                }
+                // layer 2: acc chunk n = H1 [128 x HP] * W2img[n] [128 x HP]^T, K streamed in slabs
+                for (int n = 0; n < nch; ++n, ++acc_it) {
+                    const uint32_t slot_i = acc_it % ACC_SLOTS;
+                    mbar_wait(&acc_free[slot_i], ((acc_it / ACC_SLOTS) & 1) ^ 1);
+                    for (int ksl = 0; ksl < nch; ++ksl, ++w2_it) {
+                        const uint32_t st = w2_it % NSTAGE;
+                        if (n == 0) mbar_wait(&h1_ready[ksl], step_it & 1);
+                        mbar_wait(&w2_full[st], (w2_it / NSTAGE) & 1);
                         tc_fence_after();
-                        const uint32_t d_tmem = tmem + COL_ACC + slot_i * NC;
-                        for (int ksl = 0; ksl < nslab; ++ksl, ++w2_it) {
-                            const uint32_t st = w2_it % NSTAGE;
-                            if (n == 0) {
-                                mbar_wait(&h1_ready[2 * ksl], step_it & 1);
-                                mbar_wait(&h1_ready[2 * ksl + 1], step_it & 1);
-                            }
-                            mbar_wait(&w2_full[st], (w2_it / NSTAGE) & 1);
-                            tc_fence_after();
-                            const uint32_t b_addr = smem_u32(w2_ring) + st * STAGE_BYTES;
+                        if (elect_one()) {
+                            const uint32_t d_tmem = tmem + COL_ACC + slot_i * NC;
+                            const uint32_t a_tmem = tmem + COL_H1 + ksl * (KSLAB / 2);
+                            const uint64_t b0 = make_desc(ring_addr + st * STAGE_BYTES, NC);
 #pragma unroll
                             for (int ks = 0; ks < KSLAB / 16; ++ks)
-                                umma_ts(d_tmem, tmem + COL_H1 + ksl * (KSLAB / 2) + ks * 8,
-                                        make_b_desc(b_addr + ks * 2 * (NC * 16)), IDESC, (ksl | ks) != 0);
+                                umma_ts(d_tmem, a_tmem + ks * 8, b0 + (uint64_t)((ks * 2 * (NC * 16)) >> 4), IDESC,
+                                        (ksl | ks) != 0);
                             tc_commit(&w2_empty[st]);
+                            if (ksl == nch - 1) tc_commit(&acc_full[slot_i]);
                         }
-                        tc_commit(&acc_full[slot_i]);
+                        __syncwarp();
                     }
                 }
             }
@@ -388,21 +418,20 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
     } else {
         // =============================== TMA PRODUCER =====================================
         if (lane == 0) {
-            mbar_expect_tx(w1_full, (uint32_t)(nch * 4096));
-            bulk_g2s(w1s, p.w1_img, (uint32_t)(nch * 4096), w1_full);
+            mbar_expect_tx(w1_full, (uint32_t)(nch * W1_CHUNK_BYTES));
+            bulk_g2s(w1s, p.w1_img, (uint32_t)(nch * W1_CHUNK_BYTES), w1_full);
             uint32_t w2_it = 0;
+            const int blocks = nch * nch;
             for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
                 for (int t = 0; t < a.H; ++t)
-                    for (int n = 0; n < nch; ++n)
-                        for (int ksl = 0; ksl < nslab; ++ksl, ++w2_it) {
-                            const uint32_t st = w2_it % NSTAGE;
-                            mbar_wait(&w2_empty[st], ((w2_it / NSTAGE) & 1) ^ 1);
-                            mbar_expect_tx(&w2_full[st], STAGE_BYTES);
-                            bulk_g2s(w2_ring + (size_t)st * STAGE_BYTES,
-                                     reinterpret_cast<const unsigned char*>(p.w2_img) +
-                                         ((size_t)n * nslab + ksl) * STAGE_BYTES,
-                                     STAGE_BYTES, &w2_full[st]);
-                        }
+                    for (int blk = 0; blk < blocks; ++blk, ++w2_it) {
+                        const uint32_t st = w2_it % NSTAGE;
+                        mbar_wait(&w2_empty[st], ((w2_it / NSTAGE) & 1) ^ 1);
+                        mbar_expect_tx(&w2_full[st], STAGE_BYTES);
+                        bulk_g2s(w2_ring + (size_t)st * STAGE_BYTES,
+                                 reinterpret_cast<const unsigned char*>(p.w2_img) + (size_t)blk * STAGE_BYTES,
+                                 STAGE_BYTES, &w2_full[st]);
+                    }
         }
     }
     // ---- teardown ---------------------------------------------------------------------------
@@ -446,13 +475,14 @@ int mpc_tc_prepare(ss_ctx* c) {
     const int h = c->h, d = c->d, din = c->d + c->da;
     const int hp = (h + 2 + KSLAB - 1) / KSLAB * KSLAB;
     const int nch = hp / NC, nslab = hp / KSLAB;
+    static_assert(NC == KSLAB, "the kernel walks nch K-slabs per chunk");
     const std::vector<double>&W1 = c->hw[0], &W2 = c->hw[1], &W3 = c->hw[2];
     const std::vector<double>&B1 = c->hb[0], &B2 = c->hb[1];
     // layer-1 image: K slots (3j, 3j+1, 3j+2) = (W_hi, W_lo, W_hi) of input j; then (b_hi, b_lo)
-    std::vector<uint16_t> w1((size_t)nch * 2048, 0);
+    std::vector<uint16_t> w1((size_t)nch * (W1_CHUNK_BYTES / 2), 0);
     auto w1_at = [&](int slot, int u) -> uint16_t& {
         const int cidx = u / NC, nn = u % NC;
-        return w1[(size_t)cidx * 2048 + (slot / 8) * (NC * 8) + nn * 8 + (slot % 8)];
+        return w1[(size_t)cidx * (W1_CHUNK_BYTES / 2) + (slot / 8) * (NC * 8) + nn * 8 + (slot % 8)];
     };
     for (int u = 0; u < h; ++u) {
         for (int j = 0; j < din; ++j) {
