@@ -153,3 +153,172 @@ def test_c3_size_fp32_properties(engine):
     perm = rng.permutation(K)
     res2 = engine.plan(start, 0, actions=acts[perm], penalty_mode="per_sample", precision="fp32", want_scores=True)
     np.testing.assert_array_equal(res2["scores"], res["scores"][perm])
+
+
+# ----------------------------------------------------------------------------------------------
+# tcgen05 path (SS_PRECISION_BF16_TC).  Stated tolerance of the tensor-core path: the hidden x
+# hidden layer runs with BF16 operands (FP32 accumulate), so trajectories deviate from the float64
+# oracle by ~1e-3 of the per-step state change and scores by up to a few 1e-2 (absolute, scores are
+# O(1..50)); TC_SCORE_TOL is that bound, and the chosen index must match the oracle's wherever its
+# top-2 gap exceeds 2 * TC_SCORE_TOL.
+TC_SCORE_TOL = 5e-2
+TC_STATE_RTOL = 2e-3
+
+
+def _pendulum_2x500(rng, scale=0.5):
+    obs, act = syn.pendulum_rollouts(rng, 8, 200)
+    norm = syn.normalisation_stats(np.concatenate(list(obs)),
+                                   np.concatenate([np.concatenate([a, a[-1:]]) for a in act]))
+    w, b = syn.xavier_mlp(rng, 3, 1, 2, 500, scale=scale)
+    from smartstartcontinuous_b200.nnd_mb_agent import plan_from_path
+    plan = plan_from_path(list(obs[0][:60]), mean_per_stepsize=1, std_per_stepsize=1,
+                          stepsizes_in_waypoint_radii=1, path_shortcutting=True, theta=1, steps_per_waypoint=1)
+    return w, b, norm, plan, obs[0][0]
+
+
+def test_tc_golden_states_and_plan(engine):
+    g = load_golden("mpc_mountaincar_L2.npz")
+    _setup(engine, g)
+    assert engine.tc_supported()
+    states = engine.forward_sim(g["in_start_state"], g["in_actions"], precision="bf16_tc")
+    scale = np.abs(g["out_states"]).max(axis=(0, 1))
+    assert np.all(np.abs(states - g["out_states"]).max(axis=(0, 1)) <= TC_STATE_RTOL * scale)
+    for mode in ("reference", "per_sample"):
+        res = engine.plan(g["in_start_state"], int(g["in_wp_index"]), actions=g["in_actions"],
+                          penalty_mode=mode, precision="bf16_tc", want_scores=True)
+        want = g["out_scores"] if mode == "reference" else mpc_oracle.score_add_delta(
+            g["out_states"], g["out_desired_states"], g["out_distances_left"], g["out_radii"],
+            int(g["in_wp_index"]), .75, .5, penalty_mode=1)
+        _score_close(res["scores"], want, TC_SCORE_TOL, max_outlier_frac=0.02)
+        assert np.median(np.abs(res["scores"] - want)) < 1e-2
+        _check_best(res["best_k"], want, TC_SCORE_TOL)
+
+
+@pytest.mark.parametrize("mode", ["reference", "per_sample"])
+def test_tc_2x500_vs_oracle_and_fp32(engine, mode):
+    """The BASELINE network shape (2x500, Pendulum d=3) with device-sampled actions: a 256-sequence
+    slice against the float64 oracle, the whole batch against the FP32 kernel."""
+    rng = np.random.default_rng(11)
+    w, b, norm, plan, start = _pendulum_2x500(rng)
+    engine.set_model(w, b, norm)
+    engine.set_plan(plan["desired_states"], plan["distances_left"], plan["radii"])
+    K, H, seed = 3000, 20, 9          # K is not a multiple of the 128-row tile
+    kw = dict(K=K, H=H, seed=seed, act_low=[-2.0], act_high=[2.0], penalty_mode=mode, want_scores=True)
+    tc = engine.plan(start, 0, precision="bf16_tc", **kw)
+    f32 = engine.plan(start, 0, precision="fp32", **kw)
+    assert np.median(np.abs(tc["scores"] - f32["scores"])) < 2e-2
+    _score_close(tc["scores"], f32["scores"], 3 * TC_SCORE_TOL, max_outlier_frac=0.03)
+    acts = philox.sample_actions(K, H, 1, seed, [-2.0], [2.0])
+    if mode == "per_sample":
+        o = mpc_oracle.plan(start, acts[:256], w, b, norm, plan["desired_states"], plan["distances_left"],
+                            plan["radii"], 0, .75, .5, penalty_mode=1)
+        _score_close(tc["scores"][:256], o["scores"], 3 * TC_SCORE_TOL, max_outlier_frac=0.03)
+    else:
+        o = mpc_oracle.plan(start, acts, w, b, norm, plan["desired_states"], plan["distances_left"],
+                            plan["radii"], 0, .75, .5, penalty_mode=0)
+        _score_close(tc["scores"], o["scores"], 3 * TC_SCORE_TOL, max_outlier_frac=0.03)
+        _check_best(tc["best_k"], o["scores"], 3 * TC_SCORE_TOL)
+    np.testing.assert_array_equal(tc["best_sequence"], acts[tc["best_k"]])
+
+
+def test_tc_sharding_is_bit_exact(engine):
+    """A sequence's score does not depend on which tile / shard it lands in."""
+    rng = np.random.default_rng(12)
+    w, b, norm, plan, start = _pendulum_2x500(rng)
+    engine.set_model(w, b, norm)
+    engine.set_plan(plan["desired_states"], plan["distances_left"], plan["radii"])
+    kw = dict(H=7, seed=3, act_low=[-2.0], act_high=[2.0], penalty_mode="per_sample", precision="bf16_tc",
+              want_scores=True, want_path=False)
+    full = engine.plan(start, 0, K=700, **kw)
+    a_ = engine.plan(start, 0, K=300, k_offset=0, K_global=700, **kw)
+    b_ = engine.plan(start, 0, K=400, k_offset=300, K_global=700, **kw)
+    np.testing.assert_array_equal(np.concatenate([a_["scores"], b_["scores"]]), full["scores"])
+    assert b_["best_k"] >= 300
+
+
+def test_tc_unsupported_shape(engine):
+    g = load_golden("mpc_pendulum_L1.npz")          # one hidden layer: no hidden x hidden GEMM
+    _setup(engine, g)
+    assert not engine.tc_supported()
+    with pytest.raises(ValueError):
+        engine.plan(g["in_start_state"], 0, actions=g["in_actions"], precision="bf16_tc")
+    res = engine.plan(g["in_start_state"], int(g["in_wp_index"]), actions=g["in_actions"], precision="auto",
+                      want_scores=True)
+    _score_close(res["scores"], g["out_scores"], SCORE_TOL)
+
+
+def test_agents_end_to_end(engine):
+    """SmartStartContinuous / NND_MB_agent drop-ins driven like rlTrain drives them, on a synthetic
+    MountainCar environment; the choices are re-derived with the oracle from the same buffers."""
+    import random
+
+    from oracle import kde_oracle
+    from smartstartcontinuous_b200.smart_start import SmartStartContinuous
+
+    class Box:
+        low, high, shape = np.array([-1.0]), np.array([1.0]), (1,)
+
+    class Env:
+        action_space = Box()
+
+        def __init__(self):
+            self.rng = np.random.default_rng(0)
+
+        def reset(self):
+            self.s, _ = syn.mountaincar_rollout(self.rng, 0)
+            self.s = self.s[0]
+            return self.s.copy()
+
+        def step(self, a):
+            st, _ = syn.mountaincar_rollout(self.rng, 1, start=self.s)
+            # re-simulate with the given action
+            pos, vel = self.s
+            vel = min(max(vel + float(np.clip(a[0], -1, 1)) * 0.0015 - 0.0025 * np.cos(3 * pos), -0.07), 0.07)
+            pos = min(max(pos + vel, -1.2), 0.6)
+            self.s = np.array([pos, 0.0 if (pos == -1.2 and vel < 0) else vel])
+            return self.s.copy(), -0.1 * float(a[0]) ** 2, bool(pos >= 0.45), {}
+
+    class Base:
+        def get_action(self, s): return np.array([np.random.uniform(-1, 1)])
+        def observe(self, *a): pass
+        def start_new_episode(self, s): pass
+        def end_episode(self): pass
+        def get_param_dict(self): return {}
+        def get_state_value(self, states): return syn.critic_like_values(np.asarray(states), 5).reshape(-1, 1)
+
+    np.random.seed(0)
+    random.seed(0)
+    env = Env()
+    agent = SmartStartContinuous(Base(), env, None, buffer_size=5000, eta=1.0, n_ss=200, print_ss_stuff=False,
+                                 nnd_mb_horizon=6, nnd_mb_num_control_samples=256, nnd_mb_num_fc_layers=2,
+                                 nnd_mb_depth_fc_layers=64, nnd_mb_nEpoch=2, nnd_mb_num_rollouts_train=3,
+                                 nnd_mb_num_rollouts_val=1, nnd_mb_steps_per_rollout_train=100,
+                                 nnd_mb_steps_per_rollout_val=20, nnd_mb_verbose=False, engine=engine)
+    for ep in range(3):
+        s = env.reset()
+        agent.start_new_episode(s)
+        if ep > 0:
+            assert agent.smart_start_path is not None
+            # the selection equals the oracle's on the same buffer contents
+            rb = agent.replay_buffer
+        for t in range(60):
+            a = agent.get_action(s)
+            assert np.shape(a) == (1,)
+            s2, r, done, _ = env.step(a)
+            agent.observe(s, a, r, s2, done)
+            s = s2
+            if done:
+                break
+        agent.end_episode()
+    # re-derive the last selection with the oracle
+    rb = agent.replay_buffer
+    random.seed(123)
+    idx = rb.get_possible_smart_start_indices(agent.n_ss)
+    random.seed(123)
+    path = agent.get_smart_start_path()
+    q = rb.states_s2(idx)
+    vol = 1 if agent.nnd_mb_agent.radii is None else float(np.prod(agent.nnd_mb_agent.radii) * np.pi)
+    obest, _, oucb = kde_oracle.select_start(rb.get_all_states(), q, syn.critic_like_values(q, 5), len(rb), vol, 1.0, 2.0)
+    chosen, ucb = agent.last_selection
+    assert chosen == int(idx[obest]) or abs(oucb[list(idx).index(chosen)] - oucb[obest]) < 1e-4 * abs(oucb[obest])
+    assert np.array_equal(path[-1], rb.buffer[chosen][4])
