@@ -16,13 +16,15 @@
 //                            UCB and the np.argmax-ordered arg-max (single pass, last block reduces)
 //
 // Roofline: SFU bound -- one MUFU.EX2 per kernel evaluation (16 / clk / SM); see DESIGN.md.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr int KDE_THREADS = 128;      // threads per CTA in the pair kernel
 constexpr int KDE_TILE_FLOATS = 4096;  // 16 KB of points per shared-memory stage
-constexpr int KDE_STAGES = 3;
+constexpr int KDE_STAGES = 2;
 constexpr double KDE_RESCUE_BELOW = 7.8886090522101181e-31;  // 2^-100
 
 struct KdeFit {
@@ -84,17 +86,20 @@ kde_moments_kernel(const double* __restrict__ data, long long n, int d, double* 
 }
 
 // ---- 2. fit ----------------------------------------------------------------------------
-__global__ void kde_fit_kernel(const double* __restrict__ data, long long n, int d,
-                               const double* __restrict__ partial, int nblocks,
-                               KdeFit* __restrict__ fit) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(256)
+kde_fit_kernel(const double* __restrict__ data, long long n, int d, const double* __restrict__ partial,
+               int nblocks, KdeFit* __restrict__ fit) {
+    __shared__ double mom[SS_MAX_D + SS_MAX_D * (SS_MAX_D + 1) / 2];
     const int nm = d + d * (d + 1) / 2;
-    double mom[SS_MAX_D + SS_MAX_D * (SS_MAX_D + 1) / 2];
-    for (int q = 0; q < nm; ++q) {
+    // one warp per moment: lanes stride over the per-block partials, fixed-order shuffle reduction
+    for (int q = threadIdx.x >> 5; q < nm; q += blockDim.x >> 5) {
         double s = 0.0;
-        for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * nm + q];
-        mom[q] = s;
+        for (int b = threadIdx.x & 31; b < nblocks; b += 32) s += partial[(size_t)b * nm + q];
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+        if ((threadIdx.x & 31) == 0) mom[q] = s;
     }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     const double N = (double)n;
     const double factor = pow(N, -1.0 / (d + 4));          // scotts_factor
     double cov[SS_MAX_D * SS_MAX_D];
@@ -443,8 +448,10 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
     const long long qtile = (long long)KDE_THREADS * Q;
     const long long m_pad = (m + qtile - 1) / qtile * qtile;
     const long long q_tiles = m_pad / qtile;
-    // fill the GPU: ~4 CTAs per SM
-    long long want = (long long)c->sm_count * 4;
+    // fill the GPU: many small CTAs (up to 7 resident per SM; MUFU-bound, more warps hide its latency and small work items balance the SMs)
+    int per_sm = 24;
+    if (const char* e = getenv("SS_KDE_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
+    long long want = (long long)c->sm_count * per_sm;
     long long slices = (want + q_tiles - 1) / q_tiles;
     if (slices > n_tiles) slices = n_tiles;
     if (slices < 1) slices = 1;
@@ -474,7 +481,7 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
     else
         kde_moments_kernel<SS_MAX_D><<<mom_blocks, 256, 0, c->stream>>>(data_dev, n, d,
                                                                         c->kde_moments.as<double>());
-    kde_fit_kernel<<<1, 32, 0, c->stream>>>(data_dev, n, d, c->kde_moments.as<double>(), mom_blocks,
+    kde_fit_kernel<<<1, 256, 0, c->stream>>>(data_dev, n, d, c->kde_moments.as<double>(), mom_blocks,
                                             fit);
     kde_whiten_kernel<true><<<(unsigned)((n_pad + 255) / 256), 256, 0, c->stream>>>(
         data_dev, n, n_pad, d, D, fit, c->kde_pts.as<float>());

@@ -25,6 +25,7 @@
 // accumulator chunks.  The layer-1 A operand (128 x 32 bf16) lives in shared memory.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "mpc_kernels.cuh"
@@ -32,15 +33,27 @@
 namespace tc {
 
 constexpr int TM = 128;                 // rows per tile
-constexpr int NC = 128;                 // units per accumulator chunk (MMA N)
-constexpr int KSLAB = 128;              // K elements per W2 stage
+#ifndef SS_TC_NC
+#define SS_TC_NC 128
+#endif
+constexpr int NC = SS_TC_NC;            // units per accumulator chunk (MMA N)
+#ifndef SS_TC_KSLAB
+#define SS_TC_KSLAB 128
+#endif
+#ifndef SS_TC_RING_KB
+#define SS_TC_RING_KB 128
+#endif
+constexpr int KSLAB = SS_TC_KSLAB;      // K elements per W2 stage
 constexpr int STAGE_BYTES = NC * KSLAB * 2;   // 32 KB
-constexpr int NSTAGE = 4;
+constexpr int NSTAGE = SS_TC_RING_KB * 1024 / STAGE_BYTES;
 constexpr int K1 = 32;                  // K slots of the layer-1 MMA
-constexpr int ACC_SLOTS = 2;
-constexpr int W1_CHUNK_BYTES = NC * K1 * 2;   // 8 KB
+constexpr int ACC_SLOTS = 256 / NC;
+constexpr int NC1 = NC;                 // units per layer-1 chunk (same accumulator slots as layer 2)
+constexpr int W1_CHUNK_BYTES = NC1 * K1 * 2;  // 8 KB
 constexpr int A1_BYTES = TM * K1 * 2;         // 8 KB
-constexpr int ROW_WARPS = 8;
+constexpr int ROW_WARPS = 8;                // 2 threads per row: each takes half of the columns
+constexpr int TPR = ROW_WARPS / 4;          // threads per row
+constexpr int CPT = NC / TPR;               // accumulator columns per thread and chunk
 constexpr int ROW_THREADS = ROW_WARPS * 32;
 constexpr int THREADS = ROW_THREADS + 64;
 constexpr int HP_MAX = 512;
@@ -48,15 +61,20 @@ constexpr int MAX_DIN = 10;             // 3 * din + 2 <= K1
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t COL_H1 = 0, COL_ACC = 256;
 constexpr int SPIN_LIMIT = 1 << 28;
+constexpr int CLUSTER = 2;                // CTAs sharing every W2 stage through TMA multicast
+constexpr uint16_t CLUSTER_MASK = (1u << CLUSTER) - 1;
 
 struct Params {
-    const __nv_bfloat16* w1_img;        // [HP/128][4][128][8]
+    const __nv_bfloat16* w1_img;        // [HP/64][4][64][8]
     const __nv_bfloat16* w2_img;        // [HP/128][HP/128][16][128][8]
     const float* w3;                    // [HP][DTW]
     float b3[SS_MAX_D];
     int hp;                             // padded hidden width (multiple of 128)
     int din;
     long long n_tiles;
+    int iters;                          // tile iterations per CTA (same for all: cluster lock-step)
+    int debug;                          // dev-only timing experiments (SS_TC_DEBUG), 0 in production
+    unsigned long long* prof;           // optional [grid][8] cycle counters (dev builds), else null
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------
@@ -88,11 +106,36 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                      "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// half of a stage, delivered to the same smem offset of every CTA in `mask`; each destination
+// CTA's mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void bulk_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
+                                                   uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* b) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(b))
                  : "memory");
+}
+// commit that arrives on the barrier at the same smem offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_multicast(uint64_t* b, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(b)),
+        "h"(mask)
+        : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem desc]
 __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
@@ -126,6 +169,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t rows)
 }
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) |
                            ((uint32_t)(TM >> 4) << 24);   // D f32, A/B bf16, K-major, N=128, M=128
+constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC1 >> 3) << 17) |
+                            ((uint32_t)(TM >> 4) << 24);  // same, N=64 (layer 1)
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -161,22 +206,77 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-struct Smem {
+#ifndef SS_TC_PROFILE
+#define TC_DEBUG 0
+#define TC_PROF_T0() do {} while (0)
+#define TC_PROF(slot) do {} while (0)
+#define TC_PROFW(slot) do {} while (0)
+#define TC_PROFW_T0() do {} while (0)
+#else
+#define TC_DEBUG p.debug
+#define TC_PROFW_T0() long long _pw = p.prof ? clock64() : 0
+#define TC_PROF_T0() long long _pt = p.prof ? clock64() : 0
+#define TC_PROF(slot)                                                                  \
+    do {                                                                               \
+        if (p.prof && warp == 0 && lane == 0) {                                        \
+            long long _n = clock64();                                                  \
+            p.prof[blockIdx.x * 8 + (slot)] += (unsigned long long)(_n - _pt);        \
+            _pt = _n;                                                                  \
+        } else if (p.prof) {                                                           \
+            _pt = clock64();                                                           \
+        }                                                                              \
+    } while (0)
+
+#define TC_PROFW(slot)                                                                 \
+    do {                                                                               \
+        if (p.prof && lane == 0) {                                                     \
+            long long _n = clock64();                                                  \
+            p.prof[(gridDim.x + blockIdx.x) * 8 + (slot)] += (unsigned long long)(_n - _pw); \
+            _pw = _n;                                                                  \
+        }                                                                              \
+    } while (0)
+#endif
+
+template <int DTW>
+struct SmemT {
     // dynamic shared memory carve-up (offsets in bytes from a 128-byte aligned base)
     static constexpr size_t W2_RING = 0;
     static constexpr size_t W1 = W2_RING + (size_t)NSTAGE * STAGE_BYTES;
-    static constexpr size_t A1 = W1 + (size_t)(HP_MAX / NC) * W1_CHUNK_BYTES;
+    static constexpr size_t A1 = W1 + (size_t)(HP_MAX / NC1) * W1_CHUNK_BYTES;
     static constexpr size_t W3 = A1 + (size_t)A1_BYTES;
-    static constexpr size_t ZX = W3 + (size_t)HP_MAX * 8 * 4;
-    static constexpr size_t BARS = ZX + (size_t)TM * 8 * 4;
-    static constexpr int N_BARS = 2 * NSTAGE + 2 * ACC_SLOTS + HP_MAX / NC + 2;
+    static constexpr size_t ZX = W3 + (size_t)HP_MAX * DTW * 4;
+    static constexpr size_t BARS = ZX + (size_t)TPR * TM * 8 * 4;
+    static constexpr int N_BARS = 2 * NSTAGE + 2 * ACC_SLOTS + 4 + HP_MAX / NC1 + 2;
     static constexpr size_t TMEM_PTR = BARS + (size_t)N_BARS * 8;
     static constexpr size_t SUMS = TMEM_PTR + 16;      // double [4][T][2]
 };
 
+// score one trajectory point for this row (ch-1 thread): waypoint logic, progress, penalty or
+// projection sums, optional state spill for the reference-mode second pass
+template <int DT>
+__device__ __forceinline__ void score_row(const RolloutArgs& a, int t, const float (&x)[DT], ScoreAcc& sc,
+                                          bool live, long long k_local, int q, int lane, int T, double* sums) {
+    float ab = 0.f, bb = 0.f;
+    score_point<DT>(a.plan, t, x, sc, a.per_sample != 0, ab, bb);
+    if (a.states_out && live)
+        for (int j = 0; j < a.d; ++j) a.states_out[((size_t)t * a.K_local + k_local) * a.d + j] = x[j];
+    if (a.partial_sums) {
+        double dab = live ? (double)ab : 0.0, dbb = live ? (double)bb : 0.0;
+        for (int off = 16; off > 0; off >>= 1) {
+            dab += __shfl_down_sync(0xffffffffu, dab, off);
+            dbb += __shfl_down_sync(0xffffffffu, dbb, off);
+        }
+        if (lane == 0) {
+            sums[((size_t)q * T + t) * 2] += dab;
+            sums[((size_t)q * T + t) * 2 + 1] += dbb;
+        }
+    }
+}
+
 template <int DT>
 __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const RolloutArgs a, const Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
+    using Smem = SmemT<(DT <= 4 ? 4 : 8)>;
     unsigned char* w2_ring = smem + Smem::W2_RING;
     unsigned char* w1s = smem + Smem::W1;
     unsigned char* a1s = smem + Smem::A1;
@@ -187,23 +287,30 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
     uint64_t* w2_empty = w2_full + NSTAGE;
     uint64_t* acc_full = w2_empty + NSTAGE;
     uint64_t* acc_free = acc_full + ACC_SLOTS;
-    uint64_t* h1_ready = acc_free + ACC_SLOTS;          // [HP_MAX / NC]
-    uint64_t* x_ready = h1_ready + HP_MAX / NC;
+    uint64_t* l1_full = acc_free + ACC_SLOTS;           // [2] layer-1 sub-slots
+    uint64_t* l1_free = l1_full + 2;
+    uint64_t* h1_ready = l1_free + 2;                   // [HP_MAX / NC1]
+    uint64_t* x_ready = h1_ready + HP_MAX / NC1;
     uint64_t* w1_full = x_ready + 1;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Smem::TMEM_PTR);
     double* sums = reinterpret_cast<double*>(smem + Smem::SUMS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = a.H + 1;
-    const int nch = p.hp / NC;          // accumulator chunks per layer == W2 K-slabs per chunk
+    const int nch = p.hp / NC;          // layer-2 accumulator chunks
+    const int nch1 = p.hp / NC1;        // layer-1 sub-chunks
+    const int nslab = p.hp / KSLAB;     // W2 K-slabs (stages) per chunk
+    constexpr int CPS = KSLAB >= NC ? KSLAB / NC : 1;     // layer-1 chunks per K-slab
+    constexpr int SPC = NC >= KSLAB ? NC / KSLAB : 1;     // K-slabs per layer-1 chunk
     constexpr int DTW = DT <= 4 ? 4 : 8;
 
     // ---- one-time setup ----------------------------------------------------------------
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&w2_full[s], 1); mbar_init(&w2_empty[s], 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&w2_full[s], 1); mbar_init(&w2_empty[s], CLUSTER); }
         for (int s = 0; s < ACC_SLOTS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], ROW_WARPS); }
-        for (int c = 0; c < HP_MAX / NC; ++c) mbar_init(&h1_ready[c], ROW_WARPS);
-        mbar_init(x_ready, 4);
+        for (int s = 0; s < 2; ++s) { mbar_init(&l1_full[s], 1); mbar_init(&l1_free[s], ROW_WARPS); }
+        for (int c = 0; c < HP_MAX / NC1; ++c) mbar_init(&h1_ready[c], ROW_WARPS);
+        mbar_init(x_ready, 4);   // the four ch-0 warps
         mbar_init(w1_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -216,8 +323,10 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
     for (int i = tid; i < 4 * T * 2; i += THREADS) sums[i] = 0.0;
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                  // every CTA's barriers exist before any peer signals them
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
+    const uint32_t cta_rank = cluster_ctarank();
 
     if (warp < ROW_WARPS) {
         // =============================== ROW WARPS ========================================
@@ -225,34 +334,24 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
         uint32_t acc_it = 0;
-        for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int it = 0; it < p.iters; ++it) {
+            const long long tile = (long long)it * gridDim.x + blockIdx.x;   // >= n_tiles: padding tile
             const long long k_local = tile * TM + row;
-            const bool live = k_local < a.K_local;
+            const bool live = tile < p.n_tiles && k_local < a.K_local;
+            // both threads of a row keep identical copies of the state; ch 0 feeds the network
+            // (critical path), ch 1 scores the trajectory in the shadow of the layer-2 MMAs
             float x[DT];
             ScoreAcc sc;
 #pragma unroll
             for (int j = 0; j < DT; ++j) x[j] = j < a.d ? a.state0[j] : 0.f;
-            if (ch == 0) score_init<DT>(a.plan, a.wp_index, x, sc);
-            for (int t = 0; t < T; ++t) {
-                if (ch == 0) {
-                    float ab = 0.f, bb = 0.f;
-                    score_point<DT>(a.plan, t, x, sc, a.per_sample != 0, ab, bb);
-                    if (a.states_out && live)
-                        for (int j = 0; j < a.d; ++j)
-                            a.states_out[((size_t)t * a.K_local + k_local) * a.d + j] = x[j];
-                    if (a.partial_sums) {
-                        double dab = live ? (double)ab : 0.0, dbb = live ? (double)bb : 0.0;
-                        for (int off = 16; off > 0; off >>= 1) {
-                            dab += __shfl_down_sync(0xffffffffu, dab, off);
-                            dbb += __shfl_down_sync(0xffffffffu, dbb, off);
-                        }
-                        if (lane == 0) {
-                            sums[((size_t)q * T + t) * 2] += dab;
-                            sums[((size_t)q * T + t) * 2 + 1] += dbb;
-                        }
-                    }
-                }
-                if (t == a.H) break;
+            if (ch == 1) score_init<DT>(a.plan, a.wp_index, x, sc);
+            float act[SS_MAX_DA];
+#pragma unroll
+            for (int j = 0; j < SS_MAX_DA; ++j) act[j] = 0.f;
+            if (ch == 0 && live)
+                for (int j = 0; j < a.da; ++j) act[j] = fetch_action(a.act, k_local, a.k_offset + k_local, 0, j);
+            TC_PROF_T0();
+            for (int t = 0; t < a.H; ++t) {
                 // ---- layer-1 A operand: hi/lo split of the normalised (state, action) -------
                 if (ch == 0) {
                     float xin[MAX_DIN];
@@ -261,13 +360,14 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
 #pragma unroll
                     for (int j = 0; j < DT; ++j)
                         if (j < a.d) xin[j] = (x[j] - a.norm.mean_x[j]) * a.norm.inv_std_x[j];
-                    for (int j = 0; j < a.da; ++j) {
-                        float act = live ? fetch_action(a.act, k_local, a.k_offset + k_local, t, j) : 0.f;
-                        float v = (act - a.norm.mean_y[j]) * a.norm.inv_std_y[j];
 #pragma unroll
-                        for (int jj = 0; jj < MAX_DIN; ++jj)
-                            if (jj == a.d + j) xin[jj] = v;
-                    }
+                    for (int j = 0; j < SS_MAX_DA; ++j)
+                        if (j < a.da) {
+                            const float v = (act[j] - a.norm.mean_y[j]) * a.norm.inv_std_y[j];
+#pragma unroll
+                            for (int jj = 0; jj < MAX_DIN; ++jj)
+                                if (jj == a.d + j) xin[jj] = v;
+                        }
                     float slot[K1];
 #pragma unroll
                     for (int s = 0; s < K1; ++s) slot[s] = 0.f;
@@ -297,25 +397,36 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                     __syncwarp();
                     if (lane == 0) mbar_arrive(x_ready);
                 }
+                TC_PROF(1);
                 // ---- layer-1 epilogue: relu, bf16, becomes the layer-2 A operand -------------
                 for (int c = 0; c < nch; ++c, ++acc_it) {
                     const uint32_t slot_i = acc_it % ACC_SLOTS;
                     mbar_wait(&acc_full[slot_i], (acc_it / ACC_SLOTS) & 1);
+                    TC_PROF(2);
                     tc_fence_after();
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
+                    for (int part = 0; part < CPT / 32; ++part) {
                         uint32_t v[32];
-                        tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * 64 + half * 32, v);
+                        tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * CPT + part * 32, v);
                         uint32_t pk[16];
 #pragma unroll
                         for (int c2 = 0; c2 < 16; ++c2)
                             pk[c2] = pack_bf16_relu(__uint_as_float(v[2 * c2]), __uint_as_float(v[2 * c2 + 1]));
-                        tmem_st16(lane_addr + COL_H1 + c * (NC / 2) + ch * 32 + half * 16, pk);
+                        tmem_st16(lane_addr + COL_H1 + c * (NC / 2) + ch * (CPT / 2) + part * 16, pk);
                     }
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) { mbar_arrive(&acc_free[slot_i]); mbar_arrive(&h1_ready[c]); }
+                    TC_PROF(3);
                 }
+                // ---- off the critical path (the tensor pipe is busy with layer 2 now) ----------
+                if (ch == 1) {
+                    if (!(TC_DEBUG & 2)) score_row<DT>(a, t, x, sc, live, k_local, q, lane, T, sums);
+                } else if (ch == 0 && live && t + 1 < a.H) {
+                    for (int j = 0; j < a.da; ++j)
+                        act[j] = fetch_action(a.act, k_local, a.k_offset + k_local, t + 1, j);
+                }
+                TC_PROF(0);
                 // ---- layer-2 epilogue fused with layer 3 --------------------------------------
                 float z[DT];
 #pragma unroll
@@ -323,16 +434,19 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                 for (int n = 0; n < nch; ++n, ++acc_it) {
                     const uint32_t slot_i = acc_it % ACC_SLOTS;
                     mbar_wait(&acc_full[slot_i], (acc_it / ACC_SLOTS) & 1);
+                    TC_PROF(4);
                     tc_fence_after();
+                    static_assert(CPT == 32 || CPT == 64, "one or two 32-column TMEM loads per thread and chunk");
                     uint32_t v0[32], v1[32];
-                    tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * 64, v0);
-                    tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * 64 + 32, v1);
+                    tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * CPT, v0);
+                    if (CPT > 32) tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * CPT + 32, v1);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&acc_free[slot_i]);
-                    const float* wrow = w3s + (size_t)(n * NC + ch * 64) * DTW;
+                    const float* wrow = w3s + (size_t)(n * NC + ch * CPT) * DTW;
+                    if (TC_DEBUG & 1) { z[0] += __uint_as_float(v0[lane]); continue; }
 #pragma unroll
-                    for (int j2 = 0; j2 < 64; ++j2) {
+                    for (int j2 = 0; j2 < CPT; ++j2) {
                         const float hval = fmaxf(__uint_as_float(j2 < 32 ? v0[j2 & 31] : v1[j2 & 31]), 0.f);
                         const float4 w0 = *reinterpret_cast<const float4*>(wrow + j2 * DTW);
                         z[0] = fmaf(hval, w0.x, z[0]);
@@ -347,38 +461,46 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                             if (DT > 7) z[7] = fmaf(hval, w1.w, z[7]);
                         }
                     }
+                    TC_PROF(5);
                 }
-                // ---- combine the two column halves, update the state ---------------------------
-                if (ch == 1) {
+                // ---- the two column halves exchange partial sums; both update the state ---------
 #pragma unroll
-                    for (int j = 0; j < DT; ++j) zx[row * 8 + j] = z[j];
-                }
+                for (int j = 0; j < DT; ++j) zx[(ch * TM + row) * 8 + j] = z[j];
                 asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");
-                if (ch == 0) {
 #pragma unroll
-                    for (int j = 0; j < DT; ++j)
-                        if (j < a.d) {
-                            const float zz = z[j] + zx[row * 8 + j] + p.b3[j];
-                            x[j] += fmaf(zz, a.norm.std_z[j], a.norm.mean_z[j]);
-                        }
-                }
+                for (int j = 0; j < DT; ++j)
+                    if (j < a.d) {
+                        // fixed order (half 0 + half 1) so both copies stay bit-identical
+                        float zz = zx[row * 8 + j];
+#pragma unroll
+                        for (int o = 1; o < TPR; ++o) zz += zx[(o * TM + row) * 8 + j];
+                        zz += p.b3[j];
+                        x[j] += fmaf(zz, a.norm.std_z[j], a.norm.mean_z[j]);
+                    }
+                TC_PROF(6);
             }
-            if (ch == 0 && live && a.scores_out) a.scores_out[k_local] = sc.score;
+            if (ch == 1) {
+                score_row<DT>(a, a.H, x, sc, live, k_local, q, lane, T, sums);
+                if (live && a.scores_out) a.scores_out[k_local] = sc.score;
+            }
         }
     } else if (warp == ROW_WARPS) {
         // =============================== MMA ISSUER =======================================
         // the whole warp walks the loop (warp-uniform control flow); one elected lane issues
         uint32_t acc_it = 0, w2_it = 0, step_it = 0;
         mbar_wait(w1_full, 0);
+        TC_PROFW_T0();
         const uint32_t a1_addr = smem_u32(a1s), w1_addr = smem_u32(w1s), ring_addr = smem_u32(w2_ring);
-        for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int it = 0; it < p.iters; ++it) {
             for (int t = 0; t < a.H; ++t, ++step_it) {
                 mbar_wait(x_ready, step_it & 1);
+                TC_PROFW(0);
                 tc_fence_after();
                 // layer 1: acc chunk c = A1 [128 x 32] * W1img[c] [128 x 32]^T
                 for (int c = 0; c < nch; ++c, ++acc_it) {
                     const uint32_t slot_i = acc_it % ACC_SLOTS;
                     mbar_wait(&acc_free[slot_i], ((acc_it / ACC_SLOTS) & 1) ^ 1);
+                    TC_PROFW(1);
                     tc_fence_after();
                     if (elect_one()) {
                         const uint32_t d_tmem = tmem + COL_ACC + slot_i * NC;
@@ -394,10 +516,15 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                 for (int n = 0; n < nch; ++n, ++acc_it) {
                     const uint32_t slot_i = acc_it % ACC_SLOTS;
                     mbar_wait(&acc_free[slot_i], ((acc_it / ACC_SLOTS) & 1) ^ 1);
-                    for (int ksl = 0; ksl < nch; ++ksl, ++w2_it) {
+                    TC_PROFW(2);
+                    for (int ksl = 0; ksl < nslab; ++ksl, ++w2_it) {
                         const uint32_t st = w2_it % NSTAGE;
-                        if (n == 0) mbar_wait(&h1_ready[ksl], step_it & 1);
-                        mbar_wait(&w2_full[st], (w2_it / NSTAGE) & 1);
+                        if (n == 0) {
+                            for (int i = 0; i < CPS; ++i) mbar_wait(&h1_ready[(ksl / SPC) * CPS + i], step_it & 1);
+                            TC_PROFW(3);
+                        }
+                        if (!(TC_DEBUG & 4) || w2_it < NSTAGE) mbar_wait(&w2_full[st], (w2_it / NSTAGE) & 1);
+                        TC_PROFW(4);
                         tc_fence_after();
                         if (elect_one()) {
                             const uint32_t d_tmem = tmem + COL_ACC + slot_i * NC;
@@ -407,10 +534,11 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                             for (int ks = 0; ks < KSLAB / 16; ++ks)
                                 umma_ts(d_tmem, a_tmem + ks * 8, b0 + (uint64_t)((ks * 2 * (NC * 16)) >> 4), IDESC,
                                         (ksl | ks) != 0);
-                            tc_commit(&w2_empty[st]);
-                            if (ksl == nch - 1) tc_commit(&acc_full[slot_i]);
+                            if (!(TC_DEBUG & 4)) tc_commit_multicast(&w2_empty[st], CLUSTER_MASK);
+                            if (ksl == nslab - 1) tc_commit(&acc_full[slot_i]);
                         }
                         __syncwarp();
+                        TC_PROFW(5);
                     }
                 }
             }
@@ -418,25 +546,30 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
     } else {
         // =============================== TMA PRODUCER =====================================
         if (lane == 0) {
-            mbar_expect_tx(w1_full, (uint32_t)(nch * W1_CHUNK_BYTES));
-            bulk_g2s(w1s, p.w1_img, (uint32_t)(nch * W1_CHUNK_BYTES), w1_full);
+            mbar_expect_tx(w1_full, (uint32_t)(nch1 * W1_CHUNK_BYTES));
+            bulk_g2s(w1s, p.w1_img, (uint32_t)(nch1 * W1_CHUNK_BYTES), w1_full);
             uint32_t w2_it = 0;
-            const int blocks = nch * nch;
-            for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+            const int blocks = nch * nslab;
+            constexpr uint32_t PART = STAGE_BYTES / CLUSTER;
+            for (int it = 0; it < p.iters; ++it)
                 for (int t = 0; t < a.H; ++t)
                     for (int blk = 0; blk < blocks; ++blk, ++w2_it) {
                         const uint32_t st = w2_it % NSTAGE;
+                        if ((TC_DEBUG & 4) && w2_it >= NSTAGE) continue;
+                        // the stage must be drained in EVERY CTA of the cluster (both MMA warps commit here)
                         mbar_wait(&w2_empty[st], ((w2_it / NSTAGE) & 1) ^ 1);
-                        mbar_expect_tx(&w2_full[st], STAGE_BYTES);
-                        bulk_g2s(w2_ring + (size_t)st * STAGE_BYTES,
-                                 reinterpret_cast<const unsigned char*>(p.w2_img) + (size_t)blk * STAGE_BYTES,
-                                 STAGE_BYTES, &w2_full[st]);
+                        mbar_expect_tx(&w2_full[st], STAGE_BYTES);          // my part + the peers' parts
+                        bulk_g2s_multicast(w2_ring + (size_t)st * STAGE_BYTES + cta_rank * PART,
+                                           reinterpret_cast<const unsigned char*>(p.w2_img) +
+                                               (size_t)blk * STAGE_BYTES + cta_rank * PART,
+                                           PART, &w2_full[st], CLUSTER_MASK);
                     }
         }
     }
     // ---- teardown ---------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
+    cluster_sync_all();                  // no CTA leaves while a peer may still write / signal into it
     tc_fence_after();
     if (a.partial_sums)
         for (int o = tid; o < 2 * T; o += THREADS)
@@ -461,7 +594,9 @@ static float bf16_val(uint16_t b) {
     return f;
 }
 
-static size_t smem_bytes(int T) { return Smem::SUMS + (size_t)4 * T * 2 * 8 + 128; }
+static size_t smem_bytes(int T, int d) {
+    return (d <= 4 ? SmemT<4>::SUMS : SmemT<8>::SUMS) + (size_t)4 * T * 2 * 8 + 128;
+}
 
 }  // namespace tc
 
@@ -475,14 +610,14 @@ int mpc_tc_prepare(ss_ctx* c) {
     const int h = c->h, d = c->d, din = c->d + c->da;
     const int hp = (h + 2 + KSLAB - 1) / KSLAB * KSLAB;
     const int nch = hp / NC, nslab = hp / KSLAB;
-    static_assert(NC == KSLAB, "the kernel walks nch K-slabs per chunk");
+    static_assert(KSLAB % NC == 0 || NC % KSLAB == 0, "K-slabs and layer-1 chunks must nest");
     const std::vector<double>&W1 = c->hw[0], &W2 = c->hw[1], &W3 = c->hw[2];
     const std::vector<double>&B1 = c->hb[0], &B2 = c->hb[1];
     // layer-1 image: K slots (3j, 3j+1, 3j+2) = (W_hi, W_lo, W_hi) of input j; then (b_hi, b_lo)
-    std::vector<uint16_t> w1((size_t)nch * (W1_CHUNK_BYTES / 2), 0);
+    std::vector<uint16_t> w1((size_t)(hp / NC1) * (W1_CHUNK_BYTES / 2), 0);
     auto w1_at = [&](int slot, int u) -> uint16_t& {
-        const int cidx = u / NC, nn = u % NC;
-        return w1[(size_t)cidx * (W1_CHUNK_BYTES / 2) + (slot / 8) * (NC * 8) + nn * 8 + (slot % 8)];
+        const int cidx = u / NC1, nn = u % NC1;
+        return w1[(size_t)cidx * (W1_CHUNK_BYTES / 2) + (slot / 8) * (NC1 * 8) + nn * 8 + (slot % 8)];
     };
     for (int u = 0; u < h; ++u) {
         for (int j = 0; j < din; ++j) {
@@ -531,8 +666,11 @@ int mpc_tc_prepare(ss_ctx* c) {
 }
 
 int mpc_tc_grid(const ss_ctx* c, const RolloutArgs& a) {
+    // a multiple of the cluster size; at most one CTA per SM (TMEM: 512 columns per CTA)
     const long long tiles = (a.K_local + tc::TM - 1) / tc::TM;
-    return (int)(tiles < c->sm_count ? tiles : c->sm_count);
+    const long long up = (tiles + tc::CLUSTER - 1) / tc::CLUSTER * tc::CLUSTER;
+    const long long cap = c->sm_count / tc::CLUSTER * tc::CLUSTER;
+    return (int)(up < cap ? up : cap);
 }
 
 int mpc_tc_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out) {
@@ -548,19 +686,57 @@ int mpc_tc_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out) {
     p.hp = c->tc_hp;
     p.din = c->d + c->da;
     p.n_tiles = (a.K_local + TM - 1) / TM;
+    p.prof = nullptr;
+    p.debug = getenv("SS_TC_DEBUG") ? atoi(getenv("SS_TC_DEBUG")) : 0;
+    if (getenv("SS_TC_PROF")) {
+        SS_CUDA_CHECK(c, c->tc_misc.ensure((size_t)c->sm_count * 8 * 8 * 2));
+        SS_CUDA_CHECK(c, cudaMemsetAsync(c->tc_misc.p, 0, (size_t)c->sm_count * 8 * 8 * 2, c->stream));
+        p.prof = c->tc_misc.as<unsigned long long>();
+    }
     const int grid = mpc_tc_grid(c, a);
     if (grid_blocks_out) *grid_blocks_out = grid;
-    const size_t smem = smem_bytes(a.H + 1);
+    p.iters = (int)((p.n_tiles + grid - 1) / grid);
+    const size_t smem = smem_bytes(a.H + 1, a.d);
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     cudaError_t e;
     if (a.d <= 4) {
         e = cudaFuncSetAttribute(mpc_rollout_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) mpc_rollout_tc_kernel<4><<<grid, THREADS, smem, c->stream>>>(a, p);
+        if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, mpc_rollout_tc_kernel<4>, a, p);
     } else {
         e = cudaFuncSetAttribute(mpc_rollout_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) mpc_rollout_tc_kernel<8><<<grid, THREADS, smem, c->stream>>>(a, p);
+        if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, mpc_rollout_tc_kernel<8>, a, p);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     c->launches++;
     SS_CUDA_CHECK(c, e);
+    if (p.prof) {
+        std::vector<unsigned long long> h((size_t)grid * 8 * 2);
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(h.data(), p.prof, h.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+        SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        const char* names[8] = {"score", "xsplit", "l1_wait", "l1_epi", "l2_wait", "l2_epi", "combine", "-"};
+        double tot = 0;
+        for (int s2 = 0; s2 < 7; ++s2) tot += (double)h[s2];
+        fprintf(stderr, "[tc prof, CTA 0, warp 0] total %.0f cycles:", tot);
+        for (int s2 = 0; s2 < 7; ++s2) fprintf(stderr, " %s %.1f%%", names[s2], 100.0 * h[s2] / tot);
+        fprintf(stderr, "\n");
+        const char* mn[6] = {"x_ready", "l1_acc_free", "l2_acc_free", "h1_ready", "w2_full", "issue"};
+        double mt = 0;
+        for (int s2 = 0; s2 < 6; ++s2) mt += (double)h[(size_t)grid * 8 + s2];
+        fprintf(stderr, "[tc prof, CTA 0, MMA warp] total %.0f cycles:", mt);
+        for (int s2 = 0; s2 < 6; ++s2) fprintf(stderr, " %s %.1f%%", mn[s2], 100.0 * h[(size_t)grid * 8 + s2] / mt);
+        fprintf(stderr, "\n");
+    }
     return SS_OK;
 }
