@@ -264,24 +264,12 @@ def main():
     n_act = K_PER_GPU * HORIZON
     pinned = torch.empty(n_act, dtype=torch.float64).pin_memory()
     host_actions = pinned.numpy().reshape(K_PER_GPU, HORIZON, 1)
-    k_off = rank * K_PER_GPU
     host_actions[:] = np.random.RandomState(rank).uniform(wl["low"], wl["high"], (K_PER_GPU, HORIZON, 1))
 
     def e2e_step(i):
-        # every rank plans on its own K_PER_GPU host samples; merge as in ShardedPlanner
-        eng.rollout(wl["state"], 0, actions=host_actions, penalty_mode="reference", precision=precision,
-                    k_offset=k_off, K_global=K_total)
-        if world > 1:
-            ptr, n = eng.projection_sums_ptr()
-            from smartstartcontinuous_b200.distributed import _DevView
-            dist.all_reduce(torch.as_tensor(_DevView(ptr, n), device=dev))
-        bk, bs, _ = eng.finish()
-        if world > 1:
-            mine = torch.tensor([bs, float(bk)], dtype=torch.float64, device=dev)
-            g = [torch.empty_like(mine) for _ in range(world)]
-            dist.all_gather(g, mine)
-        if k_off <= bk < k_off + K_PER_GPU:
-            eng.replay(bk)
+        # every rank feeds its own K_PER_GPU host samples through the C ABI (H2D inside the call)
+        planner.plan(wl["state"], 0, K=K_total, H=HORIZON, local_actions=host_actions, penalty_mode="reference",
+                     precision=precision, want_path=True)
 
     e2e_ms = timed(e2e_step, max(3, args.steps // 2), 2) / max(3, args.steps // 2)
     e2e_value = K_total * HORIZON / (e2e_ms * 1e-3)

@@ -211,6 +211,8 @@ __device__ __forceinline__ float fetch_action(const ActionSource& src, long long
     uint32_t r[4];
     philox4x32_10((uint32_t)k_global, (uint32_t)((uint64_t)k_global >> 32), e >> 2, 0u,
                   (uint32_t)src.seed, (uint32_t)(src.seed >> 32), r);
-    double u = (double)(r[e & 3] >> 8) * (1.0 / 16777216.0);
+    const uint32_t sel = e & 3;     // select without indexing (keeps r[] in registers)
+    const uint32_t w = sel == 0 ? r[0] : (sel == 1 ? r[1] : (sel == 2 ? r[2] : r[3]));
+    double u = (double)(w >> 8) * (1.0 / 16777216.0);
     return (float)(src.low[j] + u * src.range[j]);
 }

@@ -358,7 +358,9 @@ extern "C" int ss_mpc_replay(ss_ctx* c, int64_t k_global, double* out_sequence, 
         c->launches++;
         SS_CUDA_CHECK(c, cudaGetLastError());
     } else {
-        rc = mpc_simt_launch(c, a, nullptr);
+        // re-roll the one sequence with the kernel family that scored it (a 1-row tile on the
+        // tcgen05 kernel costs H * ~10 us; the FP32 kernel is the fallback for other shapes)
+        rc = r.precision == SS_PRECISION_BF16_TC ? mpc_tc_launch(c, a, nullptr) : mpc_simt_launch(c, a, nullptr);
         if (rc) return rc;
     }
     std::vector<float> path((size_t)T * d);

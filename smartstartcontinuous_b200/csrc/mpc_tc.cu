@@ -258,8 +258,12 @@ __device__ __forceinline__ void score_row(const RolloutArgs& a, int t, const flo
                                           bool live, long long k_local, int q, int lane, int T, double* sums) {
     float ab = 0.f, bb = 0.f;
     score_point<DT>(a.plan, t, x, sc, a.per_sample != 0, ab, bb);
-    if (a.states_out && live)
-        for (int j = 0; j < a.d; ++j) a.states_out[((size_t)t * a.K_local + k_local) * a.d + j] = x[j];
+    if (a.states_out && live) {
+        float* dst = a.states_out + ((size_t)t * a.K_local + k_local) * a.d;
+#pragma unroll
+        for (int j = 0; j < DT; ++j)
+            if (j < a.d) dst[j] = x[j];
+    }
     if (a.partial_sums) {
         double dab = live ? (double)ab : 0.0, dbb = live ? (double)bb : 0.0;
         for (int off = 16; off > 0; off >>= 1) {
@@ -348,8 +352,11 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
             float act[SS_MAX_DA];
 #pragma unroll
             for (int j = 0; j < SS_MAX_DA; ++j) act[j] = 0.f;
-            if (ch == 0 && live)
-                for (int j = 0; j < a.da; ++j) act[j] = fetch_action(a.act, k_local, a.k_offset + k_local, 0, j);
+            if (ch == 0 && live) {
+#pragma unroll
+                for (int j = 0; j < SS_MAX_DA; ++j)
+                    if (j < a.da) act[j] = fetch_action(a.act, k_local, a.k_offset + k_local, 0, j);
+            }
             TC_PROF_T0();
             for (int t = 0; t < a.H; ++t) {
                 // ---- layer-1 A operand: hi/lo split of the normalised (state, action) -------
@@ -365,8 +372,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                         if (j < a.da) {
                             const float v = (act[j] - a.norm.mean_y[j]) * a.norm.inv_std_y[j];
 #pragma unroll
-                            for (int jj = 0; jj < MAX_DIN; ++jj)
-                                if (jj == a.d + j) xin[jj] = v;
+                            for (int jj = 0; jj < MAX_DIN; ++jj) xin[jj] = (jj == a.d + j) ? v : xin[jj];
                         }
                     float slot[K1];
 #pragma unroll
@@ -381,8 +387,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                     }
                     // bias slots (b_hi, b_lo) sit right after the 3*din input slots
 #pragma unroll
-                    for (int s = 0; s < K1; ++s)
-                        if (s == 3 * p.din || s == 3 * p.din + 1) slot[s] = 1.f;
+                    for (int s = 0; s < K1; ++s) slot[s] = (s == 3 * p.din || s == 3 * p.din + 1) ? 1.f : slot[s];
                     // smem image [k/8][row][8] (K-major core matrices): 4 x 16 B per row
 #pragma unroll
                     for (int kc = 0; kc < K1 / 8; ++kc) {
@@ -423,8 +428,9 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                 if (ch == 1) {
                     if (!(TC_DEBUG & 2)) score_row<DT>(a, t, x, sc, live, k_local, q, lane, T, sums);
                 } else if (ch == 0 && live && t + 1 < a.H) {
-                    for (int j = 0; j < a.da; ++j)
-                        act[j] = fetch_action(a.act, k_local, a.k_offset + k_local, t + 1, j);
+#pragma unroll
+                    for (int j = 0; j < SS_MAX_DA; ++j)
+                        if (j < a.da) act[j] = fetch_action(a.act, k_local, a.k_offset + k_local, t + 1, j);
                 }
                 TC_PROF(0);
                 // ---- layer-2 epilogue fused with layer 3 --------------------------------------

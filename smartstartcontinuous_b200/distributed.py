@@ -84,11 +84,14 @@ class ShardedPlanner:
 
     def plan(self, state, wp_index, *, K, H, seed=0, act_low=None, act_high=None, actions=None,
              gamma=.75, horizontal_penalty_factor=.5, penalty_mode="reference", precision="auto",
-             want_path=True):
+             want_path=True, local_actions=None):
+        """actions: the GLOBAL [K, H, da] host samples (every rank passes the same array), or
+        local_actions: this rank's own [K/world, H, da] slice, or neither (device Philox)."""
         import torch
         dist = _dist()
         k_offset, k_local = shard_bounds(K, self.world, self.rank)
-        local_actions = None if actions is None else actions[k_offset:k_offset + k_local]
+        if local_actions is None and actions is not None:
+            local_actions = actions[k_offset:k_offset + k_local]
         self.engine.rollout(state, wp_index, actions=local_actions, K=k_local, H=H, seed=seed,
                             act_low=act_low, act_high=act_high, gamma=gamma,
                             horizontal_penalty_factor=horizontal_penalty_factor,
@@ -110,9 +113,11 @@ class ShardedPlanner:
             w = 0
         seq = path = None
         if want_path:
-            if self.world == 1 or actions is None:
-                seq, path = self.engine.replay(best_k)           # Philox replay works on any rank
+            if self.world == 1:
+                seq, path = self.engine.replay(best_k)
             else:
+                # the owner has the winner's trajectory (or can re-roll it cheaply); everyone else
+                # receives H*da + (H+1)*d doubles
                 d, da = self.engine._model_shape[0], self.engine._model_shape[1]
                 buf = torch.zeros(H * da + (H + 1) * d, dtype=torch.float64, device=self.device)
                 if self.rank == w:
