@@ -117,6 +117,11 @@ class ClockSampler(threading.Thread):
                     reasons=sorted(reasons), samples=len(sm))
 
 
+def workload_name():
+    return ("NND_MB random-shooting MPC, Pendulum-v0 d=3 da=1, K=%d per GPU (BASELINE config 4 = K=1M over 8 GPUs), "
+            "H=%d, MLP 2x500, reference-exact penalty" % (K_PER_GPU, HORIZON))
+
+
 def cpu_reference_mpc(wl, K, H, seed):
     """The reference's CPU planner (oracle port): npr.uniform sampling + float64 numpy rollout +
     scoring.  Returns seconds."""
@@ -145,7 +150,7 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
-def run_reference(args):
+def run_reference(args, guard):
     """--impl reference: rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -161,12 +166,12 @@ def run_reference(args):
     kv = m_s * (kw["n"] + 1) / float(np.mean(t_kde))
     cores = blas_threads()
     sample = "K=%d of %d sequences per step, H=%d (rate is K-independent: GEMM-bound)" % (K_s, K_PER_GPU, HORIZON)
-    print(json.dumps({
+    guard.emit(json.dumps({
         "impl": "reference", "metric": "mpc_rollout_steps_per_s", "value": v, "unit": "rollout-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * float(np.mean(t_mpc)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "NND_MB MPC, Pendulum d=3 da=1, MLP 2x500, H=50 (BASELINE config 4 shard)",
+        "config": {"workload": workload_name(),
                    "note": "oracle port of the reference's numpy/TF-CPU path; TensorFlow 1.5 is not installable, "
                            "its float64 GEMMs run in numpy/BLAS"},
         "cpu_baseline": {"value": v, "unit": "rollout-steps/s", "cores": cores, "kind": "port", "sample": sample},
@@ -177,7 +182,22 @@ def run_reference(args):
     }))
 
 
+class _StdoutGuard:
+    """Everything libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr; only the
+    final JSON line reaches the real stdout."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.real, (line + "\n").encode())
+
+
 def main():
+    guard = _StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -187,7 +207,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, guard)
         return
 
     import torch
@@ -316,8 +336,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16 (tcgen05, fp32 accumulate; first/last layer, state, scoring fp32)" if precision == "bf16_tc" else "f32",
         "data": "synthetic",
-        "config": {"workload": "NND_MB random-shooting MPC, Pendulum-v0 d=3 da=1, K=%d per GPU (BASELINE config 4 "
-                               "= K=1M over 8 GPUs), H=%d, MLP 2x500, reference-exact penalty" % (K_PER_GPU, HORIZON),
+        "config": {"workload": workload_name(),
                    "K_total": K_total, "H": HORIZON, "mlp": "2x500", "actions": "device Philox4x32-10",
                    "l2": "flushed between timed steps (256 MiB memset, outside the event-timed region)",
                    "parallelism": "K sharded over %d GPU(s); all-reduce of %d float64 + all-gather of (score,k)"
@@ -354,7 +373,7 @@ def main():
         out["kde"]["cpu_baseline"] = {"value": 128 * (KDE_N + 1) / float(np.mean(tk)), "unit": "kernel-evals/s", "cores": 1,
                                       "kind": "reference-library (scipy.stats.gaussian_kde)",
                                       "sample": "3 x 128 (of %d) queries x %d points" % (KDE_M, KDE_N + 1)}
-    print(json.dumps(out))
+    guard.emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
