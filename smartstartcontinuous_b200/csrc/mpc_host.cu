@@ -235,14 +235,16 @@ extern "C" int ss_mpc_rollout(ss_ctx* c, const double* state, int wp_index, int6
     SS_CUDA_CHECK(c, c->mpc_scores.ensure((size_t)K_local * 4));
     a.scores_out = c->mpc_scores.as<float>();
     const bool ref = penalty_mode == SS_PENALTY_REFERENCE;
-    const int blocks = precision == SS_PRECISION_BF16_TC ? mpc_tc_grid(c, a) : mpc_simt_grid(a);
     r.states_stored = ref;
+    const int sum_blocks = mpc_sums_reference_blocks(K_local);
     if (ref) {
+        // reference penalty: the rollout kernel only spills the trajectories; the projection sums
+        // and the scores come from two light passes over them (mpc_score.cu)
         SS_CUDA_CHECK(c, c->mpc_states.ensure((size_t)T * K_local * c->d * 4));
-        SS_CUDA_CHECK(c, c->mpc_partial_sums.ensure((size_t)blocks * T * 2 * 8));
+        SS_CUDA_CHECK(c, c->mpc_partial_sums.ensure((size_t)sum_blocks * T * 2 * 8));
         SS_CUDA_CHECK(c, c->mpc_sums.ensure((size_t)T * 2 * 8));
         a.states_out = c->mpc_states.as<float>();
-        a.partial_sums = c->mpc_partial_sums.as<double>();
+        a.partial_sums = nullptr;
     }
     timer_mark(c, "mpc_setup");
     int grid = 0;
@@ -250,9 +252,13 @@ extern "C" int ss_mpc_rollout(ss_ctx* c, const double* state, int wp_index, int6
     if (rc) return rc;
     timer_mark(c, "mpc_rollout");
     if (ref) {
-        rc = mpc_reduce_sums(c, c->mpc_partial_sums.as<double>(), grid, T, c->mpc_sums.as<double>());
+        rc = mpc_sums_reference(c, a.plan, wp_index, gpow + T, c->mpc_states.as<float>(), K_local, T,
+                                c->mpc_partial_sums.as<double>());
         if (rc) return rc;
-        r.sum_blocks = grid;
+        rc = mpc_reduce_sums(c, c->mpc_partial_sums.as<double>(), sum_blocks, T, c->mpc_sums.as<double>());
+        if (rc) return rc;
+        r.sum_blocks = sum_blocks;
+        timer_mark(c, "mpc_sums_pass1");
     }
     r.valid = true;
     return SS_OK;

@@ -17,9 +17,11 @@ struct RolloutArgs {
     float state0[SS_MAX_D];
     int wp_index, H;
     long long K_local, k_offset;
-    int per_sample;          // 1: fuse the per-sample penalty; 0: reference mode (phase A)
+    int per_sample;          // 1: score in the rollout kernel with the per-sample penalty;
+                             // 0: reference mode -- the kernel only spills the trajectories, the
+                             //    scoring passes (mpc_score.cu) run over them afterwards
     float* states_out;       // [H+1][K_local][d] or null
-    double* partial_sums;    // [gridDim.x][H+1][2] (reference mode) or null
+    double* partial_sums;    // legacy in-kernel projection sums [gridDim.x][H+1][2]; null = off
     float* scores_out;       // [K_local] (per-sample mode: final; reference mode: unused)
 };
 
@@ -35,6 +37,9 @@ int mpc_tc_grid(const ss_ctx* c, const RolloutArgs& a);
 
 // scoring tail (mpc_score.cu)
 int mpc_reduce_sums(ss_ctx* c, const double* partial, int blocks, int T, double* sums);
+int mpc_sums_reference_blocks(long long K_local);
+int mpc_sums_reference(ss_ctx* c, const PlanView& plan, int wp_index, const float* state0, const float* states,
+                       long long K_local, int T, double* partial);
 int mpc_score_reference(ss_ctx* c, const PlanView& plan, int wp_index, const float* state0,
                         const float* states, long long K_local, int T, const double* sums,
                         float* scores);

@@ -18,6 +18,47 @@ __global__ void mpc_reduce_sums_kernel(const double* __restrict__ partial, int b
     sums[o] = s;
 }
 
+// first pass over the stored trajectories: waypoint logic per sample, per-time-step block sums of
+// a'.b' and b'.b' (the two dot products of numerical.py:89-93) -> partial[block][t][2]
+template <int DT>
+__global__ void __launch_bounds__(256)
+mpc_sums_reference_kernel(const PlanView P, int wp_index, const float* __restrict__ state0,
+                          const float* __restrict__ states, long long K, int T,
+                          double* __restrict__ partial) {
+    __shared__ double s_part[8][2];
+    const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool live = k < K;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float x[DT];
+#pragma unroll
+    for (int j = 0; j < DT; ++j) x[j] = j < P.d ? state0[j] : 0.f;
+    ScoreAcc sc;
+    score_init<DT>(P, wp_index, x, sc);
+    for (int t = 0; t < T; ++t) {
+        float ab = 0.f, bb = 0.f;
+        if (live) {
+            const float* row = states + ((size_t)t * K + k) * P.d;
+#pragma unroll
+            for (int j = 0; j < DT; ++j)
+                if (j < P.d) x[j] = row[j];
+            score_point<DT>(P, t, x, sc, false, ab, bb);
+        }
+        double dab = (double)ab, dbb = (double)bb;
+        for (int off = 16; off > 0; off >>= 1) {
+            dab += __shfl_down_sync(0xffffffffu, dab, off);
+            dbb += __shfl_down_sync(0xffffffffu, dbb, off);
+        }
+        if (lane == 0) { s_part[warp][0] = dab; s_part[warp][1] = dbb; }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            double tot = 0.0;
+            for (int w = 0; w < 8; ++w) tot += s_part[w][threadIdx.x];
+            partial[((size_t)blockIdx.x * T + t) * 2 + threadIdx.x] = tot;
+        }
+        __syncthreads();
+    }
+}
+
 template <int DT>
 __global__ void __launch_bounds__(256)
 mpc_score_reference_kernel(const PlanView P, int wp_index, const float* __restrict__ state0,
@@ -89,6 +130,23 @@ mpc_argmax_kernel(const float* __restrict__ scores, long long K, long long k_off
 
 int mpc_reduce_sums(ss_ctx* c, const double* partial, int blocks, int T, double* sums) {
     mpc_reduce_sums_kernel<<<(2 * T + 127) / 128, 128, 0, c->stream>>>(partial, blocks, T, sums);
+    c->launches++;
+    SS_CUDA_CHECK(c, cudaGetLastError());
+    return SS_OK;
+}
+
+int mpc_sums_reference_blocks(long long K_local) { return (int)((K_local + 255) / 256); }
+
+int mpc_sums_reference(ss_ctx* c, const PlanView& plan, int wp_index, const float* state0, const float* states,
+                       long long K_local, int T, double* partial) {
+    const unsigned grid = (unsigned)mpc_sums_reference_blocks(K_local);
+    if (plan.d <= 4)
+        mpc_sums_reference_kernel<4><<<grid, 256, 0, c->stream>>>(plan, wp_index, state0, states, K_local, T, partial);
+    else if (plan.d <= 8)
+        mpc_sums_reference_kernel<8><<<grid, 256, 0, c->stream>>>(plan, wp_index, state0, states, K_local, T, partial);
+    else
+        mpc_sums_reference_kernel<SS_MAX_D><<<grid, 256, 0, c->stream>>>(plan, wp_index, state0, states, K_local, T,
+                                                                        partial);
     c->launches++;
     SS_CUDA_CHECK(c, cudaGetLastError());
     return SS_OK;

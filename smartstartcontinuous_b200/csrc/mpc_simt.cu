@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(ST) mpc_rollout_simt_kernel(const RolloutArgs 
         // ---- score the current point (row owners) -------------------------------------
         if (owner) {
             float ab = 0.f, bb = 0.f;
-            score_point<DT>(a.plan, t, x, sc, a.per_sample != 0, ab, bb);
+            if (a.per_sample || a.partial_sums) score_point<DT>(a.plan, t, x, sc, a.per_sample != 0, ab, bb);
             if (a.states_out && live)
                 for (int j = 0; j < a.d; ++j)
                     a.states_out[((size_t)t * a.K_local + k_local) * a.d + j] = x[j];

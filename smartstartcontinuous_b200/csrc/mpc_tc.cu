@@ -3,26 +3,31 @@
 // Replaces the H sess.run float64 GEMM round trips of Dyn_Model.do_forward_sim
 // (dynamics_model.py:204-240) + the numpy scoring of generate_scores_add_delta
 // (NND_MB_agent.py:566-628) for the 2-hidden-layer dynamics MLP (the 2x500 network of the
-// BASELINE configs).  One persistent CTA per SM owns tiles of 128 sequences ("rows" = TMEM
-// lanes) and walks them through all H steps without touching HBM for activations:
+// BASELINE configs).  Persistent CTA PAIRS (2-CTA clusters, tcgen05 cta_group::2): each CTA owns
+// tiles of 128 sequences ("rows" = TMEM lanes) and walks them through all H steps without
+// touching HBM for activations; the pair issues M = 256 MMAs so every weight byte streamed from
+// L2 feeds two tiles -- each CTA holds only its half of every B tile, which halves the per-SM
+// L2 -> shared-memory traffic that otherwise caps the kernel (~43 B/clk/SM chip-wide).
 //
-//   layer 1   [128 x 32] x [32 x HP]   tcgen05.mma, A = split-bf16 input in smem, B = W1 image
+//   layer 1   [256 x 32] x [32 x HP]   tcgen05.mma, A = split-bf16 input in smem, B = W1 image
 //             (input, weights and bias are hi/lo bf16 splits packed along K, so the layer is
 //             FP32-accurate although it runs on the tensor pipe)
 //   relu+cvt  TMEM accumulator chunk -> registers -> bf16x2 -> TMEM (becomes the A operand)
-//   layer 2   [128 x HP] x [HP x HP]   tcgen05.mma kind::f16 (BF16 in, FP32 accumulate in TMEM),
-//             A from TMEM, B = W2 streamed from L2 by the TMA engine (cp.async.bulk, 32 KB
-//             pre-packed core-matrix blocks) through a 4-stage mbarrier ring; bias folded in via
+//   layer 2   [256 x HP] x [HP x HP]   tcgen05.mma kind::f16 (BF16 in, FP32 accumulate in TMEM),
+//             A from TMEM, B = W2 streamed from L2 by the TMA engine (cp.async.bulk, pre-packed
+//             32 KB core-matrix half blocks of 256 K elements) through a 4-stage mbarrier ring; bias folded in via
 //             two constant-one hidden units (hi/lo split)
 //   layer 3   fused into the layer-2 epilogue: relu, FP32 FFMA dot with W3 from shared memory
-//   update    state += z * std_z + mean_z, waypoint logic + progress/penalty score (score.cuh),
-//             all in FP32 registers of the row's thread
+//   update    state += z * std_z + mean_z in FP32 registers; waypoint logic + progress/penalty
+//             score (score.cuh) run in the shadow of the next step's layer-2 MMAs
 //
-// Warp roles: warps 0-7 = row warps (two threads per row, each takes half the columns of every
-// accumulator chunk), warp 8 = MMA issuer (warp-uniform loop, one elected lane issues so the
-// UTCHMMA stream stays back to back), warp 9 = TMA producer.
-// TMEM (512 columns): [0,256) H1 as bf16 A operand, [256,512) 2-deep ring of 128x128 FP32
-// accumulator chunks.  The layer-1 A operand (128 x 32 bf16) lives in shared memory.
+// Warp roles per CTA: warps 0-7 = row warps (two threads per row: ch 0 feeds the network, ch 1
+// scores; each takes half the columns of every accumulator chunk), warp 8 = MMA warp (leader CTA:
+// issues every MMA of the pair, warp-uniform loop, one elected lane; peer CTA: relays "my half of
+// the stage has landed" to the leader), warp 9 = TMA producer.
+// TMEM per CTA (512 columns): [0,256) H1 as bf16 A operand, [256,512) 2-deep ring of 128x128 FP32
+// accumulator chunks.  Cross-CTA signalling: mbarrier arrives on the leader's barriers
+// (shared::cluster, release.cluster) and tcgen05.commit.cta_group::2 multicast to both CTAs.
 #include <cuda_bf16.h>
 
 #include <cstdlib>
@@ -32,28 +37,19 @@
 
 namespace tc {
 
-constexpr int TM = 128;                 // rows per tile
-#ifndef SS_TC_NC
-#define SS_TC_NC 128
-#endif
-constexpr int NC = SS_TC_NC;            // units per accumulator chunk (MMA N)
-#ifndef SS_TC_KSLAB
-#define SS_TC_KSLAB 128
-#endif
-#ifndef SS_TC_RING_KB
-#define SS_TC_RING_KB 128
-#endif
-constexpr int KSLAB = SS_TC_KSLAB;      // K elements per W2 stage
-constexpr int STAGE_BYTES = NC * KSLAB * 2;   // 32 KB
-constexpr int NSTAGE = SS_TC_RING_KB * 1024 / STAGE_BYTES;
+constexpr int TM = 128;                 // rows per tile (per CTA); the pair's MMA has M = 256
+constexpr int NC = 128;                 // units per accumulator chunk (MMA N over the pair)
+constexpr int NH = NC / 2;              // units of a chunk whose weights live in THIS CTA's smem
+constexpr int KSLAB = 256;              // K elements per W2 stage (16 MMAs: amortises the issue loop)
+constexpr int STAGE_BYTES = NH * KSLAB * 2;   // 32 KB per CTA and stage
+constexpr int NSTAGE = 4;
 constexpr int K1 = 32;                  // K slots of the layer-1 MMA
-constexpr int ACC_SLOTS = 256 / NC;
-constexpr int NC1 = NC;                 // units per layer-1 chunk (same accumulator slots as layer 2)
-constexpr int W1_CHUNK_BYTES = NC1 * K1 * 2;  // 8 KB
+constexpr int ACC_SLOTS = 2;
+constexpr int W1_CHUNK_BYTES = NH * K1 * 2;   // 4 KB per CTA and chunk
 constexpr int A1_BYTES = TM * K1 * 2;         // 8 KB
-constexpr int ROW_WARPS = 8;                // 2 threads per row: each takes half of the columns
-constexpr int TPR = ROW_WARPS / 4;          // threads per row
-constexpr int CPT = NC / TPR;               // accumulator columns per thread and chunk
+constexpr int ROW_WARPS = 8;                  // 2 threads per row: each takes half of the columns
+constexpr int TPR = ROW_WARPS / 4;
+constexpr int CPT = NC / TPR;                 // accumulator columns per thread and chunk
 constexpr int ROW_THREADS = ROW_WARPS * 32;
 constexpr int THREADS = ROW_THREADS + 64;
 constexpr int HP_MAX = 512;
@@ -61,20 +57,20 @@ constexpr int MAX_DIN = 10;             // 3 * din + 2 <= K1
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t COL_H1 = 0, COL_ACC = 256;
 constexpr int SPIN_LIMIT = 1 << 28;
-constexpr int CLUSTER = 2;                // CTAs sharing every W2 stage through TMA multicast
-constexpr uint16_t CLUSTER_MASK = (1u << CLUSTER) - 1;
+constexpr int CLUSTER = 2;
+constexpr uint16_t PAIR_MASK = 3;
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address of the even CTA of a pair
 
 struct Params {
-    const __nv_bfloat16* w1_img;        // [HP/64][4][64][8]
-    const __nv_bfloat16* w2_img;        // [HP/128][HP/128][16][128][8]
+    const __nv_bfloat16* w1_img;        // [2 (cta)][HP/128][4][64][8]
+    const __nv_bfloat16* w2_img;        // [HP/128 (n)][HP/128 (k-slab)][2 (cta)][16][64][8]
     const float* w3;                    // [HP][DTW]
     float b3[SS_MAX_D];
     int hp;                             // padded hidden width (multiple of 128)
     int din;
     long long n_tiles;
-    int iters;                          // tile iterations per CTA (same for all: cluster lock-step)
-    int debug;                          // dev-only timing experiments (SS_TC_DEBUG), 0 in production
-    unsigned long long* prof;           // optional [grid][8] cycle counters (dev builds), else null
+    int iters;                          // tile iterations per CTA (same for all: pair lock-step)
+    unsigned long long* prof;
 };
 
 // ---- PTX wrappers -----------------------------------------------------------------------
@@ -82,21 +78,24 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+// arrive on the LEADER CTA's copy of a barrier (works from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(b) & PEER_BIT_MASK)
+                 : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
+template <bool CLUSTER_SCOPE>
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
     uint32_t done = 0;
     int spins = 0;
     while (true) {
         asm volatile(
-            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(done)
-            : "r"(smem_u32(b)), "r"(parity)
-            : "memory");
+                "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(done)
+                : "r"(smem_u32(b)), "r"(parity)
+                : "memory");
         if (done) break;
         if (++spins > SPIN_LIMIT) asm volatile("trap;");   // never hang the GPU on a protocol bug
     }
@@ -105,15 +104,6 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
                      "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
-}
-// half of a stage, delivered to the same smem offset of every CTA in `mask`; each destination
-// CTA's mbarrier (same offset) receives the complete_tx
-__device__ __forceinline__ void bulk_g2s_multicast(void* dst, const void* src, uint32_t bytes, uint64_t* bar,
-                                                   uint16_t mask) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::
-            "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
-        : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -125,33 +115,29 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* b) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(b))
-                 : "memory");
-}
-// commit that arrives on the barrier at the same smem offset in every CTA of `mask`
-__device__ __forceinline__ void tc_commit_multicast(uint64_t* b, uint16_t mask) {
+// arrives (once all MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void tc_commit_pair(uint64_t* b) {
     asm volatile(
-        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
             smem_u32(b)),
-        "h"(mask)
+        "h"(PAIR_MASK)
         : "memory");
 }
-// D[tmem] (+)= A[tmem] * B[smem desc]
-__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
-                                        uint32_t accumulate) {
+// D[tmem] (+)= A[tmem] * B[smem desc], M = 256 over the CTA pair
+__device__ __forceinline__ void umma2_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
     asm volatile(
         "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc]
-__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                        uint32_t accumulate) {
+// D[tmem] (+)= A[smem desc] * B[smem desc], M = 256 over the CTA pair
+__device__ __forceinline__ void umma2_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
     asm volatile(
         "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -167,10 +153,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t rows)
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((rows * 16) >> 4) << 16) |
            ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
 }
+// D f32, A/B bf16, K-major, N = 128, M = 256 (cta_group::2)
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) |
-                           ((uint32_t)(TM >> 4) << 24);   // D f32, A/B bf16, K-major, N=128, M=128
-constexpr uint32_t IDESC1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC1 >> 3) << 17) |
-                            ((uint32_t)(TM >> 4) << 24);  // same, N=64 (layer 1)
+                           ((uint32_t)((2 * TM) >> 4) << 24);
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -206,47 +191,22 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-#ifndef SS_TC_PROFILE
-#define TC_DEBUG 0
-#define TC_PROF_T0() do {} while (0)
-#define TC_PROF(slot) do {} while (0)
-#define TC_PROFW(slot) do {} while (0)
-#define TC_PROFW_T0() do {} while (0)
-#else
-#define TC_DEBUG p.debug
-#define TC_PROFW_T0() long long _pw = p.prof ? clock64() : 0
-#define TC_PROF_T0() long long _pt = p.prof ? clock64() : 0
-#define TC_PROF(slot)                                                                  \
-    do {                                                                               \
-        if (p.prof && warp == 0 && lane == 0) {                                        \
-            long long _n = clock64();                                                  \
-            p.prof[blockIdx.x * 8 + (slot)] += (unsigned long long)(_n - _pt);        \
-            _pt = _n;                                                                  \
-        } else if (p.prof) {                                                           \
-            _pt = clock64();                                                           \
-        }                                                                              \
+#define TC_TRACE(ev)                                                                              \
+    do {                                                                                          \
+        if (p.prof && blockIdx.x == 0 && lane == 0 && trace_it == 0 && trace_t >= 10 && trace_t < 13) \
+            p.prof[(trace_t - 10) * 256 + (ev)] = (unsigned long long)clock64();                   \
     } while (0)
-
-#define TC_PROFW(slot)                                                                 \
-    do {                                                                               \
-        if (p.prof && lane == 0) {                                                     \
-            long long _n = clock64();                                                  \
-            p.prof[(gridDim.x + blockIdx.x) * 8 + (slot)] += (unsigned long long)(_n - _pw); \
-            _pw = _n;                                                                  \
-        }                                                                              \
-    } while (0)
-#endif
 
 template <int DTW>
 struct SmemT {
     // dynamic shared memory carve-up (offsets in bytes from a 128-byte aligned base)
     static constexpr size_t W2_RING = 0;
     static constexpr size_t W1 = W2_RING + (size_t)NSTAGE * STAGE_BYTES;
-    static constexpr size_t A1 = W1 + (size_t)(HP_MAX / NC1) * W1_CHUNK_BYTES;
+    static constexpr size_t A1 = W1 + (size_t)(HP_MAX / NC) * W1_CHUNK_BYTES;
     static constexpr size_t W3 = A1 + (size_t)A1_BYTES;
     static constexpr size_t ZX = W3 + (size_t)HP_MAX * DTW * 4;
     static constexpr size_t BARS = ZX + (size_t)TPR * TM * 8 * 4;
-    static constexpr int N_BARS = 2 * NSTAGE + 2 * ACC_SLOTS + 4 + HP_MAX / NC1 + 2;
+    static constexpr int N_BARS = 3 * NSTAGE + 2 * ACC_SLOTS + HP_MAX / NC + 2;
     static constexpr size_t TMEM_PTR = BARS + (size_t)N_BARS * 8;
     static constexpr size_t SUMS = TMEM_PTR + 16;      // double [4][T][2]
 };
@@ -257,7 +217,7 @@ template <int DT>
 __device__ __forceinline__ void score_row(const RolloutArgs& a, int t, const float (&x)[DT], ScoreAcc& sc,
                                           bool live, long long k_local, int q, int lane, int T, double* sums) {
     float ab = 0.f, bb = 0.f;
-    score_point<DT>(a.plan, t, x, sc, a.per_sample != 0, ab, bb);
+    if (a.per_sample || a.partial_sums) score_point<DT>(a.plan, t, x, sc, a.per_sample != 0, ab, bb);
     if (a.states_out && live) {
         float* dst = a.states_out + ((size_t)t * a.K_local + k_local) * a.d;
 #pragma unroll
@@ -287,50 +247,60 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
     float* w3s = reinterpret_cast<float*>(smem + Smem::W3);
     float* zx = reinterpret_cast<float*>(smem + Smem::ZX);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::BARS);
-    uint64_t* w2_full = bars;
-    uint64_t* w2_empty = w2_full + NSTAGE;
-    uint64_t* acc_full = w2_empty + NSTAGE;
-    uint64_t* acc_free = acc_full + ACC_SLOTS;
-    uint64_t* l1_full = acc_free + ACC_SLOTS;           // [2] layer-1 sub-slots
-    uint64_t* l1_free = l1_full + 2;
-    uint64_t* h1_ready = l1_free + 2;                   // [HP_MAX / NC1]
-    uint64_t* x_ready = h1_ready + HP_MAX / NC1;
-    uint64_t* w1_full = x_ready + 1;
+    uint64_t* w2_full = bars;                           // local: this CTA's half of the stage has landed
+    uint64_t* w2_peer = w2_full + NSTAGE;               // leader's copy: the peer's half has landed
+    uint64_t* w2_empty = w2_peer + NSTAGE;              // local: the pair's MMAs are done with the stage
+    uint64_t* acc_full = w2_empty + NSTAGE;             // local: accumulator chunk complete (commit)
+    uint64_t* acc_free = acc_full + ACC_SLOTS;          // leader's copy: both CTAs' row warps drained it
+    uint64_t* h1_ready = acc_free + ACC_SLOTS;          // leader's copy [HP_MAX / NC]
+    uint64_t* x_ready = h1_ready + HP_MAX / NC;         // leader's copy
+    uint64_t* w1_full = x_ready + 1;                    // local
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Smem::TMEM_PTR);
     double* sums = reinterpret_cast<double*>(smem + Smem::SUMS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = a.H + 1;
-    const int nch = p.hp / NC;          // layer-2 accumulator chunks
-    const int nch1 = p.hp / NC1;        // layer-1 sub-chunks
+    const int nch = p.hp / NC;          // accumulator chunks per layer
     const int nslab = p.hp / KSLAB;     // W2 K-slabs (stages) per chunk
-    constexpr int CPS = KSLAB >= NC ? KSLAB / NC : 1;     // layer-1 chunks per K-slab
-    constexpr int SPC = NC >= KSLAB ? NC / KSLAB : 1;     // K-slabs per layer-1 chunk
     constexpr int DTW = DT <= 4 ? 4 : 8;
+    static_assert(KSLAB % NC == 0, "a K-slab covers whole layer-1 chunks");
+    constexpr int CPS = KSLAB / NC;     // layer-1 chunks per K-slab
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = cta_rank == 0;
 
     // ---- one-time setup ----------------------------------------------------------------
     if (tid == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&w2_full[s], 1); mbar_init(&w2_empty[s], CLUSTER); }
-        for (int s = 0; s < ACC_SLOTS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], ROW_WARPS); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&l1_full[s], 1); mbar_init(&l1_free[s], ROW_WARPS); }
-        for (int c = 0; c < HP_MAX / NC1; ++c) mbar_init(&h1_ready[c], ROW_WARPS);
-        mbar_init(x_ready, 4);   // the four ch-0 warps
+        for (int s = 0; s < NSTAGE; ++s) {
+            mbar_init(&w2_full[s], leader ? 2 : 1);   // leader: own TMA + the peer's "landed" relay
+            mbar_init(&w2_peer[s], 1);
+            mbar_init(&w2_empty[s], 1);
+        }
+        for (int s = 0; s < ACC_SLOTS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], 2 * ROW_WARPS); }
+        for (int c = 0; c < HP_MAX / NC; ++c) mbar_init(&h1_ready[c], 2 * ROW_WARPS);
+        mbar_init(x_ready, 2 * 4);       // the four ch-0 warps of each CTA
         mbar_init(w1_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
                      "n"(TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
     }
     for (int i = tid; i < p.hp * DTW; i += THREADS) w3s[i] = p.w3[i];
     for (int i = tid; i < 4 * T * 2; i += THREADS) sums[i] = 0.0;
+    __syncthreads();
+    if (tid == 0) {
+        // this CTA's half of the layer-1 weights (resident for the whole kernel)
+        mbar_expect_tx(w1_full, (uint32_t)(nch * W1_CHUNK_BYTES));
+        bulk_g2s(w1s, reinterpret_cast<const unsigned char*>(p.w1_img) + (size_t)cta_rank * nch * W1_CHUNK_BYTES,
+                 (uint32_t)(nch * W1_CHUNK_BYTES), w1_full);
+        mbar_wait<false>(w1_full, 0);
+    }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                  // every CTA's barriers exist before any peer signals them
+    cluster_sync_all();                  // barriers, TMEM and W1 of BOTH CTAs exist from here on
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
-    const uint32_t cta_rank = cluster_ctarank();
 
     if (warp < ROW_WARPS) {
         // =============================== ROW WARPS ========================================
@@ -357,8 +327,10 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                 for (int j = 0; j < SS_MAX_DA; ++j)
                     if (j < a.da) act[j] = fetch_action(a.act, k_local, a.k_offset + k_local, 0, j);
             }
-            TC_PROF_T0();
             for (int t = 0; t < a.H; ++t) {
+                const int trace_it = (warp == 0 || warp == 4) ? it : 1, trace_t = t;
+                const int tb = warp == 4 ? 100 : 0;   // ch-1 warp's events live at +100
+                TC_TRACE(tb + 0);
                 // ---- layer-1 A operand: hi/lo split of the normalised (state, action) -------
                 if (ch == 0) {
                     float xin[MAX_DIN];
@@ -400,14 +372,14 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(x_ready);
+                    if (lane == 0) mbar_arrive_leader(x_ready);
                 }
-                TC_PROF(1);
+                TC_TRACE(tb + 1);
                 // ---- layer-1 epilogue: relu, bf16, becomes the layer-2 A operand -------------
                 for (int c = 0; c < nch; ++c, ++acc_it) {
                     const uint32_t slot_i = acc_it % ACC_SLOTS;
-                    mbar_wait(&acc_full[slot_i], (acc_it / ACC_SLOTS) & 1);
-                    TC_PROF(2);
+                    mbar_wait<false>(&acc_full[slot_i], (acc_it / ACC_SLOTS) & 1);
+                    TC_TRACE(tb + 2 + c);
                     tc_fence_after();
 #pragma unroll
                     for (int part = 0; part < CPT / 32; ++part) {
@@ -421,26 +393,26 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) { mbar_arrive(&acc_free[slot_i]); mbar_arrive(&h1_ready[c]); }
-                    TC_PROF(3);
+                    if (lane == 0) { mbar_arrive_leader(&acc_free[slot_i]); mbar_arrive_leader(&h1_ready[c]); }
+                    TC_TRACE(tb + 6 + c);
                 }
                 // ---- off the critical path (the tensor pipe is busy with layer 2 now) ----------
                 if (ch == 1) {
-                    if (!(TC_DEBUG & 2)) score_row<DT>(a, t, x, sc, live, k_local, q, lane, T, sums);
+                    score_row<DT>(a, t, x, sc, live, k_local, q, lane, T, sums);
                 } else if (ch == 0 && live && t + 1 < a.H) {
 #pragma unroll
                     for (int j = 0; j < SS_MAX_DA; ++j)
                         if (j < a.da) act[j] = fetch_action(a.act, k_local, a.k_offset + k_local, t + 1, j);
                 }
-                TC_PROF(0);
+                TC_TRACE(tb + 19);
                 // ---- layer-2 epilogue fused with layer 3 --------------------------------------
                 float z[DT];
 #pragma unroll
                 for (int j = 0; j < DT; ++j) z[j] = 0.f;
                 for (int n = 0; n < nch; ++n, ++acc_it) {
                     const uint32_t slot_i = acc_it % ACC_SLOTS;
-                    mbar_wait(&acc_full[slot_i], (acc_it / ACC_SLOTS) & 1);
-                    TC_PROF(4);
+                    mbar_wait<false>(&acc_full[slot_i], (acc_it / ACC_SLOTS) & 1);
+                    TC_TRACE(tb + 10 + n);
                     tc_fence_after();
                     static_assert(CPT == 32 || CPT == 64, "one or two 32-column TMEM loads per thread and chunk");
                     uint32_t v0[32], v1[32];
@@ -448,9 +420,8 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                     if (CPT > 32) tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * CPT + 32, v1);
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&acc_free[slot_i]);
+                    if (lane == 0) mbar_arrive_leader(&acc_free[slot_i]);
                     const float* wrow = w3s + (size_t)(n * NC + ch * CPT) * DTW;
-                    if (TC_DEBUG & 1) { z[0] += __uint_as_float(v0[lane]); continue; }
 #pragma unroll
                     for (int j2 = 0; j2 < CPT; ++j2) {
                         const float hval = fmaxf(__uint_as_float(j2 < 32 ? v0[j2 & 31] : v1[j2 & 31]), 0.f);
@@ -467,7 +438,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                             if (DT > 7) z[7] = fmaf(hval, w1.w, z[7]);
                         }
                     }
-                    TC_PROF(5);
+                    TC_TRACE(tb + 14 + n);
                 }
                 // ---- the two column halves exchange partial sums; both update the state ---------
 #pragma unroll
@@ -483,7 +454,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                         zz += p.b3[j];
                         x[j] += fmaf(zz, a.norm.std_z[j], a.norm.mean_z[j]);
                     }
-                TC_PROF(6);
+                TC_TRACE(tb + 18);
             }
             if (ch == 1) {
                 score_row<DT>(a, a.H, x, sc, live, k_local, q, lane, T, sums);
@@ -491,98 +462,108 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
             }
         }
     } else if (warp == ROW_WARPS) {
-        // =============================== MMA ISSUER =======================================
-        // the whole warp walks the loop (warp-uniform control flow); one elected lane issues
-        uint32_t acc_it = 0, w2_it = 0, step_it = 0;
-        mbar_wait(w1_full, 0);
-        TC_PROFW_T0();
-        const uint32_t a1_addr = smem_u32(a1s), w1_addr = smem_u32(w1s), ring_addr = smem_u32(w2_ring);
-        for (int it = 0; it < p.iters; ++it) {
-            for (int t = 0; t < a.H; ++t, ++step_it) {
-                mbar_wait(x_ready, step_it & 1);
-                TC_PROFW(0);
-                tc_fence_after();
-                // layer 1: acc chunk c = A1 [128 x 32] * W1img[c] [128 x 32]^T
-                for (int c = 0; c < nch; ++c, ++acc_it) {
-                    const uint32_t slot_i = acc_it % ACC_SLOTS;
-                    mbar_wait(&acc_free[slot_i], ((acc_it / ACC_SLOTS) & 1) ^ 1);
-                    TC_PROFW(1);
+        if (leader) {
+            // ============================ MMA ISSUER (leader CTA) ==============================
+            // the whole warp walks the loop (warp-uniform control flow); one elected lane issues
+            // every MMA of the pair (cta_group::2: rows 0-127 in this CTA's TMEM, 128-255 in the
+            // peer's; B halves are read from both CTAs' shared memory at the same offset)
+            uint32_t acc_it = 0, w2_it = 0, step_it = 0;
+            const uint32_t a1_addr = smem_u32(a1s), w1_addr = smem_u32(w1s), ring_addr = smem_u32(w2_ring);
+            for (int it = 0; it < p.iters; ++it) {
+                for (int t = 0; t < a.H; ++t, ++step_it) {
+                    const int trace_it = it, trace_t = t;
+                    mbar_wait<true>(x_ready, step_it & 1);
+                    TC_TRACE(20);
                     tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t d_tmem = tmem + COL_ACC + slot_i * NC;
-#pragma unroll
-                        for (int ks = 0; ks < K1 / 16; ++ks)
-                            umma_ss(d_tmem, make_desc(a1_addr + ks * 2 * (TM * 16), TM),
-                                    make_desc(w1_addr + c * W1_CHUNK_BYTES + ks * 2 * (NC * 16), NC), IDESC, ks);
-                        tc_commit(&acc_full[slot_i]);
-                    }
-                    __syncwarp();
-                }
-                // layer 2: acc chunk n = H1 [128 x HP] * W2img[n] [128 x HP]^T, K streamed in slabs
-                for (int n = 0; n < nch; ++n, ++acc_it) {
-                    const uint32_t slot_i = acc_it % ACC_SLOTS;
-                    mbar_wait(&acc_free[slot_i], ((acc_it / ACC_SLOTS) & 1) ^ 1);
-                    TC_PROFW(2);
-                    for (int ksl = 0; ksl < nslab; ++ksl, ++w2_it) {
-                        const uint32_t st = w2_it % NSTAGE;
-                        if (n == 0) {
-                            for (int i = 0; i < CPS; ++i) mbar_wait(&h1_ready[(ksl / SPC) * CPS + i], step_it & 1);
-                            TC_PROFW(3);
-                        }
-                        if (!(TC_DEBUG & 4) || w2_it < NSTAGE) mbar_wait(&w2_full[st], (w2_it / NSTAGE) & 1);
-                        TC_PROFW(4);
+                    // layer 1: acc chunk c = A1 [256 x 32] * W1img[c] [128 x 32]^T
+                    for (int c = 0; c < nch; ++c, ++acc_it) {
+                        const uint32_t slot_i = acc_it % ACC_SLOTS;
+                        mbar_wait<true>(&acc_free[slot_i], ((acc_it / ACC_SLOTS) & 1) ^ 1);
                         tc_fence_after();
                         if (elect_one()) {
                             const uint32_t d_tmem = tmem + COL_ACC + slot_i * NC;
-                            const uint32_t a_tmem = tmem + COL_H1 + ksl * (KSLAB / 2);
-                            const uint64_t b0 = make_desc(ring_addr + st * STAGE_BYTES, NC);
 #pragma unroll
-                            for (int ks = 0; ks < KSLAB / 16; ++ks)
-                                umma_ts(d_tmem, a_tmem + ks * 8, b0 + (uint64_t)((ks * 2 * (NC * 16)) >> 4), IDESC,
-                                        (ksl | ks) != 0);
-                            if (!(TC_DEBUG & 4)) tc_commit_multicast(&w2_empty[st], CLUSTER_MASK);
-                            if (ksl == nslab - 1) tc_commit(&acc_full[slot_i]);
+                            for (int ks = 0; ks < K1 / 16; ++ks)
+                                umma2_ss(d_tmem, make_desc(a1_addr + ks * 2 * (TM * 16), TM),
+                                         make_desc(w1_addr + c * W1_CHUNK_BYTES + ks * 2 * (NH * 16), NH), IDESC, ks);
+                            tc_commit_pair(&acc_full[slot_i]);
                         }
                         __syncwarp();
-                        TC_PROFW(5);
+                        TC_TRACE(21 + c);
                     }
+                    // layer 2: acc chunk n = H1 [256 x HP] * W2img[n] [128 x HP]^T, K streamed in slabs
+                    for (int n = 0; n < nch; ++n, ++acc_it) {
+                        const uint32_t slot_i = acc_it % ACC_SLOTS;
+                        mbar_wait<true>(&acc_free[slot_i], ((acc_it / ACC_SLOTS) & 1) ^ 1);
+                        TC_TRACE(41 + n);
+                        for (int ksl = 0; ksl < nslab; ++ksl, ++w2_it) {
+                            const uint32_t st = w2_it % NSTAGE;
+                            if (n == 0) {
+#pragma unroll
+                                for (int i = 0; i < CPS; ++i) mbar_wait<true>(&h1_ready[ksl * CPS + i], step_it & 1);
+                            }
+                            mbar_wait<true>(&w2_full[st], (w2_it / NSTAGE) & 1);    // both halves have landed
+                            tc_fence_after();
+                            if (elect_one()) {
+                                const uint32_t d_tmem = tmem + COL_ACC + slot_i * NC;
+                                const uint32_t a_tmem = tmem + COL_H1 + ksl * (KSLAB / 2);
+                                const uint64_t b0 = make_desc(ring_addr + st * STAGE_BYTES, NH);
+#pragma unroll
+                                for (int ks = 0; ks < KSLAB / 16; ++ks)
+                                    umma2_ts(d_tmem, a_tmem + ks * 8, b0 + (uint64_t)((ks * 2 * (NH * 16)) >> 4), IDESC,
+                                             (ksl | ks) != 0);
+                                tc_commit_pair(&w2_empty[st]);
+                                if (ksl == nslab - 1) tc_commit_pair(&acc_full[slot_i]);
+                            }
+                            __syncwarp();
+                            TC_TRACE(25 + n * 4 + ksl);
+                        }
+                    }
+                }
+            }
+        } else {
+            // ============================ STAGE RELAY (peer CTA) ===============================
+            // tell the leader's MMA warp when this CTA's half of a W2 stage has landed
+            if (lane == 0) {
+                uint32_t w2_it = 0;
+                const long long total = (long long)p.iters * a.H * nch * nslab;
+                for (long long i = 0; i < total; ++i, ++w2_it) {
+                    const uint32_t st = w2_it % NSTAGE;
+                    mbar_wait<false>(&w2_full[st], (w2_it / NSTAGE) & 1);
+                    mbar_arrive_leader(&w2_full[st]);
                 }
             }
         }
     } else {
         // =============================== TMA PRODUCER =====================================
         if (lane == 0) {
-            mbar_expect_tx(w1_full, (uint32_t)(nch1 * W1_CHUNK_BYTES));
-            bulk_g2s(w1s, p.w1_img, (uint32_t)(nch1 * W1_CHUNK_BYTES), w1_full);
             uint32_t w2_it = 0;
             const int blocks = nch * nslab;
-            constexpr uint32_t PART = STAGE_BYTES / CLUSTER;
             for (int it = 0; it < p.iters; ++it)
                 for (int t = 0; t < a.H; ++t)
                     for (int blk = 0; blk < blocks; ++blk, ++w2_it) {
                         const uint32_t st = w2_it % NSTAGE;
-                        if ((TC_DEBUG & 4) && w2_it >= NSTAGE) continue;
-                        // the stage must be drained in EVERY CTA of the cluster (both MMA warps commit here)
-                        mbar_wait(&w2_empty[st], ((w2_it / NSTAGE) & 1) ^ 1);
-                        mbar_expect_tx(&w2_full[st], STAGE_BYTES);          // my part + the peers' parts
-                        bulk_g2s_multicast(w2_ring + (size_t)st * STAGE_BYTES + cta_rank * PART,
-                                           reinterpret_cast<const unsigned char*>(p.w2_img) +
-                                               (size_t)blk * STAGE_BYTES + cta_rank * PART,
-                                           PART, &w2_full[st], CLUSTER_MASK);
+                        // drained by the pair's MMAs (the commit is multicast to both CTAs)
+                        mbar_wait<false>(&w2_empty[st], ((w2_it / NSTAGE) & 1) ^ 1);
+                        mbar_expect_tx(&w2_full[st], STAGE_BYTES);
+                        bulk_g2s(w2_ring + (size_t)st * STAGE_BYTES,
+                                 reinterpret_cast<const unsigned char*>(p.w2_img) +
+                                     ((size_t)blk * CLUSTER + cta_rank) * STAGE_BYTES,
+                                 STAGE_BYTES, &w2_full[st]);
                     }
         }
     }
     // ---- teardown ---------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                  // no CTA leaves while a peer may still write / signal into it
+    cluster_sync_all();                  // no CTA leaves while its peer may still read / signal it
     tc_fence_after();
     if (a.partial_sums)
         for (int o = tid; o < 2 * T; o += THREADS)
             a.partial_sums[(size_t)blockIdx.x * 2 * T + o] =
                 sums[o] + sums[2 * T + o] + sums[4 * T + o] + sums[6 * T + o];
     if (warp == 0)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
 }
 
 // ---- host side ---------------------------------------------------------------------------
@@ -616,14 +597,15 @@ int mpc_tc_prepare(ss_ctx* c) {
     const int h = c->h, d = c->d, din = c->d + c->da;
     const int hp = (h + 2 + KSLAB - 1) / KSLAB * KSLAB;
     const int nch = hp / NC, nslab = hp / KSLAB;
-    static_assert(KSLAB % NC == 0 || NC % KSLAB == 0, "K-slabs and layer-1 chunks must nest");
     const std::vector<double>&W1 = c->hw[0], &W2 = c->hw[1], &W3 = c->hw[2];
     const std::vector<double>&B1 = c->hb[0], &B2 = c->hb[1];
+    // Every B tile is split by output unit over the CTA pair: units [128 c + 64 r, +64) of chunk c
+    // live in CTA r.  Images are [k/8][64 units][8 k] (K-major, no-swizzle core matrices).
     // layer-1 image: K slots (3j, 3j+1, 3j+2) = (W_hi, W_lo, W_hi) of input j; then (b_hi, b_lo)
-    std::vector<uint16_t> w1((size_t)(hp / NC1) * (W1_CHUNK_BYTES / 2), 0);
+    std::vector<uint16_t> w1((size_t)CLUSTER * nch * (W1_CHUNK_BYTES / 2), 0);
     auto w1_at = [&](int slot, int u) -> uint16_t& {
-        const int cidx = u / NC1, nn = u % NC1;
-        return w1[(size_t)cidx * (W1_CHUNK_BYTES / 2) + (slot / 8) * (NC1 * 8) + nn * 8 + (slot % 8)];
+        const int cidx = u / NC, r = (u % NC) / NH, nn = u % NH;
+        return w1[((size_t)r * nch + cidx) * (W1_CHUNK_BYTES / 2) + (slot / 8) * (NH * 8) + nn * 8 + (slot % 8)];
     };
     for (int u = 0; u < h; ++u) {
         for (int j = 0; j < din; ++j) {
@@ -641,11 +623,12 @@ int mpc_tc_prepare(ss_ctx* c) {
     // constant-one hidden units h and h+1 (carry the layer-2 bias through the GEMM)
     w1_at(3 * din, h) = bf16_bits(1.f);
     w1_at(3 * din, h + 1) = bf16_bits(1.f);
-    // layer-2 image: blocks (n, kslab) of [16 k-chunks][64 units][8 k]
-    std::vector<uint16_t> w2((size_t)nch * nslab * (STAGE_BYTES / 2), 0);
+    // layer-2 image: blocks (n, kslab, cta) of [16 k-chunks][64 units][8 k]
+    std::vector<uint16_t> w2((size_t)nch * nslab * CLUSTER * (STAGE_BYTES / 2), 0);
     auto w2_at = [&](int k, int u) -> uint16_t& {
-        const int n = u / NC, nn = u % NC, ksl = k / KSLAB, kk = k % KSLAB;
-        return w2[((size_t)n * nslab + ksl) * (STAGE_BYTES / 2) + (kk / 8) * (NC * 8) + nn * 8 + (kk % 8)];
+        const int n = u / NC, r = (u % NC) / NH, nn = u % NH, ksl = k / KSLAB, kk = k % KSLAB;
+        return w2[(((size_t)n * nslab + ksl) * CLUSTER + r) * (STAGE_BYTES / 2) + (kk / 8) * (NH * 8) + nn * 8 +
+                  (kk % 8)];
     };
     for (int u = 0; u < h; ++u) {
         for (int k = 0; k < h; ++k) w2_at(k, u) = bf16_bits((float)W2[(size_t)k * h + u]);
@@ -672,7 +655,7 @@ int mpc_tc_prepare(ss_ctx* c) {
 }
 
 int mpc_tc_grid(const ss_ctx* c, const RolloutArgs& a) {
-    // a multiple of the cluster size; at most one CTA per SM (TMEM: 512 columns per CTA)
+    // a multiple of the pair size; at most one CTA per SM (TMEM: 512 columns per CTA)
     const long long tiles = (a.K_local + tc::TM - 1) / tc::TM;
     const long long up = (tiles + tc::CLUSTER - 1) / tc::CLUSTER * tc::CLUSTER;
     const long long cap = c->sm_count / tc::CLUSTER * tc::CLUSTER;
@@ -693,10 +676,9 @@ int mpc_tc_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out) {
     p.din = c->d + c->da;
     p.n_tiles = (a.K_local + TM - 1) / TM;
     p.prof = nullptr;
-    p.debug = getenv("SS_TC_DEBUG") ? atoi(getenv("SS_TC_DEBUG")) : 0;
-    if (getenv("SS_TC_PROF")) {
-        SS_CUDA_CHECK(c, c->tc_misc.ensure((size_t)c->sm_count * 8 * 8 * 2));
-        SS_CUDA_CHECK(c, cudaMemsetAsync(c->tc_misc.p, 0, (size_t)c->sm_count * 8 * 8 * 2, c->stream));
+    if (getenv("SS_TC_TRACE")) {
+        SS_CUDA_CHECK(c, c->tc_misc.ensure(3 * 256 * 8));
+        SS_CUDA_CHECK(c, cudaMemsetAsync(c->tc_misc.p, 0, 3 * 256 * 8, c->stream));
         p.prof = c->tc_misc.as<unsigned long long>();
     }
     const int grid = mpc_tc_grid(c, a);
@@ -728,21 +710,33 @@ int mpc_tc_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out) {
     c->launches++;
     SS_CUDA_CHECK(c, e);
     if (p.prof) {
-        std::vector<unsigned long long> h((size_t)grid * 8 * 2);
+        std::vector<unsigned long long> h(3 * 256);
         SS_CUDA_CHECK(c, cudaMemcpyAsync(h.data(), p.prof, h.size() * 8, cudaMemcpyDeviceToHost, c->stream));
         SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-        const char* names[8] = {"score", "xsplit", "l1_wait", "l1_epi", "l2_wait", "l2_epi", "combine", "-"};
-        double tot = 0;
-        for (int s2 = 0; s2 < 7; ++s2) tot += (double)h[s2];
-        fprintf(stderr, "[tc prof, CTA 0, warp 0] total %.0f cycles:", tot);
-        for (int s2 = 0; s2 < 7; ++s2) fprintf(stderr, " %s %.1f%%", names[s2], 100.0 * h[s2] / tot);
-        fprintf(stderr, "\n");
-        const char* mn[6] = {"x_ready", "l1_acc_free", "l2_acc_free", "h1_ready", "w2_full", "issue"};
-        double mt = 0;
-        for (int s2 = 0; s2 < 6; ++s2) mt += (double)h[(size_t)grid * 8 + s2];
-        fprintf(stderr, "[tc prof, CTA 0, MMA warp] total %.0f cycles:", mt);
-        for (int s2 = 0; s2 < 6; ++s2) fprintf(stderr, " %s %.1f%%", mn[s2], 100.0 * h[(size_t)grid * 8 + s2] / mt);
-        fprintf(stderr, "\n");
+        for (int st2 = 0; st2 < 3; ++st2) {
+            const unsigned long long* ev = &h[st2 * 256];
+            const unsigned long long t0 = ev[0];
+            fprintf(stderr, "[trace step %d] row: xsplit_done %llu | L1 full", 10 + st2, ev[1] - t0);
+            for (int c2 = 0; c2 < 4; ++c2) fprintf(stderr, " %llu", ev[2 + c2] - t0);
+            fprintf(stderr, " | L1 epi_done");
+            for (int c2 = 0; c2 < 4; ++c2) fprintf(stderr, " %llu", ev[6 + c2] - t0);
+            fprintf(stderr, " | L2 full");
+            for (int c2 = 0; c2 < 4; ++c2) fprintf(stderr, " %llu", ev[10 + c2] - t0);
+            fprintf(stderr, " | L2 epi_done");
+            for (int c2 = 0; c2 < 4; ++c2) fprintf(stderr, " %llu", ev[14 + c2] - t0);
+            fprintf(stderr, " | step_end %llu\n", ev[18] - t0);
+            fprintf(stderr, "[trace step %d] mma: x_ready %llu | L1 issued", 10 + st2, ev[20] - t0);
+            for (int c2 = 0; c2 < 4; ++c2) fprintf(stderr, " %llu", ev[21 + c2] - t0);
+            fprintf(stderr, " | L2 slab issued");
+            for (int c2 = 0; c2 < 16; ++c2) fprintf(stderr, " %llu", ev[25 + c2] - t0);
+            fprintf(stderr, " | acc_free seen");
+            for (int c2 = 0; c2 < 4; ++c2) fprintf(stderr, " %llu", ev[41 + c2] - t0);
+            fprintf(stderr, "\n[trace step %d] ch1: L1 epi_done %llu | score_done %llu | L2 full", 10 + st2, ev[109] - t0, ev[119] - t0);
+            for (int c2 = 0; c2 < 4; ++c2) fprintf(stderr, " %llu", ev[110 + c2] - t0);
+            fprintf(stderr, " | L2 epi_done");
+            for (int c2 = 0; c2 < 4; ++c2) fprintf(stderr, " %llu", ev[114 + c2] - t0);
+            fprintf(stderr, " | ch0 prefetch_done %llu\n", ev[19] - t0);
+        }
     }
     return SS_OK;
 }
