@@ -66,6 +66,11 @@ struct ActionSource {
     uint64_t seed;
     double low[SS_MAX_DA], range[SS_MAX_DA];
     int da, H;
+    // 1 when low/range are FP32-representable and low + u * range (u a 24-bit fraction) is exact in
+    // float64: then fmaf(u, range, low) in FP32 rounds the same exact value once and gives the same
+    // bits as the float64 expression (set by the host, see fill_action_source)
+    int fp32_exact;
+    float low_f[SS_MAX_DA], range_f[SS_MAX_DA];
 };
 
 struct PhaseTimer {
@@ -214,5 +219,29 @@ __device__ __forceinline__ float fetch_action(const ActionSource& src, long long
     const uint32_t sel = e & 3;     // select without indexing (keeps r[] in registers)
     const uint32_t w = sel == 0 ? r[0] : (sel == 1 ? r[1] : (sel == 2 ? r[2] : r[3]));
     double u = (double)(w >> 8) * (1.0 / 16777216.0);
+    return (float)(src.low[j] + u * src.range[j]);
+}
+
+// Same values as fetch_action() for a thread that walks t = 0, 1, 2, ... of ONE sequence: the
+// Philox block of four samples is kept in registers and recomputed only when (t * da + j) / 4
+// changes; the affine map runs in FP32 when that is bit-identical (ActionSource::fp32_exact).
+struct ActionCursor {
+    uint32_t r[4];
+    uint32_t blk;
+};
+__device__ __forceinline__ void action_cursor_init(ActionCursor& c) { c.blk = 0xffffffffu; }
+__device__ __forceinline__ float fetch_action_seq(const ActionSource& src, ActionCursor& c, long long k_local,
+                                                  long long k_global, int t, int j) {
+    if (src.host_actions) return (float)src.host_actions[((size_t)k_local * src.H + t) * src.da + j];
+    const uint32_t e = (uint32_t)(t * src.da + j);
+    if ((e >> 2) != c.blk) {
+        c.blk = e >> 2;
+        philox4x32_10((uint32_t)k_global, (uint32_t)((uint64_t)k_global >> 32), c.blk, 0u, (uint32_t)src.seed,
+                      (uint32_t)(src.seed >> 32), c.r);
+    }
+    const uint32_t sel = e & 3;
+    const uint32_t w = sel == 0 ? c.r[0] : (sel == 1 ? c.r[1] : (sel == 2 ? c.r[2] : c.r[3]));
+    if (src.fp32_exact) return fmaf((float)(w >> 8) * (1.0f / 16777216.0f), src.range_f[j], src.low_f[j]);
+    const double u = (double)(w >> 8) * (1.0 / 16777216.0);
     return (float)(src.low[j] + u * src.range[j]);
 }

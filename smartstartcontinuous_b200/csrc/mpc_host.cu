@@ -42,6 +42,21 @@ int fill_action_source(ss_ctx* c, ActionSource& s, int H, int da, uint64_t seed,
         for (int j = 0; j < da; ++j) { s.low[j] = low[j]; s.range[j] = high[j] - low[j]; }
     else if (!low != !high)
         SS_FAIL(c, SS_EINVAL, "mpc: act_low and act_high must both be given");
+    // FP32 fast path of fetch_action_seq: both constants exact in FP32 and the float64 sum
+    // low + u * range exact (u has 24 bits, range 24: the product needs 48; adding low must not
+    // push the span past 53 bits)
+    s.fp32_exact = 1;
+    for (int j = 0; j < SS_MAX_DA; ++j) {
+        s.low_f[j] = (float)s.low[j];
+        s.range_f[j] = (float)s.range[j];
+        if ((double)s.low_f[j] != s.low[j] || (double)s.range_f[j] != s.range[j]) s.fp32_exact = 0;
+        if (s.low[j] != 0.0 && s.range[j] != 0.0) {
+            int el = 0, er = 0;
+            std::frexp(s.low[j], &el);
+            std::frexp(s.range[j], &er);
+            if (el - er > 4 || !std::isfinite(s.low[j]) || !std::isfinite(s.range[j])) s.fp32_exact = 0;
+        }
+    }
     return SS_OK;
 }
 

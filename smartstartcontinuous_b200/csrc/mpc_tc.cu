@@ -43,17 +43,22 @@ constexpr int NH = NC / 2;              // units of a chunk whose weights live i
 constexpr int KSLAB = 256;              // K elements per W2 stage (16 MMAs: amortises the issue loop)
 constexpr int STAGE_BYTES = NH * KSLAB * 2;   // 32 KB per CTA and stage
 constexpr int NSTAGE = 4;
-constexpr int K1 = 32;                  // K slots of the layer-1 MMA
+constexpr int K1_MAX = 32;              // K slots of the layer-1 MMA: 16 (d + da <= 4) or 32
 constexpr int ACC_SLOTS = 2;
-constexpr int W1_CHUNK_BYTES = NH * K1 * 2;   // 4 KB per CTA and chunk
-constexpr int A1_BYTES = TM * K1 * 2;         // 8 KB
+constexpr int W1_CHUNK_BYTES_MAX = NH * K1_MAX * 2;   // 4 KB per CTA and chunk
+constexpr int A1_BYTES_MAX = TM * K1_MAX * 2;         // 8 KB
 constexpr int ROW_WARPS = 8;                  // 2 threads per row: each takes half of the columns
 constexpr int TPR = ROW_WARPS / 4;
 constexpr int CPT = NC / TPR;                 // accumulator columns per thread and chunk
 constexpr int ROW_THREADS = ROW_WARPS * 32;
 constexpr int THREADS = ROW_THREADS + 64;
 constexpr int HP_MAX = 512;
-constexpr int MAX_DIN = 10;             // 3 * din + 2 <= K1
+constexpr int MAX_DIN = (K1_MAX - 2) / 3;   // 3 slots per input + 2 bias slots <= K1
+// layer-3 outputs computed for state dimension d, and the layer-1 input slots: state j -> input j
+// (j < dz), action j -> input dz + j; three K slots per input + two bias slots
+__host__ __device__ constexpr int dz_of(int d) { return d <= 2 ? 2 : (d <= 3 ? 3 : (d <= 4 ? 4 : 8)); }
+__host__ __device__ constexpr int k1_slots(int d, int da) { return 3 * (dz_of(d) + da) + 2 <= 16 ? 16 : 32; }
+__host__ __device__ constexpr int w3_pair_floats(int dz) { return dz <= 2 ? 4 : (dz <= 4 ? 8 : 16); }
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t COL_H1 = 0, COL_ACC = 256;
 constexpr int SPIN_LIMIT = 1 << 28;
@@ -64,7 +69,7 @@ constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address of 
 struct Params {
     const __nv_bfloat16* w1_img;        // [2 (cta)][HP/128][4][64][8]
     const __nv_bfloat16* w2_img;        // [HP/128 (n)][HP/128 (k-slab)][2 (cta)][16][64][8]
-    const float* w3;                    // [HP][DTW]
+    const float* w3;                    // [HP/2 (unit pairs)][DZP][2]: packed for FFMA2
     float b3[SS_MAX_D];
     int hp;                             // padded hidden width (multiple of 128)
     int din;
@@ -123,6 +128,13 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* b) {
         "h"(PAIR_MASK)
         : "memory");
 }
+__device__ __forceinline__ void tc_commit_pair_addr(uint32_t bar_addr) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            bar_addr),
+        "h"(PAIR_MASK)
+        : "memory");
+}
 // D[tmem] (+)= A[tmem] * B[smem desc], M = 256 over the CTA pair
 __device__ __forceinline__ void umma2_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                          uint32_t accumulate) {
@@ -168,16 +180,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::
             "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
         "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
         : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // pack two floats to bf16x2 (lo -> bits [0,16), hi -> bits [16,32)), optionally with relu
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     uint32_t r;
@@ -189,24 +201,29 @@ __device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
     asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
-__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+// v rounded to bf16 (round-to-nearest-even), as a float; F2FP packing path (no XU-pipe F2F)
+__device__ __forceinline__ float bf16_hi(float v) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(v), "f"(0.f));
+    return __uint_as_float(r & 0xffff0000u);
+}
 
 #define TC_TRACE(ev)                                                                              \
     do {                                                                                          \
         if (p.prof && blockIdx.x == 0 && lane == 0 && trace_it == 0 && trace_t >= 10 && trace_t < 13) \
-            p.prof[(trace_t - 10) * 256 + (ev)] = (unsigned long long)clock64();                   \
+            trace_s[(trace_t - 10) * 256 + (ev)] = (unsigned long long)clock64();                  \
     } while (0)
 
-template <int DTW>
+template <int DZ>
 struct SmemT {
     // dynamic shared memory carve-up (offsets in bytes from a 128-byte aligned base)
     static constexpr size_t W2_RING = 0;
     static constexpr size_t W1 = W2_RING + (size_t)NSTAGE * STAGE_BYTES;
-    static constexpr size_t A1 = W1 + (size_t)(HP_MAX / NC) * W1_CHUNK_BYTES;
-    static constexpr size_t W3 = A1 + (size_t)A1_BYTES;
-    static constexpr size_t ZX = W3 + (size_t)HP_MAX * DTW * 4;
+    static constexpr size_t A1 = W1 + (size_t)(HP_MAX / NC) * W1_CHUNK_BYTES_MAX;
+    static constexpr size_t W3 = A1 + (size_t)A1_BYTES_MAX;
+    static constexpr size_t ZX = W3 + (size_t)(HP_MAX / 2) * w3_pair_floats(DZ) * 4;
     static constexpr size_t BARS = ZX + (size_t)TPR * TM * 8 * 4;
-    static constexpr int N_BARS = 3 * NSTAGE + 2 * ACC_SLOTS + HP_MAX / NC + 2;
+    static constexpr int N_BARS = 3 * NSTAGE + 2 * ACC_SLOTS + 2 * (HP_MAX / NC) + 2;
     static constexpr size_t TMEM_PTR = BARS + (size_t)N_BARS * 8;
     static constexpr size_t SUMS = TMEM_PTR + 16;      // double [4][T][2]
 };
@@ -237,10 +254,15 @@ __device__ __forceinline__ void score_row(const RolloutArgs& a, int t, const flo
     }
 }
 
-template <int DT>
+// DT: register copies of the state (4 or 8); DZ: layer-3 outputs computed (>= d; 2, 3, 4 or 8);
+// K1T: K slots of the layer-1 MMA (16 when 3 (d + da) + 2 <= 16, else 32)
+template <int DT, int DZ, int K1T>
 __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const RolloutArgs a, const Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    using Smem = SmemT<(DT <= 4 ? 4 : 8)>;
+    using Smem = SmemT<DZ>;
+    constexpr int MAXIN = (K1T - 2) / 3;            // network inputs the A tile has slots for
+    constexpr int W1_CHUNK_BYTES = NH * K1T * 2;
+    constexpr int DZP = w3_pair_floats(DZ) / 2;     // layer-3 outputs padded to 2 / 4 / 8
     unsigned char* w2_ring = smem + Smem::W2_RING;
     unsigned char* w1s = smem + Smem::W1;
     unsigned char* a1s = smem + Smem::A1;
@@ -253,16 +275,21 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
     uint64_t* acc_full = w2_empty + NSTAGE;             // local: accumulator chunk complete (commit)
     uint64_t* acc_free = acc_full + ACC_SLOTS;          // leader's copy: both CTAs' row warps drained it
     uint64_t* h1_ready = acc_free + ACC_SLOTS;          // leader's copy [HP_MAX / NC]
-    uint64_t* x_ready = h1_ready + HP_MAX / NC;         // leader's copy
+    uint64_t* l1_full = h1_ready + HP_MAX / NC;         // local: layer-1 chunk complete (commit)
+    uint64_t* x_ready = l1_full + HP_MAX / NC;          // leader's copy
     uint64_t* w1_full = x_ready + 1;                    // local
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Smem::TMEM_PTR);
     double* sums = reinterpret_cast<double*>(smem + Smem::SUMS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = a.H + 1;
+    // SS_TC_TRACE: clock stamps go to shared memory (a global store in front of a tcgen05 fence
+    // would perturb the timeline) and are copied out when the kernel ends
+    unsigned long long* trace_s = reinterpret_cast<unsigned long long*>(sums + 4 * T * 2);
+    if (p.prof && blockIdx.x == 0)
+        for (int i = tid; i < 3 * 256; i += THREADS) trace_s[i] = 0;
     const int nch = p.hp / NC;          // accumulator chunks per layer
     const int nslab = p.hp / KSLAB;     // W2 K-slabs (stages) per chunk
-    constexpr int DTW = DT <= 4 ? 4 : 8;
     static_assert(KSLAB % NC == 0, "a K-slab covers whole layer-1 chunks");
     constexpr int CPS = KSLAB / NC;     // layer-1 chunks per K-slab
     const uint32_t cta_rank = cluster_ctarank();
@@ -276,7 +303,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
             mbar_init(&w2_empty[s], 1);
         }
         for (int s = 0; s < ACC_SLOTS; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_free[s], 2 * ROW_WARPS); }
-        for (int c = 0; c < HP_MAX / NC; ++c) mbar_init(&h1_ready[c], 2 * ROW_WARPS);
+        for (int c = 0; c < HP_MAX / NC; ++c) { mbar_init(&h1_ready[c], 2 * ROW_WARPS); mbar_init(&l1_full[c], 1); }
         mbar_init(x_ready, 2 * 4);       // the four ch-0 warps of each CTA
         mbar_init(w1_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -286,7 +313,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                      "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
     }
-    for (int i = tid; i < p.hp * DTW; i += THREADS) w3s[i] = p.w3[i];
+    for (int i = tid; i < (p.hp / 2) * (2 * DZP); i += THREADS) w3s[i] = p.w3[i];
     for (int i = tid; i < 4 * T * 2; i += THREADS) sums[i] = 0.0;
     __syncthreads();
     if (tid == 0) {
@@ -307,7 +334,16 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
         const int q = warp & 3, ch = warp >> 2;
         const int row = q * 32 + lane;
         const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-        uint32_t acc_it = 0;
+        uint32_t step_it = 0;
+        // state update x += (z + b3) * std_z + mean_z as one FMA per dimension: pin the two
+        // constants in registers (a constant-bank miss here sits on the per-step critical path)
+        float upd_s[DZ], upd_c[DZ];
+#pragma unroll
+        for (int j = 0; j < DZ; ++j) {
+            upd_s[j] = j < a.d ? a.norm.std_z[j] : 0.f;
+            upd_c[j] = j < a.d ? fmaf(p.b3[j], a.norm.std_z[j], a.norm.mean_z[j]) : 0.f;
+            asm volatile("" : "+f"(upd_s[j]), "+f"(upd_c[j]));
+        }
         for (int it = 0; it < p.iters; ++it) {
             const long long tile = (long long)it * gridDim.x + blockIdx.x;   // >= n_tiles: padding tile
             const long long k_local = tile * TM + row;
@@ -322,47 +358,48 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
             float act[SS_MAX_DA];
 #pragma unroll
             for (int j = 0; j < SS_MAX_DA; ++j) act[j] = 0.f;
+            ActionCursor cur;
+            action_cursor_init(cur);
             if (ch == 0 && live) {
 #pragma unroll
                 for (int j = 0; j < SS_MAX_DA; ++j)
-                    if (j < a.da) act[j] = fetch_action(a.act, k_local, a.k_offset + k_local, 0, j);
+                    if (j < a.da) act[j] = fetch_action_seq(a.act, cur, k_local, a.k_offset + k_local, 0, j);
             }
-            for (int t = 0; t < a.H; ++t) {
+            for (int t = 0; t < a.H; ++t, ++step_it) {
                 const int trace_it = (warp == 0 || warp == 4) ? it : 1, trace_t = t;
                 const int tb = warp == 4 ? 100 : 0;   // ch-1 warp's events live at +100
                 TC_TRACE(tb + 0);
                 // ---- layer-1 A operand: hi/lo split of the normalised (state, action) -------
+                // slot layout (static): input j -> slots 3j (x_hi * W_hi), 3j+1 (x_hi * W_lo),
+                // 3j+2 (x_lo * W_hi); bias (b_hi, b_lo) in the last two slots with a constant 1
                 if (ch == 0) {
-                    float xin[MAX_DIN];
+                    // state j -> input j (j < DZ), action j -> input DZ + j: all static; the
+                    // statistics of unused inputs are zero, so they normalise to exactly 0
+                    float xin[MAXIN];
 #pragma unroll
-                    for (int j = 0; j < MAX_DIN; ++j) xin[j] = 0.f;
+                    for (int j = 0; j < MAXIN; ++j) xin[j] = 0.f;
 #pragma unroll
-                    for (int j = 0; j < DT; ++j)
-                        if (j < a.d) xin[j] = (x[j] - a.norm.mean_x[j]) * a.norm.inv_std_x[j];
+                    for (int j = 0; j < DZ; ++j)
+                        if (j < MAXIN) xin[j] = (x[j] - a.norm.mean_x[j]) * a.norm.inv_std_x[j];
 #pragma unroll
                     for (int j = 0; j < SS_MAX_DA; ++j)
-                        if (j < a.da) {
-                            const float v = (act[j] - a.norm.mean_y[j]) * a.norm.inv_std_y[j];
+                        if (DZ + j < MAXIN) xin[DZ + j] = (act[j] - a.norm.mean_y[j]) * a.norm.inv_std_y[j];
+                    float slot[K1T];
 #pragma unroll
-                            for (int jj = 0; jj < MAX_DIN; ++jj) xin[jj] = (jj == a.d + j) ? v : xin[jj];
-                        }
-                    float slot[K1];
+                    for (int s = 0; s < K1T; ++s) slot[s] = 0.f;
 #pragma unroll
-                    for (int s = 0; s < K1; ++s) slot[s] = 0.f;
-#pragma unroll
-                    for (int j = 0; j < MAX_DIN; ++j) {
-                        const float hi = bf16_round(xin[j]);
+                    for (int j = 0; j < MAXIN; ++j) {
+                        const float hi = bf16_hi(xin[j]);
                         const float lo = xin[j] - hi;
-                        slot[3 * j] = hi;          // x_hi * W_hi
-                        slot[3 * j + 1] = hi;      // x_hi * W_lo
-                        slot[3 * j + 2] = lo;      // x_lo * W_hi
+                        slot[3 * j] = hi;
+                        slot[3 * j + 1] = hi;
+                        slot[3 * j + 2] = lo;
                     }
-                    // bias slots (b_hi, b_lo) sit right after the 3*din input slots
+                    slot[K1T - 2] = 1.f;
+                    slot[K1T - 1] = 1.f;
+                    // smem image [k/8][row][8] (K-major core matrices): K1T / 8 x 16 B per row
 #pragma unroll
-                    for (int s = 0; s < K1; ++s) slot[s] = (s == 3 * p.din || s == 3 * p.din + 1) ? 1.f : slot[s];
-                    // smem image [k/8][row][8] (K-major core matrices): 4 x 16 B per row
-#pragma unroll
-                    for (int kc = 0; kc < K1 / 8; ++kc) {
+                    for (int kc = 0; kc < K1T / 8; ++kc) {
                         uint4 v;
                         v.x = pack_bf16(slot[8 * kc], slot[8 * kc + 1]);
                         v.y = pack_bf16(slot[8 * kc + 2], slot[8 * kc + 3]);
@@ -370,90 +407,126 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                         v.w = pack_bf16(slot[8 * kc + 6], slot[8 * kc + 7]);
                         *reinterpret_cast<uint4*>(a1s + kc * (TM * 16) + row * 16) = v;
                     }
+                    TC_TRACE(60);
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic -> async proxy
+                    TC_TRACE(61);
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader(x_ready);
                 }
                 TC_TRACE(tb + 1);
                 // ---- layer-1 epilogue: relu, bf16, becomes the layer-2 A operand -------------
-                for (int c = 0; c < nch; ++c, ++acc_it) {
-                    const uint32_t slot_i = acc_it % ACC_SLOTS;
-                    mbar_wait<false>(&acc_full[slot_i], (acc_it / ACC_SLOTS) & 1);
-                    TC_TRACE(tb + 2 + c);
+                // All nch layer-1 chunks are in flight at once: odd chunks accumulate in the two
+                // accumulator slots, even chunks in the (currently dead) H1 columns [0,128) / [128,256)
+                // and are converted in place.  The bf16 destination of chunk c, [64c, 64c+64), lies
+                // inside the FP32 source of chunk c & ~1, so the two threads of a row meet at a pair
+                // barrier after loading an even chunk and before anyone stores into its columns.
+                static_assert(CPT == 64, "two 32-column TMEM loads per thread and chunk");
+                for (int c0 = 0; c0 < nch; c0 += 2) {          // one K-slab of layer 2 per iteration
+                    const uint32_t slot_i = (uint32_t)(c0 >> 1);
+                    uint32_t v0[32], v1[32], pk0[16], pk1[16];
+                    // even chunk: FP32 in the dead H1 columns, converted in place
+                    mbar_wait<false>(&l1_full[c0], step_it & 1);
+                    TC_TRACE(tb + 2 + c0);
                     tc_fence_after();
+                    tmem_ld32(lane_addr + COL_H1 + slot_i * NC + ch * CPT, v0);
+                    tmem_ld32(lane_addr + COL_H1 + slot_i * NC + ch * CPT + 32, v1);
+                    tmem_wait_ld();
+                    asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");   // both threads of the row have loaded
 #pragma unroll
-                    for (int part = 0; part < CPT / 32; ++part) {
-                        uint32_t v[32];
-                        tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * CPT + part * 32, v);
-                        uint32_t pk[16];
-#pragma unroll
-                        for (int c2 = 0; c2 < 16; ++c2)
-                            pk[c2] = pack_bf16_relu(__uint_as_float(v[2 * c2]), __uint_as_float(v[2 * c2 + 1]));
-                        tmem_st16(lane_addr + COL_H1 + c * (NC / 2) + ch * (CPT / 2) + part * 16, pk);
+                    for (int c2 = 0; c2 < 16; ++c2) {
+                        pk0[c2] = pack_bf16_relu(__uint_as_float(v0[2 * c2]), __uint_as_float(v0[2 * c2 + 1]));
+                        pk1[c2] = pack_bf16_relu(__uint_as_float(v1[2 * c2]), __uint_as_float(v1[2 * c2 + 1]));
                     }
+                    tmem_st16(lane_addr + COL_H1 + c0 * (NC / 2) + ch * (CPT / 2), pk0);
+                    tmem_st16(lane_addr + COL_H1 + c0 * (NC / 2) + ch * (CPT / 2) + 16, pk1);
+                    TC_TRACE(tb + 6 + c0);
+                    // odd chunk: FP32 in accumulator slot c0 / 2 (its stores overlap the even chunk's)
+                    mbar_wait<false>(&l1_full[c0 + 1], step_it & 1);
+                    TC_TRACE(tb + 3 + c0);
+                    tc_fence_after();
+                    tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * CPT, v0);
+                    tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * CPT + 32, v1);
+                    tmem_wait_ld();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) { mbar_arrive_leader(&acc_free[slot_i]); mbar_arrive_leader(&h1_ready[c]); }
-                    TC_TRACE(tb + 6 + c);
+                    if (lane == 0) mbar_arrive_leader(&acc_free[slot_i]);
+#pragma unroll
+                    for (int c2 = 0; c2 < 16; ++c2) {
+                        pk0[c2] = pack_bf16_relu(__uint_as_float(v0[2 * c2]), __uint_as_float(v0[2 * c2 + 1]));
+                        pk1[c2] = pack_bf16_relu(__uint_as_float(v1[2 * c2]), __uint_as_float(v1[2 * c2 + 1]));
+                    }
+                    tmem_st16(lane_addr + COL_H1 + (c0 + 1) * (NC / 2) + ch * (CPT / 2), pk0);
+                    tmem_st16(lane_addr + COL_H1 + (c0 + 1) * (NC / 2) + ch * (CPT / 2) + 16, pk1);
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) { mbar_arrive_leader(&h1_ready[c0]); mbar_arrive_leader(&h1_ready[c0 + 1]); }
+                    TC_TRACE(tb + 7 + c0);
                 }
                 // ---- off the critical path (the tensor pipe is busy with layer 2 now) ----------
                 if (ch == 1) {
                     score_row<DT>(a, t, x, sc, live, k_local, q, lane, T, sums);
                 } else if (ch == 0 && live && t + 1 < a.H) {
+                    TC_TRACE(70);
 #pragma unroll
                     for (int j = 0; j < SS_MAX_DA; ++j)
-                        if (j < a.da) act[j] = fetch_action(a.act, k_local, a.k_offset + k_local, t + 1, j);
+                        if (j < a.da) act[j] = fetch_action_seq(a.act, cur, k_local, a.k_offset + k_local, t + 1, j);
+                    TC_TRACE(71);
                 }
                 TC_TRACE(tb + 19);
                 // ---- layer-2 epilogue fused with layer 3 --------------------------------------
-                float z[DT];
+                // two hidden units per packed FFMA2: zacc[j] = (sum over even units, sum over odd units)
+                float2 zacc[DZ];
 #pragma unroll
-                for (int j = 0; j < DT; ++j) z[j] = 0.f;
-                for (int n = 0; n < nch; ++n, ++acc_it) {
-                    const uint32_t slot_i = acc_it % ACC_SLOTS;
-                    mbar_wait<false>(&acc_full[slot_i], (acc_it / ACC_SLOTS) & 1);
+                for (int j = 0; j < DZ; ++j) zacc[j] = make_float2(0.f, 0.f);
+                for (int n = 0; n < nch; ++n) {
+                    const uint32_t slot_i = (uint32_t)(n & 1);
+                    // k-th completion of this slot: (nch + 1 - slot) / 2 layer-2 chunks per step use it
+                    const uint32_t full_k = step_it * (uint32_t)((nch + 1 - (int)slot_i) >> 1) + (uint32_t)(n >> 1);
+                    mbar_wait<false>(&acc_full[slot_i], full_k & 1);
                     TC_TRACE(tb + 10 + n);
                     tc_fence_after();
-                    static_assert(CPT == 32 || CPT == 64, "one or two 32-column TMEM loads per thread and chunk");
                     uint32_t v0[32], v1[32];
                     tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * CPT, v0);
-                    if (CPT > 32) tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * CPT + 32, v1);
+                    tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * CPT + 32, v1);
+                    tmem_wait_ld();
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader(&acc_free[slot_i]);
-                    const float* wrow = w3s + (size_t)(n * NC + ch * CPT) * DTW;
+                    const float* wrow = w3s + (size_t)((n * NC + ch * CPT) / 2) * (2 * DZP);
 #pragma unroll
-                    for (int j2 = 0; j2 < CPT; ++j2) {
-                        const float hval = fmaxf(__uint_as_float(j2 < 32 ? v0[j2 & 31] : v1[j2 & 31]), 0.f);
-                        const float4 w0 = *reinterpret_cast<const float4*>(wrow + j2 * DTW);
-                        z[0] = fmaf(hval, w0.x, z[0]);
-                        if (DT > 1) z[1] = fmaf(hval, w0.y, z[1]);
-                        if (DT > 2) z[2] = fmaf(hval, w0.z, z[2]);
-                        if (DT > 3) z[3] = fmaf(hval, w0.w, z[3]);
-                        if (DT > 4) {
-                            const float4 w1 = *reinterpret_cast<const float4*>(wrow + j2 * DTW + 4);
-                            z[4] = fmaf(hval, w1.x, z[4]);
-                            if (DT > 5) z[5] = fmaf(hval, w1.y, z[5]);
-                            if (DT > 6) z[6] = fmaf(hval, w1.z, z[6]);
-                            if (DT > 7) z[7] = fmaf(hval, w1.w, z[7]);
+                    for (int j2 = 0; j2 < CPT / 2; ++j2) {
+                        const uint32_t ua = j2 < 16 ? v0[(2 * j2) & 31] : v1[(2 * j2) & 31];
+                        const uint32_t ub = j2 < 16 ? v0[(2 * j2 + 1) & 31] : v1[(2 * j2 + 1) & 31];
+                        const float2 hh = make_float2(fmaxf(__uint_as_float(ua), 0.f), fmaxf(__uint_as_float(ub), 0.f));
+                        const float* wp = wrow + j2 * (2 * DZP);
+#pragma unroll
+                        for (int jq = 0; jq < DZP / 2; ++jq) {
+                            const float4 w = *reinterpret_cast<const float4*>(wp + 4 * jq);
+                            if (2 * jq < DZ) zacc[2 * jq] = __ffma2_rn(hh, make_float2(w.x, w.y), zacc[2 * jq]);
+                            if (2 * jq + 1 < DZ)
+                                zacc[2 * jq + 1] = __ffma2_rn(hh, make_float2(w.z, w.w), zacc[2 * jq + 1]);
                         }
                     }
                     TC_TRACE(tb + 14 + n);
                 }
                 // ---- the two column halves exchange partial sums; both update the state ---------
 #pragma unroll
-                for (int j = 0; j < DT; ++j) zx[(ch * TM + row) * 8 + j] = z[j];
+                for (int j = 0; j < DZ; ++j) zx[(j * TPR + ch) * TM + row] = zacc[j].x + zacc[j].y;
+                TC_TRACE(tb + 62);
                 asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");
+                TC_TRACE(tb + 63);
 #pragma unroll
-                for (int j = 0; j < DT; ++j)
-                    if (j < a.d) {
-                        // fixed order (half 0 + half 1) so both copies stay bit-identical
-                        float zz = zx[row * 8 + j];
+                for (int j = 0; j < DZ; ++j) {
+                    // fixed order (half 0 + half 1) so both copies stay bit-identical; dimensions
+                    // >= d have zero weights and zero constants: x stays 0
+                    float zz = zx[(j * TPR) * TM + row];
 #pragma unroll
-                        for (int o = 1; o < TPR; ++o) zz += zx[(o * TM + row) * 8 + j];
-                        zz += p.b3[j];
-                        x[j] += fmaf(zz, a.norm.std_z[j], a.norm.mean_z[j]);
-                    }
+                    for (int o = 1; o < TPR; ++o) zz += zx[(j * TPR + o) * TM + row];
+                    x[j] += fmaf(zz, upd_s[j], upd_c[j]);
+                }
+                // (zx is rewritten only after the next step's layer-2 MMAs, which every row warp of
+                // the pair has to enable through h1_ready: no second barrier needed)
                 TC_TRACE(tb + 18);
             }
             if (ch == 1) {
@@ -467,34 +540,65 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
             // the whole warp walks the loop (warp-uniform control flow); one elected lane issues
             // every MMA of the pair (cta_group::2: rows 0-127 in this CTA's TMEM, 128-255 in the
             // peer's; B halves are read from both CTAs' shared memory at the same offset)
-            uint32_t acc_it = 0, w2_it = 0, step_it = 0;
+            // uses of accumulator slot s per step: one layer-1 chunk (c = 2s + 1, if it exists) and
+            // the layer-2 chunks n with n & 1 == s; the k-th use waits for the (k-1)-th drain
+            uint32_t w2_it = 0, step_it = 0;
+            const uint32_t l1_use[ACC_SLOTS] = {1 < nch ? 1u : 0u, 3 < nch ? 1u : 0u};
+            const uint32_t use_per_step[ACC_SLOTS] = {l1_use[0] + (uint32_t)((nch + 1) >> 1),
+                                                      l1_use[1] + (uint32_t)(nch >> 1)};
             const uint32_t a1_addr = smem_u32(a1s), w1_addr = smem_u32(w1s), ring_addr = smem_u32(w2_ring);
+            // layer-1 operands never change: build the descriptors once and pin them in registers
+            // (the uniform-datapath arithmetic ptxas would otherwise redo per step sits on the
+            // critical path between x_ready and the first layer-1 MMA)
+            constexpr int NCH_MAX = HP_MAX / NC;
+            uint64_t l1_a[K1T / 16], l1_b[NCH_MAX][K1T / 16];
+            uint32_t l1_d[NCH_MAX], l1_bar[NCH_MAX];
+#pragma unroll
+            for (int ks = 0; ks < K1T / 16; ++ks) {
+                l1_a[ks] = make_desc(a1_addr + ks * 2 * (TM * 16), TM);
+                asm volatile("" : "+l"(l1_a[ks]));
+            }
+#pragma unroll
+            for (int c = 0; c < NCH_MAX; ++c) {
+#pragma unroll
+                for (int ks = 0; ks < K1T / 16; ++ks) {
+                    l1_b[c][ks] = make_desc(w1_addr + c * W1_CHUNK_BYTES + ks * 2 * (NH * 16), NH);
+                    asm volatile("" : "+l"(l1_b[c][ks]));
+                }
+                l1_d[c] = tmem + ((c & 1) ? COL_ACC : COL_H1) + (uint32_t)(c >> 1) * NC;
+                l1_bar[c] = smem_u32(&l1_full[c]);
+                asm volatile("" : "+r"(l1_d[c]), "+r"(l1_bar[c]));
+            }
             for (int it = 0; it < p.iters; ++it) {
                 for (int t = 0; t < a.H; ++t, ++step_it) {
                     const int trace_it = it, trace_t = t;
+                    // layer 1: chunk c = A1 [256 x K1T] * W1img[c] [128 x K1T]^T; odd chunks go to the
+                    // accumulator slots (once the previous step's layer-2 epilogue drained them --
+                    // long before x_ready, so these ~90-cycle waits are taken off the critical path),
+                    // even chunks to the dead H1 columns -- all issued back to back
+#pragma unroll
+                    for (int sl = 0; sl < ACC_SLOTS; ++sl)
+                        if (l1_use[sl]) mbar_wait<true>(&acc_free[sl], ((step_it * use_per_step[sl]) & 1) ^ 1);
                     mbar_wait<true>(x_ready, step_it & 1);
                     TC_TRACE(20);
                     tc_fence_after();
-                    // layer 1: acc chunk c = A1 [256 x 32] * W1img[c] [128 x 32]^T
-                    for (int c = 0; c < nch; ++c, ++acc_it) {
-                        const uint32_t slot_i = acc_it % ACC_SLOTS;
-                        mbar_wait<true>(&acc_free[slot_i], ((acc_it / ACC_SLOTS) & 1) ^ 1);
-                        tc_fence_after();
-                        if (elect_one()) {
-                            const uint32_t d_tmem = tmem + COL_ACC + slot_i * NC;
+                    if (elect_one()) {
 #pragma unroll
-                            for (int ks = 0; ks < K1 / 16; ++ks)
-                                umma2_ss(d_tmem, make_desc(a1_addr + ks * 2 * (TM * 16), TM),
-                                         make_desc(w1_addr + c * W1_CHUNK_BYTES + ks * 2 * (NH * 16), NH), IDESC, ks);
-                            tc_commit_pair(&acc_full[slot_i]);
-                        }
-                        __syncwarp();
-                        TC_TRACE(21 + c);
+                        for (int c = 0; c < NCH_MAX; ++c)
+                            if (c < nch) {
+#pragma unroll
+                                for (int ks = 0; ks < K1T / 16; ++ks) umma2_ss(l1_d[c], l1_a[ks], l1_b[c][ks], IDESC, ks);
+                                tc_commit_pair_addr(l1_bar[c]);
+                            }
                     }
+                    __syncwarp();
+                    TC_TRACE(21);
                     // layer 2: acc chunk n = H1 [256 x HP] * W2img[n] [128 x HP]^T, K streamed in slabs
-                    for (int n = 0; n < nch; ++n, ++acc_it) {
-                        const uint32_t slot_i = acc_it % ACC_SLOTS;
-                        mbar_wait<true>(&acc_free[slot_i], ((acc_it / ACC_SLOTS) & 1) ^ 1);
+                    for (int n = 0; n < nch; ++n) {
+                        const uint32_t slot_i = (uint32_t)(n & 1);
+                        const uint32_t free_k = slot_i ? step_it * use_per_step[1] + l1_use[1] + (uint32_t)(n >> 1)
+                                                       : step_it * use_per_step[0] + l1_use[0] + (uint32_t)(n >> 1);
+                        mbar_wait<true>(&acc_free[slot_i], (free_k & 1) ^ 1);
                         TC_TRACE(41 + n);
                         for (int ksl = 0; ksl < nslab; ++ksl, ++w2_it) {
                             const uint32_t st = w2_it % NSTAGE;
@@ -558,6 +662,8 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
     __syncthreads();
     cluster_sync_all();                  // no CTA leaves while its peer may still read / signal it
     tc_fence_after();
+    if (p.prof && blockIdx.x == 0)
+        for (int i = tid; i < 3 * 256; i += THREADS) p.prof[i] = trace_s[i];
     if (a.partial_sums)
         for (int o = tid; o < 2 * T; o += THREADS)
             a.partial_sums[(size_t)blockIdx.x * 2 * T + o] =
@@ -582,26 +688,31 @@ static float bf16_val(uint16_t b) {
 }
 
 static size_t smem_bytes(int T, int d) {
-    return (d <= 4 ? SmemT<4>::SUMS : SmemT<8>::SUMS) + (size_t)4 * T * 2 * 8 + 128;
+    const int dz = dz_of(d);
+    const size_t base = dz == 2 ? SmemT<2>::SUMS : (dz <= 4 ? SmemT<4>::SUMS : SmemT<8>::SUMS);
+    return base + (size_t)4 * T * 2 * 8 + 128;
 }
 
 }  // namespace tc
 
 bool mpc_tc_shape_supported(const ss_ctx* c) {
     // two hidden layers, hidden width + the two constant-one bias units within 512, small I/O dims
-    return c->L == 2 && c->h >= 64 && c->h + 2 <= tc::HP_MAX && c->d <= 8 && c->d + c->da <= tc::MAX_DIN;
+    return c->L == 2 && c->h >= 64 && c->h + 2 <= tc::HP_MAX && c->d <= 8 && tc::dz_of(c->d) + c->da <= tc::MAX_DIN;
 }
 
 int mpc_tc_prepare(ss_ctx* c) {
     using namespace tc;
     const int h = c->h, d = c->d, din = c->d + c->da;
+    const int k1 = k1_slots(d, c->da), dz = dz_of(d);
+    const int W1_CHUNK_BYTES = NH * k1 * 2;
     const int hp = (h + 2 + KSLAB - 1) / KSLAB * KSLAB;
     const int nch = hp / NC, nslab = hp / KSLAB;
     const std::vector<double>&W1 = c->hw[0], &W2 = c->hw[1], &W3 = c->hw[2];
     const std::vector<double>&B1 = c->hb[0], &B2 = c->hb[1];
     // Every B tile is split by output unit over the CTA pair: units [128 c + 64 r, +64) of chunk c
     // live in CTA r.  Images are [k/8][64 units][8 k] (K-major, no-swizzle core matrices).
-    // layer-1 image: K slots (3j, 3j+1, 3j+2) = (W_hi, W_lo, W_hi) of input j; then (b_hi, b_lo)
+    // layer-1 image: K slots (3j, 3j+1, 3j+2) = (W_hi, W_lo, W_hi) of input j; (b_hi, b_lo) in the
+    // last two of the k1 slots
     std::vector<uint16_t> w1((size_t)CLUSTER * nch * (W1_CHUNK_BYTES / 2), 0);
     auto w1_at = [&](int slot, int u) -> uint16_t& {
         const int cidx = u / NC, r = (u % NC) / NH, nn = u % NH;
@@ -611,18 +722,19 @@ int mpc_tc_prepare(ss_ctx* c) {
         for (int j = 0; j < din; ++j) {
             const float w = (float)W1[(size_t)j * h + u];
             const uint16_t hi = bf16_bits(w), lo = bf16_bits(w - bf16_val(hi));
-            w1_at(3 * j, u) = hi;
-            w1_at(3 * j + 1, u) = lo;
-            w1_at(3 * j + 2, u) = hi;
+            const int in = j < d ? j : dz + (j - d);      // input slot of network input j
+            w1_at(3 * in, u) = hi;
+            w1_at(3 * in + 1, u) = lo;
+            w1_at(3 * in + 2, u) = hi;
         }
         const float b = (float)B1[u];
         const uint16_t hi = bf16_bits(b), lo = bf16_bits(b - bf16_val(hi));
-        w1_at(3 * din, u) = hi;
-        w1_at(3 * din + 1, u) = lo;
+        w1_at(k1 - 2, u) = hi;
+        w1_at(k1 - 1, u) = lo;
     }
     // constant-one hidden units h and h+1 (carry the layer-2 bias through the GEMM)
-    w1_at(3 * din, h) = bf16_bits(1.f);
-    w1_at(3 * din, h + 1) = bf16_bits(1.f);
+    w1_at(k1 - 2, h) = bf16_bits(1.f);
+    w1_at(k1 - 2, h + 1) = bf16_bits(1.f);
     // layer-2 image: blocks (n, kslab, cta) of [16 k-chunks][64 units][8 k]
     std::vector<uint16_t> w2((size_t)nch * nslab * CLUSTER * (STAGE_BYTES / 2), 0);
     auto w2_at = [&](int k, int u) -> uint16_t& {
@@ -637,11 +749,11 @@ int mpc_tc_prepare(ss_ctx* c) {
         w2_at(h, u) = hi;
         w2_at(h + 1, u) = lo;
     }
-    // layer 3 (FP32, in shared memory): [hp][DTW]
-    const int dtw = d <= 4 ? 4 : 8;
-    std::vector<float> w3((size_t)hp * dtw, 0.f);
+    // layer 3 (FP32, in shared memory): [hp / 2 (unit pairs)][dzp outputs][2 units] for FFMA2
+    const int dzp = w3_pair_floats(dz) / 2;
+    std::vector<float> w3((size_t)hp * dzp, 0.f);
     for (int u = 0; u < h; ++u)
-        for (int j = 0; j < d; ++j) w3[(size_t)u * dtw + j] = (float)W3[(size_t)u * d + j];
+        for (int j = 0; j < d; ++j) w3[((size_t)(u / 2) * dzp + j) * 2 + (u & 1)] = (float)W3[(size_t)u * d + j];
     SS_CUDA_CHECK(c, c->tc_w1.ensure(w1.size() * 2));
     SS_CUDA_CHECK(c, c->tc_w2.ensure(w2.size() * 2));
     SS_CUDA_CHECK(c, c->tc_w3.ensure(w3.size() * 4));
@@ -684,7 +796,7 @@ int mpc_tc_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out) {
     const int grid = mpc_tc_grid(c, a);
     if (grid_blocks_out) *grid_blocks_out = grid;
     p.iters = (int)((p.n_tiles + grid - 1) / grid);
-    const size_t smem = smem_bytes(a.H + 1, a.d);
+    const size_t smem = smem_bytes(a.H + 1, a.d) + (p.prof ? 3 * 256 * 8 : 0);
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);
@@ -699,13 +811,18 @@ int mpc_tc_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e;
-    if (a.d <= 4) {
-        e = cudaFuncSetAttribute(mpc_rollout_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, mpc_rollout_tc_kernel<4>, a, p);
-    } else {
-        e = cudaFuncSetAttribute(mpc_rollout_tc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, mpc_rollout_tc_kernel<8>, a, p);
-    }
+    const int dz = dz_of(a.d), k1 = k1_slots(a.d, a.da);
+#define TC_LAUNCH(DT_, DZ_, K1_)                                                                              \
+    do {                                                                                                      \
+        e = cudaFuncSetAttribute(mpc_rollout_tc_kernel<DT_, DZ_, K1_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 (int)smem);                                                                  \
+        if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, mpc_rollout_tc_kernel<DT_, DZ_, K1_>, a, p);       \
+    } while (0)
+    if (dz == 2 && k1 == 16) TC_LAUNCH(4, 2, 16);          // e.g. MountainCar (d = 2, da = 1)
+    else if (dz == 3 && k1 == 16) TC_LAUNCH(4, 3, 16);     // e.g. Pendulum (d = 3, da = 1)
+    else if (dz <= 4) TC_LAUNCH(4, 4, 32);
+    else TC_LAUNCH(8, 8, 32);
+#undef TC_LAUNCH
     if (e == cudaSuccess) e = cudaGetLastError();
     c->launches++;
     SS_CUDA_CHECK(c, e);
@@ -725,6 +842,8 @@ int mpc_tc_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out) {
             fprintf(stderr, " | L2 epi_done");
             for (int c2 = 0; c2 < 4; ++c2) fprintf(stderr, " %llu", ev[14 + c2] - t0);
             fprintf(stderr, " | step_end %llu\n", ev[18] - t0);
+            fprintf(stderr, "[trace step %d] detail: slots_stored %llu fence_done %llu | zx_stored %llu (ch1 %llu) bar_done %llu (ch1 %llu) | prefetch %llu .. %llu\n",
+                    10 + st2, ev[60] - t0, ev[61] - t0, ev[62] - t0, ev[162] - t0, ev[63] - t0, ev[163] - t0, ev[70] - t0, ev[71] - t0);
             fprintf(stderr, "[trace step %d] mma: x_ready %llu | L1 issued", 10 + st2, ev[20] - t0);
             for (int c2 = 0; c2 < 4; ++c2) fprintf(stderr, " %llu", ev[21 + c2] - t0);
             fprintf(stderr, " | L2 slab issued");
