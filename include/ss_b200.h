@@ -159,6 +159,15 @@ int ss_mpc_rollout(ss_ctx* ctx, const double* state, int wp_index,
                    int penalty_mode, int precision);
 int ss_mpc_projection_sums(ss_ctx* ctx, double** sums_dev, int* count);
 int ss_mpc_finish(ss_ctx* ctx, int64_t* out_best_k, double* out_best_score, double* out_scores);
+/* ss_mpc_finish_package: ss_mpc_finish + the local winner's action sequence and predicted path
+ * (NND_MB_agent.py:516-518), all left in DEVICE memory as one float64 package
+ *   [best_score, best_k (global, as double), best_sequence (H*da), best_path ((H+1)*d)]
+ * without a host synchronisation (reference penalty mode; per-sample mode re-rolls the winner
+ * and therefore synchronises once).  Multi-GPU callers all-gather the packages and pick with
+ * np.argmax ordering -- one collective and one device->host copy per decision.  want_path = 0
+ * leaves the sequence / path part zero.  ss_mpc_read_package copies it to the host. */
+int ss_mpc_finish_package(ss_ctx* ctx, int want_path, double** package_dev, int* count);
+int ss_mpc_read_package(ss_ctx* ctx, double* out_package, int count);
 /* roll out ONE sequence of the last ss_mpc_rollout batch again (the global winner) in FP32 and
  * return its actions [H, da] and predicted path [H+1, d] (NND_MB_agent.py:516-518) */
 int ss_mpc_replay(ss_ctx* ctx, int64_t k_global, double* out_sequence, double* out_path);

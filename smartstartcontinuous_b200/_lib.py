@@ -49,6 +49,8 @@ SIGNATURES = {
                                  C.c_int, C.c_int]),
     "ss_mpc_projection_sums": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _c_int_p]),
     "ss_mpc_finish": (C.c_int, [C.c_void_p, _c_int64_p, _c_double_p, C.c_void_p]),
+    "ss_mpc_finish_package": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), _c_int_p]),
+    "ss_mpc_read_package": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "ss_mpc_get_states": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ss_mpc_replay": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ss_mpc_sample_actions": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_uint64,

@@ -88,6 +88,12 @@ struct ss_ctx {
     std::string err;
     int64_t launches = 0;
     PhaseTimer timer;
+    // second stream + events: host action samples are uploaded in chunks while earlier chunks
+    // are already rolling (ss_mpc_rollout)
+    cudaStream_t copy_stream = nullptr;
+    static constexpr int MAX_COPY_CHUNKS = 8;
+    cudaEvent_t copy_ev[MAX_COPY_CHUNKS + 1] = {};
+    bool copy_ready = false;
 
     // ---- KDE scratch
     DevBuf kde_data64, kde_q64, kde_vals, kde_pts, kde_qw, kde_partial, kde_fit, kde_moments;
@@ -111,7 +117,9 @@ struct ss_ctx {
     float inv_radii[SS_MAX_D];
     // ---- MPC run state
     DevBuf mpc_actions64, mpc_states, mpc_scores, mpc_partial_sums, mpc_sums, mpc_block_best,
-        mpc_result, mpc_replay, mpc_sampled;
+        mpc_result, mpc_replay, mpc_sampled, mpc_package;
+    double gpow_gamma = -1.0;          // gamma^t table currently resident in mpc_replay
+    int gpow_T = 0;
     struct {
         bool valid = false;
         int64_t K_local = 0, k_offset = 0, K_global = 0;
@@ -120,6 +128,7 @@ struct ss_ctx {
         float state[SS_MAX_D];
         ActionSource act;
         bool states_stored = false;
+        bool finished = false;         // the reference-mode penalty pass has rewritten the scores
         int sum_blocks = 0;
     } run;
 };

@@ -25,10 +25,39 @@ __global__ void sample_actions_kernel(ActionSource src, long long K, long long k
     }
 }
 
-__global__ void gather_path_kernel(const float* __restrict__ states, long long K, long long k, int T,
+// rows: [T][K][d + 1] (state, waypoint index) -> out [T][d]
+__global__ void gather_path_kernel(const float* __restrict__ rows, long long K, long long k, int T,
                                    int d, float* __restrict__ out) {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o < T * d) out[o] = states[((size_t)(o / d) * K + k) * d + (o % d)];
+    if (o < T * d) out[o] = rows[((size_t)(o / d) * K + k) * (d + 1) + (o % d)];
+}
+
+// package = [best_score, best_k, sequence (H*da), path (T*d)] of the arg-max result `res`.
+// rows: trajectory rows [T][K_rows][d + 1]; fixed_row >= 0 selects that row (re-rolled winner),
+// otherwise the winner's local row best_k - k_offset.
+__global__ void package_kernel(const MpcResult* __restrict__ res, const float* __restrict__ rows, long long K_rows,
+                               long long fixed_row, long long k_offset, int T, int d, ActionSource act, int want_path,
+                               double* __restrict__ pkg) {
+    const long long k = res->best_k;
+    const long long kl = k - k_offset;
+    const int n_seq = act.H * act.da, n_path = T * d;
+    if (threadIdx.x == 0) {
+        pkg[0] = res->best_score;
+        pkg[1] = (double)k;
+    }
+    for (int o = threadIdx.x; o < n_seq + n_path; o += blockDim.x) {
+        double v = 0.0;
+        if (want_path && k >= 0) {
+            if (o < n_seq) {
+                v = (double)fetch_action(act, kl, k, o / act.da, o % act.da);
+            } else {
+                const int q = o - n_seq;
+                const long long row = fixed_row >= 0 ? fixed_row : kl;
+                v = (double)rows[((size_t)(q / d) * K_rows + row) * (d + 1) + (q % d)];
+            }
+        }
+        pkg[2 + o] = v;
+    }
 }
 
 int fill_action_source(ss_ctx* c, ActionSource& s, int H, int da, uint64_t seed, const double* low,
@@ -215,6 +244,7 @@ extern "C" int ss_mpc_rollout(ss_ctx* c, const double* state, int wp_index, int6
 
     auto& r = c->run;
     r.valid = false;
+    r.finished = false;
     r.K_local = K_local; r.k_offset = k_offset; r.K_global = K_global; r.H = H;
     r.wp_index = wp_index; r.penalty_mode = penalty_mode; r.precision = precision;
     r.gamma = gamma; r.hpf = hpf;
@@ -222,20 +252,57 @@ extern "C" int ss_mpc_rollout(ss_ctx* c, const double* state, int wp_index, int6
     int rc = fill_action_source(c, r.act, H, c->da, seed, act_low, act_high);
     if (rc) return rc;
     const int T = H + 1;
+    // Host-provided samples: upload in chunks on a second stream while earlier chunks already roll
+    // (tcgen05 path, batches of at least two waves of tiles); chunk boundaries are whole waves so
+    // no launch ends on a partial wave except the last one.
+    int n_chunks = 0;
+    long long chunk_tile[ss_ctx::MAX_COPY_CHUNKS + 1] = {0};
     if (actions) {
         const size_t n = (size_t)K_local * H * c->da;
         SS_CUDA_CHECK(c, c->mpc_actions64.ensure(n * 8));
-        SS_CUDA_CHECK(c, cudaMemcpyAsync(c->mpc_actions64.p, actions, n * 8, cudaMemcpyHostToDevice, c->stream));
         r.act.host_actions = c->mpc_actions64.as<double>();
+        const long long tiles = (K_local + mpc_tc_tile_rows() - 1) / mpc_tc_tile_rows();
+        const long long wave = mpc_tc_grid(c, tiles);
+        if (precision == SS_PRECISION_BF16_TC && tiles >= 2 * wave) {
+            if (!c->copy_ready) {
+                SS_CUDA_CHECK(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+                for (int i = 0; i <= ss_ctx::MAX_COPY_CHUNKS; ++i)
+                    SS_CUDA_CHECK(c, cudaEventCreateWithFlags(&c->copy_ev[i], cudaEventDisableTiming));
+                c->copy_ready = true;
+            }
+            // first chunk one wave (start rolling early), then two waves per chunk
+            const long long waves = (tiles + wave - 1) / wave;
+            long long per = 2;
+            while (1 + (waves - 1 + per - 1) / per > ss_ctx::MAX_COPY_CHUNKS) ++per;
+            chunk_tile[0] = 0;
+            for (long long w = 1; w < waves; w += per) chunk_tile[++n_chunks] = w * wave;
+            chunk_tile[++n_chunks] = tiles;
+            // the staging buffer may still be read by earlier work on the compute stream
+            SS_CUDA_CHECK(c, cudaEventRecord(c->copy_ev[ss_ctx::MAX_COPY_CHUNKS], c->stream));
+            SS_CUDA_CHECK(c, cudaStreamWaitEvent(c->copy_stream, c->copy_ev[ss_ctx::MAX_COPY_CHUNKS], 0));
+            const size_t row_elems = (size_t)H * c->da;
+            for (int i = 0; i < n_chunks; ++i) {
+                const size_t r0 = (size_t)chunk_tile[i] * mpc_tc_tile_rows();
+                size_t r1 = (size_t)chunk_tile[i + 1] * mpc_tc_tile_rows();
+                if (r1 > (size_t)K_local) r1 = (size_t)K_local;
+                SS_CUDA_CHECK(c, cudaMemcpyAsync(c->mpc_actions64.as<double>() + r0 * row_elems, actions + r0 * row_elems,
+                                                 (r1 - r0) * row_elems * 8, cudaMemcpyHostToDevice, c->copy_stream));
+                SS_CUDA_CHECK(c, cudaEventRecord(c->copy_ev[i], c->copy_stream));
+            }
+        } else {
+            SS_CUDA_CHECK(c, cudaMemcpyAsync(c->mpc_actions64.p, actions, n * 8, cudaMemcpyHostToDevice, c->stream));
+        }
     }
-    // gamma^t table (float64 pow, rounded once) + state0 for the second pass
-    {
-        std::vector<float> misc(T + SS_MAX_D);
+    // gamma^t table (float64 pow, rounded once); re-uploaded only when gamma or the horizon change
+    if (c->gpow_gamma != gamma || c->gpow_T != T || !c->mpc_replay.p) {
+        std::vector<float> misc(T);
         for (int t = 0; t < T; ++t) misc[t] = (float)std::pow(gamma, (double)t);
-        for (int j = 0; j < SS_MAX_D; ++j) misc[T + j] = r.state[j];
-        SS_CUDA_CHECK(c, c->mpc_replay.ensure((size_t)(T + SS_MAX_D) * 4 + (size_t)T * SS_MAX_D * 4));
+        // [gamma^t (T) | pad | replay rows T x (d+1) | replay path T x d]
+        SS_CUDA_CHECK(c, c->mpc_replay.ensure((size_t)(T + SS_MAX_D + 4) * 4 + (size_t)T * (2 * SS_MAX_D + 1) * 4));
         SS_CUDA_CHECK(c, cudaMemcpyAsync(c->mpc_replay.p, misc.data(), misc.size() * 4, cudaMemcpyHostToDevice, c->stream));
         SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        c->gpow_gamma = gamma;
+        c->gpow_T = T;
     }
     const float* gpow = c->mpc_replay.as<float>();
 
@@ -255,20 +322,26 @@ extern "C" int ss_mpc_rollout(ss_ctx* c, const double* state, int wp_index, int6
     if (ref) {
         // reference penalty: the rollout kernel only spills the trajectories; the projection sums
         // and the scores come from two light passes over them (mpc_score.cu)
-        SS_CUDA_CHECK(c, c->mpc_states.ensure((size_t)T * K_local * c->d * 4));
+        SS_CUDA_CHECK(c, c->mpc_states.ensure((size_t)T * K_local * traj_row_stride(c->d) * 4));
         SS_CUDA_CHECK(c, c->mpc_partial_sums.ensure((size_t)sum_blocks * T * 2 * 8));
         SS_CUDA_CHECK(c, c->mpc_sums.ensure((size_t)T * 2 * 8));
         a.states_out = c->mpc_states.as<float>();
-        a.partial_sums = nullptr;
     }
     timer_mark(c, "mpc_setup");
     int grid = 0;
-    rc = precision == SS_PRECISION_BF16_TC ? mpc_tc_launch(c, a, &grid) : mpc_simt_launch(c, a, &grid);
-    if (rc) return rc;
+    if (n_chunks > 0) {
+        for (int i = 0; i < n_chunks; ++i) {
+            SS_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, c->copy_ev[i], 0));
+            rc = mpc_tc_launch(c, a, &grid, chunk_tile[i], chunk_tile[i + 1] - chunk_tile[i]);
+            if (rc) return rc;
+        }
+    } else {
+        rc = precision == SS_PRECISION_BF16_TC ? mpc_tc_launch(c, a, &grid) : mpc_simt_launch(c, a, &grid);
+        if (rc) return rc;
+    }
     timer_mark(c, "mpc_rollout");
     if (ref) {
-        rc = mpc_sums_reference(c, a.plan, wp_index, gpow + T, c->mpc_states.as<float>(), K_local, T,
-                                c->mpc_partial_sums.as<double>());
+        rc = mpc_sums_reference(c, a.plan, c->mpc_states.as<float>(), K_local, T, c->mpc_partial_sums.as<double>());
         if (rc) return rc;
         rc = mpc_reduce_sums(c, c->mpc_partial_sums.as<double>(), sum_blocks, T, c->mpc_sums.as<double>());
         if (rc) return rc;
@@ -292,21 +365,22 @@ extern "C" int ss_mpc_projection_sums(ss_ctx* c, double** sums_dev, int* count) 
     return SS_OK;
 }
 
-extern "C" int ss_mpc_finish(ss_ctx* c, int64_t* out_best_k, double* out_best_score, double* out_scores) {
-    if (!c) return SS_EINVAL;
+// phase B on the device: reference-mode penalty pass + arg-max -> c->mpc_result (no host sync)
+static int finish_device(ss_ctx* c) {
     auto& r = c->run;
     if (!r.valid) SS_FAIL(c, SS_ESTATE, "mpc: ss_mpc_finish without ss_mpc_rollout");
     SS_CUDA_CHECK(c, cudaSetDevice(c->device));
     const int T = r.H + 1;
     const float* gpow = c->mpc_replay.as<float>();
     int rc;
-    if (r.penalty_mode == SS_PENALTY_REFERENCE) {
+    if (r.penalty_mode == SS_PENALTY_REFERENCE && !r.finished) {
         PlanView p = make_plan_view(c, gpow, r.gamma, r.hpf);
-        rc = mpc_score_reference(c, p, r.wp_index, gpow + T, c->mpc_states.as<float>(), r.K_local, T,
-                                 c->mpc_sums.as<double>(), c->mpc_scores.as<float>());
+        rc = mpc_score_reference(c, p, c->mpc_states.as<float>(), r.K_local, T, c->mpc_sums.as<double>(),
+                                 c->mpc_scores.as<float>());
         if (rc) return rc;
         timer_mark(c, "mpc_score_pass2");
     }
+    r.finished = true;      // the second pass rewrites the scores in place: run it once per rollout
     SS_CUDA_CHECK(c, c->mpc_block_best.ensure(1024 * 16));
     if (!c->mpc_result.p) {
         SS_CUDA_CHECK(c, c->mpc_result.ensure(sizeof(MpcResult)));
@@ -317,6 +391,14 @@ extern "C" int ss_mpc_finish(ss_ctx* c, int64_t* out_best_k, double* out_best_sc
                     reinterpret_cast<long long*>(bv + 1024), c->mpc_result.p);
     if (rc) return rc;
     timer_mark(c, "mpc_argmax");
+    return SS_OK;
+}
+
+extern "C" int ss_mpc_finish(ss_ctx* c, int64_t* out_best_k, double* out_best_score, double* out_scores) {
+    if (!c) return SS_EINVAL;
+    auto& r = c->run;
+    int rc = finish_device(c);
+    if (rc) return rc;
     MpcResult h;
     SS_CUDA_CHECK(c, cudaMemcpyAsync(&h, c->mpc_result.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     std::vector<float> sc;
@@ -332,6 +414,52 @@ extern "C" int ss_mpc_finish(ss_ctx* c, int64_t* out_best_k, double* out_best_sc
     return SS_OK;
 }
 
+static int reroll_winner(ss_ctx* c, int64_t k_global, float* rows_dev);
+
+extern "C" int ss_mpc_finish_package(ss_ctx* c, int want_path, double** package_dev, int* count) {
+    if (!c) return SS_EINVAL;
+    auto& r = c->run;
+    int rc = finish_device(c);
+    if (rc) return rc;
+    const int T = r.H + 1, d = c->d, da = c->da;
+    const int n = 2 + r.H * da + T * d;
+    SS_CUDA_CHECK(c, c->mpc_package.ensure((size_t)n * 8));
+    const float* rows = c->mpc_states.as<float>();
+    long long K_rows = r.K_local, fixed_row = -1;
+    if (want_path && !r.states_stored) {
+        // per-sample mode keeps no trajectories: fetch the winner's index and re-roll that one
+        // sequence with the kernel family that scored it
+        MpcResult h;
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(&h, c->mpc_result.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        float* rows_dev = c->mpc_replay.as<float>() + (T + SS_MAX_D + 3) / 4 * 4;
+        rc = reroll_winner(c, h.best_k, rows_dev);
+        if (rc) return rc;
+        rows = rows_dev;
+        K_rows = 1;
+        fixed_row = 0;
+    }
+    package_kernel<<<1, 256, 0, c->stream>>>(reinterpret_cast<const MpcResult*>(c->mpc_result.p), rows, K_rows,
+                                             fixed_row, r.k_offset, T, d, r.act, want_path,
+                                             c->mpc_package.as<double>());
+    c->launches++;
+    SS_CUDA_CHECK(c, cudaGetLastError());
+    timer_mark(c, "mpc_package");
+    if (package_dev) *package_dev = c->mpc_package.as<double>();
+    if (count) *count = n;
+    return SS_OK;
+}
+
+extern "C" int ss_mpc_read_package(ss_ctx* c, double* out_package, int count) {
+    if (!c) return SS_EINVAL;
+    if (!out_package || count < 2 || (size_t)count * 8 > c->mpc_package.cap)
+        SS_FAIL(c, SS_EINVAL, "mpc: bad package buffer");
+    SS_CUDA_CHECK(c, cudaSetDevice(c->device));
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(out_package, c->mpc_package.p, (size_t)count * 8, cudaMemcpyDeviceToHost, c->stream));
+    SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return SS_OK;
+}
+
 extern "C" int ss_mpc_get_states(ss_ctx* c, double* out_states) {
     if (!c) return SS_EINVAL;
     auto& r = c->run;
@@ -339,12 +467,37 @@ extern "C" int ss_mpc_get_states(ss_ctx* c, double* out_states) {
         SS_FAIL(c, SS_ESTATE, "mpc: no stored trajectories (roll out in reference penalty mode first)");
     if (!out_states) SS_FAIL(c, SS_EINVAL, "mpc: null output");
     SS_CUDA_CHECK(c, cudaSetDevice(c->device));
-    const size_t n = (size_t)(r.H + 1) * r.K_local * c->d;
-    std::vector<float> tmp(n);
-    SS_CUDA_CHECK(c, cudaMemcpyAsync(tmp.data(), c->mpc_states.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    const size_t rows = (size_t)(r.H + 1) * r.K_local;
+    const int d = c->d, rs = traj_row_stride(d);
+    std::vector<float> tmp(rows * rs);
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(tmp.data(), c->mpc_states.p, tmp.size() * 4, cudaMemcpyDeviceToHost, c->stream));
     SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-    for (size_t i = 0; i < n; ++i) out_states[i] = (double)tmp[i];
+    for (size_t i = 0; i < rows; ++i)
+        for (int j = 0; j < d; ++j) out_states[i * d + j] = (double)tmp[i * rs + j];
     return SS_OK;
+}
+
+// re-roll ONE sequence of the last batch (global index) into rows_dev [T][1][d + 1]
+static int reroll_winner(ss_ctx* c, int64_t k_global, float* rows_dev) {
+    auto& r = c->run;
+    const int da = c->da;
+    const int64_t k_local = k_global - r.k_offset;
+    const bool mine = k_local >= 0 && k_local < r.K_local;
+    if (r.act.host_actions && !mine)
+        SS_FAIL(c, SS_EINVAL, "mpc: host-provided actions of another shard cannot be replayed here");
+    const float* gpow = c->mpc_replay.as<float>();
+    RolloutArgs a;
+    std::memset(&a, 0, sizeof(a));
+    fill_model_args(c, a);
+    a.act = r.act;
+    if (a.act.host_actions) a.act.host_actions += (size_t)k_local * r.H * da;
+    a.plan = make_plan_view(c, gpow, r.gamma, r.hpf);
+    for (int j = 0; j < SS_MAX_D; ++j) a.state0[j] = r.state[j];
+    a.wp_index = r.wp_index; a.H = r.H; a.K_local = 1; a.k_offset = k_global;
+    a.per_sample = 1;
+    a.states_out = rows_dev;
+    // a 1-row tile on the tcgen05 kernel costs H * ~7 us; the FP32 kernel serves the other shapes
+    return r.precision == SS_PRECISION_BF16_TC ? mpc_tc_launch(c, a, nullptr) : mpc_simt_launch(c, a, nullptr);
 }
 
 extern "C" int ss_mpc_replay(ss_ctx* c, int64_t k_global, double* out_sequence, double* out_path) {
@@ -356,21 +509,8 @@ extern "C" int ss_mpc_replay(ss_ctx* c, int64_t k_global, double* out_sequence, 
     const int T = r.H + 1, d = c->d, da = c->da;
     const int64_t k_local = k_global - r.k_offset;
     const bool mine = k_local >= 0 && k_local < r.K_local;
-    if (r.act.host_actions && !mine)
-        SS_FAIL(c, SS_EINVAL, "mpc: host-provided actions of another shard cannot be replayed here");
-    const float* gpow = c->mpc_replay.as<float>();
-    float* path_dev = c->mpc_replay.as<float>() + T + SS_MAX_D;
-
-    RolloutArgs a;
-    std::memset(&a, 0, sizeof(a));
-    fill_model_args(c, a);
-    a.act = r.act;
-    if (a.act.host_actions) a.act.host_actions += (size_t)k_local * r.H * da;
-    a.plan = make_plan_view(c, gpow, r.gamma, r.hpf);
-    for (int j = 0; j < SS_MAX_D; ++j) a.state0[j] = r.state[j];
-    a.wp_index = r.wp_index; a.H = r.H; a.K_local = 1; a.k_offset = k_global;
-    a.per_sample = 1;
-    a.states_out = path_dev;
+    float* rows_dev = c->mpc_replay.as<float>() + (T + SS_MAX_D + 3) / 4 * 4;   // 16-byte aligned rows
+    float* path_dev = rows_dev + (size_t)T * (SS_MAX_D + 1);
     int rc = SS_OK;
     if (r.states_stored && mine) {
         // the trajectories of this batch are still resident (reference mode): just gather the row
@@ -379,10 +519,11 @@ extern "C" int ss_mpc_replay(ss_ctx* c, int64_t k_global, double* out_sequence, 
         c->launches++;
         SS_CUDA_CHECK(c, cudaGetLastError());
     } else {
-        // re-roll the one sequence with the kernel family that scored it (a 1-row tile on the
-        // tcgen05 kernel costs H * ~10 us; the FP32 kernel is the fallback for other shapes)
-        rc = r.precision == SS_PRECISION_BF16_TC ? mpc_tc_launch(c, a, nullptr) : mpc_simt_launch(c, a, nullptr);
+        rc = reroll_winner(c, k_global, rows_dev);
         if (rc) return rc;
+        gather_path_kernel<<<(T * d + 127) / 128, 128, 0, c->stream>>>(rows_dev, 1, 0, T, d, path_dev);
+        c->launches++;
+        SS_CUDA_CHECK(c, cudaGetLastError());
     }
     std::vector<float> path((size_t)T * d);
     SS_CUDA_CHECK(c, cudaMemcpyAsync(path.data(), path_dev, path.size() * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -390,7 +531,9 @@ extern "C" int ss_mpc_replay(ss_ctx* c, int64_t k_global, double* out_sequence, 
         const size_t n = (size_t)r.H * da;
         SS_CUDA_CHECK(c, c->mpc_block_best.ensure(1024 * 16 + n * 8));
         double* seq_dev = reinterpret_cast<double*>(c->mpc_block_best.as<char>() + 1024 * 16);
-        sample_actions_kernel<<<1, 128, 0, c->stream>>>(a.act, 1, k_global, seq_dev);
+        ActionSource act = r.act;
+        if (act.host_actions) act.host_actions += (size_t)k_local * r.H * da;
+        sample_actions_kernel<<<1, 128, 0, c->stream>>>(act, 1, k_global, seq_dev);
         c->launches++;
         SS_CUDA_CHECK(c, cudaGetLastError());
         SS_CUDA_CHECK(c, cudaMemcpyAsync(out_sequence, seq_dev, n * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -415,13 +558,25 @@ extern "C" int ss_mpc_plan(ss_ctx* c, const double* state, int wp_index, int64_t
     int rc = ss_mpc_rollout(c, state, wp_index, K_local, k_offset, K_global, H, actions, seed, act_low,
                             act_high, gamma, hpf, penalty_mode, precision);
     if (rc) return rc;
-    int64_t best = -1;
-    rc = ss_mpc_finish(c, &best, out_best_score, out_scores);
+    const bool want_path = out_best_sequence || out_best_path;
+    double* pkg_dev = nullptr;
+    int n = 0;
+    rc = ss_mpc_finish_package(c, want_path ? 1 : 0, &pkg_dev, &n);
     if (rc) return rc;
-    if (out_best_k) *out_best_k = best;
-    if (out_best_sequence || out_best_path) {
-        rc = ss_mpc_replay(c, best, out_best_sequence, out_best_path);
-        if (rc) return rc;
+    std::vector<double> pkg(n);
+    std::vector<float> sc;
+    if (out_scores) {
+        sc.resize(K_local);
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(sc.data(), c->mpc_scores.p, (size_t)K_local * 4, cudaMemcpyDeviceToHost, c->stream));
     }
+    rc = ss_mpc_read_package(c, pkg.data(), n);       // the one host synchronisation of the decision
+    if (rc) return rc;
+    if (out_scores)
+        for (int64_t k = 0; k < K_local; ++k) out_scores[k] = (double)sc[k];
+    if (out_best_score) *out_best_score = pkg[0];
+    if (out_best_k) *out_best_k = (int64_t)pkg[1];
+    const int n_seq = H * c->da;
+    if (out_best_sequence) std::memcpy(out_best_sequence, pkg.data() + 2, (size_t)n_seq * 8);
+    if (out_best_path) std::memcpy(out_best_path, pkg.data() + 2 + n_seq, (size_t)(H + 1) * c->d * 8);
     return SS_OK;
 }

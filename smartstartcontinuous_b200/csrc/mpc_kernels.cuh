@@ -17,12 +17,12 @@ struct RolloutArgs {
     float state0[SS_MAX_D];
     int wp_index, H;
     long long K_local, k_offset;
-    int per_sample;          // 1: score in the rollout kernel with the per-sample penalty;
-                             // 0: reference mode -- the kernel only spills the trajectories, the
-                             //    scoring passes (mpc_score.cu) run over them afterwards
-    float* states_out;       // [H+1][K_local][d] or null
-    double* partial_sums;    // legacy in-kernel projection sums [gridDim.x][H+1][2]; null = off
-    float* scores_out;       // [K_local] (per-sample mode: final; reference mode: unused)
+    int per_sample;          // 1: full score in the rollout kernel (per-sample penalty);
+                             // 0: reference mode -- the kernel accumulates the progress term and
+                             //    spills (state, waypoint index) rows; the penalty passes
+                             //    (mpc_score.cu) run over them afterwards
+    float* states_out;       // [H+1][K_local][d + 1] trajectory rows (score.cuh) or null
+    float* scores_out;       // [K_local] (per-sample mode: final; reference mode: progress term)
 };
 
 // fp32 SIMT rollout (mpc_simt.cu)
@@ -32,17 +32,20 @@ int mpc_simt_grid(const RolloutArgs& a);
 // tcgen05 rollout (mpc_tc.cu)
 bool mpc_tc_shape_supported(const ss_ctx* c);
 int mpc_tc_prepare(ss_ctx* c);      // builds the BF16 operand images after ss_mpc_set_model
-int mpc_tc_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out);
-int mpc_tc_grid(const ss_ctx* c, const RolloutArgs& a);
+// rolls the tiles [tile_begin, tile_begin + tile_count) of the local batch (tile = mpc_tc_tile_rows()
+// consecutive sequences); tile_count < 0 = all of them
+int mpc_tc_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out, long long tile_begin = 0,
+                  long long tile_count = -1);
+int mpc_tc_grid(const ss_ctx* c, long long tiles);
+int mpc_tc_tile_rows();
 
 // scoring tail (mpc_score.cu)
 int mpc_reduce_sums(ss_ctx* c, const double* partial, int blocks, int T, double* sums);
 int mpc_sums_reference_blocks(long long K_local);
-int mpc_sums_reference(ss_ctx* c, const PlanView& plan, int wp_index, const float* state0, const float* states,
-                       long long K_local, int T, double* partial);
-int mpc_score_reference(ss_ctx* c, const PlanView& plan, int wp_index, const float* state0,
-                        const float* states, long long K_local, int T, const double* sums,
-                        float* scores);
+int mpc_sums_reference(ss_ctx* c, const PlanView& plan, const float* rows, long long K_local, int T,
+                       double* partial);
+int mpc_score_reference(ss_ctx* c, const PlanView& plan, const float* rows, long long K_local, int T,
+                        const double* sums, float* scores);
 int mpc_argmax(ss_ctx* c, const float* scores, long long K_local, long long k_offset,
                double* block_v, long long* block_i, void* result_dev);
 

@@ -1,89 +1,100 @@
 // mpc_score.cu -- the scoring tail of the MPC planner.
 //
-//   mpc_reduce_sums      deterministic reduction of the per-CTA projection sums
+//   mpc_sums_reference   SS_PENALTY_REFERENCE first pass over the spilled (state, waypoint index)
+//                        rows: per-block partial sums of a'.b' and b'.b' for every time step
+//   mpc_reduce_sums      deterministic reduction of those partials
 //                        (sum_k a'.b', sum_k b'.b' per time step; numerical.py:89-93)
-//   mpc_score_reference  SS_PENALTY_REFERENCE second pass: re-scan the stored trajectories with
-//                        the global projection coefficient of every step (NND_MB_agent.py:566-628)
+//   mpc_score_reference  second pass: subtract the penalties computed with the global projection
+//                        coefficient of every step (NND_MB_agent.py:616-622) from the progress term
 //   mpc_argmax           np.argmax-ordered arg-max over the scores (NND_MB_agent.py:625-626)
 #include "mpc_kernels.cuh"
 
 namespace {
 
-__global__ void mpc_reduce_sums_kernel(const double* __restrict__ partial, int blocks, int T,
-                                       double* __restrict__ sums) {
-    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+constexpr int SUMS_KPT = 4;   // sequences per thread in the projection-sum pass
+
+// sums[2t + w] = sum over the blocks' partials, one warp per output, fixed order (lanes stride over
+// the blocks, then a shuffle tree): deterministic for a given K_local
+__global__ void __launch_bounds__(256)
+mpc_reduce_sums_kernel(const double* __restrict__ partial, int blocks, int T, double* __restrict__ sums) {
+    const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (o >= 2 * T) return;
+    const int t = o >> 1, w = o & 1, lane = threadIdx.x & 31;
     double s = 0.0;
-    for (int b = 0; b < blocks; ++b) s += partial[(size_t)b * 2 * T + o];
-    sums[o] = s;
+    for (int b = lane; b < blocks; b += 32) s += partial[((size_t)t * blocks + b) * 2 + w];
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+    if (lane == 0) sums[o] = s;
 }
 
-// first pass over the stored trajectories: waypoint logic per sample, per-time-step block sums of
-// a'.b' and b'.b' (the two dot products of numerical.py:89-93) -> partial[block][t][2]
+// first pass over the spilled rows: a'.b' and b'.b' (numerical.py:89-93) of every (t, k), summed
+// over k per time step.  grid = (k blocks, T); partial[t][block][2].
 template <int DT>
 __global__ void __launch_bounds__(256)
-mpc_sums_reference_kernel(const PlanView P, int wp_index, const float* __restrict__ state0,
-                          const float* __restrict__ states, long long K, int T,
+mpc_sums_reference_kernel(const PlanView Pg, const float* __restrict__ rows, long long K, int ds_in_smem,
                           double* __restrict__ partial) {
     __shared__ double s_part[8][2];
-    const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const bool live = k < K;
+    extern __shared__ float s_dyn[];
+    PlanView P = Pg;
+    if (ds_in_smem) {          // waypoints in shared memory: the lookups depend on the loaded index
+        for (int i = threadIdx.x; i < Pg.W * Pg.d; i += blockDim.x) s_dyn[i] = Pg.ds[i];
+        P.ds = s_dyn;
+        __syncthreads();
+    }
+    const int t = blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float x[DT];
+    double dab = 0.0, dbb = 0.0;
 #pragma unroll
-    for (int j = 0; j < DT; ++j) x[j] = j < P.d ? state0[j] : 0.f;
-    ScoreAcc sc;
-    score_init<DT>(P, wp_index, x, sc);
-    for (int t = 0; t < T; ++t) {
-        float ab = 0.f, bb = 0.f;
-        if (live) {
-            const float* row = states + ((size_t)t * K + k) * P.d;
-#pragma unroll
-            for (int j = 0; j < DT; ++j)
-                if (j < P.d) x[j] = row[j];
-            score_point<DT>(P, t, x, sc, false, ab, bb);
+    for (int i = 0; i < SUMS_KPT; ++i) {
+        const long long k = ((long long)blockIdx.x * SUMS_KPT + i) * blockDim.x + threadIdx.x;
+        if (k < K) {
+            float x[DT];
+            int idx;
+            traj_load<DT>(rows, (size_t)t * K + k, P.d, x, idx);
+            float ab, bb;
+            proj_terms<DT>(P, idx, x, ab, bb);
+            dab += (double)ab;
+            dbb += (double)bb;
         }
-        double dab = (double)ab, dbb = (double)bb;
-        for (int off = 16; off > 0; off >>= 1) {
-            dab += __shfl_down_sync(0xffffffffu, dab, off);
-            dbb += __shfl_down_sync(0xffffffffu, dbb, off);
-        }
-        if (lane == 0) { s_part[warp][0] = dab; s_part[warp][1] = dbb; }
-        __syncthreads();
-        if (threadIdx.x < 2) {
-            double tot = 0.0;
-            for (int w = 0; w < 8; ++w) tot += s_part[w][threadIdx.x];
-            partial[((size_t)blockIdx.x * T + t) * 2 + threadIdx.x] = tot;
-        }
-        __syncthreads();
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        dab += __shfl_down_sync(0xffffffffu, dab, off);
+        dbb += __shfl_down_sync(0xffffffffu, dbb, off);
+    }
+    if (lane == 0) { s_part[warp][0] = dab; s_part[warp][1] = dbb; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double tot = 0.0;
+        for (int w = 0; w < 8; ++w) tot += s_part[w][threadIdx.x];
+        partial[((size_t)t * gridDim.x + blockIdx.x) * 2 + threadIdx.x] = tot;
     }
 }
 
+// second pass: scores[k] (the progress term from the rollout kernel) minus the penalties of the
+// H+1 trajectory points with the global projection coefficient of each step, in step order
 template <int DT>
 __global__ void __launch_bounds__(256)
-mpc_score_reference_kernel(const PlanView P, int wp_index, const float* __restrict__ state0,
-                           const float* __restrict__ states, long long K, int T,
+mpc_score_reference_kernel(const PlanView Pg, const float* __restrict__ rows, long long K, int T, int ds_in_smem,
                            const double* __restrict__ sums, float* __restrict__ scores) {
     extern __shared__ float s_lam[];
     for (int t = threadIdx.x; t < T; t += blockDim.x) s_lam[t] = (float)(sums[2 * t] / sums[2 * t + 1]);
+    PlanView P = Pg;
+    if (ds_in_smem) {
+        float* s_ds = s_lam + T;
+        for (int i = threadIdx.x; i < Pg.W * Pg.d; i += blockDim.x) s_ds[i] = Pg.ds[i];
+        P.ds = s_ds;
+    }
     __syncthreads();
     const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (k >= K) return;
-    float x[DT];
-#pragma unroll
-    for (int j = 0; j < DT; ++j) x[j] = j < P.d ? state0[j] : 0.f;
-    ScoreAcc sc;
-    score_init<DT>(P, wp_index, x, sc);
+    float score = scores[k];
+#pragma unroll 8
     for (int t = 0; t < T; ++t) {
-        const float* row = states + ((size_t)t * K + k) * P.d;
-#pragma unroll
-        for (int j = 0; j < DT; ++j)
-            if (j < P.d) x[j] = row[j];
-        float ab, bb;
-        score_point<DT>(P, t, x, sc, false, ab, bb);
-        sc.score -= penalty_with_lambda<DT>(P, sc.idx, x, s_lam[t]);
+        float x[DT];
+        int idx;
+        traj_load<DT>(rows, (size_t)t * K + k, P.d, x, idx);
+        score -= penalty_with_lambda<DT>(P, idx, x, s_lam[t]);
     }
-    scores[k] = sc.score;
+    scores[k] = score;
 }
 
 __global__ void __launch_bounds__(256)
@@ -129,43 +140,46 @@ mpc_argmax_kernel(const float* __restrict__ scores, long long K, long long k_off
 }  // namespace
 
 int mpc_reduce_sums(ss_ctx* c, const double* partial, int blocks, int T, double* sums) {
-    mpc_reduce_sums_kernel<<<(2 * T + 127) / 128, 128, 0, c->stream>>>(partial, blocks, T, sums);
+    mpc_reduce_sums_kernel<<<(2 * T + 7) / 8, 256, 0, c->stream>>>(partial, blocks, T, sums);
     c->launches++;
     SS_CUDA_CHECK(c, cudaGetLastError());
     return SS_OK;
 }
 
-int mpc_sums_reference_blocks(long long K_local) { return (int)((K_local + 255) / 256); }
+int mpc_sums_reference_blocks(long long K_local) {
+    return (int)((K_local + 256 * SUMS_KPT - 1) / (256 * SUMS_KPT));
+}
 
-int mpc_sums_reference(ss_ctx* c, const PlanView& plan, int wp_index, const float* state0, const float* states,
-                       long long K_local, int T, double* partial) {
-    const unsigned grid = (unsigned)mpc_sums_reference_blocks(K_local);
+int mpc_sums_reference(ss_ctx* c, const PlanView& plan, const float* rows, long long K_local, int T,
+                       double* partial) {
+    const dim3 grid((unsigned)mpc_sums_reference_blocks(K_local), (unsigned)T);
+    const size_t ds_bytes = (size_t)plan.W * plan.d * 4;
+    const int in_smem = ds_bytes <= 40 * 1024;
+    const size_t smem = in_smem ? ds_bytes : 0;
     if (plan.d <= 4)
-        mpc_sums_reference_kernel<4><<<grid, 256, 0, c->stream>>>(plan, wp_index, state0, states, K_local, T, partial);
+        mpc_sums_reference_kernel<4><<<grid, 256, smem, c->stream>>>(plan, rows, K_local, in_smem, partial);
     else if (plan.d <= 8)
-        mpc_sums_reference_kernel<8><<<grid, 256, 0, c->stream>>>(plan, wp_index, state0, states, K_local, T, partial);
+        mpc_sums_reference_kernel<8><<<grid, 256, smem, c->stream>>>(plan, rows, K_local, in_smem, partial);
     else
-        mpc_sums_reference_kernel<SS_MAX_D><<<grid, 256, 0, c->stream>>>(plan, wp_index, state0, states, K_local, T,
-                                                                        partial);
+        mpc_sums_reference_kernel<SS_MAX_D><<<grid, 256, smem, c->stream>>>(plan, rows, K_local, in_smem, partial);
     c->launches++;
     SS_CUDA_CHECK(c, cudaGetLastError());
     return SS_OK;
 }
 
-int mpc_score_reference(ss_ctx* c, const PlanView& plan, int wp_index, const float* state0,
-                        const float* states, long long K_local, int T, const double* sums,
-                        float* scores) {
+int mpc_score_reference(ss_ctx* c, const PlanView& plan, const float* rows, long long K_local, int T,
+                        const double* sums, float* scores) {
     const unsigned grid = (unsigned)((K_local + 255) / 256);
-    const size_t smem = (size_t)T * sizeof(float);
+    const size_t ds_bytes = (size_t)plan.W * plan.d * 4;
+    const int in_smem = ds_bytes + (size_t)T * 4 <= 40 * 1024;
+    const size_t smem = (size_t)T * sizeof(float) + (in_smem ? ds_bytes : 0);
     if (plan.d <= 4)
-        mpc_score_reference_kernel<4><<<grid, 256, smem, c->stream>>>(plan, wp_index, state0, states,
-                                                                      K_local, T, sums, scores);
+        mpc_score_reference_kernel<4><<<grid, 256, smem, c->stream>>>(plan, rows, K_local, T, in_smem, sums, scores);
     else if (plan.d <= 8)
-        mpc_score_reference_kernel<8><<<grid, 256, smem, c->stream>>>(plan, wp_index, state0, states,
-                                                                      K_local, T, sums, scores);
+        mpc_score_reference_kernel<8><<<grid, 256, smem, c->stream>>>(plan, rows, K_local, T, in_smem, sums, scores);
     else
-        mpc_score_reference_kernel<SS_MAX_D><<<grid, 256, smem, c->stream>>>(
-            plan, wp_index, state0, states, K_local, T, sums, scores);
+        mpc_score_reference_kernel<SS_MAX_D><<<grid, 256, smem, c->stream>>>(plan, rows, K_local, T, in_smem, sums,
+                                                                         scores);
     c->launches++;
     SS_CUDA_CHECK(c, cudaGetLastError());
     return SS_OK;

@@ -167,22 +167,9 @@ __global__ void __launch_bounds__(ST) mpc_rollout_simt_kernel(const RolloutArgs 
     for (int t = 0; t < T; ++t) {
         // ---- score the current point (row owners) -------------------------------------
         if (owner) {
-            float ab = 0.f, bb = 0.f;
-            if (a.per_sample || a.partial_sums) score_point<DT>(a.plan, t, x, sc, a.per_sample != 0, ab, bb);
+            score_point<DT>(a.plan, t, x, sc, a.per_sample != 0);
             if (a.states_out && live)
-                for (int j = 0; j < a.d; ++j)
-                    a.states_out[((size_t)t * a.K_local + k_local) * a.d + j] = x[j];
-            if (a.partial_sums) {
-                double dab = live ? (double)ab : 0.0, dbb = live ? (double)bb : 0.0;
-                for (int off = 16; off > 0; off >>= 1) {
-                    dab += __shfl_down_sync(0xffffffffu, dab, off);
-                    dbb += __shfl_down_sync(0xffffffffu, dbb, off);
-                }
-                if (tid == 0) {
-                    a.partial_sums[((size_t)blockIdx.x * T + t) * 2] = dab;
-                    a.partial_sums[((size_t)blockIdx.x * T + t) * 2 + 1] = dbb;
-                }
-            }
+                traj_store<DT>(a.states_out, (size_t)t * a.K_local + k_local, a.d, x, sc.idx);
         }
         if (t == a.H) break;
         // ---- network input: normalised state and action (dynamics_model.py:228-230) ------

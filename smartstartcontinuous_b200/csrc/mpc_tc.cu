@@ -73,7 +73,7 @@ struct Params {
     float b3[SS_MAX_D];
     int hp;                             // padded hidden width (multiple of 128)
     int din;
-    long long n_tiles;
+    long long tile_begin, tile_end;     // this launch rolls the tiles [tile_begin, tile_end) of the batch
     int iters;                          // tile iterations per CTA (same for all: pair lock-step)
     unsigned long long* prof;
 };
@@ -225,33 +225,17 @@ struct SmemT {
     static constexpr size_t BARS = ZX + (size_t)TPR * TM * 8 * 4;
     static constexpr int N_BARS = 3 * NSTAGE + 2 * ACC_SLOTS + 2 * (HP_MAX / NC) + 2;
     static constexpr size_t TMEM_PTR = BARS + (size_t)N_BARS * 8;
-    static constexpr size_t SUMS = TMEM_PTR + 16;      // double [4][T][2]
+    static constexpr size_t TRACE = TMEM_PTR + 16;     // SS_TC_TRACE stamps (only when tracing)
+    static constexpr size_t END = TRACE;
 };
 
-// score one trajectory point for this row (ch-1 thread): waypoint logic, progress, penalty or
-// projection sums, optional state spill for the reference-mode second pass
+// score one trajectory point for this row (ch-1 thread): waypoint move + progress (+ per-sample
+// penalty); in reference mode the (state, waypoint index) row is spilled for the penalty passes
 template <int DT>
 __device__ __forceinline__ void score_row(const RolloutArgs& a, int t, const float (&x)[DT], ScoreAcc& sc,
-                                          bool live, long long k_local, int q, int lane, int T, double* sums) {
-    float ab = 0.f, bb = 0.f;
-    if (a.per_sample || a.partial_sums) score_point<DT>(a.plan, t, x, sc, a.per_sample != 0, ab, bb);
-    if (a.states_out && live) {
-        float* dst = a.states_out + ((size_t)t * a.K_local + k_local) * a.d;
-#pragma unroll
-        for (int j = 0; j < DT; ++j)
-            if (j < a.d) dst[j] = x[j];
-    }
-    if (a.partial_sums) {
-        double dab = live ? (double)ab : 0.0, dbb = live ? (double)bb : 0.0;
-        for (int off = 16; off > 0; off >>= 1) {
-            dab += __shfl_down_sync(0xffffffffu, dab, off);
-            dbb += __shfl_down_sync(0xffffffffu, dbb, off);
-        }
-        if (lane == 0) {
-            sums[((size_t)q * T + t) * 2] += dab;
-            sums[((size_t)q * T + t) * 2 + 1] += dbb;
-        }
-    }
+                                          bool live, long long k_local) {
+    score_point<DT>(a.plan, t, x, sc, a.per_sample != 0);
+    if (a.states_out && live) traj_store<DT>(a.states_out, (size_t)t * a.K_local + k_local, a.d, x, sc.idx);
 }
 
 // DT: register copies of the state (4 or 8); DZ: layer-3 outputs computed (>= d; 2, 3, 4 or 8);
@@ -279,13 +263,12 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
     uint64_t* x_ready = l1_full + HP_MAX / NC;          // leader's copy
     uint64_t* w1_full = x_ready + 1;                    // local
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Smem::TMEM_PTR);
-    double* sums = reinterpret_cast<double*>(smem + Smem::SUMS);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int T = a.H + 1;
     // SS_TC_TRACE: clock stamps go to shared memory (a global store in front of a tcgen05 fence
     // would perturb the timeline) and are copied out when the kernel ends
-    unsigned long long* trace_s = reinterpret_cast<unsigned long long*>(sums + 4 * T * 2);
+    unsigned long long* trace_s = reinterpret_cast<unsigned long long*>(smem + Smem::TRACE);
     if (p.prof && blockIdx.x == 0)
         for (int i = tid; i < 3 * 256; i += THREADS) trace_s[i] = 0;
     const int nch = p.hp / NC;          // accumulator chunks per layer
@@ -314,7 +297,6 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
     }
     for (int i = tid; i < (p.hp / 2) * (2 * DZP); i += THREADS) w3s[i] = p.w3[i];
-    for (int i = tid; i < 4 * T * 2; i += THREADS) sums[i] = 0.0;
     __syncthreads();
     if (tid == 0) {
         // this CTA's half of the layer-1 weights (resident for the whole kernel)
@@ -345,9 +327,9 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
             asm volatile("" : "+f"(upd_s[j]), "+f"(upd_c[j]));
         }
         for (int it = 0; it < p.iters; ++it) {
-            const long long tile = (long long)it * gridDim.x + blockIdx.x;   // >= n_tiles: padding tile
+            const long long tile = p.tile_begin + (long long)it * gridDim.x + blockIdx.x;   // >= tile_end: padding
             const long long k_local = tile * TM + row;
-            const bool live = tile < p.n_tiles && k_local < a.K_local;
+            const bool live = tile < p.tile_end && k_local < a.K_local;
             // both threads of a row keep identical copies of the state; ch 0 feeds the network
             // (critical path), ch 1 scores the trajectory in the shadow of the layer-2 MMAs
             float x[DT];
@@ -465,7 +447,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                 }
                 // ---- off the critical path (the tensor pipe is busy with layer 2 now) ----------
                 if (ch == 1) {
-                    score_row<DT>(a, t, x, sc, live, k_local, q, lane, T, sums);
+                    score_row<DT>(a, t, x, sc, live, k_local);
                 } else if (ch == 0 && live && t + 1 < a.H) {
                     TC_TRACE(70);
 #pragma unroll
@@ -530,7 +512,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                 TC_TRACE(tb + 18);
             }
             if (ch == 1) {
-                score_row<DT>(a, a.H, x, sc, live, k_local, q, lane, T, sums);
+                score_row<DT>(a, a.H, x, sc, live, k_local);
                 if (live && a.scores_out) a.scores_out[k_local] = sc.score;
             }
         }
@@ -664,10 +646,6 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
     tc_fence_after();
     if (p.prof && blockIdx.x == 0)
         for (int i = tid; i < 3 * 256; i += THREADS) p.prof[i] = trace_s[i];
-    if (a.partial_sums)
-        for (int o = tid; o < 2 * T; o += THREADS)
-            a.partial_sums[(size_t)blockIdx.x * 2 * T + o] =
-                sums[o] + sums[2 * T + o] + sums[4 * T + o] + sums[6 * T + o];
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
 }
@@ -687,10 +665,9 @@ static float bf16_val(uint16_t b) {
     return f;
 }
 
-static size_t smem_bytes(int T, int d) {
+static size_t smem_bytes(int d) {
     const int dz = dz_of(d);
-    const size_t base = dz == 2 ? SmemT<2>::SUMS : (dz <= 4 ? SmemT<4>::SUMS : SmemT<8>::SUMS);
-    return base + (size_t)4 * T * 2 * 8 + 128;
+    return (dz == 2 ? SmemT<2>::END : (dz <= 4 ? SmemT<4>::END : SmemT<8>::END)) + 128;
 }
 
 }  // namespace tc
@@ -766,18 +743,18 @@ int mpc_tc_prepare(ss_ctx* c) {
     return SS_OK;
 }
 
-int mpc_tc_grid(const ss_ctx* c, const RolloutArgs& a) {
+int mpc_tc_tile_rows() { return tc::TM; }
+
+int mpc_tc_grid(const ss_ctx* c, long long tiles) {
     // a multiple of the pair size; at most one CTA per SM (TMEM: 512 columns per CTA)
-    const long long tiles = (a.K_local + tc::TM - 1) / tc::TM;
     const long long up = (tiles + tc::CLUSTER - 1) / tc::CLUSTER * tc::CLUSTER;
     const long long cap = c->sm_count / tc::CLUSTER * tc::CLUSTER;
     return (int)(up < cap ? up : cap);
 }
 
-int mpc_tc_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out) {
+int mpc_tc_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out, long long tile_begin, long long tile_count) {
     using namespace tc;
     if (!c->tc_ready) SS_FAIL(c, SS_EUNSUPPORTED, "mpc: tcgen05 kernel not prepared for this model");
-    if (a.H + 1 > 1024) SS_FAIL(c, SS_EUNSUPPORTED, "mpc: horizon too long for the tcgen05 kernel");
     Params p;
     std::memset(&p, 0, sizeof(p));
     p.w1_img = c->tc_w1.as<__nv_bfloat16>();
@@ -786,17 +763,22 @@ int mpc_tc_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out) {
     for (int j = 0; j < c->d; ++j) p.b3[j] = (float)c->hb[2][j];
     p.hp = c->tc_hp;
     p.din = c->d + c->da;
-    p.n_tiles = (a.K_local + TM - 1) / TM;
+    const long long all_tiles = (a.K_local + TM - 1) / TM;
+    if (tile_count < 0) tile_count = all_tiles - tile_begin;
+    if (tile_begin < 0 || tile_count < 1 || tile_begin + tile_count > all_tiles)
+        SS_FAIL(c, SS_EINVAL, "mpc: tile range outside the batch");
+    p.tile_begin = tile_begin;
+    p.tile_end = tile_begin + tile_count;
     p.prof = nullptr;
     if (getenv("SS_TC_TRACE")) {
         SS_CUDA_CHECK(c, c->tc_misc.ensure(3 * 256 * 8));
         SS_CUDA_CHECK(c, cudaMemsetAsync(c->tc_misc.p, 0, 3 * 256 * 8, c->stream));
         p.prof = c->tc_misc.as<unsigned long long>();
     }
-    const int grid = mpc_tc_grid(c, a);
+    const int grid = mpc_tc_grid(c, tile_count);
     if (grid_blocks_out) *grid_blocks_out = grid;
-    p.iters = (int)((p.n_tiles + grid - 1) / grid);
-    const size_t smem = smem_bytes(a.H + 1, a.d) + (p.prof ? 3 * 256 * 8 : 0);
+    p.iters = (int)((tile_count + grid - 1) / grid);
+    const size_t smem = smem_bytes(a.d) + (p.prof ? 3 * 256 * 8 : 0);
     cudaLaunchConfig_t cfg;
     std::memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(grid);

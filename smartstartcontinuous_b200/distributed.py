@@ -6,8 +6,10 @@ strategy: data-parallel sharding with replicated weights / plan / buffer and tin
   MPC   rank g rolls out sequences [g*K/G, (g+1)*K/G) (device Philox is indexed by the GLOBAL
         sequence number, so the samples do not depend on G); reference-exact penalty needs the
         per-time-step projection sums of ALL sequences (numerical.py:89-93) -> one all-reduce of
-        2*(H+1) float64; then one all-gather of (score, k) and an np.argmax-ordered pick; the
-        owner of the winner replays it and broadcasts (best_sequence, best_path).
+        2*(H+1) float64 (device memory, on the compute stream); then every rank packs its local
+        winner (score, k, best_sequence, best_path) on the device, ONE all-gather of those
+        packages (2 + H*da + (H+1)*d float64 per rank) and an np.argmax-ordered pick on every
+        rank: two small collectives and a single device->host copy per decision.
   KDE   rank g scores queries [g*m/G, (g+1)*m/G) against the full (replicated) buffer; one
         all-gather of (ucb, j).
 
@@ -101,32 +103,26 @@ class ShardedPlanner:
             sums = self._sums_tensor()
             if sums is not None:
                 dist.all_reduce(sums, group=self.group)      # 2*(H+1) float64
-        best_k, best_score, _ = self.engine.finish()
-        if self.world > 1:
-            mine = torch.tensor([best_score, float(best_k)], dtype=torch.float64, device=self.device)
-            gathered = [torch.empty_like(mine) for _ in range(self.world)]
-            dist.all_gather(gathered, mine, group=self.group)
-            pairs = torch.stack(gathered).cpu().numpy()
-            w = argmax_pick(pairs[:, 0].tolist(), [int(v) for v in pairs[:, 1]])
-            best_score, best_k = float(pairs[w, 0]), int(pairs[w, 1])
+        d, da = self.engine._model_shape[0], self.engine._model_shape[1]
+        if hasattr(self.engine, "finish_package_tensor"):          # CPU test double
+            mine = self.engine.finish_package_tensor(want_path)
         else:
-            w = 0
+            ptr, n = self.engine.finish_package(want_path)
+            mine = None if self.world == 1 else torch.as_tensor(_DevView(ptr, n), device=self.device)
+        if self.world > 1:
+            gathered = torch.empty(self.world * mine.numel(), dtype=torch.float64, device=mine.device)
+            dist.all_gather_into_tensor(gathered, mine, group=self.group)
+            pk = gathered.cpu().numpy().reshape(self.world, -1)        # the one host sync
+        elif mine is not None:
+            pk = mine.numpy().reshape(1, -1)
+        else:
+            pk = self.engine.read_package(n).reshape(1, -1)
+        w = argmax_pick(pk[:, 0].tolist(), [int(v) for v in pk[:, 1]])
+        best_score, best_k = float(pk[w, 0]), int(pk[w, 1])
         seq = path = None
         if want_path:
-            if self.world == 1:
-                seq, path = self.engine.replay(best_k)
-            else:
-                # the owner has the winner's trajectory (or can re-roll it cheaply); everyone else
-                # receives H*da + (H+1)*d doubles
-                d, da = self.engine._model_shape[0], self.engine._model_shape[1]
-                buf = torch.zeros(H * da + (H + 1) * d, dtype=torch.float64, device=self.device)
-                if self.rank == w:
-                    s, p = self.engine.replay(best_k)
-                    buf.copy_(torch.as_tensor(np.concatenate([s.reshape(-1), p.reshape(-1)])))
-                dist.broadcast(buf, src=dist.get_global_rank(self.group, w) if self.group else w,
-                               group=self.group)
-                flat = buf.cpu().numpy()
-                seq, path = flat[:H * da].reshape(H, da), flat[H * da:].reshape(H + 1, d)
+            seq = pk[w, 2:2 + H * da].reshape(H, da).copy()
+            path = pk[w, 2 + H * da:2 + H * da + (H + 1) * d].reshape(H + 1, d).copy()
         return dict(best_k=best_k, best_score=best_score, best_sequence=seq, best_path=path,
                     owner=w, k_offset=k_offset, k_local=k_local)
 

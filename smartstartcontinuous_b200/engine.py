@@ -228,6 +228,19 @@ class Engine:
         self._check(self._lib.ss_mpc_finish(self._h, C.byref(best), C.byref(best_score), _ptr(scores)))
         return int(best.value), float(best_score.value), scores
 
+    def finish_package(self, want_path=True):
+        """Phase B + arg-max + the local winner's sequence and path, left on the device as one
+        float64 package [score, k_global, sequence (H*da), path ((H+1)*d)]: (device ptr, count)."""
+        p = C.c_void_p()
+        n = C.c_int()
+        self._check(self._lib.ss_mpc_finish_package(self._h, 1 if want_path else 0, C.byref(p), C.byref(n)))
+        return (p.value or 0), n.value
+
+    def read_package(self, count):
+        out = np.empty(count)
+        self._check(self._lib.ss_mpc_read_package(self._h, _ptr(out), int(count)))
+        return out
+
     def get_states(self):
         """[H+1, K, d] trajectories of the last reference-mode rollout."""
         d = self._model_shape[0]

@@ -69,6 +69,12 @@ class OracleEngine:
         k = int(np.argmax(scores))
         return k + self.k_offset, float(scores[k]), scores
 
+    def finish_package_tensor(self, want_path):
+        k, score, _ = self.finish()
+        seq, path = self.replay(k)
+        body = np.concatenate([seq.reshape(-1), path.reshape(-1)]) if want_path else np.zeros(seq.size + path.size)
+        return torch.tensor(np.concatenate([[score, float(k)], body]), dtype=torch.float64)
+
     def replay(self, k_global):
         if self.sampler is not None:      # device sampling: any rank can regenerate any sequence
             H, seed, lo, hi = self.sampler
