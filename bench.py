@@ -17,7 +17,8 @@ BASELINE.json's metric, KDE kernel-evals/s, is reported in the same line under "
   roofline  tensor pipe for the rollout kernel (achieved = 507 000 FLOP x K*H / kernel time, against
             the measured sustained bf16 peak), SFU pipe for the KDE pair kernel
   --impl reference: the oracle port of the reference's CPU path (numpy float64, BLAS on all host
-            cores; scipy gaussian_kde for the KDE), timed on a bounded sample of the same workload.
+            cores; scipy gaussian_kde with the queries chunked over a multiprocessing.Pool for the
+            KDE), timed on bounded samples of the same workload.
 """
 from __future__ import annotations
 
@@ -135,11 +136,47 @@ def cpu_reference_mpc(wl, K, H, seed):
 
 
 def cpu_reference_kde(kw, m):
+    """scipy.stats.gaussian_kde fit + evaluate + UCB + argmax on one core (the reference as written,
+    smartexplorationcontinuous.py:260-280).  Returns seconds."""
     from oracle import kde_oracle
     t0 = time.perf_counter()
     kde_oracle.select_start(kw["all_states"], kw["queries"][:m], kw["values"][:m], kw["n"], kw["volume"], 1.0, 2.0,
                             density_fn=kde_oracle.scipy_density)
     return time.perf_counter() - t0
+
+
+_POOL_KDE = {}
+
+
+def _pool_kde_chunk(span):
+    lo, hi = span
+    return _POOL_KDE["kernel"](_POOL_KDE["queries"][lo:hi].T)
+
+
+def cpu_reference_kde_pool(kw, m, procs, reps):
+    """The same numeric core with the queries chunked over a multiprocessing.Pool (the reference's
+    own parallel idiom, smartstart/utilities/experimenter.py:84-92): fit once in the parent
+    (timed), evaluate in `procs` forked workers, UCB + argmax in the parent.  Returns the mean
+    seconds of `reps` repetitions (pool start-up excluded)."""
+    import multiprocessing as mp
+    from scipy.stats import gaussian_kde
+    q = np.ascontiguousarray(kw["queries"][:m])
+    _POOL_KDE["queries"] = q
+    _POOL_KDE["kernel"] = gaussian_kde(kw["all_states"].T, bw_method="scott")
+    spans = [(int(a[0]), int(a[-1]) + 1) for a in np.array_split(np.arange(m), procs) if len(a)]
+    times = []
+    with mp.get_context("fork").Pool(procs) as pool:
+        pool.map(_pool_kde_chunk, [(0, 8)] * procs)                      # warm the workers
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            kernel = gaussian_kde(kw["all_states"].T, bw_method="scott")   # the fit is part of the path
+            _ = kernel.factor
+            dens = np.concatenate(pool.map(_pool_kde_chunk, spans))
+            c_hat = kw["n"] * dens * kw["volume"]
+            ucb = 1.0 * np.asarray(kw["values"][:m], dtype=np.float64) + np.sqrt(2.0 * np.log(kw["n"]) / c_hat)
+            int(np.argmax(ucb))
+            times.append(time.perf_counter() - t0)
+    return float(np.mean(times))
 
 
 def blas_threads():
@@ -150,22 +187,32 @@ def blas_threads():
         return os.cpu_count() or 1
 
 
+REF_K_SAMPLE = 4096          # sequences per timed MPC step of the CPU arm (~0.5 s on a server CPU)
+
+
 def run_reference(args, guard):
-    """--impl reference: rank 0 only."""
+    """--impl reference: the reference's CPU path (oracle port; scipy for the KDE) on rank 0 only,
+    all host threads, bounded samples of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = make_workload()
     kw = kde_workload()
-    K_s, m_s = 2048, 256          # bounded samples: ~1 s and ~0.5 s per step on a server CPU
+    K_s = REF_K_SAMPLE
     for _ in range(args.warmup):
-        cpu_reference_mpc(wl, 256, HORIZON, 0)
+        cpu_reference_mpc(wl, 512, HORIZON, 0)
     t_mpc = [cpu_reference_mpc(wl, K_s, HORIZON, i) for i in range(args.steps)]
-    t_kde = [cpu_reference_kde(kw, m_s) for _ in range(max(1, min(args.steps, 5)))]
     v = K_s * HORIZON / float(np.mean(t_mpc))
-    kv = m_s * (kw["n"] + 1) / float(np.mean(t_kde))
     cores = blas_threads()
-    sample = "K=%d of %d sequences per step, H=%d (rate is K-independent: GEMM-bound)" % (K_s, K_PER_GPU, HORIZON)
+    procs = os.cpu_count() or 1
+    m_pool = min(KDE_M, 256 * procs)
+    reps = max(1, min(args.steps, 5))
+    t_pool = cpu_reference_kde_pool(kw, m_pool, procs, reps)
+    kv = m_pool * (kw["n"] + 1) / t_pool
+    t_one = [cpu_reference_kde(kw, 256) for _ in range(2)]
+    kv_one = 256 * (kw["n"] + 1) / float(np.mean(t_one))
+    sample = "%d steps of K=%d (of %d) sequences, H=%d (rate is K-independent: GEMM-bound)" % (
+        args.steps, K_s, K_PER_GPU, HORIZON)
     guard.emit(json.dumps({
         "impl": "reference", "metric": "mpc_rollout_steps_per_s", "value": v, "unit": "rollout-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -176,9 +223,11 @@ def run_reference(args, guard):
                            "its float64 GEMMs run in numpy/BLAS"},
         "cpu_baseline": {"value": v, "unit": "rollout-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "rollout-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "kde": {"metric": "kde_kernel_evals_per_s", "value": kv, "unit": "kernel-evals/s", "cores": 1,
-                "kind": "reference-library (scipy.stats.gaussian_kde, single thread)",
-                "sample": "%d of %d queries x %d points" % (m_s, KDE_M, kw["n"] + 1)},
+        "kde": {"metric": "kde_kernel_evals_per_s", "value": kv, "unit": "kernel-evals/s", "cores": procs,
+                "kind": "reference-library (scipy.stats.gaussian_kde; queries chunked over a "
+                        "multiprocessing.Pool, the reference's parallel idiom)",
+                "sample": "%d x %d (of %d) queries x %d points" % (reps, m_pool, KDE_M, kw["n"] + 1),
+                "single_core": {"value": kv_one, "cores": 1, "sample": "2 x 256 queries x %d points" % (kw["n"] + 1)}},
     }))
 
 
@@ -363,16 +412,17 @@ def main():
                              "traffic": None}},
     }
     if world == 1 and not args.no_cpu_baseline:
-        K_s = 1024
-        cpu_reference_mpc(wl, 128, HORIZON, 0)
-        ts = [cpu_reference_mpc(wl, K_s, HORIZON, i) for i in range(5)]
-        out["cpu_baseline"] = {"value": K_s * HORIZON / float(np.mean(ts)), "unit": "rollout-steps/s",
-                               "cores": blas_threads(), "kind": "port",
-                               "sample": "5 plans of K=%d (of %d) sequences, H=%d, float64 numpy/BLAS" % (K_s, K_PER_GPU, HORIZON)}
-        tk = [cpu_reference_kde(kw, 128) for _ in range(3)]
-        out["kde"]["cpu_baseline"] = {"value": 128 * (KDE_N + 1) / float(np.mean(tk)), "unit": "kernel-evals/s", "cores": 1,
-                                      "kind": "reference-library (scipy.stats.gaussian_kde)",
-                                      "sample": "3 x 128 (of %d) queries x %d points" % (KDE_M, KDE_N + 1)}
+        # the CPU leg runs in a fresh process (fork-based pool, no CUDA context): the same code as
+        # `--impl reference`, ~20 s of CPU work on bounded samples of the workload
+        try:
+            ref = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "16",
+                                  "--warmup", "1"], capture_output=True, text=True, timeout=600)
+            r = json.loads(ref.stdout.strip().splitlines()[-1])
+            out["cpu_baseline"] = r["cpu_baseline"]
+            out["kde"]["cpu_baseline"] = {k: r["kde"][k] for k in ("value", "unit", "cores", "kind", "sample", "single_core")}
+        except Exception as exc:                                     # never lose the GPU line
+            out["cpu_baseline"] = {"value": None, "unit": "rollout-steps/s", "cores": 0, "kind": "port",
+                                   "sample": "failed: %r" % (exc,)}
     guard.emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

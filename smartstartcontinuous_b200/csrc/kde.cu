@@ -6,16 +6,27 @@
 //   1. kde_moments_kernel    fp64 shifted first/second moments of the data set (per-block partials)
 //   2. kde_fit_kernel        fp64: mean, covariance (ddof=1), Scott factor, Cholesky, whitening
 //                            matrix  Wm = sqrt(log2(e)/2) * L^-1  and the normalisation constant
-//   3. kde_whiten_kernel     fp64 -> fp32: y = Wm (x - mean); points stored negated and duplicated
-//                            ([-y0,-y0,-y1,-y1,...]) so the pair kernel can use packed FADD2/FFMA2
+//   3. kde_whiten_kernel     fp64 -> fp32: y = Wm (x - mean); points stored as
+//                            [2y0,2y0, 2y1,2y1, ..., -|y|^2,-|y|^2] (duplicated for packed f32x2
+//                            math), queries as [y0, .., y_{D-1}, -|y|^2]; the largest |y|^2 is kept
 //   4. kde_pairs_kernel      the hot loop: sum_i exp2(-|y_q - y_i|^2) for a tile of queries x a
 //                            slice of points; points streamed through shared memory with bulk
 //                            async copies (TMA, UBLKCP) + mbarriers, two queries per packed
-//                            f32x2 instruction, MUFU.EX2 for the exponential
+//                            f32x2 instruction.
+//                            EXPANDED variant (default): the exponent is built as
+//                            -|q|^2 - |x|^2 + 2 q.x  (1 FADD2 + D FFMA2 per query pair instead of
+//                            D FADD2 + D FMUL2/FFMA2); optionally (SS_KDE_POLY_ON) every
+//                            KDE_POLY_EVERY-th point evaluates exp2 with a degree-4 polynomial on
+//                            the FMA pipe instead of MUFU.EX2.  The expansion
+//                            cancels in FP32, so it is only used while max|y|^2 <= KDE_EXPAND_LIMIT
+//                            (density error <~ 4e-8 * max|y|^2 relative, measured); otherwise the
+//                            DIFFERENCE variant (exact differences, MUFU only) runs instead.  The
+//                            choice is made on the device (no host round trip): both variants are
+//                            launched, one of them returns immediately.
 //   5. kde_finish_kernel     fp64: reduce point-slices, rescue underflowed queries in fp64, density,
 //                            UCB and the np.argmax-ordered arg-max (single pass, last block reduces)
 //
-// Roofline: SFU bound -- one MUFU.EX2 per kernel evaluation (16 / clk / SM); see DESIGN.md.
+// Roofline: SFU (MUFU.EX2, 16 / clk / SM) and FP32 pipes, co-limited; see DESIGN.md.
 #include <cstdlib>
 
 #include "common.cuh"
@@ -26,16 +37,31 @@ constexpr int KDE_THREADS = 128;      // threads per CTA in the pair kernel
 constexpr int KDE_TILE_FLOATS = 4096;  // 16 KB of points per shared-memory stage
 constexpr int KDE_STAGES = 2;
 constexpr double KDE_RESCUE_BELOW = 7.8886090522101181e-31;  // 2^-100
+#ifndef SS_KDE_POLY_EVERY
+#define SS_KDE_POLY_EVERY 5
+#endif
+// Measured on B200 (config 2): the polynomial path does not pay on the CUDA cores -- packed f32x2
+// instructions hold the dispatch port for two cycles, so the kernel is dispatch- and XU-bound at
+// the same ~13.4 evaluations/clk/SM with or without it (419 us without, 425-441 us with 1/10..1/5
+// of the points on the polynomial).  Kept behind a switch (validated: 3e-6 relative density error).
+#ifndef SS_KDE_POLY_ON
+#define SS_KDE_POLY_ON 0
+#endif
+constexpr int KDE_POLY_EVERY = SS_KDE_POLY_EVERY;   // one point in KDE_POLY_EVERY takes the polynomial exp2
+constexpr float KDE_EXPAND_LIMIT = 1000.f; // max |y|^2 for the expanded-exponent variant
 
 struct KdeFit {
     double mean[SS_MAX_D];
     double wm[SS_MAX_D * SS_MAX_D];   // whitening matrix (lower triangular), row-major d x d
     double norm;                      // N * (2 pi)^(d/2) * prod diag(L)
     int status;                       // 0 ok, 1 not positive definite
+    int max_norm2_bits;               // float bits of max |y|^2 over points and queries
 };
 
-__host__ __device__ constexpr int kde_point_stride(int D) { return ((2 * D + 3) / 4) * 4; }
-__host__ __device__ constexpr int kde_tile_pts(int D) { return (KDE_TILE_FLOATS / kde_point_stride(D)) / 4 * 4; }
+__host__ __device__ constexpr int kde_point_stride(int D) { return ((2 * D + 2 + 3) / 4) * 4; }
+__host__ __device__ constexpr int kde_tile_pts(int D) {
+    return (KDE_TILE_FLOATS / kde_point_stride(D)) / (4 * KDE_POLY_EVERY) * (4 * KDE_POLY_EVERY);
+}
 __host__ __device__ constexpr int kde_queries_per_thread(int D) {
     return D <= 4 ? 8 : (D <= 8 ? 4 : 2);
 }
@@ -146,38 +172,57 @@ kde_fit_kernel(const double* __restrict__ data, long long n, int d, const double
     for (int j = 0; j < d * d; ++j) fit->wm[j] = inv[j] * scale;
     fit->norm = N * pow(2.0 * 3.14159265358979323846, 0.5 * d) * det;
     fit->status = status;
+    fit->max_norm2_bits = 0;
 }
 
 // ---- 3. whitening ----------------------------------------------------------------------
-// points:  out[i][2j], out[i][2j+1] = -y_j (duplicated, negated); padding rows = far away
-// queries: out[i][j] = y_j
+// points:  out[i] = [2y0,2y0, .., 2y_{D-1},2y_{D-1}, -|y|^2,-|y|^2, 0..]; padding rows are far away
+//          (exp2 -> 0 in either pair-kernel variant)
+// queries: out[i] = [y0, .., y_{D-1}, -|y|^2]
+// |y|^2 is taken from the FP32-rounded coordinates, so the expanded exponent equals the squared
+// distance between the rounded points (what the difference variant computes).
 template <bool POINTS>
 __global__ void kde_whiten_kernel(const double* __restrict__ x, long long n, long long n_pad, int d,
-                                  int D, const KdeFit* __restrict__ fit, float* __restrict__ out) {
-    const int stride = POINTS ? kde_point_stride(D) : D;
+                                  int D, KdeFit* __restrict__ fit, float* __restrict__ out) {
+    const int stride = POINTS ? kde_point_stride(D) : D + 1;
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n_pad) return;
-    float* o = out + (size_t)i * stride;
-    if (i >= n) {
-        for (int j = 0; j < stride; ++j) o[j] = 0.f;
-        if (POINTS) { o[0] = -1e18f; o[1] = -1e18f; }   // exp2(-1e36) == 0
-        return;
-    }
-    double c[SS_MAX_D];
-    for (int j = 0; j < d; ++j) c[j] = x[i * d + j] - fit->mean[j];
-    for (int j = 0; j < D; ++j) {
-        double y = 0.0;
-        if (j < d)
-            for (int k = 0; k <= j; ++k) y += fit->wm[j * d + k] * c[k];
-        if (POINTS) {
-            o[2 * j] = (float)(-y);
-            o[2 * j + 1] = (float)(-y);
+    float norm2 = 0.f;
+    if (i < n_pad) {
+        float* o = out + (size_t)i * stride;
+        if (i >= n) {
+            for (int j = 0; j < stride; ++j) o[j] = 0.f;
+            // far away for both variants: 2y0 = 1e18 (difference form) and -|y|^2 = -1e30 (expanded form)
+            if (POINTS) { o[0] = 1e18f; o[1] = 1e18f; o[2 * D] = -1e30f; o[2 * D + 1] = -1e30f; }
         } else {
-            o[j] = (float)y;
+            double c[SS_MAX_D];
+            for (int j = 0; j < d; ++j) c[j] = x[i * d + j] - fit->mean[j];
+            double nn = 0.0;
+            for (int j = 0; j < D; ++j) {
+                double y = 0.0;
+                if (j < d)
+                    for (int k = 0; k <= j; ++k) y += fit->wm[j * d + k] * c[k];
+                const float yf = (float)y;
+                nn += (double)yf * (double)yf;
+                if (POINTS) {
+                    o[2 * j] = 2.f * yf;
+                    o[2 * j + 1] = 2.f * yf;
+                } else {
+                    o[j] = yf;
+                }
+            }
+            norm2 = (float)nn;
+            if (POINTS) {
+                o[2 * D] = -norm2;
+                o[2 * D + 1] = -norm2;
+                for (int j = 2 * D + 2; j < stride; ++j) o[j] = 0.f;
+            } else {
+                o[D] = -norm2;
+            }
         }
     }
-    if (POINTS)
-        for (int j = 2 * D; j < stride; ++j) o[j] = 0.f;
+    // largest |y|^2 (non-negative floats order like their bit patterns)
+    for (int off = 16; off > 0; off >>= 1) norm2 = fmaxf(norm2, __shfl_xor_sync(0xffffffffu, norm2, off));
+    if ((threadIdx.x & 31) == 0 && norm2 > 0.f) atomicMax(&fit->max_norm2_bits, __float_as_int(norm2));
 }
 
 // ---- 4. the pair kernel ----------------------------------------------------------------
@@ -214,16 +259,42 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         : "memory");
 }
 
+// exp2 of a packed pair on the FMA pipe: Cody-Waite split + degree-4 minimax polynomial on
+// [-0.5, 0.5] (max relative error 2.7e-6 in FP32), exponent inserted with an integer add.
+__device__ __forceinline__ float2 exp2_poly2(float2 e) {
+    const float MAGIC = 12582912.f;     // 1.5 * 2^23: e + MAGIC rounds e to an integer in the low mantissa bits
+    const float2 ec = make_float2(fmaxf(e.x, -126.f), fmaxf(e.y, -126.f));
+    const float2 t = __fadd2_rn(ec, make_float2(MAGIC, MAGIC));
+    const float2 nf = __fadd2_rn(t, make_float2(-MAGIC, -MAGIC));
+    const float2 f = __ffma2_rn(nf, make_float2(-1.f, -1.f), ec);
+    float2 p = __ffma2_rn(f, make_float2(0.009570102207362652f, 0.009570102207362652f),
+                          make_float2(0.05591785907745361f, 0.05591785907745361f));
+    p = __ffma2_rn(p, f, make_float2(0.240247443318367f, 0.240247443318367f));
+    p = __ffma2_rn(p, f, make_float2(0.6931217908859253f, 0.6931217908859253f));
+    p = __ffma2_rn(p, f, make_float2(0.9999992847442627f, 0.9999992847442627f));
+    // bits(MAGIC) << 23 == 0 (mod 2^32): shifting t's bits leaves exactly n << 23
+    return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23)),
+                       __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23)));
+}
+
 // grid: (query tiles, point slices).  partial[slice][q] = sum over the slice's points.
-template <int D>
+// EXPANDED: exponent = -|q|^2 - |x|^2 + 2 q.x, every KDE_POLY_EVERY-th point on the FMA-pipe exp2;
+// !EXPANDED: exponent = -|q - x|^2 from exact differences, MUFU.EX2 only.  The variant that does not
+// match the device-side decision (fit->max_norm2_bits vs KDE_EXPAND_LIMIT) returns at once.
+template <int D, bool EXPANDED>
 __global__ void __launch_bounds__(KDE_THREADS)
 kde_pairs_kernel(const float* __restrict__ pts, long long n_tiles, const float* __restrict__ qw,
-                 long long m_pad, float* __restrict__ partial) {
+                 long long m_pad, const KdeFit* __restrict__ fit, float* __restrict__ partial) {
     constexpr int PS = kde_point_stride(D);           // floats per point in smem/global
     constexpr int Q = kde_queries_per_thread(D);      // queries per thread (Q/2 packed pairs)
     constexpr int TILE_PTS = kde_tile_pts(D);
     constexpr int TILE_FLOATS = TILE_PTS * PS;
     constexpr uint32_t TILE_BYTES = TILE_FLOATS * 4;
+    constexpr int PE = KDE_POLY_EVERY;
+    static_assert(TILE_PTS % PE == 0, "tiles hold whole groups of PE points");
+
+    const bool expand_ok = __int_as_float(fit->max_norm2_bits) <= KDE_EXPAND_LIMIT;
+    if (expand_ok != EXPANDED) return;
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* tiles = reinterpret_cast<float*>(smem_raw);
@@ -249,14 +320,14 @@ kde_pairs_kernel(const float* __restrict__ pts, long long n_tiles, const float* 
         }
     }
 
-    // queries of this thread: q = (blockIdx.x * KDE_THREADS + tid) * Q + [0, Q)
+    // queries of this thread: q = (blockIdx.x * KDE_THREADS + tid) * Q + [0, Q); slot D holds -|q|^2
     const long long qbase = ((long long)blockIdx.x * KDE_THREADS + tid) * Q;
-    float2 qv[Q / 2][D];
+    float2 qv[Q / 2][D + 1];
 #pragma unroll
     for (int p = 0; p < Q / 2; ++p)
 #pragma unroll
-        for (int j = 0; j < D; ++j)
-            qv[p][j] = make_float2(qw[(qbase + 2 * p) * D + j], qw[(qbase + 2 * p + 1) * D + j]);
+        for (int j = 0; j <= D; ++j)
+            qv[p][j] = make_float2(qw[(qbase + 2 * p) * (D + 1) + j], qw[(qbase + 2 * p + 1) * (D + 1) + j]);
 
     float2 total[Q / 2];
 #pragma unroll
@@ -269,25 +340,40 @@ kde_pairs_kernel(const float* __restrict__ pts, long long n_tiles, const float* 
         float2 acc[Q / 2];
 #pragma unroll
         for (int p = 0; p < Q / 2; ++p) acc[p] = make_float2(0.f, 0.f);
-#pragma unroll 2
-        for (int i = 0; i < TILE_PTS; ++i) {
-            // broadcast loads: every lane reads the same point
-            float xs[PS];
+#pragma unroll 1
+        for (int i0 = 0; i0 < TILE_PTS; i0 += PE) {
 #pragma unroll
-            for (int v = 0; v < PS / 4; ++v) {
-                float4 f = *reinterpret_cast<const float4*>(tp + i * PS + 4 * v);
-                xs[4 * v] = f.x; xs[4 * v + 1] = f.y; xs[4 * v + 2] = f.z; xs[4 * v + 3] = f.w;
-            }
+            for (int u = 0; u < PE; ++u) {
+                // broadcast loads: every lane reads the same point
+                float xs[PS];
 #pragma unroll
-            for (int p = 0; p < Q / 2; ++p) {
-                float2 dlt = __fadd2_rn(qv[p][0], make_float2(xs[0], xs[1]));
-                float2 e = __fmul2_rn(dlt, dlt);
-#pragma unroll
-                for (int j = 1; j < D; ++j) {
-                    dlt = __fadd2_rn(qv[p][j], make_float2(xs[2 * j], xs[2 * j + 1]));
-                    e = __ffma2_rn(dlt, dlt, e);
+                for (int v = 0; v < PS / 4; ++v) {
+                    float4 f = *reinterpret_cast<const float4*>(tp + (i0 + u) * PS + 4 * v);
+                    xs[4 * v] = f.x; xs[4 * v + 1] = f.y; xs[4 * v + 2] = f.z; xs[4 * v + 3] = f.w;
                 }
-                acc[p] = __fadd2_rn(acc[p], make_float2(ex2_approx(-e.x), ex2_approx(-e.y)));
+#pragma unroll
+                for (int p = 0; p < Q / 2; ++p) {
+                    float2 e;
+                    if (EXPANDED) {
+                        e = __fadd2_rn(make_float2(xs[2 * D], xs[2 * D + 1]), qv[p][D]);
+#pragma unroll
+                        for (int j = 0; j < D; ++j) e = __ffma2_rn(qv[p][j], make_float2(xs[2 * j], xs[2 * j + 1]), e);
+                        if (SS_KDE_POLY_ON && u == PE - 1)
+                            acc[p] = __fadd2_rn(acc[p], exp2_poly2(e));
+                        else
+                            acc[p] = __fadd2_rn(acc[p], make_float2(ex2_approx(e.x), ex2_approx(e.y)));
+                    } else {
+                        // q - x from the stored 2x: dlt = q - 0.5 * (2x), one FFMA2 per dimension
+                        float2 dlt = __ffma2_rn(make_float2(xs[0], xs[1]), make_float2(-.5f, -.5f), qv[p][0]);
+                        e = __fmul2_rn(dlt, dlt);
+#pragma unroll
+                        for (int j = 1; j < D; ++j) {
+                            dlt = __ffma2_rn(make_float2(xs[2 * j], xs[2 * j + 1]), make_float2(-.5f, -.5f), qv[p][j]);
+                            e = __ffma2_rn(dlt, dlt, e);
+                        }
+                        acc[p] = __fadd2_rn(acc[p], make_float2(ex2_approx(-e.x), ex2_approx(-e.y)));
+                    }
+                }
             }
         }
 #pragma unroll
@@ -413,15 +499,19 @@ kde_finish_kernel(const float* __restrict__ partial, int n_slices, long long m, 
 
 template <int D>
 cudaError_t launch_pairs(ss_ctx* c, const float* pts, long long n_tiles, const float* qw,
-                         long long m_pad, int slices, float* partial) {
+                         long long m_pad, int slices, const KdeFit* fit, float* partial) {
     constexpr int Q = kde_queries_per_thread(D);
     const size_t smem = (size_t)KDE_STAGES * kde_tile_pts(D) * kde_point_stride(D) * 4 + KDE_STAGES * 8;
-    cudaError_t e = cudaFuncSetAttribute(kde_pairs_kernel<D>,
+    cudaError_t e = cudaFuncSetAttribute(kde_pairs_kernel<D, true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(kde_pairs_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)(m_pad / (KDE_THREADS * Q)), (unsigned)slices);
-    kde_pairs_kernel<D><<<grid, KDE_THREADS, smem, c->stream>>>(pts, n_tiles, qw, m_pad, partial);
-    c->launches++;
+    // both variants are launched; the device-side max |y|^2 decides which one does the work
+    kde_pairs_kernel<D, true><<<grid, KDE_THREADS, smem, c->stream>>>(pts, n_tiles, qw, m_pad, fit, partial);
+    kde_pairs_kernel<D, false><<<grid, KDE_THREADS, smem, c->stream>>>(pts, n_tiles, qw, m_pad, fit, partial);
+    c->launches += 2;
     return cudaGetLastError();
 }
 
@@ -467,7 +557,7 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
     SS_CUDA_CHECK(c, c->kde_moments.ensure((size_t)mom_blocks * nm * 8));
     SS_CUDA_CHECK(c, c->kde_fit.ensure(sizeof(KdeFit)));
     SS_CUDA_CHECK(c, c->kde_pts.ensure((size_t)n_pad * PS * 4));
-    SS_CUDA_CHECK(c, c->kde_qw.ensure((size_t)m_pad * D * 4));
+    SS_CUDA_CHECK(c, c->kde_qw.ensure((size_t)m_pad * (D + 1) * 4));
     SS_CUDA_CHECK(c, c->kde_partial.ensure((size_t)slices * m_pad * 4));
     SS_CUDA_CHECK(c, c->kde_block_best.ensure((size_t)fin_blocks * 16));
     SS_CUDA_CHECK(c, c->kde_result.ensure(sizeof(KdeResult)));
@@ -497,7 +587,7 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
     float* partial = c->kde_partial.as<float>();
     switch (D) {
 #define KDE_CASE(DD) \
-    case DD: e = launch_pairs<DD>(c, pts, n_tiles, qw, m_pad, (int)slices, partial); break;
+    case DD: e = launch_pairs<DD>(c, pts, n_tiles, qw, m_pad, (int)slices, fit, partial); break;
         KDE_CASE(1) KDE_CASE(2) KDE_CASE(3) KDE_CASE(4) KDE_CASE(6) KDE_CASE(8)
         KDE_CASE(12) KDE_CASE(16) KDE_CASE(24) KDE_CASE(32)
 #undef KDE_CASE

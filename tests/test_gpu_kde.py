@@ -76,6 +76,24 @@ def test_far_queries_are_rescued_in_fp64(engine):
     assert best == obest
 
 
+def test_expanded_and_difference_pair_kernels_agree(engine):
+    """The pair kernel builds the exponent as -|q|^2 - |x|^2 + 2 q.x while max|y|^2 is small and
+    from exact differences otherwise (decided on the device).  One far-away extra query flips the
+    whole call to the difference variant: the densities of the other queries must not move."""
+    rng = np.random.default_rng(6)
+    data, s2, _ = syn.pendulum_buffer(30000, seed=3)
+    q = s2[rng.choice(len(s2), 2000, replace=False)]
+    vals = np.zeros(len(q) + 1, dtype=np.float32)
+    _, _, dens_a, _ = engine.select_start(data, q, vals[:-1], len(data) - 1, 1.0, 1.0, 2.0, want_density=True)
+    far = np.concatenate([q, [[300.0, -250.0, 900.0]]])
+    _, _, dens_b, _ = engine.select_start(data, far, vals, len(data) - 1, 1.0, 1.0, 2.0, want_density=True)
+    assert dens_b[-1] == 0.0
+    np.testing.assert_allclose(dens_a, dens_b[:-1], rtol=2e-5)
+    _, odens, _ = kde_oracle.select_start(data, q[:300], vals[:300], len(data) - 1, 1.0, 1.0, 2.0)
+    np.testing.assert_allclose(dens_a[:300], odens, rtol=RTOL)
+    np.testing.assert_allclose(dens_b[:300], odens, rtol=RTOL)
+
+
 def test_first_max_and_nan_semantics(engine):
     """np.argmax: first maximum wins; a NaN counts as the maximum."""
     rng = np.random.default_rng(6)
