@@ -27,7 +27,10 @@
 //                            UCB and the np.argmax-ordered arg-max (single pass, last block reduces)
 //
 // Roofline: SFU (MUFU.EX2, 16 / clk / SM) and FP32 pipes, co-limited; see DESIGN.md.
+#include <cuda_bf16.h>
+
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -278,9 +281,8 @@ __device__ __forceinline__ float2 exp2_poly2(float2 e) {
 }
 
 // grid: (query tiles, point slices).  partial[slice][q] = sum over the slice's points.
-// EXPANDED: exponent = -|q|^2 - |x|^2 + 2 q.x, every KDE_POLY_EVERY-th point on the FMA-pipe exp2;
-// !EXPANDED: exponent = -|q - x|^2 from exact differences, MUFU.EX2 only.  The variant that does not
-// match the device-side decision (fit->max_norm2_bits vs KDE_EXPAND_LIMIT) returns at once.
+// EXPANDED: exponent = -|q|^2 - |x|^2 + 2 q.x (optionally every KDE_POLY_EVERY-th point on the
+// FMA-pipe exp2); !EXPANDED: exponent = -|q - x|^2 from exact differences, MUFU.EX2 only.
 template <int D, bool EXPANDED>
 __global__ void __launch_bounds__(KDE_THREADS)
 kde_pairs_kernel(const float* __restrict__ pts, long long n_tiles, const float* __restrict__ qw,
@@ -293,9 +295,7 @@ kde_pairs_kernel(const float* __restrict__ pts, long long n_tiles, const float* 
     constexpr int PE = KDE_POLY_EVERY;
     static_assert(TILE_PTS % PE == 0, "tiles hold whole groups of PE points");
 
-    const bool expand_ok = __int_as_float(fit->max_norm2_bits) <= KDE_EXPAND_LIMIT;
-    if (expand_ok != EXPANDED) return;
-
+    (void)fit;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* tiles = reinterpret_cast<float*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)KDE_STAGES * TILE_BYTES);
@@ -392,6 +392,8 @@ kde_pairs_kernel(const float* __restrict__ pts, long long n_tiles, const float* 
         out[2 * p + 1] = total[p].y;
     }
 }
+
+#include "kde_tc.cuh"
 
 // ---- 5. finish: slice reduction, fp64 rescue, density, UCB, arg-max --------------------
 struct KdeResult {
@@ -498,7 +500,7 @@ kde_finish_kernel(const float* __restrict__ partial, int n_slices, long long m, 
 }
 
 template <int D>
-cudaError_t launch_pairs(ss_ctx* c, const float* pts, long long n_tiles, const float* qw,
+cudaError_t launch_pairs(ss_ctx* c, bool expanded, const float* pts, long long n_tiles, const float* qw,
                          long long m_pad, int slices, const KdeFit* fit, float* partial) {
     constexpr int Q = kde_queries_per_thread(D);
     const size_t smem = (size_t)KDE_STAGES * kde_tile_pts(D) * kde_point_stride(D) * 4 + KDE_STAGES * 8;
@@ -508,10 +510,11 @@ cudaError_t launch_pairs(ss_ctx* c, const float* pts, long long n_tiles, const f
         e = cudaFuncSetAttribute(kde_pairs_kernel<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((unsigned)(m_pad / (KDE_THREADS * Q)), (unsigned)slices);
-    // both variants are launched; the device-side max |y|^2 decides which one does the work
-    kde_pairs_kernel<D, true><<<grid, KDE_THREADS, smem, c->stream>>>(pts, n_tiles, qw, m_pad, fit, partial);
-    kde_pairs_kernel<D, false><<<grid, KDE_THREADS, smem, c->stream>>>(pts, n_tiles, qw, m_pad, fit, partial);
-    c->launches += 2;
+    if (expanded)
+        kde_pairs_kernel<D, true><<<grid, KDE_THREADS, smem, c->stream>>>(pts, n_tiles, qw, m_pad, fit, partial);
+    else
+        kde_pairs_kernel<D, false><<<grid, KDE_THREADS, smem, c->stream>>>(pts, n_tiles, qw, m_pad, fit, partial);
+    c->launches++;
     return cudaGetLastError();
 }
 
@@ -524,41 +527,22 @@ int pad_dim(int d) {
 
 }  // namespace
 
+// pair-stage variants, fastest first; a call starts optimistically with the fastest one its shape
+// allows and repeats the pair stage with KDE_DIFFERENCE when the precision guard (max |y|^2, known
+// only after whitening) rejects the expanded exponent.
+enum KdeVariant { KDE_TC = 0, KDE_EXPANDED = 1, KDE_DIFFERENCE = 2 };
+
 int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double* queries_dev,
             long long m, const float* values_dev, long long n_transitions, double volume,
             double alpha, double beta, double* density_dev, double* ucb_dev, int64_t* out_best_j,
             double* out_best_ucb) {
     const int D = pad_dim(d);
     if (D < 0) SS_FAIL(c, SS_EUNSUPPORTED, "kde: state dimension > 32 is not supported");
-    const int Q = kde_queries_per_thread(D);
-    const int PS = kde_point_stride(D);
-    const int tile_pts = kde_tile_pts(D);
-    const long long n_tiles = (n + tile_pts - 1) / tile_pts;
-    const long long n_pad = n_tiles * tile_pts;
-    const long long qtile = (long long)KDE_THREADS * Q;
-    const long long m_pad = (m + qtile - 1) / qtile * qtile;
-    const long long q_tiles = m_pad / qtile;
-    // fill the GPU: many small CTAs (up to 7 resident per SM; MUFU-bound, more warps hide its latency and small work items balance the SMs)
-    int per_sm = 24;
-    if (const char* e = getenv("SS_KDE_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
-    long long want = (long long)c->sm_count * per_sm;
-    long long slices = (want + q_tiles - 1) / q_tiles;
-    if (slices > n_tiles) slices = n_tiles;
-    if (slices < 1) slices = 1;
-    // drop empty trailing slices
-    {
-        long long per = (n_tiles + slices - 1) / slices;
-        slices = (n_tiles + per - 1) / per;
-    }
     const int mom_blocks = (int)std::min<long long>(c->sm_count * 2, (n + 255) / 256);
     const int nm = d + d * (d + 1) / 2;
     const int fin_blocks = (int)((m + 255) / 256);
-
     SS_CUDA_CHECK(c, c->kde_moments.ensure((size_t)mom_blocks * nm * 8));
     SS_CUDA_CHECK(c, c->kde_fit.ensure(sizeof(KdeFit)));
-    SS_CUDA_CHECK(c, c->kde_pts.ensure((size_t)n_pad * PS * 4));
-    SS_CUDA_CHECK(c, c->kde_qw.ensure((size_t)m_pad * (D + 1) * 4));
-    SS_CUDA_CHECK(c, c->kde_partial.ensure((size_t)slices * m_pad * 4));
     SS_CUDA_CHECK(c, c->kde_block_best.ensure((size_t)fin_blocks * 16));
     SS_CUDA_CHECK(c, c->kde_result.ensure(sizeof(KdeResult)));
     KdeFit* fit = c->kde_fit.as<KdeFit>();
@@ -566,53 +550,135 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
 
     SS_CUDA_CHECK(c, cudaMemsetAsync(res, 0, sizeof(KdeResult), c->stream));
     if (d <= 8)
-        kde_moments_kernel<8><<<mom_blocks, 256, 0, c->stream>>>(data_dev, n, d,
-                                                                 c->kde_moments.as<double>());
+        kde_moments_kernel<8><<<mom_blocks, 256, 0, c->stream>>>(data_dev, n, d, c->kde_moments.as<double>());
     else
-        kde_moments_kernel<SS_MAX_D><<<mom_blocks, 256, 0, c->stream>>>(data_dev, n, d,
-                                                                        c->kde_moments.as<double>());
-    kde_fit_kernel<<<1, 256, 0, c->stream>>>(data_dev, n, d, c->kde_moments.as<double>(), mom_blocks,
-                                            fit);
-    kde_whiten_kernel<true><<<(unsigned)((n_pad + 255) / 256), 256, 0, c->stream>>>(
-        data_dev, n, n_pad, d, D, fit, c->kde_pts.as<float>());
-    kde_whiten_kernel<false><<<(unsigned)((m_pad + 255) / 256), 256, 0, c->stream>>>(
-        queries_dev, m, m_pad, d, D, fit, c->kde_qw.as<float>());
-    c->launches += 4;
+        kde_moments_kernel<SS_MAX_D><<<mom_blocks, 256, 0, c->stream>>>(data_dev, n, d, c->kde_moments.as<double>());
+    kde_fit_kernel<<<1, 256, 0, c->stream>>>(data_dev, n, d, c->kde_moments.as<double>(), mom_blocks, fit);
+    c->launches += 2;
     SS_CUDA_CHECK(c, cudaGetLastError());
-    timer_mark(c, "kde_fit_whiten");
 
-    cudaError_t e = cudaSuccess;
-    const float* pts = c->kde_pts.as<float>();
-    const float* qw = c->kde_qw.as<float>();
-    float* partial = c->kde_partial.as<float>();
-    switch (D) {
+    int variant = KDE_EXPANDED;
+    if (d <= kdetc::MAX_D && !getenv("SS_KDE_NO_TC")) variant = KDE_TC;
+    if (getenv("SS_KDE_DIFFERENCE")) variant = KDE_DIFFERENCE;
+
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        long long m_pad = 0;
+        int n_slices = 0;
+        if (variant == KDE_TC) {
+            using namespace kdetc;
+            const long long n_tiles = (n + NP - 1) / NP, n_pad = n_tiles * NP;
+            const long long q_tiles = (m + QT - 1) / QT;
+            m_pad = q_tiles * QT;
+            // work items (query tile x slice of point tiles) for the persistent CTAs: a whole number
+            // of waves of items with ~8 or more point tiles each (slices are balanced in the kernel)
+            long long gcd_a = q_tiles, gcd_b = c->sm_count;
+            while (gcd_b) { const long long r = gcd_a % gcd_b; gcd_a = gcd_b; gcd_b = r; }
+            const long long step = c->sm_count / gcd_a;          // slices % step == 0 -> items % SMs == 0
+            long long slices = n_tiles / 8 / step * step;
+            if (slices < step) slices = step;
+            if (slices * q_tiles > 32LL * c->sm_count) {
+                slices = 32LL * c->sm_count / q_tiles / step * step;
+                if (slices < step) slices = step;
+            }
+            if (slices > n_tiles) slices = n_tiles;
+            if (slices < 1) slices = 1;
+            n_slices = (int)slices * (EPI_WARPS / 4);            // one partial row per (slice, column group)
+            SS_CUDA_CHECK(c, c->kde_pts.ensure((size_t)n_tiles * B_BYTES));
+            SS_CUDA_CHECK(c, c->kde_qw.ensure((size_t)q_tiles * A_BYTES));
+            SS_CUDA_CHECK(c, c->kde_partial.ensure((size_t)n_slices * m_pad * 4));
+            kde_whiten_tc_kernel<true><<<(unsigned)((n_pad + 255) / 256), 256, 0, c->stream>>>(
+                data_dev, n, n_pad, d, fit, c->kde_pts.as<__nv_bfloat16>());
+            kde_whiten_tc_kernel<false><<<(unsigned)((m_pad + 255) / 256), 256, 0, c->stream>>>(
+                queries_dev, m, m_pad, d, fit, c->kde_qw.as<__nv_bfloat16>());
+            c->launches += 2;
+            SS_CUDA_CHECK(c, cudaGetLastError());
+            timer_mark(c, "kde_fit_whiten");
+            SS_CUDA_CHECK(c, cudaFuncSetAttribute(kde_pairs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                  (int)SMEM_BYTES));
+            const long long items = q_tiles * slices;
+            const unsigned grid = (unsigned)(items < c->sm_count ? items : c->sm_count);
+            kde_pairs_tc_kernel<<<grid, THREADS, SMEM_BYTES, c->stream>>>(
+                c->kde_qw.as<__nv_bfloat16>(), c->kde_pts.as<__nv_bfloat16>(), n_tiles, (int)q_tiles, (int)slices, m_pad,
+                fit, c->kde_partial.as<float>());
+            c->launches++;
+            SS_CUDA_CHECK(c, cudaGetLastError());
+            timer_mark(c, "kde_pairs");
+        } else {
+            const int Q = kde_queries_per_thread(D);
+            const int PS = kde_point_stride(D);
+            const int tile_pts = kde_tile_pts(D);
+            const long long n_tiles = (n + tile_pts - 1) / tile_pts;
+            const long long n_pad = n_tiles * tile_pts;
+            const long long qtile = (long long)KDE_THREADS * Q;
+            m_pad = (m + qtile - 1) / qtile * qtile;
+            const long long q_tiles = m_pad / qtile;
+            // fill the GPU: many small CTAs (up to 7 resident per SM; more warps hide the MUFU
+            // latency and small work items balance the SMs)
+            int per_sm = 24;
+            if (const char* e = getenv("SS_KDE_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;
+            long long want = (long long)c->sm_count * per_sm;
+            long long slices = (want + q_tiles - 1) / q_tiles;
+            if (slices > n_tiles) slices = n_tiles;
+            if (slices < 1) slices = 1;
+            {
+                long long per = (n_tiles + slices - 1) / slices;      // drop empty trailing slices
+                slices = (n_tiles + per - 1) / per;
+            }
+            n_slices = (int)slices;
+            SS_CUDA_CHECK(c, c->kde_pts.ensure((size_t)n_pad * PS * 4));
+            SS_CUDA_CHECK(c, c->kde_qw.ensure((size_t)m_pad * (D + 1) * 4));
+            SS_CUDA_CHECK(c, c->kde_partial.ensure((size_t)slices * m_pad * 4));
+            kde_whiten_kernel<true><<<(unsigned)((n_pad + 255) / 256), 256, 0, c->stream>>>(
+                data_dev, n, n_pad, d, D, fit, c->kde_pts.as<float>());
+            kde_whiten_kernel<false><<<(unsigned)((m_pad + 255) / 256), 256, 0, c->stream>>>(
+                queries_dev, m, m_pad, d, D, fit, c->kde_qw.as<float>());
+            c->launches += 2;
+            SS_CUDA_CHECK(c, cudaGetLastError());
+            timer_mark(c, "kde_fit_whiten");
+            cudaError_t e = cudaSuccess;
+            const float* pts = c->kde_pts.as<float>();
+            const float* qw = c->kde_qw.as<float>();
+            float* partial = c->kde_partial.as<float>();
+            const bool expanded = variant == KDE_EXPANDED;
+            switch (D) {
 #define KDE_CASE(DD) \
-    case DD: e = launch_pairs<DD>(c, pts, n_tiles, qw, m_pad, (int)slices, fit, partial); break;
-        KDE_CASE(1) KDE_CASE(2) KDE_CASE(3) KDE_CASE(4) KDE_CASE(6) KDE_CASE(8)
-        KDE_CASE(12) KDE_CASE(16) KDE_CASE(24) KDE_CASE(32)
+    case DD: e = launch_pairs<DD>(c, expanded, pts, n_tiles, qw, m_pad, (int)slices, fit, partial); break;
+                KDE_CASE(1) KDE_CASE(2) KDE_CASE(3) KDE_CASE(4) KDE_CASE(6) KDE_CASE(8)
+                KDE_CASE(12) KDE_CASE(16) KDE_CASE(24) KDE_CASE(32)
 #undef KDE_CASE
+            }
+            SS_CUDA_CHECK(c, e);
+            timer_mark(c, "kde_pairs");
+        }
+
+        double* bv = c->kde_block_best.as<double>();
+        long long* bi = reinterpret_cast<long long*>(bv + fin_blocks);
+        kde_finish_kernel<<<fin_blocks, 256, 0, c->stream>>>(
+            c->kde_partial.as<float>(), n_slices, m, m_pad, data_dev, n, d, queries_dev, values_dev, fit,
+            (double)n_transitions, volume, alpha, beta, density_dev, ucb_dev, bv, bi, res);
+        c->launches++;
+        SS_CUDA_CHECK(c, cudaGetLastError());
+        timer_mark(c, "kde_finish");
+
+        KdeResult hres;
+        int hstat[2] = {0, 0};     // fit->status, fit->max_norm2_bits (adjacent ints)
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(&hres, res, sizeof(KdeResult), cudaMemcpyDeviceToHost, c->stream));
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(hstat, &fit->status, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        if (hstat[0] != 0)
+            SS_FAIL(c, SS_ESINGULAR, "kde: data covariance is not positive definite (singular matrix)");
+        float max_norm2;
+        std::memcpy(&max_norm2, &hstat[1], 4);
+        if (variant != KDE_DIFFERENCE && !(max_norm2 <= KDE_EXPAND_LIMIT)) {
+            // the expanded exponent would cancel too much for this data: redo the pair stage with
+            // exact differences (rare: some |y|^2 above KDE_EXPAND_LIMIT, e.g. a far outlier query)
+            variant = KDE_DIFFERENCE;
+            SS_CUDA_CHECK(c, cudaMemsetAsync(res, 0, sizeof(KdeResult), c->stream));
+            continue;
+        }
+        *out_best_j = hres.best_j;
+        *out_best_ucb = hres.best_ucb;
+        return SS_OK;
     }
-    SS_CUDA_CHECK(c, e);
-    timer_mark(c, "kde_pairs");
-
-    double* bv = c->kde_block_best.as<double>();
-    long long* bi = reinterpret_cast<long long*>(bv + fin_blocks);
-    kde_finish_kernel<<<fin_blocks, 256, 0, c->stream>>>(
-        partial, (int)slices, m, m_pad, data_dev, n, d, queries_dev, values_dev, fit,
-        (double)n_transitions, volume, alpha, beta, density_dev, ucb_dev, bv, bi, res);
-    c->launches++;
-    SS_CUDA_CHECK(c, cudaGetLastError());
-    timer_mark(c, "kde_finish");
-
-    KdeResult hres;
-    KdeFit hfit_status;
-    SS_CUDA_CHECK(c, cudaMemcpyAsync(&hres, res, sizeof(KdeResult), cudaMemcpyDeviceToHost, c->stream));
-    SS_CUDA_CHECK(c, cudaMemcpyAsync(&hfit_status.status, &fit->status, sizeof(int),
-                                     cudaMemcpyDeviceToHost, c->stream));
-    SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-    if (hfit_status.status != 0)
-        SS_FAIL(c, SS_ESINGULAR, "kde: data covariance is not positive definite (singular matrix)");
-    *out_best_j = hres.best_j;
-    *out_best_ucb = hres.best_ucb;
-    return SS_OK;
+    SS_FAIL(c, SS_ECUDA, "kde: pair stage did not settle");
 }
