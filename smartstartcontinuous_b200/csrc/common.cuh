@@ -98,6 +98,7 @@ struct ss_ctx {
     // ---- KDE scratch
     DevBuf kde_data64, kde_q64, kde_vals, kde_pts, kde_qw, kde_partial, kde_fit, kde_moments;
     DevBuf kde_density, kde_ucb, kde_block_best, kde_result;
+    bool kde_tc_attr_set = false;
 
     // ---- MPC model
     bool model_set = false;

@@ -3,9 +3,9 @@
 // smartexplorationcontinuous.py:260-280.
 //
 // Pipeline (all on the context stream):
-//   1. kde_moments_kernel    fp64 shifted first/second moments of the data set (per-block partials)
-//   2. kde_fit_kernel        fp64: mean, covariance (ddof=1), Scott factor, Cholesky, whitening
-//                            matrix  Wm = sqrt(log2(e)/2) * L^-1  and the normalisation constant
+//   1. kde_moments_kernel    fp64 shifted first/second moments of the data set (per-block partials);
+//   2.  + kde_fit_block      the last block fits: mean, covariance (ddof=1), Scott factor, Cholesky,
+//                            whitening matrix  Wm = sqrt(log2(e)/2) * L^-1, normalisation constant
 //   3. kde_whiten_kernel     fp64 -> fp32: y = Wm (x - mean); points stored as
 //                            [2y0,2y0, 2y1,2y1, ..., -|y|^2,-|y|^2] (duplicated for packed f32x2
 //                            math), queries as [y0, .., y_{D-1}, -|y|^2]; the largest |y|^2 is kept
@@ -40,6 +40,7 @@ constexpr int KDE_THREADS = 128;      // threads per CTA in the pair kernel
 constexpr int KDE_TILE_FLOATS = 4096;  // 16 KB of points per shared-memory stage
 constexpr int KDE_STAGES = 2;
 constexpr double KDE_RESCUE_BELOW = 7.8886090522101181e-31;  // 2^-100
+constexpr int KDE_FIN_SPLIT = 4;           // threads per query in the finish kernel's slice reduction
 #ifndef SS_KDE_POLY_EVERY
 #define SS_KDE_POLY_EVERY 5
 #endif
@@ -51,7 +52,9 @@ constexpr double KDE_RESCUE_BELOW = 7.8886090522101181e-31;  // 2^-100
 #define SS_KDE_POLY_ON 0
 #endif
 constexpr int KDE_POLY_EVERY = SS_KDE_POLY_EVERY;   // one point in KDE_POLY_EVERY takes the polynomial exp2
-constexpr float KDE_EXPAND_LIMIT = 1000.f; // max |y|^2 for the expanded-exponent variant
+constexpr float KDE_EXPAND_LIMIT = 1000.f; // max |y|^2 for the expanded-exponent CUDA-core variant
+                                           // (density error ~4e-8 * max|y|^2 relative, measured)
+constexpr float KDE_TC_LIMIT = 700.f;      // same for the tcgen05 variant (~7e-8 * max|y|^2, measured)
 
 struct KdeFit {
     double mean[SS_MAX_D];
@@ -72,10 +75,17 @@ __host__ __device__ constexpr int kde_queries_per_thread(int D) {
 // ---- 1. moments ------------------------------------------------------------------------
 // partial[b] = { sum (x - x0) [d], sum (x - x0)(x - x0)^T lower-tri [d(d+1)/2] }, x0 = data[0]
 // (shifted by the first data point so the fp64 one-pass covariance does not cancel)
+__device__ void kde_fit_block(const double* __restrict__ data, long long n, int d, const double* __restrict__ partial,
+                              int nblocks, KdeFit* __restrict__ fit);
+
+// The last block to finish (atomic ticket) reduces the per-block partials and fits the estimator
+// (kde_fit_block), so moments + fit are one launch.
 template <int DM>
 __global__ void __launch_bounds__(256)
-kde_moments_kernel(const double* __restrict__ data, long long n, int d, double* __restrict__ partial) {
+kde_moments_kernel(const double* __restrict__ data, long long n, int d, double* __restrict__ partial,
+                   unsigned int* __restrict__ ticket, KdeFit* __restrict__ fit) {
     __shared__ double sm[8];
+    __shared__ bool s_last;
     constexpr int NM = DM + DM * (DM + 1) / 2;
     const int nm = d + d * (d + 1) / 2;
     double loc[NM];
@@ -112,12 +122,21 @@ kde_moments_kernel(const double* __restrict__ data, long long n, int d, double* 
         }
         __syncthreads();
     }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        kde_fit_block(data, n, d, partial, (int)gridDim.x, fit);
+        if (threadIdx.x == 0) *ticket = 0;
+    }
 }
 
 // ---- 2. fit ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-kde_fit_kernel(const double* __restrict__ data, long long n, int d, const double* __restrict__ partial,
-               int nblocks, KdeFit* __restrict__ fit) {
+__device__ void kde_fit_block(const double* __restrict__ data, long long n, int d, const double* __restrict__ partial,
+                              int nblocks, KdeFit* __restrict__ fit) {
     __shared__ double mom[SS_MAX_D + SS_MAX_D * (SS_MAX_D + 1) / 2];
     const int nm = d + d * (d + 1) / 2;
     // one warp per moment: lanes stride over the per-block partials, fixed-order shuffle reduction
@@ -401,6 +420,8 @@ struct KdeResult {
     long long best_j;
     unsigned int blocks_done;
     int n_rescued;
+    unsigned int moments_ticket;      // last-block election of kde_moments_kernel
+    int pad;
 };
 
 __global__ void __launch_bounds__(256)
@@ -420,19 +441,25 @@ kde_finish_kernel(const float* __restrict__ partial, int n_slices, long long m, 
     if (threadIdx.x == 0) s_nlist = 0;
     __syncthreads();
 
-    const long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    // four threads per query split the slice reduction (fixed order: slices sub, sub + 4, ..., then
+    // a shuffle tree); the thread with sub == 0 owns the query from here on
+    const int sub = threadIdx.x & (KDE_FIN_SPLIT - 1);
+    const long long jq0 = blockIdx.x * (long long)(blockDim.x / KDE_FIN_SPLIT) + (threadIdx.x / KDE_FIN_SPLIT);
+    const long long j = sub == 0 ? jq0 : m;          // non-owners behave like out-of-range threads
     double sum = 0.0;
-    if (j < m) {
-        for (int s = 0; s < n_slices; ++s) sum += (double)partial[(size_t)s * m_pad + j];
-        if (!(sum >= KDE_RESCUE_BELOW)) s_list[atomicAdd(&s_nlist, 1)] = threadIdx.x;
+    if (jq0 < m) {
+#pragma unroll 4
+        for (int s = sub; s < n_slices; s += KDE_FIN_SPLIT) sum += (double)partial[(size_t)s * m_pad + jq0];
     }
+    for (int off = 1; off < KDE_FIN_SPLIT; off <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    if (j < m && !(sum >= KDE_RESCUE_BELOW)) s_list[atomicAdd(&s_nlist, 1)] = threadIdx.x;
     __syncthreads();
     // fp64 rescue of queries whose fp32 sum underflowed (far from every data point):
     // the whole block recomputes sum_i exp(-|L^-1 (q - x_i)|^2 / 2) exactly as scipy does.
     const int nres = s_nlist;
     for (int r = 0; r < nres; ++r) {
         const int owner = s_list[r];
-        const long long jq = blockIdx.x * (long long)blockDim.x + owner;
+        const long long jq = blockIdx.x * (long long)(blockDim.x / KDE_FIN_SPLIT) + owner / KDE_FIN_SPLIT;
         double yq[SS_MAX_D];
         for (int a = 0; a < d; ++a) {
             double y = 0.0;
@@ -540,7 +567,7 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
     if (D < 0) SS_FAIL(c, SS_EUNSUPPORTED, "kde: state dimension > 32 is not supported");
     const int mom_blocks = (int)std::min<long long>(c->sm_count * 2, (n + 255) / 256);
     const int nm = d + d * (d + 1) / 2;
-    const int fin_blocks = (int)((m + 255) / 256);
+    const int fin_blocks = (int)((m + 256 / KDE_FIN_SPLIT - 1) / (256 / KDE_FIN_SPLIT));
     SS_CUDA_CHECK(c, c->kde_moments.ensure((size_t)mom_blocks * nm * 8));
     SS_CUDA_CHECK(c, c->kde_fit.ensure(sizeof(KdeFit)));
     SS_CUDA_CHECK(c, c->kde_block_best.ensure((size_t)fin_blocks * 16));
@@ -550,11 +577,12 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
 
     SS_CUDA_CHECK(c, cudaMemsetAsync(res, 0, sizeof(KdeResult), c->stream));
     if (d <= 8)
-        kde_moments_kernel<8><<<mom_blocks, 256, 0, c->stream>>>(data_dev, n, d, c->kde_moments.as<double>());
+        kde_moments_kernel<8><<<mom_blocks, 256, 0, c->stream>>>(data_dev, n, d, c->kde_moments.as<double>(),
+                                                                 &res->moments_ticket, fit);
     else
-        kde_moments_kernel<SS_MAX_D><<<mom_blocks, 256, 0, c->stream>>>(data_dev, n, d, c->kde_moments.as<double>());
-    kde_fit_kernel<<<1, 256, 0, c->stream>>>(data_dev, n, d, c->kde_moments.as<double>(), mom_blocks, fit);
-    c->launches += 2;
+        kde_moments_kernel<SS_MAX_D><<<mom_blocks, 256, 0, c->stream>>>(data_dev, n, d, c->kde_moments.as<double>(),
+                                                                        &res->moments_ticket, fit);
+    c->launches += 1;
     SS_CUDA_CHECK(c, cudaGetLastError());
 
     int variant = KDE_EXPANDED;
@@ -586,15 +614,18 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
             SS_CUDA_CHECK(c, c->kde_pts.ensure((size_t)n_tiles * B_BYTES));
             SS_CUDA_CHECK(c, c->kde_qw.ensure((size_t)q_tiles * A_BYTES));
             SS_CUDA_CHECK(c, c->kde_partial.ensure((size_t)n_slices * m_pad * 4));
-            kde_whiten_tc_kernel<true><<<(unsigned)((n_pad + 255) / 256), 256, 0, c->stream>>>(
-                data_dev, n, n_pad, d, fit, c->kde_pts.as<__nv_bfloat16>());
-            kde_whiten_tc_kernel<false><<<(unsigned)((m_pad + 255) / 256), 256, 0, c->stream>>>(
-                queries_dev, m, m_pad, d, fit, c->kde_qw.as<__nv_bfloat16>());
-            c->launches += 2;
+            const unsigned pblocks = (unsigned)((n_pad + 255) / 256), qblocks = (unsigned)((m_pad + 255) / 256);
+            kde_whiten_tc_kernel<<<pblocks + qblocks, 256, 0, c->stream>>>(
+                data_dev, n, n_pad, c->kde_pts.as<__nv_bfloat16>(), queries_dev, m, m_pad,
+                c->kde_qw.as<__nv_bfloat16>(), d, fit, pblocks);
+            c->launches += 1;
             SS_CUDA_CHECK(c, cudaGetLastError());
             timer_mark(c, "kde_fit_whiten");
-            SS_CUDA_CHECK(c, cudaFuncSetAttribute(kde_pairs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                  (int)SMEM_BYTES));
+            if (!c->kde_tc_attr_set) {
+                SS_CUDA_CHECK(c, cudaFuncSetAttribute(kde_pairs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                      (int)SMEM_BYTES));
+                c->kde_tc_attr_set = true;
+            }
             const long long items = q_tiles * slices;
             const unsigned grid = (unsigned)(items < c->sm_count ? items : c->sm_count);
             kde_pairs_tc_kernel<<<grid, THREADS, SMEM_BYTES, c->stream>>>(
@@ -669,7 +700,7 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
             SS_FAIL(c, SS_ESINGULAR, "kde: data covariance is not positive definite (singular matrix)");
         float max_norm2;
         std::memcpy(&max_norm2, &hstat[1], 4);
-        if (variant != KDE_DIFFERENCE && !(max_norm2 <= KDE_EXPAND_LIMIT)) {
+        if (variant != KDE_DIFFERENCE && !(max_norm2 <= (variant == KDE_TC ? KDE_TC_LIMIT : KDE_EXPAND_LIMIT))) {
             // the expanded exponent would cancel too much for this data: redo the pair stage with
             // exact differences (rare: some |y|^2 above KDE_EXPAND_LIMIT, e.g. a far outlier query)
             variant = KDE_DIFFERENCE;

@@ -120,11 +120,11 @@ __device__ __forceinline__ void split3(float v, __nv_bfloat16& h, __nv_bfloat16&
 // One thread per row.  POINTS: tiles of NP rows, image [tile][KS/8][NP][8]; queries: tiles of QT rows.
 // Rows >= n are padding: points far away (-|x|^2 = -1e30), queries zero.
 template <bool POINTS>
-__global__ void __launch_bounds__(256)
-kde_whiten_tc_kernel(const double* __restrict__ x, long long n, long long n_pad, int d, KdeFit* __restrict__ fit,
-                     __nv_bfloat16* __restrict__ img) {
+__device__ __forceinline__ void whiten_tc_rows(long long block, const double* __restrict__ x, long long n,
+                                               long long n_pad, int d, KdeFit* __restrict__ fit,
+                                               __nv_bfloat16* __restrict__ img) {
     constexpr int ROWS = POINTS ? NP : QT;
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long i = block * (long long)blockDim.x + threadIdx.x;
     float norm2 = 0.f;
     if (i < n_pad) {
         __nv_bfloat16 slot[KS];
@@ -205,6 +205,17 @@ kde_whiten_tc_kernel(const double* __restrict__ x, long long n, long long n_pad,
     }
     for (int off = 16; off > 0; off >>= 1) norm2 = fmaxf(norm2, __shfl_xor_sync(0xffffffffu, norm2, off));
     if ((threadIdx.x & 31) == 0 && norm2 > 0.f) atomicMax(&fit->max_norm2_bits, __float_as_int(norm2));
+}
+
+// points (blocks [0, point_blocks)) and queries (the remaining blocks) in one launch
+__global__ void __launch_bounds__(256)
+kde_whiten_tc_kernel(const double* __restrict__ data, long long n, long long n_pad, __nv_bfloat16* __restrict__ p_img,
+                     const double* __restrict__ queries, long long m, long long m_pad,
+                     __nv_bfloat16* __restrict__ q_img, int d, KdeFit* __restrict__ fit, unsigned point_blocks) {
+    if (blockIdx.x < point_blocks)
+        whiten_tc_rows<true>(blockIdx.x, data, n, n_pad, d, fit, p_img);
+    else
+        whiten_tc_rows<false>(blockIdx.x - point_blocks, queries, m, m_pad, d, fit, q_img);
 }
 
 // ---- the pair kernel -----------------------------------------------------------------------
