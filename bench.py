@@ -15,7 +15,8 @@ BASELINE.json's metric, KDE kernel-evals/s, is reported in the same line under "
             pinned host memory -> H2D inside the call -> rollout -> score -> D2H of the result
   kde       BASELINE config 2: 100 001 Pendulum states x 16 384 candidate queries per GPU
   roofline  tensor pipe for the rollout kernel (achieved = 507 000 FLOP x K*H / kernel time, against
-            the measured sustained bf16 peak), SFU pipe for the KDE pair kernel
+            the measured sustained bf16 peak; frac_of_burst_peak = against the burst figure), SFU pipe
+            (16 MUFU.EX2 / clk / SM) for the KDE pair kernel
   --impl reference: the oracle port of the reference's CPU path (numpy float64, BLAS on all host
             cores; scipy gaussian_kde with the queries chunked over a multiprocessing.Pool for the
             KDE), timed on bounded samples of the same workload.
@@ -41,6 +42,9 @@ HORIZON = 50
 KDE_N = 100_000
 KDE_M = 16_384
 SFU_PER_CLK_PER_SM = 16                        # MUFU.EX2 lanes per SM per clock (sm_100)
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
+# captures of exactly these workloads (profiles/r01c_ncu_summary.md); not measurable live
+NCU_TRAFFIC = {"mpc_rollout_tc_kernel": 621_056 + 50_215_680, "kde_pairs_tc_kernel": 7_490_816}
 
 
 def measured_peaks():
@@ -396,7 +400,10 @@ def main():
                 "path": "ss_mpc_rollout/ss_mpc_finish/ss_mpc_replay with host float64 action samples (pinned)"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / peaks["bf16_sustained"], "traffic": None,
+                     "frac": achieved_tf / peaks["bf16_sustained"],
+                     "traffic": NCU_TRAFFIC["mpc_rollout_tc_kernel"] if precision == "bf16_tc" else None,
+                     "traffic_source": "profiles/r01c_ncu_summary.md (ncu --set full, same workload)",
+                     "frac_of_burst_peak": achieved_tf / peaks["bf16_burst"],
                      "kernel": "mpc_rollout_tc_kernel" if precision == "bf16_tc" else "mpc_rollout_simt_kernel",
                      "kernel_ms": k_ms, "peak_source": peaks["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
                      "algorithmic_flop_per_rollout_step": FLOP_PER_STEP[3]},
@@ -406,10 +413,13 @@ def main():
                 "e2e": {"value": evals / (kde_e2e_ms * 1e-3), "unit": "kernel-evals/s", "ms_per_step": kde_e2e_ms,
                         "h2d_bytes_per_step": int(8 * 3 * (KDE_N + 1 + KDE_M) + 4 * KDE_M), "d2h_bytes_per_step": 16},
                 "roofline": {"bound": "sfu", "achieved": kde_achieved, "peak": sfu_peak, "unit": "kernel-evals/s",
-                             "frac": kde_achieved / sfu_peak, "kernel": "kde_pairs_kernel<3>", "kernel_ms": p_ms,
-                             "peak_source": "16 MUFU.EX2/clk/SM x %d SMs x %.0f MHz (max SM clock)" % (info["sm_count"], peaks["sm_max_mhz"]),
+                             "frac": kde_achieved / sfu_peak, "kernel": "kde_pairs_tc_kernel", "kernel_ms": p_ms,
+                             "peak_source": "16 MUFU.EX2/clk/SM x %d SMs x %.0f MHz (max SM clock); the kernel takes 3/8 of "
+                                            "its exp2 evaluations on the FMA pipe (polynomial) and the exponents from the "
+                                            "tensor pipe, so frac > 1 is possible" % (info["sm_count"], peaks["sm_max_mhz"]),
                              "hbm_achieved_gbs": kde_bytes / (p_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
-                             "traffic": None}},
+                             "traffic": NCU_TRAFFIC["kde_pairs_tc_kernel"],
+                             "traffic_source": "profiles/r01c_ncu_summary.md (ncu --set full, same workload)"}},
     }
     if world == 1 and not args.no_cpu_baseline:
         # the CPU leg runs in a fresh process (fork-based pool, no CUDA context): the same code as
