@@ -421,6 +421,29 @@ def main():
                              "traffic": NCU_TRAFFIC["kde_pairs_tc_kernel"],
                              "traffic_source": "profiles/r01c_ncu_summary.md (ncu --set full, same workload)"}},
     }
+    # ---- row f3 (plan set-up): pair extraction of path_shortcutter, P = 1000 path states ----------
+    try:
+        from smartstartcontinuous_b200 import numerical as num
+        from smartstartcontinuous_b200 import synthetic as syn
+        obs, _ = syn.pendulum_rollouts(np.random.default_rng(7), 1, 1000)
+        path = np.asarray(obs[0][:1000])
+        stds, means = num.path_deltas_stds_and_means_per_dim(path)
+        radii = num.radii_calc(means, stds, 1, 1, 1)
+        dist_fn = num.elliptical_euclidean_distance_function_generator(radii)
+        eng.path_close_pairs(path, radii, 1.0)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            pairs = eng.path_close_pairs(path, radii, 1.0)
+        t_dev = (time.perf_counter() - t0) / 10
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ref_pairs = np.argwhere(np.triu(dist_fn(path[:, None, :], path[None, :, :]) <= 1.0, k=2))
+        t_np = (time.perf_counter() - t0) / 3
+        out["plan_setup"] = {"what": "path_shortcutter pair extraction (numerical.py:226-246), P=1000, d=3, host buffers in and out",
+                             "gpu_ms": 1e3 * t_dev, "numpy_ms": 1e3 * t_np, "pairs": int(len(pairs)),
+                             "identical": bool(np.array_equal(pairs, ref_pairs))}
+    except Exception as exc:
+        out["plan_setup"] = {"error": repr(exc)}
     if world == 1 and not args.no_cpu_baseline:
         # the CPU leg runs in a fresh process (fork-based pool, no CUDA context): the same code as
         # `--impl reference`, ~20 s of CPU work on bounded samples of the workload

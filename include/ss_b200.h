@@ -182,6 +182,17 @@ int ss_mpc_sample_actions(ss_ctx* ctx, int64_t K_local, int64_t k_offset, int H,
 /* 1 when ss_mpc_set_model's shape can run on the tcgen05 kernel */
 int ss_mpc_tc_supported(ss_ctx* ctx);
 
+/* ---- plan set-up geometry ------------------------------------------
+ * ss_path_close_pairs: the pair-extraction half of path_shortcutter (numerical.py:226-246,
+ * called from start_new_episode_plan, NND_MB_agent.py:398-401): all (s, e) with e >= s + 2 whose
+ * elliptical distance sqrt(sum(((path[s] - path[e]) / radii)^2)) (numerical.py:116-124) is <= theta,
+ * in np.argwhere(np.triu(mask, k=2)) order.  float64 with the reference's operation order, so the
+ * threshold decisions are the ones numpy makes.  out_pairs [max_pairs][2] int32 receives the first
+ * min(*out_count, max_pairs) pairs; *out_count is the total (call again with a larger buffer if it
+ * exceeds max_pairs).  The interval-scheduling DP (numerical.py:189-222) stays on the host. */
+int ss_path_close_pairs(ss_ctx* ctx, const double* path, int P, int d, const double* radii, double theta,
+                        int32_t* out_pairs, int64_t max_pairs, int64_t* out_count);
+
 #ifdef __cplusplus
 }
 #endif

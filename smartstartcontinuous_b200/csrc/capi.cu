@@ -59,7 +59,8 @@ extern "C" int ss_destroy(ss_ctx* c) {
                       &c->kde_block_best, &c->kde_result, &c->tc_w1, &c->tc_w2, &c->tc_w3,
                       &c->tc_misc, &c->plan_ds, &c->plan_dl, &c->mpc_actions64, &c->mpc_states,
                       &c->mpc_scores, &c->mpc_partial_sums, &c->mpc_sums, &c->mpc_block_best,
-                      &c->mpc_result, &c->mpc_replay, &c->mpc_sampled, &c->mpc_package};
+                      &c->mpc_result, &c->mpc_replay, &c->mpc_sampled, &c->mpc_package,
+                      &c->geom_in, &c->geom_rows, &c->geom_pairs};
     for (DevBuf* b : bufs) b->release();
     for (auto& b : c->w32) b.release();
     for (auto& b : c->b32) b.release();

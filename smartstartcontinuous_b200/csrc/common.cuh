@@ -99,6 +99,8 @@ struct ss_ctx {
     DevBuf kde_data64, kde_q64, kde_vals, kde_pts, kde_qw, kde_partial, kde_fit, kde_moments;
     DevBuf kde_density, kde_ucb, kde_block_best, kde_result;
     bool kde_tc_attr_set = false;
+    // ---- plan set-up geometry scratch (plan_geom.cu)
+    DevBuf geom_in, geom_rows, geom_pairs;
 
     // ---- MPC model
     bool model_set = false;

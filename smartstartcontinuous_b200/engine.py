@@ -119,6 +119,24 @@ class Engine:
             C.c_void_p(ucb_ptr) if ucb_ptr else None, C.byref(best), C.byref(best_ucb)))
         return int(best.value), float(best_ucb.value)
 
+    # ------------------------------------------------------------------ plan set-up geometry
+    def path_close_pairs(self, path, radii, theta):
+        """Pairs (s, e), e >= s + 2, of path states within theta of each other in the elliptical
+        metric, in np.argwhere order: the O(P^2) half of path_shortcutter (numerical.py:226-246)."""
+        p = _f64(path)
+        r = _f64(radii).reshape(-1)
+        if p.ndim != 2 or r.shape[0] != p.shape[1]:
+            raise ValueError("path [P, d] and radii [d] expected")
+        cap = max(1024, 4 * p.shape[0])
+        while True:
+            out = np.empty((cap, 2), dtype=np.int32)
+            cnt = C.c_int64(0)
+            self._check(self._lib.ss_path_close_pairs(self._h, _ptr(p), p.shape[0], p.shape[1], _ptr(r), float(theta),
+                                                      _ptr(out), cap, C.byref(cnt)))
+            if cnt.value <= cap:
+                return out[:cnt.value]
+            cap = int(cnt.value)
+
     # ------------------------------------------------------------------ stage 2
     def set_model(self, weights, biases, norm):
         """weights[l] [in, out] (y = x W + b), biases[l] [out]; norm: dict mean_x std_x mean_y

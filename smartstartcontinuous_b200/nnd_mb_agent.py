@@ -34,13 +34,13 @@ from .replay_buffer import ReplayBuffer
 
 
 def plan_from_path(path_to_follow, *, mean_per_stepsize, std_per_stepsize, stepsizes_in_waypoint_radii,
-                   path_shortcutting, theta, steps_per_waypoint):
+                   path_shortcutting, theta, steps_per_waypoint, engine=None):
     """Host part of start_new_episode_plan (NND_MB_agent.py:385-418): radii from the step-size
     statistics, elliptical distance, optional shortcutting, waypoints, distances left."""
     stds, means = path_deltas_stds_and_means_per_dim(path_to_follow)
     radii = radii_calc(means, stds, mean_per_stepsize, std_per_stepsize, stepsizes_in_waypoint_radii)
     dist = elliptical_euclidean_distance_function_generator(radii)
-    followed = path_shortcutter(path_to_follow, dist, theta) if path_shortcutting else path_to_follow
+    followed = path_shortcutter(path_to_follow, dist, theta, engine=engine) if path_shortcutting else path_to_follow
     desired = np.asarray(get_start_waypoints_final_states_steps(followed, steps_per_waypoint))
     if len(desired) >= 2:
         hops = np.append(dist(desired[:-1], desired[1:]), 0.0)
@@ -268,7 +268,7 @@ class NND_MB_agent(NavigationRLAgent):
                               std_per_stepsize=self.std_per_stepsize,
                               stepsizes_in_waypoint_radii=self.stepsizes_in_waypoint_radii,
                               path_shortcutting=self.path_shortcutting, theta=self.theta,
-                              steps_per_waypoint=self.steps_per_waypoint)
+                              steps_per_waypoint=self.steps_per_waypoint, engine=self.engine)
         self.stds = plan["stds"]
         self.radii = plan["radii"]
         self.distance_function = plan["distance_function"]

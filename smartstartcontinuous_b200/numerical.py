@@ -154,11 +154,18 @@ def length_weighted_activities_solver(activities, sub_extra=0):
     return best[-1], chosen
 
 
-def path_shortcutter(path, distance_func, theta):
-    """Drop interior states between any two states (>= 2 apart) that are within theta."""
+def path_shortcutter(path, distance_func, theta, engine=None):
+    """Drop interior states between any two states (>= 2 apart) that are within theta.
+
+    With ``engine`` (a CUDA Engine) and an elliptical ``distance_func`` the O(P^2) pair extraction
+    runs on the device (ss_path_close_pairs: same float64 operations, same pair order); the
+    interval-scheduling DP stays here."""
     p = np.asarray(path)
-    pair_dist = distance_func(p[:, None, :], p[None, :, :])
-    pairs = np.argwhere(np.triu(pair_dist <= theta, k=2))
+    if engine is not None and getattr(distance_func, "radii", None) is not None:
+        pairs = engine.path_close_pairs(p, distance_func.radii, theta)
+    else:
+        pair_dist = distance_func(p[:, None, :], p[None, :, :])
+        pairs = np.argwhere(np.triu(pair_dist <= theta, k=2))
     _, chosen = length_weighted_activities_solver(pairs.tolist(), sub_extra=1)
     drop = [i for s, e in chosen for i in range(s + 1, e)]
     return np.delete(p, drop, axis=0)

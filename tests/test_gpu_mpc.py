@@ -367,3 +367,31 @@ def test_agents_end_to_end(engine):
     chosen, ucb = agent.last_selection
     assert chosen == int(idx[obest]) or abs(oucb[list(idx).index(chosen)] - oucb[obest]) < 1e-4 * abs(oucb[obest])
     assert np.array_equal(path[-1], rb.buffer[chosen][4])
+
+
+def test_path_close_pairs_matches_numpy(engine):
+    """Row f3 (plan set-up geometry): the device pair extraction of path_shortcutter returns exactly
+    np.argwhere(np.triu(dist <= theta, k=2)) -- same pairs, same order -- so the shortcut path and
+    the plan built from it are identical to the host-only route."""
+    from smartstartcontinuous_b200 import numerical as num
+    from smartstartcontinuous_b200.nnd_mb_agent import plan_from_path
+    rng = np.random.default_rng(21)
+    for P, d in ((2, 2), (3, 3), (60, 2), (333, 3), (1000, 3), (700, 7)):
+        steps = rng.normal(size=(P, d)) * rng.uniform(0.2, 2.0, size=d)
+        path = np.cumsum(steps, axis=0) * (rng.random((P, 1)) < 0.9)       # some exact repeats of the origin
+        stds, means = num.path_deltas_stds_and_means_per_dim(path) if P > 1 else (np.ones(d), np.ones(d))
+        radii = num.radii_calc(means, stds, 1, 1, 1) + 1e-3
+        dist = num.elliptical_euclidean_distance_function_generator(radii)
+        for theta in (0.5, 1.0, 3.0):
+            want = np.argwhere(np.triu(dist(path[:, None, :], path[None, :, :]) <= theta, k=2))
+            got = engine.path_close_pairs(path, radii, theta)
+            np.testing.assert_array_equal(got, want.reshape(-1, 2))
+    path = [np.asarray(p) for p in path]
+    kw = dict(mean_per_stepsize=1, std_per_stepsize=1, stepsizes_in_waypoint_radii=1, path_shortcutting=True, theta=1,
+              steps_per_waypoint=1)
+    host = plan_from_path(path, **kw)
+    dev = plan_from_path(path, engine=engine, **kw)
+    np.testing.assert_array_equal(dev["desired_states"], host["desired_states"])
+    np.testing.assert_array_equal(dev["distances_left"], host["distances_left"])
+    with pytest.raises(ValueError):
+        engine.path_close_pairs(np.zeros((4, 2)), [1.0, 0.0], 1.0)
