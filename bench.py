@@ -368,6 +368,33 @@ def main():
         eng.select_start(kw["all_states"], kw["queries"], kw["values"], kw["n"], kw["volume"], 1.0, 2.0)
 
     kde_e2e_ms = timed(kde_e2e_step, max(3, args.steps // 2), 2) / max(3, args.steps // 2)
+
+    # the same selection from the device mirror of the replay buffer's state ring (row f2): the
+    # buffer is resident, each step uploads the 64 newest states + the candidate indices and values
+    from smartstartcontinuous_b200.replay_buffer import _StateRing
+    ring = _StateRing(KDE_N, 3)
+    st_all = kw["all_states"]
+    ring.alloc = KDE_N
+    ring.s = np.ascontiguousarray(st_all[:KDE_N])
+    ring.s2 = np.ascontiguousarray(np.concatenate([st_all[1:KDE_N], st_all[KDE_N:KDE_N + 1]]))
+    ring.count = ring.pushes = KDE_N
+    cand = np.random.default_rng(0).choice(KDE_N, KDE_M, replace=False)
+    eng.mirror_sync(ring)
+
+    def kde_mirror_step(i):
+        # 64 transitions arrived since the last selection (written like ReplayBuffer.add does, as one
+        # block: the per-step Python cost of add() belongs to the environment loop, not to selection)
+        r0 = ring.pushes % KDE_N                          # the ring is full: the oldest rows are overwritten
+        if r0 + 64 > KDE_N:
+            r0 = 0
+            ring.pushes += KDE_N - ring.pushes % KDE_N
+        ring.s[r0:r0 + 64] = st_all[r0:r0 + 64]
+        ring.s2[r0:r0 + 64] = st_all[r0 + 1:r0 + 65]
+        ring.pushes += 64
+        ring.head = ring.pushes % KDE_N
+        eng.select_start_mirror(ring, cand, kw["values"], kw["n"], kw["volume"], 1.0, 2.0)
+
+    kde_mirror_ms = timed(kde_mirror_step, max(3, args.steps // 2), 2) / max(3, args.steps // 2)
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -412,6 +439,10 @@ def main():
                                        % (KDE_N + 1, KDE_M)},
                 "e2e": {"value": evals / (kde_e2e_ms * 1e-3), "unit": "kernel-evals/s", "ms_per_step": kde_e2e_ms,
                         "h2d_bytes_per_step": int(8 * 3 * (KDE_N + 1 + KDE_M) + 4 * KDE_M), "d2h_bytes_per_step": 16},
+                "e2e_mirror": {"value": evals / (kde_mirror_ms * 1e-3), "unit": "kernel-evals/s", "ms_per_step": kde_mirror_ms,
+                               "h2d_bytes_per_step": int(2 * 64 * 3 * 8 + 12 * KDE_M), "d2h_bytes_per_step": 16,
+                               "path": "Engine.select_start_mirror: replay-state ring mirrored on the device, 64 new "
+                                       "transitions + candidate indices + values uploaded per selection"},
                 "roofline": {"bound": "sfu", "achieved": kde_achieved, "peak": sfu_peak, "unit": "kernel-evals/s",
                              "frac": kde_achieved / sfu_peak, "kernel": "kde_pairs_tc_kernel", "kernel_ms": p_ms,
                              "peak_source": "16 MUFU.EX2/clk/SM x %d SMs x %.0f MHz (max SM clock); the kernel takes 3/8 of "

@@ -182,6 +182,21 @@ int ss_mpc_sample_actions(ss_ctx* ctx, int64_t K_local, int64_t k_offset, int H,
 /* 1 when ss_mpc_set_model's shape can run on the tcgen05 kernel */
 int ss_mpc_tc_supported(ss_ctx* ctx);
 
+/* ---- device-resident replay-state mirror ------------------------------
+ * The KDE data set is every `s` in the buffer plus the newest `s2` (ReplayBuffer.get_all_states,
+ * replay_buffer.py:102) and the candidate queries are `s2` rows of sampled steps (:136-152, :205).
+ * Instead of shipping both from the host at every selection, the caller mirrors its ring of
+ * (s, s2) rows on the device incrementally -- ss_mirror_write(which = 0 for s / 1 for s2, ring
+ * capacity, d, first physical row, row count, rows) after the adds since the last selection --
+ * and ss_kde_ucb_argmax_mirror selects from the mirror: only m row indices and m values cross
+ * PCIe.  count = rows in use, last_row = physical row of the newest step, query_rows = physical
+ * rows of the candidates.  Everything else as ss_kde_ucb_argmax. */
+int ss_mirror_write(ss_ctx* ctx, int which, int64_t capacity, int d, int64_t row0, int64_t n_rows,
+                    const double* rows);
+int ss_kde_ucb_argmax_mirror(ss_ctx* ctx, int64_t count, int64_t last_row, const int64_t* query_rows, int64_t m,
+                             const float* values, int64_t n_transitions, double volume, double alpha, double beta,
+                             double* out_density, double* out_ucb, int64_t* out_best_j, double* out_best_ucb);
+
 /* ---- plan set-up geometry ------------------------------------------
  * ss_path_close_pairs: the pair-extraction half of path_shortcutter (numerical.py:226-246,
  * called from start_new_episode_plan, NND_MB_agent.py:398-401): all (s, e) with e >= s + 2 whose

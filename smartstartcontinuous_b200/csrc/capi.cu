@@ -60,7 +60,7 @@ extern "C" int ss_destroy(ss_ctx* c) {
                       &c->tc_misc, &c->plan_ds, &c->plan_dl, &c->mpc_actions64, &c->mpc_states,
                       &c->mpc_scores, &c->mpc_partial_sums, &c->mpc_sums, &c->mpc_block_best,
                       &c->mpc_result, &c->mpc_replay, &c->mpc_sampled, &c->mpc_package,
-                      &c->geom_in, &c->geom_rows, &c->geom_pairs};
+                      &c->geom_in, &c->geom_rows, &c->geom_pairs, &c->mirror_s, &c->mirror_s2, &c->mirror_idx};
     for (DevBuf* b : bufs) b->release();
     for (auto& b : c->w32) b.release();
     for (auto& b : c->b32) b.release();
@@ -201,5 +201,102 @@ extern "C" int ss_kde_ucb_argmax(ss_ctx* c, const double* data, int64_t n_pts, i
     if (out_ucb)
         SS_CUDA_CHECK(c, cudaMemcpyAsync(out_ucb, ucb_dev, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream));
     SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return SS_OK;
+}
+
+// ---- device-resident mirror of the replay buffer's state ring --------------
+// rows: [capacity + 1][d] float64 for `s` (the extra row receives the newest s2 at selection time,
+// replay_buffer.py:102) and [capacity][d] for `s2`; row index = physical ring row.
+extern "C" int ss_mirror_write(ss_ctx* c, int which, int64_t capacity, int d, int64_t row0, int64_t n_rows,
+                               const double* rows) {
+    if (!c) return SS_EINVAL;
+    if ((which != 0 && which != 1) || capacity < 1 || d < 1 || d > SS_MAX_D || row0 < 0 || n_rows < 0 ||
+        row0 + n_rows > capacity || (n_rows > 0 && !rows))
+        SS_FAIL(c, SS_EINVAL, "mirror: bad arguments");
+    SS_CUDA_CHECK(c, cudaSetDevice(c->device));
+    if (c->mirror_capacity != capacity || c->mirror_d != d) {
+        // a new ring (other capacity / dimension): both mirrors start empty
+        c->mirror_s.release();
+        c->mirror_s2.release();
+        c->mirror_capacity = capacity;
+        c->mirror_d = d;
+    }
+    // allocate geometrically up to capacity + 1 rows, keeping what is there
+    DevBuf& buf = which == 0 ? c->mirror_s : c->mirror_s2;
+    const size_t need = (size_t)(row0 + n_rows + 1) * d * 8;
+    if (need > buf.cap) {
+        size_t want = buf.cap ? buf.cap * 2 : (size_t)4096 * d * 8;
+        const size_t full = (size_t)(capacity + 1) * d * 8;
+        if (want < need) want = need;
+        if (want > full) want = full;
+        void* np_ = nullptr;
+        SS_CUDA_CHECK(c, cudaMalloc(&np_, want));
+        if (buf.p) {
+            SS_CUDA_CHECK(c, cudaMemcpyAsync(np_, buf.p, buf.cap, cudaMemcpyDeviceToDevice, c->stream));
+            SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+            cudaFree(buf.p);
+        }
+        buf.p = np_;
+        buf.cap = want;
+    }
+    if (n_rows > 0)
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(buf.as<double>() + (size_t)row0 * d, rows, (size_t)n_rows * d * 8,
+                                         cudaMemcpyHostToDevice, c->stream));
+    return SS_OK;
+}
+
+__global__ void mirror_gather_kernel(const double* __restrict__ s2_rows, double* __restrict__ s_rows, int d,
+                                     long long count, long long last_row, const long long* __restrict__ query_rows,
+                                     long long m, double* __restrict__ queries) {
+    const long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (o < m * d) queries[o] = s2_rows[query_rows[o / d] * d + (o % d)];
+    if (o < d) s_rows[count * d + o] = s2_rows[last_row * d + o];       // data set = every s + the newest s2
+}
+
+extern "C" int ss_kde_ucb_argmax_mirror(ss_ctx* c, int64_t count, int64_t last_row, const int64_t* query_rows,
+                                        int64_t m, const float* values, int64_t n_transitions, double volume,
+                                        double alpha, double beta, double* out_density, double* out_ucb,
+                                        int64_t* out_best_j, double* out_best_ucb) {
+    if (!c) return SS_EINVAL;
+    const int d = c->mirror_d;
+    if (!c->mirror_s.p || !c->mirror_s2.p) SS_FAIL(c, SS_ESTATE, "mirror: nothing uploaded yet (ss_mirror_write)");
+    if (count < 1 || count > c->mirror_capacity || last_row < 0 || last_row >= count ||
+        (size_t)(count + 1) * d * 8 > c->mirror_s.cap || (size_t)count * d * 8 > c->mirror_s2.cap)
+        SS_FAIL(c, SS_EINVAL, "mirror: count / last_row outside the uploaded rows");
+    int rc = kde_check(c, c->mirror_s.p, count + 1, d, query_rows, m, values, n_transitions, out_best_j, out_best_ucb);
+    if (rc) return rc;
+    for (int64_t j = 0; j < m; ++j)
+        if (query_rows[j] < 0 || query_rows[j] >= count) SS_FAIL(c, SS_EINVAL, "mirror: query row outside the buffer");
+    SS_CUDA_CHECK(c, cudaSetDevice(c->device));
+    timer_begin(c);
+    SS_CUDA_CHECK(c, c->kde_q64.ensure((size_t)m * d * 8));
+    SS_CUDA_CHECK(c, c->kde_vals.ensure((size_t)m * 4));
+    SS_CUDA_CHECK(c, c->mirror_idx.ensure((size_t)m * 8));
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(c->mirror_idx.p, query_rows, (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(c->kde_vals.p, values, (size_t)m * 4, cudaMemcpyHostToDevice, c->stream));
+    mirror_gather_kernel<<<(unsigned)((m * d + 255) / 256), 256, 0, c->stream>>>(
+        c->mirror_s2.as<double>(), c->mirror_s.as<double>(), d, count, last_row, c->mirror_idx.as<long long>(), m,
+        c->kde_q64.as<double>());
+    c->launches++;
+    SS_CUDA_CHECK(c, cudaGetLastError());
+    double* dens_dev = nullptr;
+    double* ucb_dev = nullptr;
+    if (out_density) {
+        SS_CUDA_CHECK(c, c->kde_density.ensure((size_t)m * 8));
+        dens_dev = c->kde_density.as<double>();
+    }
+    if (out_ucb) {
+        SS_CUDA_CHECK(c, c->kde_ucb.ensure((size_t)m * 8));
+        ucb_dev = c->kde_ucb.as<double>();
+    }
+    timer_mark(c, "kde_h2d");
+    rc = kde_run(c, c->mirror_s.as<double>(), count + 1, d, c->kde_q64.as<double>(), m, c->kde_vals.as<float>(),
+                 n_transitions, volume, alpha, beta, dens_dev, ucb_dev, out_best_j, out_best_ucb);
+    if (rc) return rc;
+    if (out_density)
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(out_density, dens_dev, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (out_ucb)
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(out_ucb, ucb_dev, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (out_density || out_ucb) SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     return SS_OK;
 }

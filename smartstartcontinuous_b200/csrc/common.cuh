@@ -101,6 +101,10 @@ struct ss_ctx {
     bool kde_tc_attr_set = false;
     // ---- plan set-up geometry scratch (plan_geom.cu)
     DevBuf geom_in, geom_rows, geom_pairs;
+    // ---- device mirror of the replay buffer's state ring (capi.cu)
+    DevBuf mirror_s, mirror_s2, mirror_idx;
+    int64_t mirror_capacity = 0;
+    int mirror_d = 0;
 
     // ---- MPC model
     bool model_set = false;

@@ -107,6 +107,50 @@ class Engine:
             C.byref(best), C.byref(best_ucb)))
         return int(best.value), float(best_ucb.value), dens, ucb
 
+    # device-resident mirror of the replay buffer's state ring
+    def mirror_sync(self, ring):
+        """Upload the (s, s2) rows written to ``ring`` (replay_buffer._StateRing) since the last
+        call: at most two contiguous H2D copies per array; a new ring object is uploaded whole."""
+        state = getattr(self, "_mirror_state", None)
+        if state is None or state[0] is not ring or ring.pushes < state[1]:
+            state = (ring, 0)
+        done = state[1]
+        cap, d = ring.capacity, ring.dim
+        todo = ring.pushes - done
+        if todo >= ring.count:                       # everything in use changed (or first sync)
+            spans = [(0, ring.count)] if ring.count else []
+        else:
+            r0 = done % cap
+            spans = [(r0, min(todo, cap - r0))]
+            if todo > cap - r0:
+                spans.append((0, todo - (cap - r0)))
+        for which, arr in ((0, ring.s), (1, ring.s2)):
+            for r0, cnt in spans:
+                if cnt > 0:
+                    rows = np.ascontiguousarray(arr[r0:r0 + cnt], dtype=np.float64)
+                    self._check(self._lib.ss_mirror_write(self._h, which, int(cap), int(d), int(r0), int(cnt), _ptr(rows)))
+        self._mirror_state = (ring, ring.pushes)
+
+    def select_start_mirror(self, ring, buffer_indices, values, n_transitions, volume=1.0, alpha=1.0, beta=2.0,
+                            want_density=False, want_ucb=False):
+        """select_start with the data set and the candidate states taken from the device mirror of
+        ``ring``: data = every s + the newest s2, queries = s2 of ``buffer_indices`` (logical buffer
+        indices).  Only the m row indices and values are uploaded."""
+        self.mirror_sync(ring)
+        rows = np.ascontiguousarray(ring.physical_rows(buffer_indices), dtype=np.int64)
+        last = int(ring.physical_rows([ring.count - 1])[0])
+        v = np.ascontiguousarray(np.asarray(values).reshape(-1), dtype=np.float32)
+        if v.shape[0] != rows.shape[0]:
+            raise ValueError("values must have one entry per query")
+        dens = np.empty(rows.shape[0]) if want_density else None
+        ucb = np.empty(rows.shape[0]) if want_ucb else None
+        best = C.c_int64(-1)
+        best_ucb = C.c_double(0.0)
+        self._check(self._lib.ss_kde_ucb_argmax_mirror(
+            self._h, int(ring.count), last, _ptr(rows), rows.shape[0], _ptr(v), int(n_transitions), float(volume),
+            float(alpha), float(beta), _ptr(dens), _ptr(ucb), C.byref(best), C.byref(best_ucb)))
+        return int(best.value), float(best_ucb.value), dens, ucb
+
     def select_start_dev(self, data_ptr, n_pts, d, queries_ptr, m, values_ptr, n_transitions,
                          volume=1.0, alpha=1.0, beta=2.0, density_ptr=None, ucb_ptr=None):
         """Same with device pointers (e.g. torch tensors' data_ptr()); returns (best_j, best_ucb)."""

@@ -30,6 +30,7 @@ class _StateRing:
         self.s2 = np.empty((self.alloc, dim))
         self.head = 0        # physical row of buffer index 0
         self.count = 0
+        self.pushes = 0      # total rows ever written: push p lives in physical row p % capacity
 
     def _grow(self):
         new_alloc = min(self.capacity, self.alloc * 2)
@@ -51,15 +52,18 @@ class _StateRing:
             self.head = (self.head + 1) % self.capacity
         self.s[row] = s
         self.s2[row] = s2
+        self.pushes += 1
 
     def ordered(self, arr):
         if self.head == 0:
             return arr[:self.count]
         return np.concatenate([arr[self.head:self.count], arr[:self.head]], axis=0)
 
+    def physical_rows(self, buffer_indices):
+        return (np.asarray(buffer_indices, dtype=np.int64) + self.head) % max(self.count, 1)
+
     def rows(self, arr, buffer_indices):
-        phys = (np.asarray(buffer_indices, dtype=np.int64) + self.head) % max(self.count, 1)
-        return arr[phys]
+        return arr[self.physical_rows(buffer_indices)]
 
 
 class ReplayBuffer(object):
@@ -174,6 +178,12 @@ class ReplayBuffer(object):
             return ring.rows(ring.s2, buffer_indices)
         return np.asarray([np.asarray(self.buffer[int(i)][4], dtype=np.float64)
                            for i in buffer_indices])
+
+    def state_ring(self):
+        """The contiguous (s, s2) ring when it mirrors the deque exactly, else None (the device
+        mirror of Engine.select_start_mirror is built from it)."""
+        ring = self._ring
+        return ring if ring is not None and ring.count == len(self.buffer) else None
 
     def get_possible_smart_start_indices(self, n_ss):
         """Up to n_ss buffer indices sampled without replacement from the first fully

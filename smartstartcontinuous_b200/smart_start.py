@@ -160,18 +160,26 @@ class SmartStartContinuous(RLAgent):
         possible_start_indices = self.replay_buffer.get_possible_smart_start_indices(self.n_ss)
         if possible_start_indices is None:
             return None
-        all_states = np.asarray(self.replay_buffer.get_all_states(), dtype=np.float64)
-        if all_states.ndim == 1:
-            all_states = all_states[:, None]
         if self.nnd_mb_agent.radii is not None:
             one_radii_volume = volume_of_n_dimensional_hyperellipsoid(self.nnd_mb_agent.radii)
         else:
             one_radii_volume = 1
         possible_ss_states = self._candidate_states(possible_start_indices)
         ss_state_values = np.asarray(self.agent.get_state_value(possible_ss_states)).T   # 1 x m
-        best_j, best_ucb, _, _ = self.engine.select_start(
-            all_states, possible_ss_states, ss_state_values.reshape(-1), len(self.replay_buffer),
-            one_radii_volume, self.exploitation_param, self.exploration_param)
+        ring = self.replay_buffer.state_ring() if hasattr(self.replay_buffer, "state_ring") else None
+        if ring is not None and hasattr(self.engine, "select_start_mirror"):
+            # the buffer's states already live on the device (incremental mirror): only the m candidate
+            # indices and values are uploaded
+            best_j, best_ucb, _, _ = self.engine.select_start_mirror(
+                ring, possible_start_indices, ss_state_values.reshape(-1), len(self.replay_buffer),
+                one_radii_volume, self.exploitation_param, self.exploration_param)
+        else:
+            all_states = np.asarray(self.replay_buffer.get_all_states(), dtype=np.float64)
+            if all_states.ndim == 1:
+                all_states = all_states[:, None]
+            best_j, best_ucb, _, _ = self.engine.select_start(
+                all_states, possible_ss_states, ss_state_values.reshape(-1), len(self.replay_buffer),
+                one_radii_volume, self.exploitation_param, self.exploration_param)
         smart_start_index = int(possible_start_indices[best_j])
         self.last_selection = (smart_start_index, best_ucb)
         return self.replay_buffer.get_episodic_path_to_buffer_index(smart_start_index)

@@ -162,3 +162,40 @@ def test_full_size_c5_properties(engine):
     _, _, dens_part, _ = engine.select_start(all_states, q[part], vals[part], 1_000_000, 1e-3, 1.0, 2.0,
                                              want_density=True)
     np.testing.assert_allclose(dens_part, dens[part], rtol=2e-5)
+
+
+def test_device_mirror_selection_matches_host_path(engine):
+    """Row f2: selection from the incrementally synced device mirror of the replay buffer's state
+    ring equals selection from host arrays -- while the buffer grows, after it wraps (eviction),
+    and after it is rebuilt."""
+    from smartstartcontinuous_b200.replay_buffer import ReplayBuffer
+    rng = np.random.default_rng(31)
+    agent = object()
+    rb = ReplayBuffer(agent, 3000)
+    obs, _ = syn.pendulum_rollouts(rng, 30, 200)
+    vals_all = rng.normal(size=4096).astype(np.float32)
+    added = 0
+    for ep, traj in enumerate(obs):
+        rb.start_new_episode(agent)
+        for t in range(len(traj) - 1):
+            rb.add(agent, traj[t], np.zeros(1), 0.0, False, traj[t + 1])
+            added += 1
+        if ep in (3, 9, 14, 22, 29):                      # grows, fills (ep 14), wraps, wraps again
+            ring = rb.state_ring()
+            assert ring is not None
+            idx = rb.get_possible_smart_start_indices(500)
+            vals = vals_all[:len(idx)]
+            want = engine.select_start(rb.get_all_states(), rb.states_s2(idx), vals, len(rb), 0.5, 1.0, 2.0,
+                                       want_density=True, want_ucb=True)
+            got = engine.select_start_mirror(ring, idx, vals, len(rb), 0.5, 1.0, 2.0, want_density=True, want_ucb=True)
+            np.testing.assert_allclose(got[2], want[2], rtol=1e-5)      # same points, other summation order
+            _ucb_close(got[3], want[3], vals)
+            _check_choice(got[0], want[3])
+    assert added > 3000                                    # the ring did wrap
+    rb._rebuild_mirror()                                   # new ring object: uploaded whole again
+    ring = rb.state_ring()
+    idx = rb.get_possible_smart_start_indices(200)
+    want = engine.select_start(rb.get_all_states(), rb.states_s2(idx), vals_all[:len(idx)], len(rb), 0.5, 1.0, 2.0,
+                               want_density=True)
+    got = engine.select_start_mirror(ring, idx, vals_all[:len(idx)], len(rb), 0.5, 1.0, 2.0, want_density=True)
+    np.testing.assert_allclose(got[2], want[2], rtol=1e-5)
