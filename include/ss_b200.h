@@ -182,6 +182,26 @@ int ss_mpc_sample_actions(ss_ctx* ctx, int64_t K_local, int64_t k_offset, int H,
 /* 1 when ss_mpc_set_model's shape can run on the tcgen05 kernel */
 int ss_mpc_tc_supported(ss_ctx* ctx);
 
+/* ---- critic value batch in front of the UCB --------------------------
+ * V_j = critic(q_j, actor(q_j)) of the DDPG base agent (agent.get_state_value,
+ * smartexplorationcontinuous.py:274 -> ddpg_editted.py:274-279; graph :106-131; networks
+ * models_editted.py:22-100), FP32 like the TF graph.  Weights [in, out] (tf.layers.dense kernels);
+ * critic W2 is [(h1c + da), h2c] (the action is concatenated after the first hidden layer).
+ * gamma / beta pointers are only read with layer_norm; obs_mean / obs_std NULL = no observation
+ * normalisation (normalize_observations=False); has_ret_norm = 0 = no return normalisation.
+ * Once set, ss_kde_ucb_argmax / _mirror accept values = NULL and compute them on the device. */
+typedef struct {
+    int d, da, h1a, h2a, h1c, h2c, layer_norm, last_layer_tanh;
+    const float *aW1, *ab1, *ag1, *abe1, *aW2, *ab2, *ag2, *abe2, *aW3, *ab3;
+    const float *cW1, *cb1, *cg1, *cbe1, *cW2, *cb2, *cg2, *cbe2, *cW3, *cb3;
+    const double *obs_mean, *obs_std;
+    double obs_clip_lo, obs_clip_hi;
+    int has_ret_norm;
+    double ret_mean, ret_std, ret_clip_lo, ret_clip_hi;
+} ss_value_net;
+int ss_value_net_set(ss_ctx* ctx, const ss_value_net* net);      /* net = NULL clears it */
+int ss_value_net_eval(ss_ctx* ctx, const double* queries, int64_t m, int d, float* out_values);
+
 /* ---- device-resident replay-state mirror ------------------------------
  * The KDE data set is every `s` in the buffer plus the newest `s2` (ReplayBuffer.get_all_states,
  * replay_buffer.py:102) and the candidate queries are `s2` rows of sampled steps (:136-152, :205).

@@ -18,6 +18,17 @@ _c_int64_p = C.POINTER(C.c_int64)
 _c_int_p = C.POINTER(C.c_int)
 
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
+class ValueNetStruct(C.Structure):
+    """ss_value_net of include/ss_b200.h."""
+    _fields_ = ([(n, C.c_int) for n in ("d", "da", "h1a", "h2a", "h1c", "h2c", "layer_norm", "last_layer_tanh")] +
+                [(n, C.c_void_p) for n in ("aW1", "ab1", "ag1", "abe1", "aW2", "ab2", "ag2", "abe2", "aW3", "ab3",
+                                           "cW1", "cb1", "cg1", "cbe1", "cW2", "cb2", "cg2", "cbe2", "cW3", "cb3",
+                                           "obs_mean", "obs_std")] +
+                [("obs_clip_lo", C.c_double), ("obs_clip_hi", C.c_double), ("has_ret_norm", C.c_int),
+                 ("ret_mean", C.c_double), ("ret_std", C.c_double), ("ret_clip_lo", C.c_double),
+                 ("ret_clip_hi", C.c_double)])
+
+
 SIGNATURES = {
     "ss_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
     "ss_destroy": (C.c_int, [C.c_void_p]),
@@ -56,6 +67,8 @@ SIGNATURES = {
     "ss_mpc_sample_actions": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_uint64,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "ss_mpc_tc_supported": (C.c_int, [C.c_void_p]),
+    "ss_value_net_set": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ss_value_net_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "ss_mirror_write": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_void_p]),
     "ss_kde_ucb_argmax_mirror": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                            C.c_int64, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p,

@@ -8,6 +8,8 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
             double alpha, double beta, double* density_dev, double* ucb_dev, int64_t* out_best_j,
             double* out_best_ucb);
 
+int value_net_eval_dev(ss_ctx* c, const double* queries_dev, long long m, float* values_dev);
+
 static std::string g_create_error;
 
 extern "C" int ss_create(ss_ctx** out, int device) {
@@ -60,7 +62,7 @@ extern "C" int ss_destroy(ss_ctx* c) {
                       &c->tc_misc, &c->plan_ds, &c->plan_dl, &c->mpc_actions64, &c->mpc_states,
                       &c->mpc_scores, &c->mpc_partial_sums, &c->mpc_sums, &c->mpc_block_best,
                       &c->mpc_result, &c->mpc_replay, &c->mpc_sampled, &c->mpc_package,
-                      &c->geom_in, &c->geom_rows, &c->geom_pairs, &c->mirror_s, &c->mirror_s2, &c->mirror_idx};
+                      &c->geom_in, &c->geom_rows, &c->geom_pairs, &c->mirror_s, &c->mirror_s2, &c->mirror_idx, &c->value_net_params};
     for (DevBuf* b : bufs) b->release();
     for (auto& b : c->w32) b.release();
     for (auto& b : c->b32) b.release();
@@ -139,8 +141,9 @@ extern "C" int ss_memcpy_h2d(ss_ctx* c, void* dst, const void* src, int64_t byte
 
 static int kde_check(ss_ctx* c, const void* data, int64_t n_pts, int d, const void* queries, int64_t m,
                      const void* values, int64_t n_transitions, int64_t* out_best_j, double* out_best_ucb) {
-    if (!data || !queries || !values || !out_best_j || !out_best_ucb)
-        SS_FAIL(c, SS_EINVAL, "kde: null pointer");
+    if (!data || !queries || !out_best_j || !out_best_ucb) SS_FAIL(c, SS_EINVAL, "kde: null pointer");
+    if (!values && !c->value_net_set)
+        SS_FAIL(c, SS_EINVAL, "kde: values is NULL and no value net is set (ss_value_net_set)");
     if (d < 1 || d > SS_MAX_D) SS_FAIL(c, SS_EUNSUPPORTED, "kde: need 1 <= d <= 32");
     if (m < 1) SS_FAIL(c, SS_EINVAL, "kde: no candidate queries");
     if (n_transitions < 1) SS_FAIL(c, SS_EINVAL, "kde: empty replay buffer");
@@ -160,6 +163,12 @@ extern "C" int ss_kde_ucb_argmax_dev(ss_ctx* c, const double* data_dev, int64_t 
     if (rc) return rc;
     SS_CUDA_CHECK(c, cudaSetDevice(c->device));
     timer_begin(c);
+    if (!values_dev) {
+        SS_CUDA_CHECK(c, c->kde_vals.ensure((size_t)m * 4));
+        rc = value_net_eval_dev(c, queries_dev, m, c->kde_vals.as<float>());
+        if (rc) return rc;
+        values_dev = c->kde_vals.as<float>();
+    }
     return kde_run(c, data_dev, n_pts, d, queries_dev, m, values_dev, n_transitions, volume, alpha, beta,
                    out_density_dev, out_ucb_dev, out_best_j, out_best_ucb);
 }
@@ -180,7 +189,12 @@ extern "C" int ss_kde_ucb_argmax(ss_ctx* c, const double* data, int64_t n_pts, i
     SS_CUDA_CHECK(c, c->kde_vals.ensure((size_t)m * 4));
     SS_CUDA_CHECK(c, cudaMemcpyAsync(c->kde_data64.p, data, nd, cudaMemcpyHostToDevice, c->stream));
     SS_CUDA_CHECK(c, cudaMemcpyAsync(c->kde_q64.p, queries, nq, cudaMemcpyHostToDevice, c->stream));
-    SS_CUDA_CHECK(c, cudaMemcpyAsync(c->kde_vals.p, values, (size_t)m * 4, cudaMemcpyHostToDevice, c->stream));
+    if (values) {
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(c->kde_vals.p, values, (size_t)m * 4, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        rc = value_net_eval_dev(c, c->kde_q64.as<double>(), m, c->kde_vals.as<float>());
+        if (rc) return rc;
+    }
     double* dens_dev = nullptr;
     double* ucb_dev = nullptr;
     if (out_density) {
@@ -273,12 +287,17 @@ extern "C" int ss_kde_ucb_argmax_mirror(ss_ctx* c, int64_t count, int64_t last_r
     SS_CUDA_CHECK(c, c->kde_vals.ensure((size_t)m * 4));
     SS_CUDA_CHECK(c, c->mirror_idx.ensure((size_t)m * 8));
     SS_CUDA_CHECK(c, cudaMemcpyAsync(c->mirror_idx.p, query_rows, (size_t)m * 8, cudaMemcpyHostToDevice, c->stream));
-    SS_CUDA_CHECK(c, cudaMemcpyAsync(c->kde_vals.p, values, (size_t)m * 4, cudaMemcpyHostToDevice, c->stream));
+    if (values)
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(c->kde_vals.p, values, (size_t)m * 4, cudaMemcpyHostToDevice, c->stream));
     mirror_gather_kernel<<<(unsigned)((m * d + 255) / 256), 256, 0, c->stream>>>(
         c->mirror_s2.as<double>(), c->mirror_s.as<double>(), d, count, last_row, c->mirror_idx.as<long long>(), m,
         c->kde_q64.as<double>());
     c->launches++;
     SS_CUDA_CHECK(c, cudaGetLastError());
+    if (!values) {
+        rc = value_net_eval_dev(c, c->kde_q64.as<double>(), m, c->kde_vals.as<float>());
+        if (rc) return rc;
+    }
     double* dens_dev = nullptr;
     double* ucb_dev = nullptr;
     if (out_density) {

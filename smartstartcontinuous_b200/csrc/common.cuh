@@ -4,7 +4,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
 #include <cmath>
+#include <cstring>
 #include <cstdio>
 #include <string>
 #include <vector>
@@ -101,6 +103,10 @@ struct ss_ctx {
     bool kde_tc_attr_set = false;
     // ---- plan set-up geometry scratch (plan_geom.cu)
     DevBuf geom_in, geom_rows, geom_pairs;
+    // ---- critic value net in front of the UCB (value_net.cu)
+    DevBuf value_net_params;
+    std::vector<char> value_net_desc;
+    bool value_net_set = false;
     // ---- device mirror of the replay buffer's state ring (capi.cu)
     DevBuf mirror_s, mirror_s2, mirror_idx;
     int64_t mirror_capacity = 0;

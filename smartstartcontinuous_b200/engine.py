@@ -94,8 +94,8 @@ class Engine:
         q = _f64(queries)
         if data.ndim != 2 or q.ndim != 2 or data.shape[1] != q.shape[1]:
             raise ValueError("all_states [n+1, d] and queries [m, d] must be 2-D with the same d")
-        v = np.ascontiguousarray(np.asarray(values).reshape(-1), dtype=np.float32)
-        if v.shape[0] != q.shape[0]:
+        v = None if values is None else np.ascontiguousarray(np.asarray(values).reshape(-1), dtype=np.float32)
+        if v is not None and v.shape[0] != q.shape[0]:
             raise ValueError("values must have one entry per query")
         dens = np.empty(q.shape[0]) if want_density else None
         ucb = np.empty(q.shape[0]) if want_ucb else None
@@ -106,6 +106,64 @@ class Engine:
             int(n_transitions), float(volume), float(alpha), float(beta), _ptr(dens), _ptr(ucb),
             C.byref(best), C.byref(best_ucb)))
         return int(best.value), float(best_ucb.value), dens, ucb
+
+    # critic value net in front of the UCB
+    def set_value_net(self, net):
+        """net: dict with 'actor' = [(W1, b1), (W2, b2), (W3, b3)], 'critic' = same (critic W2 is
+        [(h1 + da), h2]), optional 'actor_ln' / 'critic_ln' = [(gamma1, beta1), (gamma2, beta2)],
+        'last_layer_tanh', 'obs_mean' / 'obs_std' / 'obs_clip', 'ret_mean' / 'ret_std' / 'ret_clip'
+        (models_editted.py:22-100, ddpg_editted.py:106-131).  None clears it.  With a net set,
+        select_start / select_start_mirror accept values=None and compute them on the device."""
+        from ._lib import ValueNetStruct
+        if net is None:
+            self._check(self._lib.ss_value_net_set(self._h, None))
+            self._value_net_keep = None
+            return
+        f32 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float32))
+        keep = []
+
+        def ptr(a):
+            a = f32(a)
+            keep.append(a)
+            return a.ctypes.data_as(C.c_void_p)
+
+        (aW1, ab1), (aW2, ab2), (aW3, ab3) = net["actor"]
+        (cW1, cb1), (cW2, cb2), (cW3, cb3) = net["critic"]
+        st = ValueNetStruct()
+        st.d, st.h1a = np.shape(aW1)
+        st.h2a, st.da = np.shape(aW3)
+        st.h1c, st.h2c = np.shape(cW1)[1], np.shape(cW3)[0]
+        if np.shape(cW2) != (st.h1c + st.da, st.h2c) or np.shape(aW2) != (st.h1a, st.h2a) or np.shape(cW1)[0] != st.d:
+            raise ValueError("value net: inconsistent layer shapes")
+        ln = net.get("actor_ln") is not None
+        st.layer_norm, st.last_layer_tanh = int(ln), int(bool(net.get("last_layer_tanh", False)))
+        for name, arr in (("aW1", aW1), ("ab1", ab1), ("aW2", aW2), ("ab2", ab2), ("aW3", aW3), ("ab3", ab3),
+                          ("cW1", cW1), ("cb1", cb1), ("cW2", cW2), ("cb2", cb2), ("cW3", cW3), ("cb3", cb3)):
+            setattr(st, name, ptr(arr))
+        if ln:
+            (ag1, abe1), (ag2, abe2) = net["actor_ln"]
+            (cg1, cbe1), (cg2, cbe2) = net["critic_ln"]
+            for name, arr in (("ag1", ag1), ("abe1", abe1), ("ag2", ag2), ("abe2", abe2),
+                              ("cg1", cg1), ("cbe1", cbe1), ("cg2", cg2), ("cbe2", cbe2)):
+                setattr(st, name, ptr(arr))
+        if net.get("obs_mean") is not None:
+            om, os_ = _f64(net["obs_mean"]).reshape(-1), _f64(net["obs_std"]).reshape(-1)
+            keep += [om, os_]
+            st.obs_mean, st.obs_std = _ptr(om), _ptr(os_)
+            st.obs_clip_lo, st.obs_clip_hi = [float(v) for v in net.get("obs_clip", (-5.0, 5.0))]
+        if net.get("ret_mean") is not None:
+            st.has_ret_norm = 1
+            st.ret_mean, st.ret_std = float(net["ret_mean"]), float(net["ret_std"])
+            st.ret_clip_lo, st.ret_clip_hi = [float(v) for v in net.get("ret_clip", (-np.inf, np.inf))]
+        self._check(self._lib.ss_value_net_set(self._h, C.byref(st)))
+        self._value_net_keep = keep
+
+    def state_values(self, queries):
+        """agent.get_state_value(queries) of the value net set with set_value_net: [m] float32."""
+        q = _f64(queries)
+        out = np.empty(q.shape[0], dtype=np.float32)
+        self._check(self._lib.ss_value_net_eval(self._h, _ptr(q), q.shape[0], q.shape[1], _ptr(out)))
+        return out
 
     # device-resident mirror of the replay buffer's state ring (SURVEY 8f row f2)
     def mirror_sync(self, ring):
@@ -139,8 +197,8 @@ class Engine:
         self.mirror_sync(ring)
         rows = np.ascontiguousarray(ring.physical_rows(buffer_indices), dtype=np.int64)
         last = int(ring.physical_rows([ring.count - 1])[0])
-        v = np.ascontiguousarray(np.asarray(values).reshape(-1), dtype=np.float32)
-        if v.shape[0] != rows.shape[0]:
+        v = None if values is None else np.ascontiguousarray(np.asarray(values).reshape(-1), dtype=np.float32)
+        if v is not None and v.shape[0] != rows.shape[0]:
             raise ValueError("values must have one entry per query")
         dens = np.empty(rows.shape[0]) if want_density else None
         ucb = np.empty(rows.shape[0]) if want_ucb else None

@@ -199,3 +199,44 @@ def test_device_mirror_selection_matches_host_path(engine):
                                want_density=True)
     got = engine.select_start_mirror(ring, idx, vals_all[:len(idx)], len(rb), 0.5, 1.0, 2.0, want_density=True)
     np.testing.assert_allclose(got[2], want[2], rtol=1e-5)
+
+
+def _random_value_net(rng, d, da, h1, h2, layer_norm, last_tanh, norms):
+    def lin(i, o, scale=None):
+        s = scale if scale is not None else 1.0 / np.sqrt(i)
+        return rng.uniform(-s, s, (i, o)).astype(np.float32), rng.uniform(-s, s, o).astype(np.float32)
+    net = dict(actor=[lin(d, h1), lin(h1, h2), lin(h2, da, 3e-3)],
+               critic=[lin(d, h1), lin(h1 + da, h2), lin(h2, 1, 3e-3)], last_layer_tanh=last_tanh)
+    if layer_norm:
+        gb = lambda n: (rng.uniform(0.5, 1.5, n).astype(np.float32), rng.normal(0, 0.1, n).astype(np.float32))
+        net["actor_ln"], net["critic_ln"] = [gb(h1), gb(h2)], [gb(h1), gb(h2)]
+    if norms:
+        net.update(obs_mean=rng.normal(size=d), obs_std=rng.uniform(0.5, 2.0, d), obs_clip=(-5.0, 5.0),
+                   ret_mean=-3.0, ret_std=2.5, ret_clip=(-4.0, 4.0))
+    return net
+
+
+@pytest.mark.parametrize("cfg", [(3, 1, 64, 32, False, True, False),      # the example's DDPG nets
+                                 (2, 1, 64, 64, True, False, True), (4, 2, 200, 100, True, True, True)])
+def test_value_net_matches_oracle_and_feeds_the_ucb(engine, cfg):
+    """Row f4: critic(q, actor(q)) on the device vs the float32 numpy restatement, and a selection
+    with values=None equals the selection fed with the host-evaluated values."""
+    from oracle import value_oracle
+    d, da, h1, h2, ln, last_tanh, norms = cfg
+    rng = np.random.default_rng(41 + d)
+    net = _random_value_net(rng, d, da, h1, h2, ln, last_tanh, norms)
+    data = rng.normal(size=(6000, d)) * rng.uniform(0.5, 3.0, d)
+    q = data[rng.choice(6000, 700, replace=False)]
+    engine.set_value_net(net)
+    try:
+        got = engine.state_values(q)
+        want = value_oracle.state_values(q, net)
+        np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-6)
+        a = engine.select_start(data, q, None, 5999, 0.3, 1.0, 2.0, want_ucb=True)
+        b = engine.select_start(data, q, got, 5999, 0.3, 1.0, 2.0, want_ucb=True)
+        assert a[0] == b[0]
+        np.testing.assert_array_equal(a[3], b[3])
+    finally:
+        engine.set_value_net(None)
+    with pytest.raises(ValueError):
+        engine.select_start(data, q, None, 5999, 0.3, 1.0, 2.0)
