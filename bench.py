@@ -395,6 +395,25 @@ def main():
         eng.select_start_mirror(ring, cand, kw["values"], kw["n"], kw["volume"], 1.0, 2.0)
 
     kde_mirror_ms = timed(kde_mirror_step, max(3, args.steps // 2), 2) / max(3, args.steps // 2)
+    # ---- BASELINE config 5 (strong scaling): 1 000 001-state buffer KDE with the 16 384 candidates
+    # sharded over the ranks + MPC with K = 262 144 sequences in total, both device-resident ----------
+    C5_K = 262_144
+    kw5 = kde_workload(seed=1, n=1_000_000)
+    d5_data = torch.as_tensor(kw5["all_states"], device=dev)
+    d5_q = torch.as_tensor(kw5["queries"], device=dev)
+    d5_v = torch.as_tensor(kw5["values"], device=dev)
+
+    def c5_kde_step(i):
+        selector.select_start_dev(d5_data.data_ptr(), d5_data.shape[0], 3, d5_q.data_ptr(), d5_q.shape[0],
+                                  d5_v.data_ptr(), kw5["n"], kw5["volume"], 1.0, 2.0)
+
+    def c5_mpc_step(i):
+        planner.plan(wl["state"], 0, K=C5_K, H=HORIZON, seed=2000 + i, act_low=wl["low"], act_high=wl["high"],
+                     penalty_mode="reference", precision=precision, want_path=True)
+
+    c5_kde_ms = timed(c5_kde_step, 5, 3) / 5
+    c5_mpc_ms = timed(c5_mpc_step, 5, 3) / 5
+    del d5_data, d5_q, d5_v
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -452,6 +471,12 @@ def main():
                              "traffic": NCU_TRAFFIC["kde_pairs_tc_kernel"],
                              "traffic_source": "profiles/r01c_ncu_summary.md (ncu --set full, same workload)"}},
     }
+    out["config5"] = {"workload": "BASELINE config 5, strong scaling over %d GPU(s): KDE 1 000 001 states x %d queries "
+                                  "(queries sharded) + MPC K=%d total, H=%d (sequences sharded), device-resident"
+                                  % (world, KDE_M, C5_K, HORIZON),
+                      "kde_ms": c5_kde_ms, "kde_evals_per_s": KDE_M * 1_000_001 / (c5_kde_ms * 1e-3),
+                      "mpc_ms": c5_mpc_ms, "mpc_rollout_steps_per_s": C5_K * HORIZON / (c5_mpc_ms * 1e-3),
+                      "episode_ms": c5_kde_ms + c5_mpc_ms}
     # ---- row f3 (plan set-up): pair extraction of path_shortcutter, P = 1000 path states ----------
     try:
         from smartstartcontinuous_b200 import numerical as num

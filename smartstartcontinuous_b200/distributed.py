@@ -138,6 +138,32 @@ class ShardedSelector:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.device = device
 
+    def _merge(self, j, ucb):
+        import torch
+        dist = _dist()
+        if self.world == 1:
+            return j, ucb
+        mine = torch.tensor([ucb, float(j)], dtype=torch.float64, device=self.device)
+        gathered = torch.empty(2 * self.world, dtype=torch.float64, device=self.device)
+        dist.all_gather_into_tensor(gathered, mine, group=self.group)
+        pairs = gathered.cpu().numpy().reshape(self.world, 2)
+        w = argmax_pick(pairs[:, 0].tolist(), [int(v) for v in pairs[:, 1]])
+        return int(pairs[w, 1]), float(pairs[w, 0])
+
+    def select_start_dev(self, data_ptr, n_pts, d, queries_ptr, m, values_ptr, n_transitions, volume=1.0,
+                         alpha=1.0, beta=2.0):
+        """Same with everything already resident on this rank's GPU (device pointers to the full
+        [n_pts, d] float64 buffer, [m, d] float64 queries, [m] float32 values): each rank scores its
+        contiguous slice of the queries."""
+        off, cnt = shard_bounds(m, self.world, self.rank)
+        if cnt > 0:
+            j, ucb = self.engine.select_start_dev(data_ptr, n_pts, d, queries_ptr + off * d * 8, cnt,
+                                                  values_ptr + off * 4, n_transitions, volume, alpha, beta)
+            j += off
+        else:
+            j, ucb = -1, 0.0
+        return self._merge(j, ucb)
+
     def select_start(self, all_states, queries, values, n_transitions, volume=1.0, alpha=1.0, beta=2.0):
         import torch
         dist = _dist()
@@ -149,11 +175,4 @@ class ShardedSelector:
             j += off
         else:
             j, ucb = -1, 0.0
-        if self.world == 1:
-            return j, ucb
-        mine = torch.tensor([ucb, float(j)], dtype=torch.float64, device=self.device)
-        gathered = [torch.empty_like(mine) for _ in range(self.world)]
-        dist.all_gather(gathered, mine, group=self.group)
-        pairs = torch.stack(gathered).cpu().numpy()
-        w = argmax_pick(pairs[:, 0].tolist(), [int(v) for v in pairs[:, 1]])
-        return int(pairs[w, 1]), float(pairs[w, 0])
+        return self._merge(j, ucb)
