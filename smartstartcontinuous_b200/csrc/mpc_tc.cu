@@ -9,15 +9,18 @@
 // L2 feeds two tiles -- each CTA holds only its half of every B tile, which halves the per-SM
 // L2 -> shared-memory traffic that otherwise caps the kernel (~43 B/clk/SM chip-wide).
 //
-//   layer 1   [256 x 32] x [32 x HP]   tcgen05.mma, A = split-bf16 input in smem, B = W1 image
-//             (input, weights and bias are hi/lo bf16 splits packed along K, so the layer is
-//             FP32-accurate although it runs on the tensor pipe)
+//   layer 1   [256 x K1] x [K1 x HP]   tcgen05.mma, A = split-bf16 input in smem (K1 = 16 or 32 slots),
+//             B = W1 image (input, weights and bias are hi/lo bf16 splits packed along K, so the
+//             layer is FP32-accurate although it runs on the tensor pipe); all HP/128 chunks are
+//             issued back to back: odd chunks into the accumulator slots, even chunks into the
+//             (then dead) H1 columns, converted in place
 //   relu+cvt  TMEM accumulator chunk -> registers -> bf16x2 -> TMEM (becomes the A operand)
 //   layer 2   [256 x HP] x [HP x HP]   tcgen05.mma kind::f16 (BF16 in, FP32 accumulate in TMEM),
 //             A from TMEM, B = W2 streamed from L2 by the TMA engine (cp.async.bulk, pre-packed
-//             32 KB core-matrix half blocks of 256 K elements) through a 4-stage mbarrier ring; bias folded in via
-//             two constant-one hidden units (hi/lo split)
-//   layer 3   fused into the layer-2 epilogue: relu, FP32 FFMA dot with W3 from shared memory
+//             32 KB core-matrix half blocks of 256 K elements) through a 4-stage mbarrier ring;
+//             bias folded in via two constant-one hidden units (hi/lo split)
+//   layer 3   fused into the layer-2 epilogue: relu, packed FP32 FFMA2 dot with W3 pairs from
+//             shared memory
 //   update    state += z * std_z + mean_z in FP32 registers; waypoint logic + progress/penalty
 //             score (score.cuh) run in the shadow of the next step's layer-2 MMAs
 //
