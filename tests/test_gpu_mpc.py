@@ -395,3 +395,22 @@ def test_path_close_pairs_matches_numpy(engine):
     np.testing.assert_array_equal(dev["distances_left"], host["distances_left"])
     with pytest.raises(ValueError):
         engine.path_close_pairs(np.zeros((4, 2)), [1.0, 0.0], 1.0)
+
+
+def test_tc_decisions_are_repeatable_bit_for_bit(engine):
+    """The same decision (same seed) gives identical bits every time: a race in the tcgen05 pipelines
+    (in-place TMEM conversion, accumulator-slot hand-over, W2 ring reuse across the CTA pair) would
+    show up as an occasional mismatch.  (scripts/dev/stress.py runs the long version.)"""
+    rng = np.random.default_rng(15)
+    w, b, norm, plan, start = _pendulum_2x500(rng)
+    engine.set_model(w, b, norm)
+    engine.set_plan(plan["desired_states"], plan["distances_left"], plan["radii"])
+    for mode in ("reference", "per_sample"):
+        kw = dict(K=40000, H=13, seed=5, act_low=[-2.0], act_high=[2.0], penalty_mode=mode, precision="bf16_tc",
+                  want_scores=True)
+        ref = engine.plan(start, 0, **kw)
+        for _ in range(15):
+            r = engine.plan(start, 0, **kw)
+            np.testing.assert_array_equal(r["scores"], ref["scores"])
+            assert r["best_k"] == ref["best_k"]
+            np.testing.assert_array_equal(r["best_path"], ref["best_path"])
