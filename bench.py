@@ -347,6 +347,15 @@ def main():
     e2e_ms = timed(e2e_step, max(3, args.steps // 2), 2) / max(3, args.steps // 2)
     e2e_value = K_total * HORIZON / (e2e_ms * 1e-3)
 
+    # ---- the same decision with the per-sample projection (penalty_mode=1: the evidently intended
+    # maths; fully fused, no trajectory spill, no second pass) -----------------------
+    def mpc_per_sample_step(i):
+        planner.plan(wl["state"], 0, K=K_total, H=HORIZON, seed=3000 + i, act_low=wl["low"], act_high=wl["high"],
+                     penalty_mode="per_sample", precision=precision, want_path=True)
+
+    ps_steps = max(3, args.steps // 2)
+    per_sample_ms = timed(mpc_per_sample_step, ps_steps, 2) / ps_steps
+
     # ---- KDE (BASELINE config 2 per GPU) -----------------------------------------------------
     kw = kde_workload()
     d_data = torch.as_tensor(kw["all_states"], device=dev)
@@ -445,6 +454,9 @@ def main():
                 "h2d_bytes_per_step": int(n_act * 8 + 3 * 8), "d2h_bytes_per_step": int(16 + HORIZON * 8 + (HORIZON + 1) * 3 * 8),
                 "path": "ss_mpc_rollout/ss_mpc_finish/ss_mpc_replay with host float64 action samples (pinned)"},
         "gpu_launches": int(launches),
+        "per_sample_penalty": {"value": K_total * HORIZON / (per_sample_ms * 1e-3), "unit": "rollout-steps/s",
+                               "ms_per_step": per_sample_ms,
+                               "note": "penalty_mode=per_sample (fully fused scoring, no penalty passes); measured after the headline and e2e legs"},
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": achieved_tf / peaks["bf16_sustained"],
                      "traffic": NCU_TRAFFIC["mpc_rollout_tc_kernel"] if precision == "bf16_tc" else None,

@@ -162,8 +162,8 @@ int ss_mpc_finish(ss_ctx* ctx, int64_t* out_best_k, double* out_best_score, doub
 /* ss_mpc_finish_package: ss_mpc_finish + the local winner's action sequence and predicted path
  * (NND_MB_agent.py:516-518), all left in DEVICE memory as one float64 package
  *   [best_score, best_k (global, as double), best_sequence (H*da), best_path ((H+1)*d)]
- * without a host synchronisation (reference penalty mode; per-sample mode re-rolls the winner
- * and therefore synchronises once).  Multi-GPU callers all-gather the packages and pick with
+ * without a host synchronisation (the trajectory rows of the batch are kept on the device in both
+ * penalty modes, the winner's path is a gather).  Multi-GPU callers all-gather the packages and pick with
  * np.argmax ordering -- one collective and one device->host copy per decision.  want_path = 0
  * leaves the sequence / path part zero.  ss_mpc_read_package copies it to the host. */
 int ss_mpc_finish_package(ss_ctx* ctx, int want_path, double** package_dev, int* count);
@@ -171,8 +171,8 @@ int ss_mpc_read_package(ss_ctx* ctx, double* out_package, int count);
 /* roll out ONE sequence of the last ss_mpc_rollout batch again (the global winner) in FP32 and
  * return its actions [H, da] and predicted path [H+1, d] (NND_MB_agent.py:516-518) */
 int ss_mpc_replay(ss_ctx* ctx, int64_t k_global, double* out_sequence, double* out_path);
-/* trajectories of the last ss_mpc_rollout made in SS_PENALTY_REFERENCE mode (they are kept for
- * the second scoring pass): out_states [H+1, K_local, d], as do_forward_sim returns them
+/* trajectories of the last ss_mpc_rollout (kept on the device for the reference-mode passes and
+ * for the winner's path): out_states [H+1, K_local, d], as do_forward_sim returns them
  * (dynamics_model.py:199-240). */
 int ss_mpc_get_states(ss_ctx* ctx, double* out_states);
 /* the device sampler alone: actions [K_local, H, da] for sequences k_offset.. (tests / oracle) */

@@ -317,15 +317,18 @@ extern "C" int ss_mpc_rollout(ss_ctx* c, const double* state, int wp_index, int6
     SS_CUDA_CHECK(c, c->mpc_scores.ensure((size_t)K_local * 4));
     a.scores_out = c->mpc_scores.as<float>();
     const bool ref = penalty_mode == SS_PENALTY_REFERENCE;
-    r.states_stored = ref;
     const int sum_blocks = mpc_sums_reference_blocks(K_local);
+    // The trajectory rows (state, waypoint index) are spilled in both penalty modes: the stores
+    // hide behind the layer-2 MMAs (no measurable cost), the reference-mode passes need them, and the
+    // winner's predicted path (NND_MB_agent.py:517) is then a gather instead of a re-roll.
+    r.states_stored = true;
+    SS_CUDA_CHECK(c, c->mpc_states.ensure((size_t)T * K_local * traj_row_stride(c->d) * 4));
+    a.states_out = c->mpc_states.as<float>();
     if (ref) {
-        // reference penalty: the rollout kernel only spills the trajectories; the projection sums
-        // and the scores come from two light passes over them (mpc_score.cu)
-        SS_CUDA_CHECK(c, c->mpc_states.ensure((size_t)T * K_local * traj_row_stride(c->d) * 4));
+        // reference penalty: the projection sums and the penalties come from two light passes
+        // over the rows (mpc_score.cu)
         SS_CUDA_CHECK(c, c->mpc_partial_sums.ensure((size_t)sum_blocks * T * 2 * 8));
         SS_CUDA_CHECK(c, c->mpc_sums.ensure((size_t)T * 2 * 8));
-        a.states_out = c->mpc_states.as<float>();
     }
     timer_mark(c, "mpc_setup");
     int grid = 0;
