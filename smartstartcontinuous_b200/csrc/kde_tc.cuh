@@ -36,9 +36,9 @@ constexpr int CG_COLS = NP / (EPI_WARPS / 4);   // 64 columns per warp and tile
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
 constexpr int MAX_D = 4;            // 6 D + 6 <= KS
 #ifndef SS_KDE_TC_POLY_MASK
-#define SS_KDE_TC_POLY_MASK 0x52    // bits 1, 4, 6: three of every eight evaluations take the polynomial
+#define SS_KDE_TC_POLY_MASK 0x5252  // bits 1, 4, 6 (+8): six of every sixteen evaluations take the polynomial
 #endif
-constexpr unsigned POLY_MASK = SS_KDE_TC_POLY_MASK;
+constexpr unsigned POLY_MASK = SS_KDE_TC_POLY_MASK;   // over the column index mod 16
 
 __device__ __forceinline__ void tc_commit1(uint64_t* b) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(b))
@@ -97,12 +97,12 @@ __device__ __forceinline__ void tmem_wait_ld_regs(uint32_t (&r)[32]) {
 __device__ __forceinline__ void exp_sum32(const uint32_t (&v)[32], float (&acc)[4], float2& accp) {
 #pragma unroll
     for (int i = 0; i < 32; ++i)
-        if (!((POLY_MASK >> (i & 7)) & 1u)) acc[i & 3] += ex2_approx(__uint_as_float(v[i]));
+        if (!((POLY_MASK >> (i & 15)) & 1u)) acc[i & 3] += ex2_approx(__uint_as_float(v[i]));
     float pe[32];
     int np = 0;
 #pragma unroll
     for (int i = 0; i < 32; ++i)
-        if ((POLY_MASK >> (i & 7)) & 1u) pe[np++] = __uint_as_float(v[i]);
+        if ((POLY_MASK >> (i & 15)) & 1u) pe[np++] = __uint_as_float(v[i]);
 #pragma unroll
     for (int i = 0; i + 1 < np; i += 2) accp = __fadd2_rn(accp, exp2_poly2(make_float2(pe[i], pe[i + 1])));
     if (np & 1) acc[0] += ex2_approx(pe[np - 1]);
