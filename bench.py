@@ -507,9 +507,20 @@ def main():
         for _ in range(3):
             ref_pairs = np.argwhere(np.triu(dist_fn(path[:, None, :], path[None, :, :]) <= 1.0, k=2))
         t_np = (time.perf_counter() - t0) / 3
-        out["plan_setup"] = {"what": "path_shortcutter pair extraction (numerical.py:226-246), P=1000, d=3, host buffers in and out",
-                             "gpu_ms": 1e3 * t_dev, "numpy_ms": 1e3 * t_np, "pairs": int(len(pairs)),
-                             "identical": bool(np.array_equal(pairs, ref_pairs))}
+        eng.path_shortcut(path, radii, 1.0)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            keep = eng.path_shortcut(path, radii, 1.0)
+        t_full_dev = (time.perf_counter() - t0) / 10
+        t0 = time.perf_counter()
+        host_path = num.path_shortcutter(path, dist_fn, 1.0)
+        t_full_host = time.perf_counter() - t0
+        out["plan_setup"] = {"what": "path_shortcutter (numerical.py:226-246), P=1000, d=3, host buffers in and out",
+                             "pairs_gpu_ms": 1e3 * t_dev, "pairs_numpy_ms": 1e3 * t_np, "pairs": int(len(pairs)),
+                             "pairs_identical": bool(np.array_equal(pairs, ref_pairs)),
+                             "shortcut_gpu_ms": 1e3 * t_full_dev, "shortcut_host_ms": 1e3 * t_full_host,
+                             "shortcut_identical": bool(np.array_equal(path[keep], host_path)),
+                             "kept_states": int(len(keep))}
     except Exception as exc:
         out["plan_setup"] = {"error": repr(exc)}
     if world == 1 and not args.no_cpu_baseline:

@@ -227,6 +227,13 @@ int ss_kde_ucb_argmax_mirror(ss_ctx* ctx, int64_t count, int64_t last_row, const
  * exceeds max_pairs).  The interval-scheduling DP (numerical.py:189-222) stays on the host. */
 int ss_path_close_pairs(ss_ctx* ctx, const double* path, int P, int d, const double* radii, double theta,
                         int32_t* out_pairs, int64_t max_pairs, int64_t* out_count);
+/* ss_path_shortcut: all of path_shortcutter (numerical.py:226-246) on the device -- the pair mask
+ * above plus the weighted-interval-scheduling DP of length_weighted_activities_solver
+ * (numerical.py:189-222, weight = end - start - 1, ties resolved as the reference does, including
+ * its first-interval quirk at :202).  out_keep [P] receives the indices of the states that remain
+ * (ascending), *out_count how many. */
+int ss_path_shortcut(ss_ctx* ctx, const double* path, int P, int d, const double* radii, double theta,
+                     int32_t* out_keep, int* out_count);
 
 #ifdef __cplusplus
 }

@@ -73,6 +73,8 @@ SIGNATURES = {
     "ss_kde_ucb_argmax_mirror": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                            C.c_int64, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
                                            _c_int64_p, _c_double_p]),
+    "ss_path_shortcut": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p,
+                                   _c_int_p]),
     "ss_path_close_pairs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_void_p,
                                       C.c_int64, _c_int64_p]),
 }

@@ -239,6 +239,19 @@ class Engine:
                 return out[:cnt.value]
             cap = int(cnt.value)
 
+    def path_shortcut(self, path, radii, theta):
+        """Indices of the path states path_shortcutter (numerical.py:226-246) keeps: pair mask and
+        interval-scheduling DP both on the device."""
+        p = _f64(path)
+        r = _f64(radii).reshape(-1)
+        if p.ndim != 2 or r.shape[0] != p.shape[1]:
+            raise ValueError("path [P, d] and radii [d] expected")
+        keep = np.empty(p.shape[0], dtype=np.int32)
+        cnt = C.c_int(0)
+        self._check(self._lib.ss_path_shortcut(self._h, _ptr(p), p.shape[0], p.shape[1], _ptr(r), float(theta),
+                                               _ptr(keep), C.byref(cnt)))
+        return keep[:cnt.value]
+
     # ------------------------------------------------------------------ stage 2
     def set_model(self, weights, biases, norm):
         """weights[l] [in, out] (y = x W + b), biases[l] [out]; norm: dict mean_x std_x mean_y

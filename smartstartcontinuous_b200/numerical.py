@@ -157,10 +157,12 @@ def length_weighted_activities_solver(activities, sub_extra=0):
 def path_shortcutter(path, distance_func, theta, engine=None):
     """Drop interior states between any two states (>= 2 apart) that are within theta.
 
-    With ``engine`` (a CUDA Engine) and an elliptical ``distance_func`` the O(P^2) pair extraction
-    runs on the device (ss_path_close_pairs: same float64 operations, same pair order); the
-    interval-scheduling DP stays here."""
+    With ``engine`` (a CUDA Engine) and an elliptical ``distance_func`` the whole function runs on
+    the device (ss_path_shortcut: same float64 pair decisions, same DP tie-breaking)."""
     p = np.asarray(path)
+    if engine is not None and getattr(distance_func, "radii", None) is not None and hasattr(engine, "path_shortcut") \
+            and len(p) <= 16384:
+        return p[engine.path_shortcut(p, distance_func.radii, theta)]
     if engine is not None and getattr(distance_func, "radii", None) is not None:
         pairs = engine.path_close_pairs(p, distance_func.radii, theta)
     else:

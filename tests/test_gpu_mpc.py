@@ -414,3 +414,27 @@ def test_tc_decisions_are_repeatable_bit_for_bit(engine):
             np.testing.assert_array_equal(r["scores"], ref["scores"])
             assert r["best_k"] == ref["best_k"]
             np.testing.assert_array_equal(r["best_path"], ref["best_path"])
+
+
+def test_path_shortcut_dp_matches_host_solver(engine):
+    """Row f3: ss_path_shortcut (pair mask + weighted-interval-scheduling DP on the device) keeps
+    exactly the states the host path_shortcutter keeps -- random walks, lattice walks full of exact
+    ties, loops that revisit earlier states, and the degenerate short paths."""
+    from smartstartcontinuous_b200 import numerical as num
+    rng = np.random.default_rng(23)
+    cases = []
+    for P, d in ((2, 2), (3, 2), (5, 3), (40, 2), (200, 3), (1000, 3), (1500, 2)):
+        cases.append(np.cumsum(rng.normal(size=(P, d)), axis=0))                       # random walk
+        cases.append(np.cumsum(rng.integers(-1, 2, size=(P, d)), axis=0).astype(float))  # lattice: many ties
+    t = np.linspace(0, 6 * np.pi, 600)
+    cases.append(np.stack([np.cos(t), np.sin(t)], axis=1) * 5)                         # three laps of a circle
+    cases.append(np.zeros((50, 2)))                                                    # all states identical
+    for path in cases:
+        d = path.shape[1]
+        radii = np.full(d, 0.8)
+        dist = num.elliptical_euclidean_distance_function_generator(radii)
+        for theta in (0.5, 1.0, 2.5):
+            want = num.path_shortcutter(path, dist, theta)
+            keep = engine.path_shortcut(path, radii, theta)
+            np.testing.assert_array_equal(path[keep], want)
+            np.testing.assert_array_equal(num.path_shortcutter(path, dist, theta, engine=engine), want)
