@@ -611,27 +611,33 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
             if (slices > n_tiles) slices = n_tiles;
             if (slices < 1) slices = 1;
             n_slices = (int)slices * (EPI_WARPS / 4);            // one partial row per (slice, column group)
-            SS_CUDA_CHECK(c, c->kde_pts.ensure((size_t)n_tiles * B_BYTES));
-            SS_CUDA_CHECK(c, c->kde_qw.ensure((size_t)q_tiles * A_BYTES));
+            const int ks = ks_for(d);
+            SS_CUDA_CHECK(c, c->kde_pts.ensure((size_t)n_tiles * b_bytes(ks)));
+            SS_CUDA_CHECK(c, c->kde_qw.ensure((size_t)q_tiles * a_bytes(ks)));
             SS_CUDA_CHECK(c, c->kde_partial.ensure((size_t)n_slices * m_pad * 4));
             const unsigned pblocks = (unsigned)((n_pad + 255) / 256), qblocks = (unsigned)((m_pad + 255) / 256);
-            kde_whiten_tc_kernel<<<pblocks + qblocks, 256, 0, c->stream>>>(
-                data_dev, n, n_pad, c->kde_pts.as<__nv_bfloat16>(), queries_dev, m, m_pad,
-                c->kde_qw.as<__nv_bfloat16>(), d, fit, pblocks);
-            c->launches += 1;
-            SS_CUDA_CHECK(c, cudaGetLastError());
-            timer_mark(c, "kde_fit_whiten");
-            if (!c->kde_tc_attr_set) {
-                SS_CUDA_CHECK(c, cudaFuncSetAttribute(kde_pairs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                      (int)SMEM_BYTES));
-                c->kde_tc_attr_set = true;
-            }
             const long long items = q_tiles * slices;
             const unsigned grid = (unsigned)(items < c->sm_count ? items : c->sm_count);
-            kde_pairs_tc_kernel<<<grid, THREADS, SMEM_BYTES, c->stream>>>(
-                c->kde_qw.as<__nv_bfloat16>(), c->kde_pts.as<__nv_bfloat16>(), n_tiles, (int)q_tiles, (int)slices, m_pad,
-                fit, c->kde_partial.as<float>());
-            c->launches++;
+            cudaError_t e = cudaSuccess;
+#define KDE_TC_CASE(KS_)                                                                                          \
+    do {                                                                                                          \
+        kde_whiten_tc_kernel<KS_><<<pblocks + qblocks, 256, 0, c->stream>>>(                                      \
+            data_dev, n, n_pad, c->kde_pts.as<__nv_bfloat16>(), queries_dev, m, m_pad,                            \
+            c->kde_qw.as<__nv_bfloat16>(), d, fit, pblocks);                                                      \
+        timer_mark(c, "kde_fit_whiten");                                                                         \
+        e = cudaFuncSetAttribute(kde_pairs_tc_kernel<KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                 (int)smem_bytes(KS_));                                                           \
+        if (e == cudaSuccess)                                                                                     \
+            kde_pairs_tc_kernel<KS_><<<grid, THREADS, smem_bytes(KS_), c->stream>>>(                              \
+                c->kde_qw.as<__nv_bfloat16>(), c->kde_pts.as<__nv_bfloat16>(), n_tiles, (int)q_tiles, (int)slices, \
+                m_pad, fit, c->kde_partial.as<float>());                                                          \
+    } while (0)
+            if (ks == 32) KDE_TC_CASE(32);
+            else if (ks == 64) KDE_TC_CASE(64);
+            else KDE_TC_CASE(128);
+#undef KDE_TC_CASE
+            c->launches += 2;
+            SS_CUDA_CHECK(c, e);
             SS_CUDA_CHECK(c, cudaGetLastError());
             timer_mark(c, "kde_pairs");
         } else {

@@ -1,9 +1,9 @@
-// kde_tc.cuh -- tcgen05 variant of the KDE pair kernel (included by kde.cu; d <= 4).
+// kde_tc.cuh -- tcgen05 variant of the KDE pair kernel (included by kde.cu; d <= 20).
 //
 // The CUDA-core pair kernel is dispatch-bound: every kernel evaluation costs ~6 issue cycles for
 // the exponent (differences or the expanded form) before the MUFU.EX2 it is nominally limited by.
 // Here the exponent  e'[q][i] = -|q|^2 - |x_i|^2 + 2 q.x_i  of a 128-query x 256-point block comes
-// out of ONE pair of tcgen05.mma instructions (M = 128, N = 256, K = 32, BF16 in, FP32 accumulate
+// out of KS / 16 tcgen05.mma instructions (M = 128, N = 256, K = KS = 32 / 64 / 128, BF16 in, FP32 accumulate
 // in TMEM): every FP32 operand is split into three BF16 pieces (hi, mid, lo; 24 bits) and the six
 // significant partial products per dimension get their own K slot, so the product is FP32-accurate
 // although it runs on the tensor pipe:
@@ -27,14 +27,16 @@ namespace kdetc {
 
 constexpr int QT = 128;             // queries per work item (MMA M, TMEM lanes)
 constexpr int NP = 256;             // points per tile (MMA N, FP32 columns per accumulator buffer)
-constexpr int KS = 32;              // K slots (BF16)
-constexpr int A_BYTES = QT * KS * 2;   // 8 KB
-constexpr int B_BYTES = NP * KS * 2;   // 16 KB
-constexpr int NSTAGE = 4;
+// K slots (BF16) of the MMA: 6 d + 6 must fit -> KS = 32 (d <= 4), 64 (d <= 9), 128 (d <= 20)
+__host__ __device__ constexpr int ks_for(int d) { return 6 * d + 6 <= 32 ? 32 : (6 * d + 6 <= 64 ? 64 : 128); }
+__host__ __device__ constexpr int max_d_for(int ks) { return (ks - 6) / 6; }
+__host__ __device__ constexpr int a_bytes(int ks) { return QT * ks * 2; }     // 8 / 16 / 32 KB per query tile
+__host__ __device__ constexpr int b_bytes(int ks) { return NP * ks * 2; }     // 16 / 32 / 64 KB per point tile
+__host__ __device__ constexpr int nstage_for(int ks) { return ks <= 64 ? 4 : 2; }
 constexpr int EPI_WARPS = 16;       // warp w: TMEM lane quarter w % 4, column group w / 4
 constexpr int CG_COLS = NP / (EPI_WARPS / 4);   // 64 columns per warp and tile
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
-constexpr int MAX_D = 4;            // 6 D + 6 <= KS
+constexpr int MAX_D = 20;           // largest state dimension of the tcgen05 variant (KS = 128)
 #ifndef SS_KDE_TC_POLY_MASK
 #define SS_KDE_TC_POLY_MASK 0x5252  // bits 1, 4, 6 (+8): six of every sixteen evaluations take the polynomial
 #endif
@@ -119,11 +121,12 @@ __device__ __forceinline__ void split3(float v, __nv_bfloat16& h, __nv_bfloat16&
 
 // One thread per row.  POINTS: tiles of NP rows, image [tile][KS/8][NP][8]; queries: tiles of QT rows.
 // Rows >= n are padding: points far away (-|x|^2 = -1e30), queries zero.
-template <bool POINTS>
+template <bool POINTS, int KS>
 __device__ __forceinline__ void whiten_tc_rows(long long block, const double* __restrict__ x, long long n,
                                                long long n_pad, int d, KdeFit* __restrict__ fit,
                                                __nv_bfloat16* __restrict__ img) {
     constexpr int ROWS = POINTS ? NP : QT;
+    constexpr int MAX_D = max_d_for(KS);
     const long long i = block * (long long)blockDim.x + threadIdx.x;
     float norm2 = 0.f;
     if (i < n_pad) {
@@ -208,26 +211,29 @@ __device__ __forceinline__ void whiten_tc_rows(long long block, const double* __
 }
 
 // points (blocks [0, point_blocks)) and queries (the remaining blocks) in one launch
+template <int KS>
 __global__ void __launch_bounds__(256)
 kde_whiten_tc_kernel(const double* __restrict__ data, long long n, long long n_pad, __nv_bfloat16* __restrict__ p_img,
                      const double* __restrict__ queries, long long m, long long m_pad,
                      __nv_bfloat16* __restrict__ q_img, int d, KdeFit* __restrict__ fit, unsigned point_blocks) {
     if (blockIdx.x < point_blocks)
-        whiten_tc_rows<true>(blockIdx.x, data, n, n_pad, d, fit, p_img);
+        whiten_tc_rows<true, KS>(blockIdx.x, data, n, n_pad, d, fit, p_img);
     else
-        whiten_tc_rows<false>(blockIdx.x - point_blocks, queries, m, m_pad, d, fit, q_img);
+        whiten_tc_rows<false, KS>(blockIdx.x - point_blocks, queries, m, m_pad, d, fit, q_img);
 }
 
 // ---- the pair kernel -----------------------------------------------------------------------
 // Persistent CTAs; work item = (query tile, slice of point tiles); slices <= n_tiles.
 // partial[slice * 4 + column group][m_pad].
+template <int KS>
 __global__ void __launch_bounds__(THREADS, 1)
 kde_pairs_tc_kernel(const __nv_bfloat16* __restrict__ q_img, const __nv_bfloat16* __restrict__ p_img,
                     long long n_tiles, int q_tiles, int slices, long long m_pad,
                     const KdeFit* __restrict__ fit, float* __restrict__ partial) {
+    constexpr int A_BYTES = a_bytes(KS), B_BYTES = b_bytes(KS), NSTAGE = nstage_for(KS);
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* b_ring = smem;                                   // NSTAGE x 16 KB
-    unsigned char* a_buf = smem + (size_t)NSTAGE * B_BYTES;         // 2 x 8 KB
+    unsigned char* b_ring = smem;                                   // NSTAGE point tiles
+    unsigned char* a_buf = smem + (size_t)NSTAGE * B_BYTES;         // 2 query tiles
     uint64_t* bars = reinterpret_cast<uint64_t*>(a_buf + 2 * A_BYTES);
     uint64_t* b_full = bars;                 // [NSTAGE] TMA -> MMA
     uint64_t* b_empty = b_full + NSTAGE;     // [NSTAGE] MMA (commit) -> TMA
@@ -347,6 +353,6 @@ kde_pairs_tc_kernel(const __nv_bfloat16* __restrict__ q_img, const __nv_bfloat16
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
-constexpr size_t SMEM_BYTES = (size_t)NSTAGE * B_BYTES + 2 * A_BYTES + 16 * 8 + 16 + 128;
+__host__ constexpr size_t smem_bytes(int ks) { return (size_t)nstage_for(ks) * b_bytes(ks) + 2 * a_bytes(ks) + 16 * 8 + 16 + 128; }
 
 }  // namespace kdetc
