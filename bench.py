@@ -452,7 +452,9 @@ def main():
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "rollout-steps/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(n_act * 8 + 3 * 8), "d2h_bytes_per_step": int(16 + HORIZON * 8 + (HORIZON + 1) * 3 * 8),
-                "path": "ss_mpc_rollout/ss_mpc_finish/ss_mpc_replay with host float64 action samples (pinned)"},
+                "path": "ShardedPlanner.plan -> ss_mpc_rollout / ss_mpc_finish_package with HOST float64 action samples "
+                        "(pinned, uploaded in chunks that overlap the rollout) + D2H of the winner package; the agent's "
+                        "default call (device Philox sampling: 24 B of state in, the same package out) is what `value` times"},
         "gpu_launches": int(launches),
         "per_sample_penalty": {"value": K_total * HORIZON / (per_sample_ms * 1e-3), "unit": "rollout-steps/s",
                                "ms_per_step": per_sample_ms,
