@@ -95,7 +95,7 @@ def golden_kde(ref, name, *, env, n_transitions, n_ss, with_radii, seed):
           (len(all_states), len(idx), d, int(np.argmax(cap["ucb"])), len(cap["path"])))
 
 
-def golden_mpc(ref, name, *, env, L, h, K, H, wp_index, seed, fit_epochs):
+def golden_mpc(ref, name, *, env, L, h, K, H, wp_index, seed, fit_epochs, weight_seed=None, weight_scale=1.0):
     rng = np.random.default_rng(seed)
     if env == "pendulum":
         obs, act = syn.pendulum_rollouts(rng, 12, 120)
@@ -110,7 +110,10 @@ def golden_mpc(ref, name, *, env, L, h, K, H, wp_index, seed, fit_epochs):
         w, b, norm = syn.fit_dynamics_mlp(states_list, actions_list, L, h, seed=seed, epochs=fit_epochs,
                                           batch=128)
     else:
-        w, b = syn.xavier_mlp(rng, d, 1, L, h)
+        # weight_seed: the weights are regenerated from the seed by the tests (conftest.golden_model)
+        # instead of being stored -- keeps the fixture of a 2x500 network small
+        wrng = rng if weight_seed is None else np.random.default_rng(weight_seed)
+        w, b = syn.xavier_mlp(wrng, d, 1, L, h, scale=weight_scale)
         norm = syn.normalisation_stats(np.concatenate(states_list), np.concatenate(
             [np.concatenate([a, a[-1:]]) for a in actions_list])[:len(np.concatenate(states_list))])
     nnd = rh.make_nnd_agent(ref, w, b, norm, low, high, horizon=H, num_control_samples=K)
@@ -134,9 +137,12 @@ def golden_mpc(ref, name, *, env, L, h, K, H, wp_index, seed, fit_epochs):
     best_action, best_k, best_seq, best_path = nnd.get_best_sim_actions(start_state)
     assert np.array_equal(best_seq, actions[best_k])
     flat = {}
-    for i, (wi, bi) in enumerate(zip(w, b)):
-        flat["in_w%d" % i] = wi
-        flat["in_b%d" % i] = bi
+    if weight_seed is None:
+        for i, (wi, bi) in enumerate(zip(w, b)):
+            flat["in_w%d" % i] = wi
+            flat["in_b%d" % i] = bi
+    else:
+        flat.update(in_weight_seed=weight_seed, in_weight_scale=weight_scale, in_hidden=h, in_d=d)
     np.savez_compressed(
         os.path.join(GOLDEN, name),
         in_path=np.array(path), in_start_state=start_state, in_actions=actions,
@@ -166,6 +172,9 @@ def main():
                seed=2, fit_epochs=15)
     golden_mpc(ref, "mpc_mountaincar_L3_xavier.npz", env="mountaincar", L=3, h=40, K=96, H=4,
                wp_index=1, seed=3, fit_epochs=0)
+    # the BASELINE network shape (Pendulum, 2x500) through the reference's own get_best_sim_actions
+    golden_mpc(ref, "mpc_pendulum_2x500.npz", env="pendulum", L=2, h=500, K=600, H=20, wp_index=0,
+               seed=4, fit_epochs=0, weight_seed=1004, weight_scale=0.5)
 
 
 if __name__ == "__main__":

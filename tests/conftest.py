@@ -22,8 +22,13 @@ def load_golden(name):
 
 def golden_model(g):
     L = int(g["in_num_layers"])
-    weights = [g["in_w%d" % i] for i in range(L + 1)]
-    biases = [g["in_b%d" % i] for i in range(L + 1)]
+    if "in_weight_seed" in g:        # big networks: weights regenerated from the seed (oracle/make_golden.py)
+        from smartstartcontinuous_b200 import synthetic as syn
+        weights, biases = syn.xavier_mlp(np.random.default_rng(int(g["in_weight_seed"])), int(g["in_d"]), 1, L,
+                                         int(g["in_hidden"]), scale=float(g["in_weight_scale"]))
+    else:
+        weights = [g["in_w%d" % i] for i in range(L + 1)]
+        biases = [g["in_b%d" % i] for i in range(L + 1)]
     norm = {k: g["in_" + k] for k in ("mean_x", "std_x", "mean_y", "std_y", "mean_z", "std_z")}
     return weights, biases, norm
 

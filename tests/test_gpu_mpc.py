@@ -8,7 +8,8 @@ from smartstartcontinuous_b200 import synthetic as syn
 
 pytestmark = pytest.mark.gpu
 
-MPC_CASES = ["mpc_mountaincar_L2.npz", "mpc_pendulum_L1.npz", "mpc_mountaincar_L3_xavier.npz"]
+MPC_CASES = ["mpc_mountaincar_L2.npz", "mpc_pendulum_L1.npz", "mpc_mountaincar_L3_xavier.npz",
+             "mpc_pendulum_2x500.npz"]
 STATE_RTOL = 1e-4     # fp32 path, north-star tolerance
 SCORE_TOL = 1e-4
 
@@ -176,8 +177,11 @@ def _pendulum_2x500(rng, scale=0.5):
     return w, b, norm, plan, obs[0][0]
 
 
-def test_tc_golden_states_and_plan(engine):
-    g = load_golden("mpc_mountaincar_L2.npz")
+@pytest.mark.parametrize("name", ["mpc_mountaincar_L2.npz", "mpc_pendulum_2x500.npz"])
+def test_tc_golden_states_and_plan(engine, name):
+    """tcgen05 path against the reference's own outputs: the small fitted network and the BASELINE
+    shape (Pendulum, 2x500, K = 600 ragged, H = 20)."""
+    g = load_golden(name)
     _setup(engine, g)
     assert engine.tc_supported()
     states = engine.forward_sim(g["in_start_state"], g["in_actions"], precision="bf16_tc")

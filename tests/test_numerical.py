@@ -97,7 +97,7 @@ def test_waypoints():
 
 
 @pytest.mark.parametrize("name", ["mpc_mountaincar_L2.npz", "mpc_pendulum_L1.npz",
-                                  "mpc_mountaincar_L3_xavier.npz"])
+                                  "mpc_mountaincar_L3_xavier.npz", "mpc_pendulum_2x500.npz"])
 def test_plan_setup_matches_reference(name):
     """radii / shortcut path / waypoints / distances_left as the reference's
     start_new_episode_plan produced them (NND_MB_agent.py:375-418)."""

@@ -7,7 +7,8 @@ from conftest import golden_model, load_golden
 from oracle import kde_oracle, mpc_oracle
 
 KDE_CASES = ["kde_pendulum.npz", "kde_mountaincar.npz"]
-MPC_CASES = ["mpc_mountaincar_L2.npz", "mpc_pendulum_L1.npz", "mpc_mountaincar_L3_xavier.npz"]
+MPC_CASES = ["mpc_mountaincar_L2.npz", "mpc_pendulum_L1.npz", "mpc_mountaincar_L3_xavier.npz",
+             "mpc_pendulum_2x500.npz"]
 
 
 @pytest.mark.parametrize("name", KDE_CASES)
