@@ -284,6 +284,8 @@ def main():
     wl = make_workload()
     eng.set_model(wl["w"], wl["b"], wl["norm"])
     eng.set_plan(wl["plan"]["desired_states"], wl["plan"]["distances_left"], wl["plan"]["radii"])
+    if world > 1 and os.environ.get("SS_PEER", "1") != "0":
+        eng.peer_setup()         # projection sums + winner packages over NVLink peer memory, inside the kernels
     planner = ShardedPlanner(eng, device=dev)
     selector = ShardedSelector(eng, device=dev)
     K_total = K_PER_GPU * world
@@ -447,8 +449,10 @@ def main():
         "config": {"workload": workload_name(),
                    "K_total": K_total, "H": HORIZON, "mlp": "2x500", "actions": "device Philox4x32-10",
                    "l2": "flushed between timed steps (256 MiB memset, outside the event-timed region)",
-                   "parallelism": "K sharded over %d GPU(s); all-reduce of %d float64 + all-gather of (score,k)"
-                                  % (world, 2 * (HORIZON + 1))},
+                   "parallelism": "K sharded over %d GPU(s); all-reduce of %d float64 + all-gather of the winner packages, %s"
+                                  % (world, 2 * (HORIZON + 1),
+                                     "fused into the kernels over NVLink peer memory (csrc/peer.cu)" if eng.peer_ready
+                                     else ("NCCL" if world > 1 else "none at N=1"))},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "rollout-steps/s", "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": int(n_act * 8 + 3 * 8), "d2h_bytes_per_step": int(16 + HORIZON * 8 + (HORIZON + 1) * 3 * 8),

@@ -168,6 +168,19 @@ int ss_mpc_finish(ss_ctx* ctx, int64_t* out_best_k, double* out_best_score, doub
  * leaves the sequence / path part zero.  ss_mpc_read_package copies it to the host. */
 int ss_mpc_finish_package(ss_ctx* ctx, int want_path, double** package_dev, int* count);
 int ss_mpc_read_package(ss_ctx* ctx, double* out_package, int count);
+/* ---- NVLink peer-memory exchange for sharded batches (one process per GPU, one node) -------
+ * ss_peer_init allocates this rank's exchange buffer and returns its 64-byte CUDA IPC handle; the
+ * caller all-gathers the handles (any transport) and passes all of them, in rank order, to
+ * ss_peer_open.  From then on a sharded ss_mpc_rollout (K_global != K_local) in reference penalty
+ * mode leaves the GLOBAL projection sums in place (the reduction kernel stores its sums into every
+ * peer's slot and adds the peers' in rank order), and ss_mpc_finish_package leaves the GLOBAL
+ * winner's package on every rank (np.argmax ordering over the ranks' winners) -- no NCCL call and no
+ * host synchronisation between the phases.  Every rank must make the same sequence of sharded
+ * calls.  world <= 8. */
+int ss_peer_init(ss_ctx* ctx, int rank, int world, void* out_ipc_handle_64_bytes);
+int ss_peer_open(ss_ctx* ctx, const void* all_handles_world_x_64_bytes, int world);
+int ss_peer_close(ss_ctx* ctx);
+int ss_peer_ready(ss_ctx* ctx);
 /* roll out ONE sequence of the last ss_mpc_rollout batch again (the global winner) in FP32 and
  * return its actions [H, da] and predicted path [H+1, d] (NND_MB_agent.py:516-518) */
 int ss_mpc_replay(ss_ctx* ctx, int64_t k_global, double* out_sequence, double* out_path);

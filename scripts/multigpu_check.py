@@ -23,6 +23,10 @@ eng.set_model(wl["w"], wl["b"], wl["norm"])
 eng.set_plan(wl["plan"]["desired_states"], wl["plan"]["distances_left"], wl["plan"]["radii"])
 planner = ShardedPlanner(eng, device=dev)
 ok = True
+if os.environ.get("SS_PEER", "1") != "0":
+    eng.peer_setup()
+if rank == 0:
+    print("peer exchange:", eng.peer_ready)
 for mode in ("reference", "per_sample"):
     for prec in ("fp32", "bf16_tc"):
         K, H = 20000, 12

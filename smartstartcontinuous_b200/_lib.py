@@ -67,6 +67,10 @@ SIGNATURES = {
     "ss_mpc_sample_actions": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_uint64,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "ss_mpc_tc_supported": (C.c_int, [C.c_void_p]),
+    "ss_peer_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "ss_peer_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "ss_peer_close": (C.c_int, [C.c_void_p]),
+    "ss_peer_ready": (C.c_int, [C.c_void_p]),
     "ss_value_net_set": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ss_value_net_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "ss_mirror_write": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_void_p]),

@@ -68,6 +68,8 @@ extern "C" int ss_destroy(ss_ctx* c) {
     for (auto& b : c->b32) b.release();
     if (c->timer.created)
         for (int i = 0; i <= SS_MAX_PHASES; ++i) cudaEventDestroy(c->timer.ev[i]);
+    ss_peer_close(c);
+    c->mpc_package_local.release();
     if (c->copy_ready) {
         for (int i = 0; i <= ss_ctx::MAX_COPY_CHUNKS; ++i) cudaEventDestroy(c->copy_ev[i]);
         cudaStreamDestroy(c->copy_stream);

@@ -75,6 +75,14 @@ struct ActionSource {
     float low_f[SS_MAX_DA], range_f[SS_MAX_DA];
 };
 
+// NVLink peer-memory exchange (peer.cu)
+constexpr int SS_PEER_MAX_WORLD = 8;
+constexpr int SS_PEER_SLOT_DOUBLES = 8192;     // 64 KB per (channel, parity, source rank)
+struct PeerView {
+    double* base[SS_PEER_MAX_WORLD];           // exchange buffer of every rank (own: local pointer)
+    int rank, world;
+};
+
 struct PhaseTimer {
     cudaEvent_t ev[SS_MAX_PHASES + 1];
     const char* names[SS_MAX_PHASES];
@@ -103,6 +111,13 @@ struct ss_ctx {
     bool kde_tc_attr_set = false;
     // ---- plan set-up geometry scratch (plan_geom.cu)
     DevBuf geom_in, geom_rows, geom_pairs;
+    // ---- peer-memory exchange of the sharded planner (peer.cu)
+    void* peer_buf = nullptr;
+    void* peer_opened[SS_PEER_MAX_WORLD] = {};
+    PeerView peer_view = {};
+    unsigned long long peer_epoch[2] = {0, 0};
+    bool peer_ready = false;
+    DevBuf mpc_package_local;
     // ---- critic value net in front of the UCB (value_net.cu)
     DevBuf value_net_params;
     std::vector<char> value_net_desc;
@@ -142,6 +157,7 @@ struct ss_ctx {
         ActionSource act;
         bool states_stored = false;
         bool finished = false;         // the reference-mode penalty pass has rewritten the scores
+        bool peer_sums = false;        // the projection sums were all-reduced over peer memory
         int sum_blocks = 0;
     } run;
 };

@@ -346,7 +346,11 @@ extern "C" int ss_mpc_rollout(ss_ctx* c, const double* state, int wp_index, int6
     if (ref) {
         rc = mpc_sums_reference(c, a.plan, c->mpc_states.as<float>(), K_local, T, c->mpc_partial_sums.as<double>());
         if (rc) return rc;
-        rc = mpc_reduce_sums(c, c->mpc_partial_sums.as<double>(), sum_blocks, T, c->mpc_sums.as<double>());
+        // a sharded batch on a context with an open peer exchange: the reduction kernel also
+        // all-reduces the sums over NVLink peer memory (no NCCL call, no host round trip)
+        r.peer_sums = c->peer_ready && K_global != K_local;
+        rc = r.peer_sums ? peer_allreduce_sums(c, c->mpc_partial_sums.as<double>(), sum_blocks, T, c->mpc_sums.as<double>())
+                         : mpc_reduce_sums(c, c->mpc_partial_sums.as<double>(), sum_blocks, T, c->mpc_sums.as<double>());
         if (rc) return rc;
         r.sum_blocks = sum_blocks;
         timer_mark(c, "mpc_sums_pass1");
@@ -442,11 +446,21 @@ extern "C" int ss_mpc_finish_package(ss_ctx* c, int want_path, double** package_
         K_rows = 1;
         fixed_row = 0;
     }
+    const bool peer = c->peer_ready && r.K_global != r.K_local;
+    double* pkg_dst = c->mpc_package.as<double>();
+    if (peer) {
+        SS_CUDA_CHECK(c, c->mpc_package_local.ensure((size_t)n * 8));
+        pkg_dst = c->mpc_package_local.as<double>();
+    }
     package_kernel<<<1, 256, 0, c->stream>>>(reinterpret_cast<const MpcResult*>(c->mpc_result.p), rows, K_rows,
-                                             fixed_row, r.k_offset, T, d, r.act, want_path,
-                                             c->mpc_package.as<double>());
+                                             fixed_row, r.k_offset, T, d, r.act, want_path, pkg_dst);
     c->launches++;
     SS_CUDA_CHECK(c, cudaGetLastError());
+    if (peer) {
+        // every rank's package goes to every peer; the same kernel picks the global winner
+        rc = peer_package_exchange(c, pkg_dst, n, c->mpc_package.as<double>());
+        if (rc) return rc;
+    }
     timer_mark(c, "mpc_package");
     if (package_dev) *package_dev = c->mpc_package.as<double>();
     if (count) *count = n;

@@ -49,6 +49,11 @@ int mpc_score_reference(ss_ctx* c, const PlanView& plan, const float* rows, long
 int mpc_argmax(ss_ctx* c, const float* scores, long long K_local, long long k_offset,
                double* block_v, long long* block_i, void* result_dev);
 
+// peer-memory exchange (peer.cu): fused reduce + all-reduce of the projection sums, and the
+// all-gather + pick of the winner packages
+int peer_allreduce_sums(ss_ctx* c, const double* partial, int blocks, int T, double* sums);
+int peer_package_exchange(ss_ctx* c, const double* pkg_local, int n, double* pkg_out);
+
 struct MpcResult {
     double best_score;
     long long best_k;

@@ -99,7 +99,10 @@ class ShardedPlanner:
                             horizontal_penalty_factor=horizontal_penalty_factor,
                             penalty_mode=penalty_mode, precision=precision, k_offset=k_offset,
                             K_global=K)
-        if self.world > 1 and penalty_mode in ("reference", 0):
+        # with an open peer exchange (Engine.peer_setup) both merges already happened inside the
+        # kernels over NVLink peer memory; otherwise they are two small collectives
+        peer = self.world > 1 and bool(getattr(self.engine, "peer_ready", False))
+        if self.world > 1 and not peer and penalty_mode in ("reference", 0):
             sums = self._sums_tensor()
             if sums is not None:
                 dist.all_reduce(sums, group=self.group)      # 2*(H+1) float64
@@ -108,8 +111,10 @@ class ShardedPlanner:
             mine = self.engine.finish_package_tensor(want_path)
         else:
             ptr, n = self.engine.finish_package(want_path)
-            mine = None if self.world == 1 else torch.as_tensor(_DevView(ptr, n), device=self.device)
-        if self.world > 1:
+            mine = None if (self.world == 1 or peer) else torch.as_tensor(_DevView(ptr, n), device=self.device)
+        if peer:
+            pk = self.engine.read_package(n).reshape(1, -1)            # already the global winner
+        elif self.world > 1:
             gathered = torch.empty(self.world * mine.numel(), dtype=torch.float64, device=mine.device)
             dist.all_gather_into_tensor(gathered, mine, group=self.group)
             pk = gathered.cpu().numpy().reshape(self.world, -1)        # the one host sync
@@ -117,12 +122,16 @@ class ShardedPlanner:
             pk = mine.numpy().reshape(1, -1)
         else:
             pk = self.engine.read_package(n).reshape(1, -1)
-        w = argmax_pick(pk[:, 0].tolist(), [int(v) for v in pk[:, 1]])
-        best_score, best_k = float(pk[w, 0]), int(pk[w, 1])
+        row = argmax_pick(pk[:, 0].tolist(), [int(v) for v in pk[:, 1]])
+        best_score, best_k = float(pk[row, 0]), int(pk[row, 1])
+        w = row
+        if peer:                                                       # owner = the shard that holds best_k
+            w = next((r for r in range(self.world)
+                      if shard_bounds(K, self.world, r)[0] <= best_k < sum(shard_bounds(K, self.world, r))), 0)
         seq = path = None
         if want_path:
-            seq = pk[w, 2:2 + H * da].reshape(H, da).copy()
-            path = pk[w, 2 + H * da:2 + H * da + (H + 1) * d].reshape(H + 1, d).copy()
+            seq = pk[row, 2:2 + H * da].reshape(H, da).copy()
+            path = pk[row, 2 + H * da:2 + H * da + (H + 1) * d].reshape(H + 1, d).copy()
         return dict(best_k=best_k, best_score=best_score, best_sequence=seq, best_path=path,
                     owner=w, k_offset=k_offset, k_local=k_local)
 

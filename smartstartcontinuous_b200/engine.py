@@ -107,6 +107,31 @@ class Engine:
             C.byref(best), C.byref(best_ucb)))
         return int(best.value), float(best_ucb.value), dens, ucb
 
+    # NVLink peer-memory exchange for sharded batches (one process per GPU)
+    def peer_setup(self, group=None):
+        """Open the peer-memory exchange between the Engines of a torch.distributed group (one node,
+        <= 8 ranks): CUDA IPC handles are all-gathered once; afterwards sharded decisions exchange
+        their projection sums and winner packages inside the kernels (csrc/peer.cu)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        handle = (C.c_ubyte * 64)()
+        self._check(self._lib.ss_peer_init(self._h, rank, world, handle))
+        dev = torch.device("cuda", self.device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=dev)
+        gathered = torch.empty(64 * world, dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(gathered, mine, group=group)
+        blob = bytes(gathered.cpu().numpy().tobytes())
+        self._check(self._lib.ss_peer_open(self._h, blob, world))
+        dist.barrier(group)
+
+    @property
+    def peer_ready(self):
+        return bool(self._lib.ss_peer_ready(self._h))
+
+    def peer_close(self):
+        self._check(self._lib.ss_peer_close(self._h))
+
     # critic value net in front of the UCB (SURVEY 8f row f4)
     def set_value_net(self, net):
         """net: dict with 'actor' = [(W1, b1), (W2, b2), (W3, b3)], 'critic' = same (critic W2 is
