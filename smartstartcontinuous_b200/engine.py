@@ -125,6 +125,13 @@ class Engine:
         self._check(self._lib.ss_peer_open(self._h, blob, world))
         dist.barrier(group)
 
+    def peer_setup_single(self):
+        """A one-rank exchange (this GPU only): the fused kernels then write to and read from their own
+        slots -- used by the single-GPU tests to exercise the exchange kernels."""
+        handle = (C.c_ubyte * 64)()
+        self._check(self._lib.ss_peer_init(self._h, 0, 1, handle))
+        self._check(self._lib.ss_peer_open(self._h, bytes(handle), 1))
+
     @property
     def peer_ready(self):
         return bool(self._lib.ss_peer_ready(self._h))

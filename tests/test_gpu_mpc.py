@@ -442,3 +442,32 @@ def test_path_shortcut_dp_matches_host_solver(engine):
             keep = engine.path_shortcut(path, radii, theta)
             np.testing.assert_array_equal(path[keep], want)
             np.testing.assert_array_equal(num.path_shortcutter(path, dist, theta, engine=engine), want)
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16_tc"])
+def test_peer_exchange_kernels_single_rank(engine, prec):
+    """The peer-memory exchange kernels (csrc/peer.cu) with a one-rank exchange: a shard of a larger
+    batch is planned once through the plain reduction / package kernels and once through the fused
+    exchange kernels (which then write to and read from their own slots); sums-dependent scores, the
+    winner and its package must be identical, repeatedly (epoch double-buffering)."""
+    rng = np.random.default_rng(16)
+    w, b, norm, plan, start = _pendulum_2x500(rng)
+    engine.set_model(w, b, norm)
+    engine.set_plan(plan["desired_states"], plan["distances_left"], plan["radii"])
+
+    def shard(mode, seed):
+        engine.rollout(start, 0, K=3000, H=9, seed=seed, act_low=[-2.0], act_high=[2.0], penalty_mode=mode,
+                       precision=prec, k_offset=5000, K_global=20000)
+        ptr, n = engine.finish_package(True)
+        return engine.read_package(n)
+
+    plain = {(m, s): shard(m, s) for m in ("reference", "per_sample") for s in (1, 2, 3)}
+    engine.peer_setup_single()
+    try:
+        assert engine.peer_ready
+        for (m, s), want in plain.items():
+            np.testing.assert_array_equal(shard(m, s), want)
+    finally:
+        engine.peer_close()
+    assert not engine.peer_ready
+    np.testing.assert_array_equal(shard("reference", 1), plain[("reference", 1)])
