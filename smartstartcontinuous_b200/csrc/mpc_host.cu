@@ -324,11 +324,16 @@ extern "C" int ss_mpc_rollout(ss_ctx* c, const double* state, int wp_index, int6
     r.states_stored = true;
     SS_CUDA_CHECK(c, c->mpc_states.ensure((size_t)T * K_local * traj_row_stride(c->d) * 4));
     a.states_out = c->mpc_states.as<float>();
+    const long long tc_qcols = 4 * ((K_local + mpc_tc_tile_rows() - 1) / mpc_tc_tile_rows());
+    const bool tc_sums = ref && precision == SS_PRECISION_BF16_TC;   // projection sums inside the rollout kernel
     if (ref) {
-        // reference penalty: the projection sums and the penalties come from two light passes
-        // over the rows (mpc_score.cu)
-        SS_CUDA_CHECK(c, c->mpc_partial_sums.ensure((size_t)sum_blocks * T * 2 * 8));
+        // reference penalty: the projection sums come out of the tcgen05 kernel (one table column per
+        // tile and row warp) or, on the FP32 path, from a pass over the rows; the penalties from a
+        // second light pass (mpc_score.cu)
+        const size_t cols = tc_sums ? (size_t)tc_qcols : (size_t)sum_blocks;
+        SS_CUDA_CHECK(c, c->mpc_partial_sums.ensure((cols + 64) * T * 2 * 8));     // + room for the folded columns
         SS_CUDA_CHECK(c, c->mpc_sums.ensure((size_t)T * 2 * 8));
+        if (tc_sums) a.qsums = c->mpc_partial_sums.as<double>();
     }
     timer_mark(c, "mpc_setup");
     int grid = 0;
@@ -344,15 +349,26 @@ extern "C" int ss_mpc_rollout(ss_ctx* c, const double* state, int wp_index, int6
     }
     timer_mark(c, "mpc_rollout");
     if (ref) {
-        rc = mpc_sums_reference(c, a.plan, c->mpc_states.as<float>(), K_local, T, c->mpc_partial_sums.as<double>());
-        if (rc) return rc;
+        int red_blocks = tc_sums ? (int)tc_qcols : sum_blocks;
+        const double* red_src = c->mpc_partial_sums.as<double>();
+        if (!tc_sums) {
+            rc = mpc_sums_reference(c, a.plan, c->mpc_states.as<float>(), K_local, T, c->mpc_partial_sums.as<double>());
+            if (rc) return rc;
+        }
+        if (red_blocks > 256) {
+            // thousands of columns (one per tile and row warp): fold them to 16 per output first
+            double* folded = c->mpc_partial_sums.as<double>() + (size_t)red_blocks * T * 2;
+            rc = mpc_fold_partials(c, red_src, red_blocks, T, folded, &red_blocks);
+            if (rc) return rc;
+            red_src = folded;
+        }
         // a sharded batch on a context with an open peer exchange: the reduction kernel also
         // all-reduces the sums over NVLink peer memory (no NCCL call, no host round trip)
         r.peer_sums = c->peer_ready && K_global != K_local;
-        rc = r.peer_sums ? peer_allreduce_sums(c, c->mpc_partial_sums.as<double>(), sum_blocks, T, c->mpc_sums.as<double>())
-                         : mpc_reduce_sums(c, c->mpc_partial_sums.as<double>(), sum_blocks, T, c->mpc_sums.as<double>());
+        rc = r.peer_sums ? peer_allreduce_sums(c, red_src, red_blocks, T, c->mpc_sums.as<double>())
+                         : mpc_reduce_sums(c, red_src, red_blocks, T, c->mpc_sums.as<double>());
         if (rc) return rc;
-        r.sum_blocks = sum_blocks;
+        r.sum_blocks = red_blocks;
         timer_mark(c, "mpc_sums_pass1");
     }
     r.valid = true;

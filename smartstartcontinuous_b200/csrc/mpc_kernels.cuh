@@ -23,6 +23,8 @@ struct RolloutArgs {
                              //    (mpc_score.cu) run over them afterwards
     float* states_out;       // [H+1][K_local][d + 1] trajectory rows (score.cuh) or null
     float* scores_out;       // [K_local] (per-sample mode: final; reference mode: progress term)
+    double* qsums;           // tcgen05 kernel, reference mode: [H+1][2][4 * tiles] a'.b' and b'.b' summed over the
+                             // 32 rows of every (tile, row warp), or null (then mpc_sums_reference computes them)
 };
 
 // fp32 SIMT rollout (mpc_simt.cu)
@@ -41,6 +43,7 @@ int mpc_tc_tile_rows();
 
 // scoring tail (mpc_score.cu)
 int mpc_reduce_sums(ss_ctx* c, const double* partial, int blocks, int T, double* sums);
+int mpc_fold_partials(ss_ctx* c, const double* partial, int blocks, int T, double* folded, int* blocks_out);
 int mpc_sums_reference_blocks(long long K_local);
 int mpc_sums_reference(ss_ctx* c, const PlanView& plan, const float* rows, long long K_local, int T,
                        double* partial);

@@ -21,13 +21,29 @@ mpc_reduce_sums_kernel(const double* __restrict__ partial, int blocks, int T, do
     if (o >= 2 * T) return;
     const int t = o >> 1, w = o & 1, lane = threadIdx.x & 31;
     double s = 0.0;
-    for (int b = lane; b < blocks; b += 32) s += partial[((size_t)t * blocks + b) * 2 + w];
+    for (int b = lane; b < blocks; b += 32) s += partial[(size_t)o * blocks + b];      // [t][2][blocks]
     for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
     if (lane == 0) sums[o] = s;
 }
 
+// many partial columns (one per tile and row warp from the tcgen05 kernel) -> FOLD columns per
+// output, fixed order: column segment f of output o is summed by one warp (lanes stride, shuffle tree)
+constexpr int SUMS_FOLD = 16;
+__global__ void __launch_bounds__(256)
+mpc_fold_partials_kernel(const double* __restrict__ partial, int blocks, int n_out, double* __restrict__ folded) {
+    const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wid >= n_out * SUMS_FOLD) return;
+    const int o = wid / SUMS_FOLD, f = wid % SUMS_FOLD, lane = threadIdx.x & 31;
+    const int seg = (blocks + SUMS_FOLD - 1) / SUMS_FOLD;
+    const int b0 = f * seg, b1 = min(blocks, b0 + seg);
+    double s = 0.0;
+    for (int b = b0 + lane; b < b1; b += 32) s += partial[(size_t)o * blocks + b];
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+    if (lane == 0) folded[(size_t)o * SUMS_FOLD + f] = s;
+}
+
 // first pass over the spilled rows: a'.b' and b'.b' (numerical.py:89-93) of every (t, k), summed
-// over k per time step.  grid = (k blocks, T); partial[t][block][2].
+// over k per time step.  grid = (k blocks, T); partial[t][2][block].
 template <int DT>
 __global__ void __launch_bounds__(256)
 mpc_sums_reference_kernel(const PlanView Pg, const float* __restrict__ rows, long long K, int ds_in_smem,
@@ -65,7 +81,7 @@ mpc_sums_reference_kernel(const PlanView Pg, const float* __restrict__ rows, lon
     if (threadIdx.x < 2) {
         double tot = 0.0;
         for (int w = 0; w < 8; ++w) tot += s_part[w][threadIdx.x];
-        partial[((size_t)t * gridDim.x + blockIdx.x) * 2 + threadIdx.x] = tot;
+        partial[((size_t)t * 2 + threadIdx.x) * gridDim.x + blockIdx.x] = tot;
     }
 }
 
@@ -143,6 +159,17 @@ int mpc_reduce_sums(ss_ctx* c, const double* partial, int blocks, int T, double*
     mpc_reduce_sums_kernel<<<(2 * T + 7) / 8, 256, 0, c->stream>>>(partial, blocks, T, sums);
     c->launches++;
     SS_CUDA_CHECK(c, cudaGetLastError());
+    return SS_OK;
+}
+
+// folds [2T][blocks] partial columns in place-compatible layout into [2T][SUMS_FOLD] at `folded`
+// (blocks > SUMS_FOLD); returns the new column count through *blocks_out
+int mpc_fold_partials(ss_ctx* c, const double* partial, int blocks, int T, double* folded, int* blocks_out) {
+    const int warps = 2 * T * SUMS_FOLD;
+    mpc_fold_partials_kernel<<<(warps + 7) / 8, 256, 0, c->stream>>>(partial, blocks, 2 * T, folded);
+    c->launches++;
+    SS_CUDA_CHECK(c, cudaGetLastError());
+    *blocks_out = SUMS_FOLD;
     return SS_OK;
 }
 

@@ -234,11 +234,29 @@ struct SmemT {
 
 // score one trajectory point for this row (ch-1 thread): waypoint move + progress (+ per-sample
 // penalty); in reference mode the (state, waypoint index) row is spilled for the penalty passes
+// qcol >= 0: this warp's column (tile * 4 + row warp) of the projection-sum table a.qsums
 template <int DT>
 __device__ __forceinline__ void score_row(const RolloutArgs& a, int t, const float (&x)[DT], ScoreAcc& sc,
-                                          bool live, long long k_local) {
+                                          bool live, long long k_local, long long qcol, long long n_qcols, int lane) {
     score_point<DT>(a.plan, t, x, sc, a.per_sample != 0);
     if (a.states_out && live) traj_store<DT>(a.states_out, (size_t)t * a.K_local + k_local, a.d, x, sc.idx);
+    if (a.qsums && qcol >= 0) {
+        // reference penalty: a'.b' and b'.b' of this step (numerical.py:89-93) summed over the warp's
+        // 32 sequences -- in the shadow of the layer-2 MMAs, so the separate pass over the spilled rows
+        // is not needed.  The 32-term warp sum runs in FP32 (FP64 shuffles + DADDs in these warps cost
+        // the kernel 10 %: measured), everything above it in float64; one table column per (tile, row
+        // warp) keeps the final sum independent of how tiles are spread over CTAs and launches.
+        float ab = 0.f, bb = 0.f;
+        if (live) proj_terms<DT>(a.plan, sc.idx, x, ab, bb);
+        for (int off = 16; off > 0; off >>= 1) {
+            ab += __shfl_down_sync(0xffffffffu, ab, off);
+            bb += __shfl_down_sync(0xffffffffu, bb, off);
+        }
+        if (lane == 0) {
+            a.qsums[((size_t)t * 2) * n_qcols + qcol] = (double)ab;
+            a.qsums[((size_t)t * 2 + 1) * n_qcols + qcol] = (double)bb;
+        }
+    }
 }
 
 // DT: register copies of the state (4 or 8); DZ: layer-3 outputs computed (>= d; 2, 3, 4 or 8);
@@ -333,6 +351,8 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
             const long long tile = p.tile_begin + (long long)it * gridDim.x + blockIdx.x;   // >= tile_end: padding
             const long long k_local = tile * TM + row;
             const bool live = tile < p.tile_end && k_local < a.K_local;
+            const long long n_qcols = 4 * ((a.K_local + TM - 1) / TM);
+            const long long qcol = tile < p.tile_end ? tile * 4 + q : -1;
             // both threads of a row keep identical copies of the state; ch 0 feeds the network
             // (critical path), ch 1 scores the trajectory in the shadow of the layer-2 MMAs
             float x[DT];
@@ -450,7 +470,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                 }
                 // ---- off the critical path (the tensor pipe is busy with layer 2 now) ----------
                 if (ch == 1) {
-                    score_row<DT>(a, t, x, sc, live, k_local);
+                    score_row<DT>(a, t, x, sc, live, k_local, qcol, n_qcols, lane);
                 } else if (ch == 0 && live && t + 1 < a.H) {
                     TC_TRACE(70);
 #pragma unroll
@@ -515,7 +535,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                 TC_TRACE(tb + 18);
             }
             if (ch == 1) {
-                score_row<DT>(a, a.H, x, sc, live, k_local);
+                score_row<DT>(a, a.H, x, sc, live, k_local, qcol, n_qcols, lane);
                 if (live && a.scores_out) a.scores_out[k_local] = sc.score;
             }
         }

@@ -69,7 +69,7 @@ mpc_reduce_allreduce_kernel(const double* __restrict__ partial, int blocks, int 
     for (int o = warp; o < n; o += 32) {                 // same fixed order as mpc_reduce_sums_kernel
         const int t = o >> 1, w = o & 1;
         double s = 0.0;
-        for (int b = lane; b < blocks; b += 32) s += partial[((size_t)t * blocks + b) * 2 + w];
+        for (int b = lane; b < blocks; b += 32) s += partial[(size_t)o * blocks + b];      // [t][2][blocks]
         for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
         if (lane == 0) s_my[o] = s;
     }
