@@ -43,8 +43,8 @@ KDE_N = 100_000
 KDE_M = 16_384
 SFU_PER_CLK_PER_SM = 16                        # MUFU.EX2 lanes per SM per clock (sm_100)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
-# captures of exactly these workloads (profiles/r01c_ncu_summary.md); not measurable live
-NCU_TRAFFIC = {"mpc_rollout_tc_kernel": 621_056 + 50_215_680, "kde_pairs_tc_kernel": 7_490_816}
+# captures of exactly these workloads (profiles/r01e_ncu_summary.md); not measurable live
+NCU_TRAFFIC = {"mpc_rollout_tc_kernel": 675_072 + 52_459_008, "kde_pairs_tc_kernel": 7_491_072}
 
 
 def measured_peaks():
@@ -466,7 +466,7 @@ def main():
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                      "frac": achieved_tf / peaks["bf16_sustained"],
                      "traffic": NCU_TRAFFIC["mpc_rollout_tc_kernel"] if precision == "bf16_tc" else None,
-                     "traffic_source": "profiles/r01c_ncu_summary.md (ncu --set full, same workload)",
+                     "traffic_source": "profiles/r01e_ncu_summary.md (ncu --set full, same workload)",
                      "frac_of_burst_peak": achieved_tf / peaks["bf16_burst"],
                      "kernel": "mpc_rollout_tc_kernel" if precision == "bf16_tc" else "mpc_rollout_simt_kernel",
                      "kernel_ms": k_ms, "peak_source": peaks["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
@@ -487,7 +487,7 @@ def main():
                                             "tensor pipe, so frac > 1 is possible" % (info["sm_count"], peaks["sm_max_mhz"]),
                              "hbm_achieved_gbs": kde_bytes / (p_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
                              "traffic": NCU_TRAFFIC["kde_pairs_tc_kernel"],
-                             "traffic_source": "profiles/r01c_ncu_summary.md (ncu --set full, same workload)"}},
+                             "traffic_source": "profiles/r01e_ncu_summary.md (ncu --set full, same workload)"}},
     }
     out["config5"] = {"workload": "BASELINE config 5, strong scaling over %d GPU(s): KDE 1 000 001 states x %d queries "
                                   "(queries sharded) + MPC K=%d total, H=%d (sequences sharded), device-resident"
