@@ -11,15 +11,26 @@ BASELINE.json's metric, KDE kernel-evals/s, is reported in the same line under "
             (reference-exact penalty mode).  Workload per GPU: Pendulum d=3, da=1, K=131072
             (= BASELINE config 4's K=1M / 8), H=50 -- at N=8 this is exactly config 4.
   value     K_total * H / device time, inputs resident (actions sampled on the device, Philox)
-  e2e       same decision through the C ABI with HOST buffers: action samples [K,H,da] float64 in
-            pinned host memory -> H2D inside the call -> rollout -> score -> D2H of the result
-  kde       BASELINE config 2: 100 001 Pendulum states x 16 384 candidate queries per GPU
-  roofline  tensor pipe for the rollout kernel (achieved = 507 000 FLOP x K*H / kernel time, against
-            the measured sustained bf16 peak; frac_of_burst_peak = against the burst figure), SFU pipe
-            (16 MUFU.EX2 / clk / SM) for the KDE pair kernel
-  --impl reference: the oracle port of the reference's CPU path (numpy float64, BLAS on all host
-            cores; scipy gaussian_kde with the queries chunked over a multiprocessing.Pool for the
-            KDE), timed on bounded samples of the same workload.
+  e2e       the same decision through the drop-in plugin call NND_MB_agent.get_best_sim_actions
+            (NND_MB_agent.py:498-520) in its DEFAULT configuration: K*H*da float64 action samples
+            drawn on the host with numpy's legacy MT19937 stream exactly like :500-501 (inside the
+            timer), uploaded inside the call, winner package read back.  e2e_device_sampling is the
+            same call with device_sampling=True (Philox on the GPU), e2e_host_samples the C-ABI call
+            on pre-drawn pinned samples (no host RNG in the timer).
+  kde       BASELINE config 2: 100 001 Pendulum states x 16 384 candidate queries per GPU; its e2e
+            goes through SmartStartContinuous.get_smart_start_path (smartexplorationcontinuous.py:223-305)
+  small_k   BASELINE configs 3 (MountainCar, K=4096, H=20, 2x500) and 1 (the example's shapes:
+            K=5000, H=4, MLP 1x32; KDE n_ss=2000): ms per decision resident and through the agent
+  roofline  tensor pipe for the rollout kernel: achieved = 507 000 FLOP x K*H / kernel time against the
+            measured BURST bf16 peak (the timed region is ~50 ms at the maximum SM clock; the ratio
+            to the sustained figure is kept as frac_of_sustained_peak); SFU pipe (16 MUFU.EX2 / clk /
+            SM) for the KDE pair kernel
+  --impl reference: the reference's own CPU code for the path (NND_MB_agent.get_best_sim_actions
+            executed from the staged copy oracle/_ref through oracle/ref_harness.py; TensorFlow's
+            sess.run evaluated in float64 numpy/BLAS on all host cores) -- or the oracle port when the
+            staged copy is absent -- and scipy gaussian_kde with the queries chunked over a
+            multiprocessing.Pool, timed on bounded samples of the same workload plus one full-size
+            step.
 """
 from __future__ import annotations
 
@@ -41,10 +52,13 @@ K_PER_GPU = 131_072
 HORIZON = 50
 KDE_N = 100_000
 KDE_M = 16_384
+C3_K, C3_H = 4096, 20                          # BASELINE config 3
+C1_K, C1_H, C1_NSS = 5000, 4, 2000             # BASELINE config 1 (the example's hyper-parameters)
 SFU_PER_CLK_PER_SM = 16                        # MUFU.EX2 lanes per SM per clock (sm_100)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
-# captures of exactly these workloads (profiles/r01e_ncu_summary.md); not measurable live
+# captures of exactly these workloads (profiles/r02_ncu_summary.md); not measurable live
 NCU_TRAFFIC = {"mpc_rollout_tc_kernel": 675_072 + 52_459_008, "kde_pairs_tc_kernel": 7_491_072}
+NCU_TRAFFIC_SOURCE = "profiles/r01e_ncu_summary.md (ncu --set full, same workload)"
 
 
 def measured_peaks():
@@ -58,18 +72,37 @@ def measured_peaks():
                 source="fallback (B200_PROFILING.md)")
 
 
-def make_workload(seed=0):
-    """Seeded synthetic inputs of the benchmark shapes."""
-    from smartstartcontinuous_b200 import synthetic as syn
+# --------------------------------------------------------------------------- workloads
+def _plan(path):
     from smartstartcontinuous_b200.nnd_mb_agent import plan_from_path
+    return plan_from_path(path, mean_per_stepsize=1, std_per_stepsize=1, stepsizes_in_waypoint_radii=1,
+                          path_shortcutting=True, theta=1, steps_per_waypoint=1)
+
+
+def make_workload(seed=0):
+    """BASELINE config 4 / 5 shapes: Pendulum d=3, da=1, MLP 2x500 (seeded synthetic)."""
+    from smartstartcontinuous_b200 import synthetic as syn
     rng = np.random.default_rng(seed)
     obs, act = syn.pendulum_rollouts(rng, 25, 333)          # 25 x 333 random-policy transitions
     norm = syn.normalisation_stats(np.concatenate(list(obs)),
                                    np.concatenate([np.concatenate([a, a[-1:]]) for a in act]))
     w, b = syn.xavier_mlp(rng, 3, 1, 2, 500, scale=0.5)
-    plan = plan_from_path(list(obs[0][:80]), mean_per_stepsize=1, std_per_stepsize=1,
-                          stepsizes_in_waypoint_radii=1, path_shortcutting=True, theta=1, steps_per_waypoint=1)
-    return dict(w=w, b=b, norm=norm, plan=plan, state=obs[0][0].copy(), low=[-2.0], high=[2.0])
+    path = list(obs[0][:80])
+    return dict(w=w, b=b, norm=norm, plan=_plan(path), path=path, state=obs[0][0].copy(), low=[-2.0], high=[2.0],
+                d=3, da=1, L=2, h=500)
+
+
+def make_workload_mountaincar(L, h, seed=3):
+    """BASELINE configs 3 (L=2, h=500) and 1 (L=1, h=32): MountainCar d=2, da=1."""
+    from smartstartcontinuous_b200 import synthetic as syn
+    rng = np.random.default_rng(seed)
+    roll = [syn.mountaincar_rollout(rng, 200) for _ in range(8)]
+    norm = syn.normalisation_stats(np.concatenate([r[0] for r in roll]),
+                                   np.concatenate([np.concatenate([r[1], r[1][-1:]]) for r in roll]))
+    w, b = syn.xavier_mlp(rng, 2, 1, L, h, scale=0.5)
+    path = list(roll[0][0][:60])
+    return dict(w=w, b=b, norm=norm, plan=_plan(path), path=path, state=roll[0][0][0].copy(), low=[-1.0], high=[1.0],
+                d=2, da=1, L=L, h=h)
 
 
 def kde_workload(seed=0, n=KDE_N, m=KDE_M):
@@ -78,6 +111,17 @@ def kde_workload(seed=0, n=KDE_N, m=KDE_M):
     rng = np.random.default_rng(seed)
     q = np.ascontiguousarray(s2[rng.choice(n, m, replace=False)])
     return dict(all_states=all_states, queries=q, values=syn.critic_like_values(q), n=n, volume=1e-3)
+
+
+def workload_name():
+    return ("NND_MB random-shooting MPC, Pendulum-v0 d=3 da=1, K=%d per GPU (BASELINE config 4 = K=1M over 8 GPUs), "
+            "H=%d, MLP 2x500, reference-exact penalty" % (K_PER_GPU, HORIZON))
+
+
+def shared_config(world):
+    """`config` of the JSON line: identical keys and values in both arms (ours / --impl reference)."""
+    return {"workload": workload_name(), "K_per_gpu": K_PER_GPU, "K_total": K_PER_GPU * world, "H": HORIZON,
+            "mlp": "2x500", "d": 3, "da": 1, "penalty_mode": "reference", "gamma": .75, "horizontal_penalty_factor": .5}
 
 
 class ClockSampler(threading.Thread):
@@ -122,21 +166,44 @@ class ClockSampler(threading.Thread):
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def workload_name():
-    return ("NND_MB random-shooting MPC, Pendulum-v0 d=3 da=1, K=%d per GPU (BASELINE config 4 = K=1M over 8 GPUs), "
-            "H=%d, MLP 2x500, reference-exact penalty" % (K_PER_GPU, HORIZON))
+# --------------------------------------------------------------------------- CPU (reference) arm
+class CpuPlanner:
+    """The reference's CPU planner for one workload.  With the reference staged (oracle/_ref, or
+    /root/reference in the build container) this is its OWN NND_MB_agent: start_new_episode_plan +
+    get_best_sim_actions (npr.uniform sampling, do_forward_sim, generate_scores_add_delta, argmax),
+    the TF session replaced by a float64 numpy evaluation of the same MLP (oracle/ref_harness.py).
+    Otherwise the oracle port of the same functions."""
 
+    def __init__(self, wl, K, H):
+        from oracle import ref_harness as rh
+        self.wl, self.K, self.H = wl, K, H
+        self.kind = "port"
+        self.agent = None
+        if rh.available():
+            ref = rh.load_reference()
+            self.agent = rh.make_nnd_agent(ref, wl["w"], wl["b"], wl["norm"], wl["low"], wl["high"], horizon=H,
+                                           num_control_samples=K)
+            self.agent.start_new_episode_plan(wl["state"], [np.asarray(p) for p in wl["path"]])
+            self.kind = "reference"
 
-def cpu_reference_mpc(wl, K, H, seed):
-    """The reference's CPU planner (oracle port): npr.uniform sampling + float64 numpy rollout +
-    scoring.  Returns seconds."""
-    from oracle import mpc_oracle
-    rs = np.random.RandomState(seed)
-    t0 = time.perf_counter()
-    acts = rs.uniform(wl["low"], wl["high"], (K, H, 1))
-    mpc_oracle.plan(wl["state"], acts, wl["w"], wl["b"], wl["norm"], wl["plan"]["desired_states"],
-                    wl["plan"]["distances_left"], wl["plan"]["radii"], 0, .75, .5)
-    return time.perf_counter() - t0
+    def set_K(self, K):
+        self.K = K
+        if self.agent is not None:
+            self.agent.N = K
+
+    def decide(self, seed):
+        """One decision; returns seconds (sampling included, as in the reference)."""
+        wl = self.wl
+        np.random.seed(seed)
+        t0 = time.perf_counter()
+        if self.agent is not None:
+            self.agent.get_best_sim_actions(wl["state"])
+        else:
+            from oracle import mpc_oracle
+            acts = np.random.uniform(wl["low"], wl["high"], (self.K, self.H, wl["da"]))
+            mpc_oracle.plan(wl["state"], acts, wl["w"], wl["b"], wl["norm"], wl["plan"]["desired_states"],
+                            wl["plan"]["distances_left"], wl["plan"]["radii"], 0, .75, .5)
+        return time.perf_counter() - t0
 
 
 def cpu_reference_kde(kw, m):
@@ -183,31 +250,54 @@ def cpu_reference_kde_pool(kw, m, procs, reps):
     return float(np.mean(times))
 
 
-def blas_threads():
+def pin_blas_threads():
+    """All host cores for the BLAS behind numpy, whatever OMP_NUM_THREADS says (torch.distributed.run
+    exports OMP_NUM_THREADS=1 to its workers).  Returns (controller to keep alive, threads in use)."""
+    n = os.cpu_count() or 1
     try:
-        from threadpoolctl import threadpool_info
-        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+        from threadpoolctl import threadpool_info, threadpool_limits
+        ctl = threadpool_limits(limits=n)
+        used = max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+        return ctl, used
     except Exception:
-        return os.cpu_count() or 1
+        return None, 1
 
 
-REF_K_SAMPLE = 4096          # sequences per timed MPC step of the CPU arm (~0.5 s on a server CPU)
+REF_K_SAMPLE = 4096          # sequences per timed MPC step of the CPU arm
 
 
 def run_reference(args, guard):
-    """--impl reference: the reference's CPU path (oracle port; scipy for the KDE) on rank 0 only,
-    all host threads, bounded samples of the same workload."""
+    """--impl reference: the reference's CPU path on rank 0 only, all host threads, bounded samples of
+    the same workload (+ one full-size step unless --no-full-step)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    ctl, cores = pin_blas_threads()
     wl = make_workload()
     kw = kde_workload()
     K_s = REF_K_SAMPLE
+    cpu = CpuPlanner(wl, K_s, HORIZON)
     for _ in range(args.warmup):
-        cpu_reference_mpc(wl, 512, HORIZON, 0)
-    t_mpc = [cpu_reference_mpc(wl, K_s, HORIZON, i) for i in range(args.steps)]
+        cpu.set_K(512)
+        cpu.decide(0)
+    cpu.set_K(K_s)
+    t_mpc = [cpu.decide(i) for i in range(args.steps)]
     v = K_s * HORIZON / float(np.mean(t_mpc))
-    cores = blas_threads()
+    full = None
+    if not args.no_full_step:
+        cpu.set_K(K_PER_GPU)
+        t_full = cpu.decide(99)
+        full = {"K": K_PER_GPU, "H": HORIZON, "seconds": t_full, "value": K_PER_GPU * HORIZON / t_full,
+                "unit": "rollout-steps/s"}
+    # BASELINE configs 3 and 1 on the CPU (whole decisions, these are small)
+    small = {}
+    for name, (L, h, K, H) in (("config3", (2, 500, C3_K, C3_H)), ("config1", (1, 32, C1_K, C1_H))):
+        wls = make_workload_mountaincar(L, h)
+        cp = CpuPlanner(wls, K, H)
+        cp.decide(0)
+        ts = [cp.decide(i) for i in range(3)]
+        small[name] = {"ms_per_decision": 1e3 * float(np.mean(ts)), "rollout_steps_per_s": K * H / float(np.mean(ts)),
+                       "K": K, "H": H, "mlp": "%dx%d" % (L, h), "kind": cp.kind, "cores": cores}
     procs = os.cpu_count() or 1
     m_pool = min(KDE_M, 256 * procs)
     reps = max(1, min(args.steps, 5))
@@ -215,24 +305,34 @@ def run_reference(args, guard):
     kv = m_pool * (kw["n"] + 1) / t_pool
     t_one = [cpu_reference_kde(kw, 256) for _ in range(2)]
     kv_one = 256 * (kw["n"] + 1) / float(np.mean(t_one))
-    sample = "%d steps of K=%d (of %d) sequences, H=%d (rate is K-independent: GEMM-bound)" % (
-        args.steps, K_s, K_PER_GPU, HORIZON)
+    kw1 = kde_workload(seed=2, n=KDE_N, m=C1_NSS)
+    t_c1 = [cpu_reference_kde(kw1, 256) for _ in range(2)]
+    small["config1"]["kde_n_ss_2000_ms_one_core_scaled"] = 1e3 * float(np.mean(t_c1)) * C1_NSS / 256
+    sample = "%d steps of K=%d (of %d) sequences, H=%d (rate is K-independent: GEMM-bound)%s" % (
+        args.steps, K_s, K_PER_GPU, HORIZON,
+        "; one full K=%d step: %.1f s = %.3g rollout-steps/s" % (K_PER_GPU, full["seconds"], full["value"]) if full else "")
+    note = ("the reference's own NND_MB_agent.get_best_sim_actions (staged copy, oracle/ref_harness.py) with sess.run "
+            "evaluated in float64 numpy/BLAS" if cpu.kind == "reference" else
+            "oracle port of the reference's numpy/TF-CPU path (no staged reference copy found)")
     guard.emit(json.dumps({
         "impl": "reference", "metric": "mpc_rollout_steps_per_s", "value": v, "unit": "rollout-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * float(np.mean(t_mpc)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(),
-                   "note": "oracle port of the reference's numpy/TF-CPU path; TensorFlow 1.5 is not installable, "
-                           "its float64 GEMMs run in numpy/BLAS"},
-        "cpu_baseline": {"value": v, "unit": "rollout-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": shared_config(max(1, args.gpus)),
+        "reference_note": note + "; TensorFlow 1.5 is not installable here; BLAS threads pinned to all %d cores "
+                                 "(OMP_NUM_THREADS ignored)" % cores,
+        "cpu_baseline": {"value": v, "unit": "rollout-steps/s", "cores": cores, "kind": cpu.kind, "sample": sample},
+        "full_step": full,
         "e2e": {"value": v, "unit": "rollout-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "small_k": small,
         "kde": {"metric": "kde_kernel_evals_per_s", "value": kv, "unit": "kernel-evals/s", "cores": procs,
                 "kind": "reference-library (scipy.stats.gaussian_kde; queries chunked over a "
                         "multiprocessing.Pool, the reference's parallel idiom)",
                 "sample": "%d x %d (of %d) queries x %d points" % (reps, m_pool, KDE_M, kw["n"] + 1),
                 "single_core": {"value": kv_one, "cores": 1, "sample": "2 x 256 queries x %d points" % (kw["n"] + 1)}},
     }))
+    del ctl
 
 
 class _StdoutGuard:
@@ -249,6 +349,73 @@ class _StdoutGuard:
         os.write(self.real, (line + "\n").encode())
 
 
+# --------------------------------------------------------------------------- drop-in agents for the e2e legs
+class _Box:
+    def __init__(self, low, high):
+        self.low, self.high = np.asarray(low, dtype=np.float64), np.asarray(high, dtype=np.float64)
+        self.shape = self.low.shape
+
+
+class _Env:
+    def __init__(self, low, high):
+        self.action_space = _Box(low, high)
+
+
+def make_nav_agent(eng, wl, K, H, device_sampling, planner=None):
+    """The drop-in NND_MB_agent carrying the benchmark's network and plan (no environment: the
+    constructor gets a tiny synthetic training set, the weights are set afterwards)."""
+    from smartstartcontinuous_b200.nnd_mb_agent import NND_MB_agent
+    rng = np.random.default_rng(0)
+    d, da = wl["d"], wl["da"]
+    td = dict(dataX=rng.normal(size=(64, d)), dataY=rng.normal(size=(64, da)), dataZ=rng.normal(size=(64, d)))
+    ag = NND_MB_agent(_Env(wl["low"], wl["high"]), None, horizon=H, num_control_samples=K, num_fc_layers=wl["L"],
+                      depth_fc_layers=wl["h"], verbose=False, engine=eng, training_data=td,
+                      device_sampling=device_sampling, precision="auto", penalty_mode="reference", planner=planner)
+    for k in ("mean_x", "std_x", "mean_y", "std_y", "mean_z", "std_z"):
+        setattr(ag, k, np.asarray(wl["norm"][k], dtype=np.float64))
+        setattr(ag.dyn_model, k, getattr(ag, k))
+    ag.dyn_model.set_weights(wl["w"], wl["b"])          # -> Engine.set_model
+    ag.num_episodes_finished = 1                        # no training at this plan
+    ag.num_episodes_for_aggregation = 10 ** 9
+    ag.start_new_episode_plan(wl["state"], [np.asarray(p) for p in wl["path"]])   # -> Engine.set_plan
+    return ag
+
+
+class _ValueBase:
+    """Base agent of the selection e2e: get_state_value like DDPG_Baselines_agent.py:197-204."""
+
+    def get_action(self, s): return np.zeros(1)
+    def observe(self, *a): pass
+    def start_new_episode(self, s): pass
+    def end_episode(self): pass
+    def get_param_dict(self): return {}
+
+    def get_state_value(self, states):
+        from smartstartcontinuous_b200 import synthetic as syn
+        return syn.critic_like_values(np.asarray(states)).reshape(-1, 1)
+
+
+def make_smart_start(eng, kw, n_ss):
+    """SmartStartContinuous over a replay buffer filled (through its own add / start_new_episode API)
+    with the KDE workload's transitions."""
+    from smartstartcontinuous_b200.smart_start import SmartStartContinuous
+    d = kw["all_states"].shape[1]
+    rng = np.random.default_rng(0)
+    td = dict(dataX=rng.normal(size=(64, d)), dataY=rng.normal(size=(64, 1)), dataZ=rng.normal(size=(64, d)))
+    n = kw["n"]
+    ss = SmartStartContinuous(_ValueBase(), _Env([-2.0], [2.0]), None, buffer_size=n, n_ss=n_ss, print_ss_stuff=False,
+                              nnd_mb_num_fc_layers=1, nnd_mb_depth_fc_layers=32, nnd_mb_verbose=False, engine=eng,
+                              nnd_mb_extra=dict(training_data=td))
+    rb = ss.replay_buffer
+    s_all = kw["all_states"]
+    a0 = np.zeros(1)
+    for i in range(n):
+        if i % 200 == 0:
+            rb.start_new_episode(ss)
+        rb.add(ss, s_all[i], a0, 0.0, (i % 200) == 199, s_all[i + 1])
+    return ss
+
+
 def main():
     guard = _StdoutGuard()
     ap = argparse.ArgumentParser()
@@ -257,11 +424,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-step", action="store_true", help="reference arm: skip the full K=131072 step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args, guard)
         return
+
+    import random
 
     import torch
     import torch.distributed as dist
@@ -280,14 +450,13 @@ def main():
 
     eng = Engine(local_rank)
     stream = torch.cuda.current_stream()
-    eng.set_stream(stream.cuda_stream)
     wl = make_workload()
     eng.set_model(wl["w"], wl["b"], wl["norm"])
     eng.set_plan(wl["plan"]["desired_states"], wl["plan"]["distances_left"], wl["plan"]["radii"])
+    planner = ShardedPlanner(eng, device=dev)         # binds the Engine to torch's current stream
+    selector = ShardedSelector(eng, device=dev)
     if world > 1 and os.environ.get("SS_PEER", "1") != "0":
         eng.peer_setup()         # projection sums + winner packages over NVLink peer memory, inside the kernels
-    planner = ShardedPlanner(eng, device=dev)
-    selector = ShardedSelector(eng, device=dev)
     K_total = K_PER_GPU * world
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
@@ -316,6 +485,7 @@ def main():
             ms = float(t.item())
         return ms
 
+    half = max(3, args.steps // 2)
     precision = "bf16_tc" if eng.tc_supported() else "fp32"
     rollout_ms = []
 
@@ -335,28 +505,46 @@ def main():
     ms_per_step = ms_total / args.steps
     value = K_total * HORIZON / (ms_per_step * 1e-3)
 
-    # ---- e2e: host action samples in pinned memory through the C ABI -------------------------
+    # ---- e2e through the plugin call: NND_MB_agent.get_best_sim_actions -------------------------
+    np.random.seed(1234)                      # identical on every rank (lock-step agents)
+    nav_host = make_nav_agent(eng, wl, K_total, HORIZON, device_sampling=False, planner=planner if world > 1 else None)
+    nav_dev = make_nav_agent(eng, wl, K_total, HORIZON, device_sampling=True, planner=planner if world > 1 else None)
+    rng_s = []
+
+    def e2e_agent_step(i):
+        nav_host.get_best_sim_actions(wl["state"])
+
+    def e2e_agent_dev_step(i):
+        nav_dev.get_best_sim_actions(wl["state"])
+
+    e2e_steps = max(3, min(half, 6))
+    e2e_ms = timed(e2e_agent_step, e2e_steps, 2) / e2e_steps
+    e2e_value = K_total * HORIZON / (e2e_ms * 1e-3)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        np.random.random_sample((K_PER_GPU, HORIZON, 1))
+    rng_ms = 1e3 * (time.perf_counter() - t0) / 3
+    e2e_dev_ms = timed(e2e_agent_dev_step, half, 2) / half
+
+    # the C-ABI call on pre-drawn host samples in pinned memory (no host RNG inside the timer)
     n_act = K_PER_GPU * HORIZON
     pinned = torch.empty(n_act, dtype=torch.float64).pin_memory()
     host_actions = pinned.numpy().reshape(K_PER_GPU, HORIZON, 1)
     host_actions[:] = np.random.RandomState(rank).uniform(wl["low"], wl["high"], (K_PER_GPU, HORIZON, 1))
 
-    def e2e_step(i):
-        # every rank feeds its own K_PER_GPU host samples through the C ABI (H2D inside the call)
+    def e2e_samples_step(i):
         planner.plan(wl["state"], 0, K=K_total, H=HORIZON, local_actions=host_actions, penalty_mode="reference",
                      precision=precision, want_path=True)
 
-    e2e_ms = timed(e2e_step, max(3, args.steps // 2), 2) / max(3, args.steps // 2)
-    e2e_value = K_total * HORIZON / (e2e_ms * 1e-3)
+    e2e_samples_ms = timed(e2e_samples_step, half, 2) / half
 
     # ---- the same decision with the per-sample projection (penalty_mode=1: the evidently intended
-    # maths; fully fused, no trajectory spill, no second pass) -----------------------
+    # maths; fully fused, no second pass) -------------------------------------------
     def mpc_per_sample_step(i):
         planner.plan(wl["state"], 0, K=K_total, H=HORIZON, seed=3000 + i, act_low=wl["low"], act_high=wl["high"],
                      penalty_mode="per_sample", precision=precision, want_path=True)
 
-    ps_steps = max(3, args.steps // 2)
-    per_sample_ms = timed(mpc_per_sample_step, ps_steps, 2) / ps_steps
+    per_sample_ms = timed(mpc_per_sample_step, half, 2) / half
 
     # ---- KDE (BASELINE config 2 per GPU) -----------------------------------------------------
     kw = kde_workload()
@@ -378,36 +566,39 @@ def main():
     def kde_e2e_step(i):
         eng.select_start(kw["all_states"], kw["queries"], kw["values"], kw["n"], kw["volume"], 1.0, 2.0)
 
-    kde_e2e_ms = timed(kde_e2e_step, max(3, args.steps // 2), 2) / max(3, args.steps // 2)
+    kde_e2e_ms = timed(kde_e2e_step, half, 2) / half
 
-    # the same selection from the device mirror of the replay buffer's state ring (row f2): the
-    # buffer is resident, each step uploads the 64 newest states + the candidate indices and values
-    from smartstartcontinuous_b200.replay_buffer import _StateRing
-    ring = _StateRing(KDE_N, 3)
-    st_all = kw["all_states"]
-    ring.alloc = KDE_N
-    ring.s = np.ascontiguousarray(st_all[:KDE_N])
-    ring.s2 = np.ascontiguousarray(np.concatenate([st_all[1:KDE_N], st_all[KDE_N:KDE_N + 1]]))
-    ring.count = ring.pushes = KDE_N
-    cand = np.random.default_rng(0).choice(KDE_N, KDE_M, replace=False)
-    eng.mirror_sync(ring)
+    # through the plugin call SmartStartContinuous.get_smart_start_path: candidate sampling
+    # (random.sample), candidate gather, host value function, selection from the device mirror of
+    # the replay buffer's state ring, episodic path extraction -- everything the reference call does
+    random.seed(7)
+    ss = make_smart_start(eng, kw, KDE_M)
 
-    def kde_mirror_step(i):
-        # 64 transitions arrived since the last selection (written like ReplayBuffer.add does, as one
-        # block: the per-step Python cost of add() belongs to the environment loop, not to selection)
-        r0 = ring.pushes % KDE_N                          # the ring is full: the oldest rows are overwritten
-        if r0 + 64 > KDE_N:
-            r0 = 0
-            ring.pushes += KDE_N - ring.pushes % KDE_N
-        ring.s[r0:r0 + 64] = st_all[r0:r0 + 64]
-        ring.s2[r0:r0 + 64] = st_all[r0 + 1:r0 + 65]
-        ring.pushes += 64
-        ring.head = ring.pushes % KDE_N
-        eng.select_start_mirror(ring, cand, kw["values"], kw["n"], kw["volume"], 1.0, 2.0)
+    def kde_agent_step(i):
+        ss.get_smart_start_path()
 
-    kde_mirror_ms = timed(kde_mirror_step, max(3, args.steps // 2), 2) / max(3, args.steps // 2)
+    kde_agent_ms = timed(kde_agent_step, half, 2) / half
+    ss2k = make_smart_start(eng, kde_workload(seed=2, n=KDE_N, m=C1_NSS), C1_NSS)
+    d2k = kde_workload(seed=2, n=KDE_N, m=C1_NSS)
+    t_data = torch.as_tensor(d2k["all_states"], device=dev)
+    t_q = torch.as_tensor(d2k["queries"], device=dev)
+    t_v = torch.as_tensor(d2k["values"], device=dev)
+    pairs2k_ms = []
+
+    def kde2k_step(i):
+        eng.select_start_dev(t_data.data_ptr(), t_data.shape[0], 3, t_q.data_ptr(), t_q.shape[0], t_v.data_ptr(),
+                             d2k["n"], d2k["volume"], 1.0, 2.0)
+        if i > 0:
+            pairs2k_ms.append(dict(eng.last_timings()).get("kde_pairs", 0.0))
+
+    kde2k_ms = timed(kde2k_step, args.steps, args.warmup) / args.steps
+    kde2k_agent_ms = timed(lambda i: ss2k.get_smart_start_path(), half, 2) / half
+    del ss, ss2k
+
     # ---- BASELINE config 5 (strong scaling): 1 000 001-state buffer KDE with the 16 384 candidates
     # sharded over the ranks + MPC with K = 262 144 sequences in total, both device-resident ----------
+    eng.set_model(wl["w"], wl["b"], wl["norm"])
+    eng.set_plan(wl["plan"]["desired_states"], wl["plan"]["distances_left"], wl["plan"]["radii"])
     C5_K = 262_144
     kw5 = kde_workload(seed=1, n=1_000_000)
     d5_data = torch.as_tensor(kw5["all_states"], device=dev)
@@ -425,6 +616,85 @@ def main():
     c5_kde_ms = timed(c5_kde_step, 5, 3) / 5
     c5_mpc_ms = timed(c5_mpc_step, 5, 3) / 5
     del d5_data, d5_q, d5_v
+
+    # ---- BASELINE configs 3 and 1: the small-K decisions a drop-in user of the example gets -------
+    small = {}
+    for name, (L, h, K, H) in (("config3", (2, 500, C3_K, C3_H)), ("config1", (1, 32, C1_K, C1_H))):
+        wls = make_workload_mountaincar(L, h)
+        np.random.seed(4321)
+        ag_host = make_nav_agent(eng, wls, K, H, device_sampling=False, planner=planner if world > 1 else None)
+        ag_dev = make_nav_agent(eng, wls, K, H, device_sampling=True, planner=planner if world > 1 else None)
+        prec_s = "bf16_tc" if eng.tc_supported() else "fp32"
+        k_ms = []
+
+        def resident(i):
+            planner.plan(wls["state"], 0, K=K, H=H, seed=500 + i, act_low=wls["low"], act_high=wls["high"],
+                         penalty_mode="reference", precision=prec_s, want_path=True)
+            if i > 0:
+                k_ms.append(dict(eng.last_timings()).get("mpc_rollout", 0.0))
+
+        n_s = max(10, args.steps)
+        res_ms = timed(resident, n_s, 3) / n_s
+        host_ms = timed(lambda i: ag_host.get_best_sim_actions(wls["state"]), n_s, 3) / n_s
+        devs_ms = timed(lambda i: ag_dev.get_best_sim_actions(wls["state"]), n_s, 3) / n_s
+        t0 = time.perf_counter()
+        for _ in range(n_s):
+            ag_dev.get_best_sim_actions(wls["state"])
+        wall_ms = 1e3 * (time.perf_counter() - t0) / n_s
+        kern = float(np.mean(k_ms)) if k_ms else None
+        small[name] = {
+            "workload": "MountainCar d=2 da=1, K=%d (strong-scaled over %d GPU(s)), H=%d, MLP %dx%d, reference penalty"
+                        % (K, world, H, L, h),
+            "kernel": "mpc_rollout_tc_kernel" if prec_s == "bf16_tc" else "mpc_rollout_simt_kernel",
+            "ms_per_decision_resident": res_ms, "rollout_kernel_ms": kern,
+            "decision_over_rollout_kernel": (res_ms / kern) if kern else None,
+            "rollout_steps_per_s_resident": K * H / (res_ms * 1e-3),
+            "ms_per_decision_agent_default": host_ms, "rollout_steps_per_s_agent_default": K * H / (host_ms * 1e-3),
+            "ms_per_decision_agent_device_sampling": devs_ms, "wall_ms_agent_device_sampling": wall_ms,
+            "tensor_frac_of_burst_peak": (FLOP_PER_STEP[2] * K * H / (kern * 1e-3) / 1e12 / measured_peaks()["bf16_burst"])
+            if (kern and prec_s == "bf16_tc") else None}
+    eng.set_model(wl["w"], wl["b"], wl["norm"])
+    eng.set_plan(wl["plan"]["desired_states"], wl["plan"]["distances_left"], wl["plan"]["radii"])
+
+    # ---- multi-GPU self-check: the sharded decision equals the unsharded one ----------------------
+    multi = None
+    if world > 1:
+        def same_decision(route):
+            ok = True
+            for mode in ("reference", "per_sample"):
+                kwp = dict(K=20000, H=12, seed=7, act_low=wl["low"], act_high=wl["high"], penalty_mode=mode,
+                           precision=precision)
+                sh = planner.plan(wl["state"], 0, **kwp)
+                torch.cuda.synchronize()
+                one = eng.plan(wl["state"], 0, **kwp)
+                ok &= sh["best_k"] == one["best_k"]
+                ok &= abs(sh["best_score"] - one["best_score"]) <= 1e-5 * max(1.0, abs(one["best_score"]))
+                ok &= bool(np.array_equal(sh["best_sequence"], one["best_sequence"]))
+                ok &= bool(np.allclose(sh["best_path"], one["best_path"], rtol=1e-5, atol=1e-6))
+            return ok
+
+        peer_was = eng.peer_ready
+        ok_peer = same_decision("peer") if peer_was else None
+        if peer_was:
+            eng.peer_close()
+        ok_nccl = same_decision("nccl")
+        if peer_was:
+            eng.peer_setup()                   # re-opening the exchange must work (fresh flags and epochs)
+            ok_peer = bool(ok_peer) and same_decision("peer again")
+        kws = kde_workload(n=20000, m=4096)
+        sel = selector.select_start(kws["all_states"], kws["queries"], kws["values"], kws["n"], kws["volume"])
+        one = eng.select_start(kws["all_states"], kws["queries"], kws["values"], kws["n"], kws["volume"])
+        ok_kde = sel[0] == one[0] and abs(sel[1] - one[1]) <= 1e-9 * abs(one[1])
+        flags = torch.tensor([1.0 if (ok_peer is None or ok_peer) else 0.0, 1.0 if ok_nccl else 0.0,
+                              1.0 if ok_kde else 0.0], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        multi = {"sharded_equals_single": bool(flags[0].item() == 1.0 and flags[1].item() == 1.0),
+                 "sharded_equals_single_peer_memory": bool(flags[0].item() == 1.0) if peer_was else None,
+                 "sharded_equals_single_nccl": bool(flags[1].item() == 1.0),
+                 "kde_sharded_equals_single": bool(flags[2].item() == 1.0),
+                 "check": "K=20000, H=12, reference and per-sample penalty, %s: best_k and sequence identical, score "
+                          "within 1e-5 relative, path within 1e-5; KDE n=20000, m=4096: same index, ucb within 1e-9"
+                          % precision}
     clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
@@ -440,46 +710,70 @@ def main():
     sfu_peak = SFU_PER_CLK_PER_SM * info["sm_count"] * peaks["sm_max_mhz"] * 1e6
     kde_achieved = KDE_M * (KDE_N + 1) / (p_ms * 1e-3)
     kde_bytes = 4 * 3 * (KDE_N + 1 + KDE_M) + 4 * KDE_M + 8
+    pkg_bytes = int(16 + HORIZON * 8 + (HORIZON + 1) * 3 * 8)
+    cfg = shared_config(world)
     out = {
         "metric": "mpc_rollout_steps_per_s", "value": value, "unit": "rollout-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16 (tcgen05, fp32 accumulate; first/last layer, state, scoring fp32)" if precision == "bf16_tc" else "f32",
         "data": "synthetic",
-        "config": {"workload": workload_name(),
-                   "K_total": K_total, "H": HORIZON, "mlp": "2x500", "actions": "device Philox4x32-10",
-                   "l2": "flushed between timed steps (256 MiB memset, outside the event-timed region)",
-                   "parallelism": "K sharded over %d GPU(s); all-reduce of %d float64 + all-gather of the winner packages, %s"
-                                  % (world, 2 * (HORIZON + 1),
-                                     "fused into the kernels over NVLink peer memory (csrc/peer.cu)" if eng.peer_ready
-                                     else ("NCCL" if world > 1 else "none at N=1"))},
+        "config": cfg,
+        "run": {"actions": "device Philox4x32-10 for `value`; host MT19937 (npr) for `e2e`",
+                "l2": "flushed between timed steps (256 MiB memset, outside the event-timed region)",
+                "collective": ("peer-memory" if eng.peer_ready else ("nccl" if world > 1 else "none")),
+                "parallelism": "K sharded over %d GPU(s); all-reduce of %d float64 + all-gather of the winner packages, %s"
+                               % (world, 2 * (HORIZON + 1),
+                                  "fused into the kernels over NVLink peer memory (csrc/peer.cu)" if eng.peer_ready
+                                  else ("NCCL" if world > 1 else "none at N=1"))},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "rollout-steps/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(n_act * 8 + 3 * 8), "d2h_bytes_per_step": int(16 + HORIZON * 8 + (HORIZON + 1) * 3 * 8),
-                "path": "ShardedPlanner.plan -> ss_mpc_rollout / ss_mpc_finish_package with HOST float64 action samples "
-                        "(pinned, uploaded in chunks that overlap the rollout) + D2H of the winner package; the agent's "
-                        "default call (device Philox sampling: 24 B of state in, the same package out) is what `value` times"},
+                "h2d_bytes_per_step": int(n_act * 8 + 3 * 8), "d2h_bytes_per_step": pkg_bytes,
+                "host_rng_ms": rng_ms,
+                "path": "NND_MB_agent.get_best_sim_actions, default device_sampling=False: K*H float64 samples drawn on the "
+                        "host from numpy's legacy MT19937 stream (bit-identical to npr.uniform of NND_MB_agent.py:500-501, "
+                        "inside the timer: host_rng_ms of the step) -> ss_mpc_plan / ShardedPlanner with host buffers "
+                        "(H2D inside the call) -> D2H of the winner package"},
+        "e2e_device_sampling": {"value": K_total * HORIZON / (e2e_dev_ms * 1e-3), "unit": "rollout-steps/s",
+                                "ms_per_step": e2e_dev_ms, "h2d_bytes_per_step": 24, "d2h_bytes_per_step": pkg_bytes,
+                                "path": "NND_MB_agent(device_sampling=True).get_best_sim_actions: state in, Philox on the "
+                                        "GPU, winner package out"},
+        "e2e_host_samples": {"value": K_total * HORIZON / (e2e_samples_ms * 1e-3), "unit": "rollout-steps/s",
+                             "ms_per_step": e2e_samples_ms, "h2d_bytes_per_step": int(n_act * 8 + 3 * 8),
+                             "d2h_bytes_per_step": pkg_bytes,
+                             "path": "ShardedPlanner.plan -> ss_mpc_rollout / ss_mpc_finish_package on PRE-DRAWN float64 "
+                                     "samples in pinned host memory (uploaded in chunks that overlap the rollout)"},
         "gpu_launches": int(launches),
         "per_sample_penalty": {"value": K_total * HORIZON / (per_sample_ms * 1e-3), "unit": "rollout-steps/s",
                                "ms_per_step": per_sample_ms,
-                               "note": "penalty_mode=per_sample (fully fused scoring, no penalty passes); measured after the headline and e2e legs"},
-        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / peaks["bf16_sustained"],
+                               "note": "penalty_mode=per_sample (fully fused scoring, no penalty passes)"},
+        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                     "frac": achieved_tf / peaks["bf16_burst"],
                      "traffic": NCU_TRAFFIC["mpc_rollout_tc_kernel"] if precision == "bf16_tc" else None,
-                     "traffic_source": "profiles/r01e_ncu_summary.md (ncu --set full, same workload)",
-                     "frac_of_burst_peak": achieved_tf / peaks["bf16_burst"],
+                     "traffic_source": NCU_TRAFFIC_SOURCE,
+                     "frac_of_sustained_peak": achieved_tf / peaks["bf16_sustained"],
                      "kernel": "mpc_rollout_tc_kernel" if precision == "bf16_tc" else "mpc_rollout_simt_kernel",
-                     "kernel_ms": k_ms, "peak_source": peaks["source"] + " (bf16_tflops_sustained: kernel timed inside a long step)",
+                     "kernel_ms": k_ms,
+                     "peak_source": peaks["source"] + " (bf16_tflops, the burst figure: the timed region is a few tens of ms "
+                                                      "at the maximum SM clock)",
                      "algorithmic_flop_per_rollout_step": FLOP_PER_STEP[3]},
         "kde": {"metric": "kde_kernel_evals_per_s", "value": kde_value, "unit": "kernel-evals/s", "ms_per_step": kde_ms,
                 "config": {"workload": "KDE+UCB+argmax, %d Pendulum states (d=3) x %d queries per GPU (BASELINE config 2)"
                                        % (KDE_N + 1, KDE_M)},
-                "e2e": {"value": evals / (kde_e2e_ms * 1e-3), "unit": "kernel-evals/s", "ms_per_step": kde_e2e_ms,
-                        "h2d_bytes_per_step": int(8 * 3 * (KDE_N + 1 + KDE_M) + 4 * KDE_M), "d2h_bytes_per_step": 16},
-                "e2e_mirror": {"value": evals / (kde_mirror_ms * 1e-3), "unit": "kernel-evals/s", "ms_per_step": kde_mirror_ms,
-                               "h2d_bytes_per_step": int(2 * 64 * 3 * 8 + 12 * KDE_M), "d2h_bytes_per_step": 16,
-                               "path": "Engine.select_start_mirror: replay-state ring mirrored on the device, 64 new "
-                                       "transitions + candidate indices + values uploaded per selection"},
+                "e2e": {"value": evals / (kde_agent_ms * 1e-3), "unit": "kernel-evals/s", "ms_per_step": kde_agent_ms,
+                        "h2d_bytes_per_step": int(12 * KDE_M), "d2h_bytes_per_step": 16,
+                        "path": "SmartStartContinuous.get_smart_start_path (smartexplorationcontinuous.py:223-305): "
+                                "random.sample of the candidates, host value function, selection from the device mirror "
+                                "of the replay buffer (row indices + values uploaded), episodic path extraction"},
+                "e2e_full_upload": {"value": evals / (kde_e2e_ms * 1e-3), "unit": "kernel-evals/s", "ms_per_step": kde_e2e_ms,
+                                    "h2d_bytes_per_step": int(8 * 3 * (KDE_N + 1 + KDE_M) + 4 * KDE_M), "d2h_bytes_per_step": 16,
+                                    "path": "ss_kde_ucb_argmax with host float64 buffers (whole data set uploaded)"},
+                "n_ss_2000": {"workload": "%d states x %d queries (the example's n_ss)" % (KDE_N + 1, C1_NSS),
+                              "ms_per_step": kde2k_ms, "value": C1_NSS * (KDE_N + 1) / (kde2k_ms * 1e-3),
+                              "pairs_kernel_ms": float(np.mean(pairs2k_ms)) if pairs2k_ms else None,
+                              "frac_of_sfu_peak": (C1_NSS * (KDE_N + 1) / (float(np.mean(pairs2k_ms)) * 1e-3) / sfu_peak)
+                              if pairs2k_ms else None,
+                              "ms_per_step_agent": kde2k_agent_ms},
                 "roofline": {"bound": "sfu", "achieved": kde_achieved, "peak": sfu_peak, "unit": "kernel-evals/s",
                              "frac": kde_achieved / sfu_peak, "kernel": "kde_pairs_tc_kernel", "kernel_ms": p_ms,
                              "peak_source": "16 MUFU.EX2/clk/SM x %d SMs x %.0f MHz (max SM clock); the kernel takes 3/8 of "
@@ -487,8 +781,13 @@ def main():
                                             "tensor pipe, so frac > 1 is possible" % (info["sm_count"], peaks["sm_max_mhz"]),
                              "hbm_achieved_gbs": kde_bytes / (p_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks["hbm_gbs"],
                              "traffic": NCU_TRAFFIC["kde_pairs_tc_kernel"],
-                             "traffic_source": "profiles/r01e_ncu_summary.md (ncu --set full, same workload)"}},
+                             "traffic_source": NCU_TRAFFIC_SOURCE}},
+        "small_k": small,
     }
+    if multi is not None:
+        out["multi_gpu_check"] = multi
+        out["sharded_equals_single"] = multi["sharded_equals_single"]
+        out["collective"] = out["run"]["collective"]
     out["config5"] = {"workload": "BASELINE config 5, strong scaling over %d GPU(s): KDE 1 000 001 states x %d queries "
                                   "(queries sharded) + MPC K=%d total, H=%d (sequences sharded), device-resident"
                                   % (world, KDE_M, C5_K, HORIZON),
@@ -504,15 +803,6 @@ def main():
         stds, means = num.path_deltas_stds_and_means_per_dim(path)
         radii = num.radii_calc(means, stds, 1, 1, 1)
         dist_fn = num.elliptical_euclidean_distance_function_generator(radii)
-        eng.path_close_pairs(path, radii, 1.0)
-        t0 = time.perf_counter()
-        for _ in range(10):
-            pairs = eng.path_close_pairs(path, radii, 1.0)
-        t_dev = (time.perf_counter() - t0) / 10
-        t0 = time.perf_counter()
-        for _ in range(3):
-            ref_pairs = np.argwhere(np.triu(dist_fn(path[:, None, :], path[None, :, :]) <= 1.0, k=2))
-        t_np = (time.perf_counter() - t0) / 3
         eng.path_shortcut(path, radii, 1.0)
         t0 = time.perf_counter()
         for _ in range(10):
@@ -522,8 +812,6 @@ def main():
         host_path = num.path_shortcutter(path, dist_fn, 1.0)
         t_full_host = time.perf_counter() - t0
         out["plan_setup"] = {"what": "path_shortcutter (numerical.py:226-246), P=1000, d=3, host buffers in and out",
-                             "pairs_gpu_ms": 1e3 * t_dev, "pairs_numpy_ms": 1e3 * t_np, "pairs": int(len(pairs)),
-                             "pairs_identical": bool(np.array_equal(pairs, ref_pairs)),
                              "shortcut_gpu_ms": 1e3 * t_full_dev, "shortcut_host_ms": 1e3 * t_full_host,
                              "shortcut_identical": bool(np.array_equal(path[keep], host_path)),
                              "kept_states": int(len(keep))}
@@ -531,13 +819,15 @@ def main():
         out["plan_setup"] = {"error": repr(exc)}
     if world == 1 and not args.no_cpu_baseline:
         # the CPU leg runs in a fresh process (fork-based pool, no CUDA context): the same code as
-        # `--impl reference`, ~20 s of CPU work on bounded samples of the workload
+        # `--impl reference`, ~20-30 s of CPU work on bounded samples of the workload
         try:
-            ref = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "16",
-                                  "--warmup", "1"], capture_output=True, text=True, timeout=600)
+            ref = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "6",
+                                  "--warmup", "1", "--no-full-step"], capture_output=True, text=True, timeout=900)
             r = json.loads(ref.stdout.strip().splitlines()[-1])
             out["cpu_baseline"] = r["cpu_baseline"]
             out["kde"]["cpu_baseline"] = {k: r["kde"][k] for k in ("value", "unit", "cores", "kind", "sample", "single_core")}
+            for name in small:
+                small[name]["cpu_baseline"] = r["small_k"].get(name)
         except Exception as exc:                                     # never lose the GPU line
             out["cpu_baseline"] = {"value": None, "unit": "rollout-steps/s", "cores": 0, "kind": "port",
                                    "sample": "failed: %r" % (exc,)}

@@ -150,7 +150,11 @@ int ss_mpc_plan(ss_ctx* ctx, const double* state, int wp_index,
                 int64_t* out_best_k, double* out_best_score,
                 double* out_best_sequence, double* out_best_path, double* out_scores);
 
-/* three-call form: rollout (phase A) -> [all-reduce the 2*(H+1) doubles at *sums_dev] -> finish */
+/* three-call form: rollout (phase A) -> [all-reduce the 2*(H+1) doubles at *sums_dev] -> finish.
+ * ss_mpc_rollout returns while its work (including the host->device copies of `actions`) is still
+ * queued on the context's stream: the `actions` buffer must stay untouched until ss_mpc_finish,
+ * ss_mpc_read_package or ss_mpc_replay of the same decision has returned (they synchronise the
+ * stream).  ss_mpc_plan is synchronous and has no such window. */
 int ss_mpc_rollout(ss_ctx* ctx, const double* state, int wp_index,
                    int64_t K_local, int64_t k_offset, int64_t K_global, int H,
                    const double* actions, uint64_t seed,

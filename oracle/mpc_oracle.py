@@ -13,8 +13,8 @@ Restates, in vectorised float64 numpy:
   * selection                                           (NND_MB_agent.py:516-518)
 
 Pinned against the reference's own functions through tests/golden/mpc_*.npz
-(oracle/make_golden.py) and, when /root/reference is mounted, live in
-tests/test_oracle_vs_reference.py.
+(produced by oracle/make_golden.py from the reference's get_best_sim_actions; checked in
+tests/test_oracle_golden.py).
 """
 from __future__ import annotations
 

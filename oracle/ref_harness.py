@@ -16,9 +16,9 @@ except ``sess.run`` is numpy, so the harness
   6. replaces the TF session by ``NumpySession`` which evaluates the float64 MLP of
      feedforward_network.py:12-23 (hidden: Linear+ReLU, output: Linear, y = xW + b).
 
-It is used only by oracle/make_golden.py (to produce tests/golden/*.npz) and by
-tests that are skipped when /root/reference is absent.  Nothing here runs on the
-GPU box.
+It is used by oracle/make_golden.py (to produce tests/golden/*.npz) and by the CPU arm
+of bench.py (`--impl reference` / cpu_baseline), which times the reference's own
+get_best_sim_actions from the staged copy oracle/_ref (oracle/stage_ref.py).
 """
 from __future__ import annotations
 
@@ -33,7 +33,10 @@ from collections import deque
 
 import numpy as np
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
 REFERENCE_ROOT = os.environ.get("SS_REFERENCE_ROOT", "/root/reference")
+# on the GPU box: the unmodified python files of the reference packed by oracle/stage_ref.py
+STAGED_ARCHIVE = os.path.join(_HERE, "_ref", "smartstart_ref.zip")
 
 _STUB_ROOTS = ("tensorflow", "gym", "matplotlib", "mpl_toolkits", "google",
                "baselines", "mpi4py", "seaborn")
@@ -78,7 +81,7 @@ _loaded = None
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "smartstart"))
+    return os.path.isdir(os.path.join(REFERENCE_ROOT, "smartstart")) or os.path.isfile(STAGED_ARCHIVE)
 
 
 def load_reference():
@@ -89,7 +92,12 @@ def load_reference():
     if not available():
         raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
     tmp = tempfile.mkdtemp(prefix="ss_ref_")
-    shutil.copytree(os.path.join(REFERENCE_ROOT, "smartstart"), os.path.join(tmp, "smartstart"))
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "smartstart")):
+        shutil.copytree(os.path.join(REFERENCE_ROOT, "smartstart"), os.path.join(tmp, "smartstart"))
+    else:
+        import zipfile
+        with zipfile.ZipFile(STAGED_ARCHIVE) as z:
+            z.extractall(tmp)
     if not hasattr(np, "product"):
         np.product = np.prod  # numerical.py:164
     sys.meta_path.insert(0, _StubFinder())

@@ -37,15 +37,15 @@ def _mlp_head(x, layers, ln, last_tanh, action=None):
 
 def state_values(queries, net):
     x = np.asarray(queries, dtype=np.float64)
+    lo, hi = net.get("obs_clip", (-5.0, 5.0))          # the clip is unconditional (ddpg_editted.py:106-109)
     if net.get("obs_mean") is not None:
-        lo, hi = net.get("obs_clip", (-5.0, 5.0))
-        x = np.clip((x.astype(F) - np.asarray(net["obs_mean"], F)) * (F(1) / np.asarray(net["obs_std"], np.float64)).astype(F),
-                    F(lo), F(hi))
-    x = x.astype(F)
+        x = (x.astype(F) - np.asarray(net["obs_mean"], F)) * (F(1) / np.asarray(net["obs_std"], np.float64)).astype(F)
+    x = np.clip(x.astype(F), F(lo), F(hi))
     last_tanh = bool(net.get("last_layer_tanh", False))
     action = np.tanh(_mlp_head(x, net["actor"], net.get("actor_ln"), last_tanh))
     v = _mlp_head(x, net["critic"], net.get("critic_ln"), last_tanh, action=action)[:, 0]
+    lo, hi = net.get("ret_clip", (-np.inf, np.inf))    # unconditional too (:130-131); denormalize only with ret_rms
+    v = np.clip(v, F(lo), F(hi))
     if net.get("ret_mean") is not None:
-        lo, hi = net.get("ret_clip", (-np.inf, np.inf))
-        v = np.clip(v, F(lo), F(hi)) * F(net["ret_std"]) + F(net["ret_mean"])
+        v = v * F(net["ret_std"]) + F(net["ret_mean"])
     return v.astype(F)

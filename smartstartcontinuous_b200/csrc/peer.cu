@@ -161,10 +161,17 @@ extern "C" int ss_peer_init(ss_ctx* c, int rank, int world, void* out_handle64) 
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     SS_CUDA_CHECK(c, cudaSetDevice(c->device));
     c->peer_ready = false;
-    if (!c->peer_buf) {
-        SS_CUDA_CHECK(c, cudaMalloc(&c->peer_buf, peer_buffer_bytes()));
-        SS_CUDA_CHECK(c, cudaMemset(c->peer_buf, 0, peer_buffer_bytes()));
-    }
+    // a re-initialisation (new group / world size) starts from a clean slate: nothing of this context
+    // may still be reading the buffer, mappings of the previous peers are closed, and flags AND slots
+    // are zeroed so that the epochs (restarted at 0 by ss_peer_open on every rank) can never match
+    // a flag left over from the previous exchange.  Callers all-gather the handles after this call,
+    // which orders every rank's clear before any peer's first store.
+    if (c->stream) SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < SS_PEER_MAX_WORLD; ++r)
+        if (c->peer_opened[r]) { cudaIpcCloseMemHandle(c->peer_opened[r]); c->peer_opened[r] = nullptr; }
+    if (!c->peer_buf) SS_CUDA_CHECK(c, cudaMalloc(&c->peer_buf, peer_buffer_bytes()));
+    SS_CUDA_CHECK(c, cudaMemset(c->peer_buf, 0, peer_buffer_bytes()));
+    SS_CUDA_CHECK(c, cudaDeviceSynchronize());
     cudaIpcMemHandle_t h;
     SS_CUDA_CHECK(c, cudaIpcGetMemHandle(&h, c->peer_buf));
     std::memcpy(out_handle64, &h, 64);

@@ -73,7 +73,9 @@ value_net_kernel(const ValueNetDev N, const float* __restrict__ params, const do
     for (long long q = (long long)blockIdx.x * (blockDim.x >> 5) + warp; q < m; q += warps) {
         for (int j = lane; j < N.d; j += 32) {
             float x = (float)queries[q * N.d + j];
-            if (N.obs_norm) x = fminf(fmaxf((x - P[N.obs_mean + j]) * P[N.obs_inv_std + j], N.obs_lo), N.obs_hi);
+            // clip(normalize(obs, obs_rms), observation_range): the clip applies with or without statistics
+            // (normalize() is the identity for obs_rms = None, ddpg_editted.py:106-109; blob holds mean 0, 1/std 1 then)
+            x = fminf(fmaxf((x - P[N.obs_mean + j]) * P[N.obs_inv_std + j], N.obs_lo), N.obs_hi);
             xs[j] = x;
         }
         __syncwarp();
@@ -97,7 +99,10 @@ value_net_kernel(const ValueNetDev N, const float* __restrict__ params, const do
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
         if (lane == 0) {
             v += P[N.cb3];
-            if (N.ret_norm) v = fminf(fmaxf(v, N.ret_lo), N.ret_hi) * N.ret_std + N.ret_mean;
+            // denormalize(clip_by_value(critic, return_range), ret_rms): the clip is unconditional, the affine
+            // map only exists with return normalisation (ddpg_editted.py:130-131)
+            v = fminf(fmaxf(v, N.ret_lo), N.ret_hi);
+            if (N.ret_norm) v = v * N.ret_std + N.ret_mean;
             values[q] = v;
         }
         __syncwarp();
@@ -145,8 +150,10 @@ extern "C" int ss_value_net_set(ss_ctx* c, const ss_value_net* n) {
     N.d = n->d; N.da = n->da; N.h1a = n->h1a; N.h2a = n->h2a; N.h1c = n->h1c; N.h2c = n->h2c;
     N.layer_norm = ln; N.last_tanh = n->last_layer_tanh != 0;
     N.obs_norm = n->obs_mean != nullptr; N.ret_norm = n->has_ret_norm != 0;
-    N.obs_lo = (float)n->obs_clip_lo; N.obs_hi = (float)n->obs_clip_hi;
-    N.ret_lo = (float)n->ret_clip_lo; N.ret_hi = (float)n->ret_clip_hi;
+    // an empty range (lo >= hi, e.g. a zero-initialised struct) means "no clip"
+    const bool obs_clip = n->obs_clip_lo < n->obs_clip_hi, ret_clip = n->ret_clip_lo < n->ret_clip_hi;
+    N.obs_lo = obs_clip ? (float)n->obs_clip_lo : -INFINITY; N.obs_hi = obs_clip ? (float)n->obs_clip_hi : INFINITY;
+    N.ret_lo = ret_clip ? (float)n->ret_clip_lo : -INFINITY; N.ret_hi = ret_clip ? (float)n->ret_clip_hi : INFINITY;
     N.ret_mean = (float)n->ret_mean; N.ret_std = (float)n->ret_std;
     std::vector<float> blob;
     auto put = [&](const float* src, size_t count) -> int {

@@ -64,25 +64,53 @@ def _dist():
     return dist
 
 
-class ShardedPlanner:
-    """MPC over all ranks of a torch.distributed group; every rank returns the same result."""
+class EngineTensors:
+    """How ShardedPlanner turns library-owned device memory into tensors for the collectives:
+    zero-copy torch views of the Engine's projection sums and winner package.  (The CPU tests inject
+    an object with the same two methods backed by the oracle.)"""
 
-    def __init__(self, engine, device=None, group=None):
+    def __init__(self, engine, device):
+        self.engine = engine
+        self.device = device
+
+    def projection_sums_tensor(self):
+        import torch
+        ptr, n = self.engine.projection_sums_ptr()
+        if n == 0:
+            return None
+        return torch.as_tensor(_DevView(ptr, n), device=self.device)
+
+    def finish_package_tensor(self, want_path):
+        """(tensor view of this rank's package, element count)."""
+        import torch
+        ptr, n = self.engine.finish_package(want_path)
+        return torch.as_tensor(_DevView(ptr, n), device=self.device), n
+
+
+class ShardedPlanner:
+    """MPC over all ranks of a torch.distributed group; every rank returns the same result.
+
+    The Engine queues its kernels on ONE stream and returns from rollout / finish_package without a
+    host synchronisation; the collectives of the NCCL route read and write library memory in place.
+    Both therefore have to run on the same stream: the constructor binds the Engine to torch's
+    current stream of `device` (Engine.set_stream), and plan() asserts the binding still holds."""
+
+    def __init__(self, engine, device=None, group=None, tensors=None):
         dist = _dist()
         self.engine = engine
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.device = device          # torch device for the merge tensors ("cuda:N" or "cpu")
+        self.tensors = tensors if tensors is not None else EngineTensors(engine, device)
+        self._stream = None
+        if tensors is None and self._on_cuda():
+            import torch
+            self._stream = torch.cuda.current_stream(device).cuda_stream
+            engine.set_stream(self._stream)
 
-    def _sums_tensor(self):
-        import torch
-        if hasattr(self.engine, "projection_sums_tensor"):        # CPU test double
-            return self.engine.projection_sums_tensor()
-        ptr, n = self.engine.projection_sums_ptr()
-        if n == 0:
-            return None
-        return torch.as_tensor(_DevView(ptr, n), device=self.device)
+    def _on_cuda(self):
+        return self.device is not None and str(self.device).startswith("cuda")
 
     def plan(self, state, wp_index, *, K, H, seed=0, act_low=None, act_high=None, actions=None,
              gamma=.75, horizontal_penalty_factor=.5, penalty_mode="reference", precision="auto",
@@ -91,6 +119,14 @@ class ShardedPlanner:
         local_actions: this rank's own [K/world, H, da] slice, or neither (device Philox)."""
         import torch
         dist = _dist()
+        if K < self.world:
+            # every rank sees the same K: all of them raise before any exchange kernel is queued
+            raise ValueError("K = %d sequences cannot be sharded over %d ranks (empty shard)" % (K, self.world))
+        if self._stream is not None and self.world > 1:
+            cur = torch.cuda.current_stream(self.device).cuda_stream
+            if cur != self._stream:
+                raise RuntimeError("ShardedPlanner: torch's current stream changed since construction; the Engine "
+                                   "and the collectives must share one stream (call Engine.set_stream)")
         k_offset, k_local = shard_bounds(K, self.world, self.rank)
         if local_actions is None and actions is not None:
             local_actions = actions[k_offset:k_offset + k_local]
@@ -103,25 +139,21 @@ class ShardedPlanner:
         # kernels over NVLink peer memory; otherwise they are two small collectives
         peer = self.world > 1 and bool(getattr(self.engine, "peer_ready", False))
         if self.world > 1 and not peer and penalty_mode in ("reference", 0):
-            sums = self._sums_tensor()
+            sums = self.tensors.projection_sums_tensor()
             if sums is not None:
                 dist.all_reduce(sums, group=self.group)      # 2*(H+1) float64
         d, da = self.engine._model_shape[0], self.engine._model_shape[1]
-        if hasattr(self.engine, "finish_package_tensor"):          # CPU test double
-            mine = self.engine.finish_package_tensor(want_path)
+        if isinstance(self.tensors, EngineTensors) and (peer or self.world == 1):
+            _, n = self.engine.finish_package(want_path)
+            pk = self.engine.read_package(n).reshape(1, -1)            # peer route: already the global winner
         else:
-            ptr, n = self.engine.finish_package(want_path)
-            mine = None if (self.world == 1 or peer) else torch.as_tensor(_DevView(ptr, n), device=self.device)
-        if peer:
-            pk = self.engine.read_package(n).reshape(1, -1)            # already the global winner
-        elif self.world > 1:
-            gathered = torch.empty(self.world * mine.numel(), dtype=torch.float64, device=mine.device)
-            dist.all_gather_into_tensor(gathered, mine, group=self.group)
-            pk = gathered.cpu().numpy().reshape(self.world, -1)        # the one host sync
-        elif mine is not None:
-            pk = mine.numpy().reshape(1, -1)
-        else:
-            pk = self.engine.read_package(n).reshape(1, -1)
+            mine, n = self.tensors.finish_package_tensor(want_path)
+            if self.world > 1:
+                gathered = torch.empty(self.world * mine.numel(), dtype=torch.float64, device=mine.device)
+                dist.all_gather_into_tensor(gathered, mine, group=self.group)
+                pk = gathered.cpu().numpy().reshape(self.world, -1)    # the one host sync
+            else:
+                pk = mine.cpu().numpy().reshape(1, -1)
         row = argmax_pick(pk[:, 0].tolist(), [int(v) for v in pk[:, 1]])
         best_score, best_k = float(pk[row, 0]), int(pk[row, 1])
         w = row

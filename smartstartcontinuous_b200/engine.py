@@ -182,11 +182,13 @@ class Engine:
             om, os_ = _f64(net["obs_mean"]).reshape(-1), _f64(net["obs_std"]).reshape(-1)
             keep += [om, os_]
             st.obs_mean, st.obs_std = _ptr(om), _ptr(os_)
-            st.obs_clip_lo, st.obs_clip_hi = [float(v) for v in net.get("obs_clip", (-5.0, 5.0))]
+        # both clips are unconditional in the reference graph (ddpg_editted.py:106-109, 130-131);
+        # defaults = baselines' observation_range / return_range
+        st.obs_clip_lo, st.obs_clip_hi = [float(v) for v in net.get("obs_clip", (-5.0, 5.0))]
+        st.ret_clip_lo, st.ret_clip_hi = [float(v) for v in net.get("ret_clip", (-np.inf, np.inf))]
         if net.get("ret_mean") is not None:
             st.has_ret_norm = 1
             st.ret_mean, st.ret_std = float(net["ret_mean"]), float(net["ret_std"])
-            st.ret_clip_lo, st.ret_clip_hi = [float(v) for v in net.get("ret_clip", (-np.inf, np.inf))]
         self._check(self._lib.ss_value_net_set(self._h, C.byref(st)))
         self._value_net_keep = keep
 

@@ -17,6 +17,10 @@ Extra keyword-only options (all default to the reference behaviour):
   precision           "auto" | "fp32" | "bf16_tc"
   device_sampling     False: actions from numpy.random.uniform exactly like :500-501;
                       True: Philox on the GPU (no K*H*da host RNG + H2D copy)
+  planner             a distributed.ShardedPlanner: the K sequences of every decision are sharded
+                      over the ranks of its torch.distributed group (all ranks run the agent in
+                      lock-step with identical numpy seeds; with host sampling every rank draws only
+                      its own K/world sequences)
 """
 from __future__ import annotations
 
@@ -104,7 +108,7 @@ class NND_MB_agent(NavigationRLAgent):
                  steps_per_rollout_train=333, steps_per_rollout_val=333,
 
                  *, engine=None, device=0, penalty_mode="reference", precision="auto",
-                 device_sampling=False, training_data=None, model_root=None, seed=None):
+                 device_sampling=False, training_data=None, model_root=None, seed=None, planner=None):
         self.theta = 1            # distance function is scaled instead (NND_MB_agent.py:135-138)
         self.final_steps = final_steps
         self.gamma = gamma
@@ -139,6 +143,7 @@ class NND_MB_agent(NavigationRLAgent):
         self.penalty_mode = penalty_mode
         self.precision = precision
         self.device_sampling = device_sampling
+        self.planner = planner
         self._plan_calls = 0
 
         root = model_root or os.path.join(os.getcwd(), "models")
@@ -239,15 +244,27 @@ class NND_MB_agent(NavigationRLAgent):
         da = int(np.prod(self.env.action_space.shape))
         common = dict(gamma=self.gamma, horizontal_penalty_factor=self.horizontal_penalty_factor,
                       penalty_mode=self.penalty_mode, precision=self.precision)
+        K_draw, plan = self.N, self.engine.plan
+        if self.planner is not None:
+            from .distributed import shard_bounds
+            K_draw = shard_bounds(self.N, self.planner.world, self.planner.rank)[1]
+            plan = self.planner.plan
         if self.device_sampling:
             self._plan_calls += 1
             seed = int(npr.randint(0, 2 ** 31 - 1)) * 4099 + self._plan_calls
-            res = self.engine.plan(curr_nn_state, self.current_desired_state_index, K=self.N,
-                                   H=self.horizon, seed=seed, act_low=low, act_high=high, **common)
+            res = plan(curr_nn_state, self.current_desired_state_index, K=self.N,
+                       H=self.horizon, seed=seed, act_low=low, act_high=high, **common)
         else:
-            all_samples = npr.uniform(low, high, (self.N, self.horizon, da))     # :500-501
-            res = self.engine.plan(curr_nn_state, self.current_desired_state_index,
-                                   actions=all_samples, **common)
+            # npr.uniform(low, high, (N, H, da)) of :500-501, bit for bit (legacy uniform =
+            # low + (high - low) * random_sample in draw order) without its slow broadcast path
+            all_samples = npr.random_sample((K_draw, self.horizon, da))
+            all_samples *= np.asarray(high, dtype=np.float64) - np.asarray(low, dtype=np.float64)
+            all_samples += np.asarray(low, dtype=np.float64)
+            if self.planner is not None:
+                res = plan(curr_nn_state, self.current_desired_state_index, K=self.N, H=self.horizon,
+                           local_actions=all_samples, **common)
+            else:
+                res = plan(curr_nn_state, self.current_desired_state_index, actions=all_samples, **common)
         best_sequence = res["best_sequence"]
         return np.copy(best_sequence[0]), res["best_k"], best_sequence, res["best_path"]
 

@@ -160,8 +160,7 @@ def path_shortcutter(path, distance_func, theta, engine=None):
     With ``engine`` (a CUDA Engine) and an elliptical ``distance_func`` the whole function runs on
     the device (ss_path_shortcut: same float64 pair decisions, same DP tie-breaking)."""
     p = np.asarray(path)
-    if engine is not None and getattr(distance_func, "radii", None) is not None and hasattr(engine, "path_shortcut") \
-            and len(p) <= 16384:
+    if engine is not None and getattr(distance_func, "radii", None) is not None and len(p) <= 16384:
         return p[engine.path_shortcut(p, distance_func.radii, theta)]
     if engine is not None and getattr(distance_func, "radii", None) is not None:
         pairs = engine.path_close_pairs(p, distance_func.radii, theta)

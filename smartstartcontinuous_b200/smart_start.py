@@ -70,9 +70,9 @@ class SmartStartContinuous(RLAgent):
                  nnd_mb_steps_per_rollout_train=333,
                  nnd_mb_steps_per_rollout_val=333,
 
-                 *, engine=None, device=0, nnd_mb_extra=None):
+                 *, engine=None, device=0, nnd_mb_extra=None, device_mirror=True):
         self.param_dict = {k: v for k, v in locals().items()
-                           if k not in ("self", "sess", "env", "agent", "engine", "nnd_mb_extra", "__class__")}
+                           if k not in ("self", "sess", "env", "agent", "engine", "nnd_mb_extra", "device_mirror", "__class__")}
         for name in ("self", "sess", "env", "__class__"):
             self.param_dict[name] = "Not serializable"
         self.param_dict["agent"] = agent.get_param_dict()
@@ -100,6 +100,9 @@ class SmartStartContinuous(RLAgent):
             from .engine import Engine
             engine = Engine(device)
         self.engine = engine
+        # select from the device-resident mirror of the replay buffer's state ring
+        # whenever the buffer keeps one; False = upload the whole buffer at every selection
+        self.device_mirror = bool(device_mirror)
 
         self.nnd_mb_agent = NND_MB_agent(
             env, sess, replay_buffer=self.replay_buffer,
@@ -167,7 +170,7 @@ class SmartStartContinuous(RLAgent):
         possible_ss_states = self._candidate_states(possible_start_indices)
         ss_state_values = np.asarray(self.agent.get_state_value(possible_ss_states)).T   # 1 x m
         ring = self.replay_buffer.state_ring() if hasattr(self.replay_buffer, "state_ring") else None
-        if ring is not None and hasattr(self.engine, "select_start_mirror"):
+        if ring is not None and self.device_mirror:
             # the buffer's states already live on the device (incremental mirror): only the m candidate
             # indices and values are uploaded
             best_j, best_ucb, _, _ = self.engine.select_start_mirror(

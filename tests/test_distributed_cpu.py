@@ -73,7 +73,8 @@ class OracleEngine:
         k, score, _ = self.finish()
         seq, path = self.replay(k)
         body = np.concatenate([seq.reshape(-1), path.reshape(-1)]) if want_path else np.zeros(seq.size + path.size)
-        return torch.tensor(np.concatenate([[score, float(k)], body]), dtype=torch.float64)
+        t = torch.tensor(np.concatenate([[score, float(k)], body]), dtype=torch.float64)
+        return t, t.numel()
 
     def replay(self, k_global):
         if self.sampler is not None:      # device sampling: any rank can regenerate any sequence
@@ -118,7 +119,7 @@ def _worker(rank, world, port, mode, out):
     try:
         g = load_golden("mpc_mountaincar_L2.npz")
         eng = OracleEngine(g)
-        planner = ShardedPlanner(eng, device="cpu")
+        planner = ShardedPlanner(eng, device="cpu", tensors=eng)   # the oracle double is its own tensor strategy
         res = planner.plan(g["in_start_state"], 0, K=101, H=6, seed=11, act_low=[-1.0], act_high=[1.0],
                            penalty_mode=mode)
         res_host = planner.plan(g["in_start_state"], 0, K=len(g["in_actions"]), H=g["in_actions"].shape[1],

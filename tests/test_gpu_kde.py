@@ -210,14 +210,18 @@ def _random_value_net(rng, d, da, h1, h2, layer_norm, last_tanh, norms):
     if layer_norm:
         gb = lambda n: (rng.uniform(0.5, 1.5, n).astype(np.float32), rng.normal(0, 0.1, n).astype(np.float32))
         net["actor_ln"], net["critic_ln"] = [gb(h1), gb(h2)], [gb(h1), gb(h2)]
-    if norms:
+    if norms == "clip_only":
+        # normalize_returns=False with a finite return_range: the clip still applies (ddpg_editted.py:130-131)
+        net.update(ret_clip=(-0.002, 0.002), obs_clip=(-2.0, 2.0))
+    elif norms:
         net.update(obs_mean=rng.normal(size=d), obs_std=rng.uniform(0.5, 2.0, d), obs_clip=(-5.0, 5.0),
                    ret_mean=-3.0, ret_std=2.5, ret_clip=(-4.0, 4.0))
     return net
 
 
 @pytest.mark.parametrize("cfg", [(3, 1, 64, 32, False, True, False),      # the example's DDPG nets
-                                 (2, 1, 64, 64, True, False, True), (4, 2, 200, 100, True, True, True)])
+                                 (2, 1, 64, 64, True, False, True), (4, 2, 200, 100, True, True, True),
+                                 (3, 1, 64, 32, False, True, "clip_only")])
 def test_value_net_matches_oracle_and_feeds_the_ucb(engine, cfg):
     """Row f4: critic(q, actor(q)) on the device vs the float32 numpy restatement, and a selection
     with values=None equals the selection fed with the host-evaluated values."""

@@ -159,11 +159,31 @@ def test_c3_size_fp32_properties(engine):
 # ----------------------------------------------------------------------------------------------
 # tcgen05 path (SS_PRECISION_BF16_TC).  Stated tolerance of the tensor-core path: the hidden x
 # hidden layer runs with BF16 operands (FP32 accumulate), so trajectories deviate from the float64
-# oracle by ~1e-3 of the per-step state change and scores by up to a few 1e-2 (absolute, scores are
-# O(1..50)); TC_SCORE_TOL is that bound, and the chosen index must match the oracle's wherever its
-# top-2 gap exceeds 2 * TC_SCORE_TOL.
-TC_SCORE_TOL = 5e-2
-TC_STATE_RTOL = 2e-3
+# oracle by ~1e-4 of the state scale per 10-20 steps and scores by an ABSOLUTE error that does not
+# grow with |score| (it is a sum of H+1 distance differences).  Measured with
+# tests/manual/tc_error_report.py on B200: see the table there; the bounds
+# below are ~3x the largest measured value.  At most 1 % of the samples may exceed the bound (a
+# sample sitting on a waypoint-switch boundary, dc <= 1 or dn <= dc, can flip and jump), and the
+# chosen index must EQUAL the oracle's whenever the oracle's top-2 gap exceeds 2x the bound;
+# otherwise the chosen sample's oracle score must be within 2x the bound of the oracle's best.
+TC_SCORE_ATOL = 5e-2       # absolute, every configuration incl. H = 50
+TC_STATE_RTOL = 2e-3       # of the per-dimension state scale
+
+
+def _score_close_abs(got, want, atol, max_outlier_frac=0.01):
+    bad = np.abs(got - want) > atol
+    assert bad.mean() <= max_outlier_frac, "%.2f%% of scores off by more than %g (max %.3g)" % (
+        100 * bad.mean(), atol, np.abs(got - want).max())
+    return bad
+
+
+def _check_best_abs(best_k, want_scores, atol):
+    order = np.argsort(-want_scores, kind="stable")
+    top, second = want_scores[order[0]], want_scores[order[1]]
+    if top - second > 2 * atol:
+        assert best_k == int(order[0]), "arg-best %d, oracle %d (gap %.3g > 2 x %g)" % (best_k, order[0], top - second, atol)
+    else:
+        assert want_scores[best_k] >= top - 2 * atol, "chosen score %.6g, oracle top %.6g" % (want_scores[best_k], top)
 
 
 def _pendulum_2x500(rng, scale=0.5):
@@ -193,9 +213,9 @@ def test_tc_golden_states_and_plan(engine, name):
         want = g["out_scores"] if mode == "reference" else mpc_oracle.score_add_delta(
             g["out_states"], g["out_desired_states"], g["out_distances_left"], g["out_radii"],
             int(g["in_wp_index"]), .75, .5, penalty_mode=1)
-        _score_close(res["scores"], want, TC_SCORE_TOL, max_outlier_frac=0.02)
+        _score_close_abs(res["scores"], want, TC_SCORE_ATOL)
         assert np.median(np.abs(res["scores"] - want)) < 1e-2
-        _check_best(res["best_k"], want, TC_SCORE_TOL)
+        _check_best_abs(res["best_k"], want, TC_SCORE_ATOL)
 
 
 @pytest.mark.parametrize("mode", ["reference", "per_sample"])
@@ -210,18 +230,18 @@ def test_tc_2x500_vs_oracle_and_fp32(engine, mode):
     kw = dict(K=K, H=H, seed=seed, act_low=[-2.0], act_high=[2.0], penalty_mode=mode, want_scores=True)
     tc = engine.plan(start, 0, precision="bf16_tc", **kw)
     f32 = engine.plan(start, 0, precision="fp32", **kw)
-    assert np.median(np.abs(tc["scores"] - f32["scores"])) < 2e-2
-    _score_close(tc["scores"], f32["scores"], 3 * TC_SCORE_TOL, max_outlier_frac=0.03)
+    assert np.median(np.abs(tc["scores"] - f32["scores"])) < 1e-2
+    _score_close_abs(tc["scores"], f32["scores"], TC_SCORE_ATOL)
     acts = philox.sample_actions(K, H, 1, seed, [-2.0], [2.0])
     if mode == "per_sample":
         o = mpc_oracle.plan(start, acts[:256], w, b, norm, plan["desired_states"], plan["distances_left"],
                             plan["radii"], 0, .75, .5, penalty_mode=1)
-        _score_close(tc["scores"][:256], o["scores"], 3 * TC_SCORE_TOL, max_outlier_frac=0.03)
+        _score_close_abs(tc["scores"][:256], o["scores"], TC_SCORE_ATOL, max_outlier_frac=0.02)
     else:
         o = mpc_oracle.plan(start, acts, w, b, norm, plan["desired_states"], plan["distances_left"],
                             plan["radii"], 0, .75, .5, penalty_mode=0)
-        _score_close(tc["scores"], o["scores"], 3 * TC_SCORE_TOL, max_outlier_frac=0.03)
-        _check_best(tc["best_k"], o["scores"], 3 * TC_SCORE_TOL)
+        _score_close_abs(tc["scores"], o["scores"], TC_SCORE_ATOL)
+        _check_best_abs(tc["best_k"], o["scores"], TC_SCORE_ATOL)
     np.testing.assert_array_equal(tc["best_sequence"], acts[tc["best_k"]])
 
 
@@ -283,6 +303,62 @@ def test_tc_config4_shard_properties(engine):
     np.testing.assert_array_equal(ref["best_sequence"],
                                   philox.sample_actions(1, H, 1, seed, [-2.0], [2.0], k_offset=ref["best_k"])[0])
     np.testing.assert_allclose(ref["best_path"][0], start, rtol=0, atol=1e-6)
+
+
+def _assert_tc_matches_oracle(engine, start, acts, w, b, norm, plan, mode="reference"):
+    """Whole-batch comparison of the tcgen05 decision with the float64 oracle: every trajectory,
+    every score (absolute bound, <= 1 % switch-boundary outliers), the arg-best, the returned
+    sequence and path."""
+    res = engine.plan(start, 0, actions=acts, penalty_mode=mode, precision="bf16_tc", want_scores=True)
+    states = engine.get_states()
+    o = mpc_oracle.plan(start, acts, w, b, norm, plan["desired_states"], plan["distances_left"], plan["radii"],
+                        0, .75, .5, penalty_mode=0 if mode == "reference" else 1)
+    scale = np.abs(o["states"]).max(axis=(0, 1))
+    assert np.all(np.abs(states - o["states"]).max(axis=(0, 1)) <= TC_STATE_RTOL * scale)
+    _score_close_abs(res["scores"], o["scores"], TC_SCORE_ATOL)
+    _check_best_abs(res["best_k"], o["scores"], TC_SCORE_ATOL)
+    assert res["best_k"] == int(np.argmax(res["scores"]))
+    np.testing.assert_array_equal(res["best_sequence"], acts[res["best_k"]].astype(np.float32).astype(np.float64))
+    np.testing.assert_allclose(res["best_path"], o["states"][:, res["best_k"]], rtol=0, atol=TC_STATE_RTOL * scale.max())
+    return res, o
+
+
+def test_tc_config3_full_vs_oracle(engine):
+    """BASELINE config 3 on the path it actually takes: MountainCar (d=2, da=1), MLP 2x500, K=4096,
+    H=20, reference penalty, tcgen05 kernel, host action samples (npr.uniform like
+    NND_MB_agent.py:500-501) -- the whole batch against the float64 oracle."""
+    rng = np.random.default_rng(3)
+    roll = [syn.mountaincar_rollout(rng, 200) for _ in range(8)]
+    norm = syn.normalisation_stats(np.concatenate([r[0] for r in roll]),
+                                   np.concatenate([np.concatenate([r[1], r[1][-1:]]) for r in roll]))
+    w, b = syn.xavier_mlp(rng, 2, 1, 2, 500, scale=0.5)
+    from smartstartcontinuous_b200.nnd_mb_agent import plan_from_path
+    plan = plan_from_path(list(roll[0][0][:60]), mean_per_stepsize=1, std_per_stepsize=1,
+                          stepsizes_in_waypoint_radii=1, path_shortcutting=True, theta=1, steps_per_waypoint=1)
+    engine.set_model(w, b, norm)
+    engine.set_plan(plan["desired_states"], plan["distances_left"], plan["radii"])
+    assert engine.tc_supported()
+    acts = np.random.RandomState(1).uniform(-1, 1, (4096, 20, 1))
+    for mode in ("reference", "per_sample"):
+        _assert_tc_matches_oracle(engine, roll[0][0][0], acts, w, b, norm, plan, mode)
+
+
+def test_tc_config4_shard_vs_oracle(engine):
+    """BASELINE config 4's per-GPU shard = the bench workload (Pendulum, 2x500, K=131072, H=50,
+    reference penalty, same weights / plan / start state as bench.make_workload): the whole batch
+    against the float64 oracle (~20-40 s of numpy on the host)."""
+    import bench
+    wl = bench.make_workload()
+    engine.set_model(wl["w"], wl["b"], wl["norm"])
+    engine.set_plan(wl["plan"]["desired_states"], wl["plan"]["distances_left"], wl["plan"]["radii"])
+    K, H, seed = bench.K_PER_GPU, bench.HORIZON, 1001
+    acts = philox.sample_actions(K, H, 1, seed, wl["low"], wl["high"])
+    res, o = _assert_tc_matches_oracle(engine, wl["state"], acts, wl["w"], wl["b"], wl["norm"], wl["plan"])
+    # the same decision with the samples drawn on the device (what the bench times) is bit-identical
+    dev = engine.plan(wl["state"], 0, K=K, H=H, seed=seed, act_low=wl["low"], act_high=wl["high"],
+                      penalty_mode="reference", precision="bf16_tc", want_scores=True)
+    np.testing.assert_array_equal(dev["scores"], res["scores"])
+    assert dev["best_k"] == res["best_k"]
 
 
 def test_tc_unsupported_shape(engine):
