@@ -634,21 +634,28 @@ def main():
                 k_ms.append(dict(eng.last_timings()).get("mpc_rollout", 0.0))
 
         n_s = max(10, args.steps)
-        res_ms = timed(resident, n_s, 3) / n_s
+        res_ms = timed(resident, n_s, 3) / n_s                 # per-phase events on: gives the rollout kernel's time
+        kern_ms = list(k_ms)
+        eng.set_timing(False)                                  # the lean path a latency-sensitive caller uses
+        fast_ms = timed(resident, n_s, 3) / n_s
         host_ms = timed(lambda i: ag_host.get_best_sim_actions(wls["state"]), n_s, 3) / n_s
         devs_ms = timed(lambda i: ag_dev.get_best_sim_actions(wls["state"]), n_s, 3) / n_s
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(n_s):
             ag_dev.get_best_sim_actions(wls["state"])
         wall_ms = 1e3 * (time.perf_counter() - t0) / n_s
+        eng.set_timing(True)
+        k_ms = kern_ms
         kern = float(np.mean(k_ms)) if k_ms else None
         small[name] = {
             "workload": "MountainCar d=2 da=1, K=%d (strong-scaled over %d GPU(s)), H=%d, MLP %dx%d, reference penalty"
                         % (K, world, H, L, h),
             "kernel": "mpc_rollout_tc_kernel" if prec_s == "bf16_tc" else "mpc_rollout_simt_kernel",
-            "ms_per_decision_resident": res_ms, "rollout_kernel_ms": kern,
-            "decision_over_rollout_kernel": (res_ms / kern) if kern else None,
-            "rollout_steps_per_s_resident": K * H / (res_ms * 1e-3),
+            "ms_per_decision_resident": fast_ms, "ms_per_decision_resident_with_phase_events": res_ms,
+            "rollout_kernel_ms": kern,
+            "decision_over_rollout_kernel": (fast_ms / kern) if kern else None,
+            "rollout_steps_per_s_resident": K * H / (fast_ms * 1e-3),
             "ms_per_decision_agent_default": host_ms, "rollout_steps_per_s_agent_default": K * H / (host_ms * 1e-3),
             "ms_per_decision_agent_device_sampling": devs_ms, "wall_ms_agent_device_sampling": wall_ms,
             "tensor_frac_of_burst_peak": (FLOP_PER_STEP[2] * K * H / (kern * 1e-3) / 1e12 / measured_peaks()["bf16_burst"])

@@ -69,6 +69,9 @@ int ss_device_info(ss_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int
 /* device time (ms, CUDA events on the context's stream) of the most recent call, split in
  * up to 8 named phases; returns the number of phases written */
 int ss_last_timings(ss_ctx* ctx, float* ms, const char** names, int max_phases);
+/* per-phase CUDA events are recorded by default (they feed ss_last_timings); ss_set_timing(ctx, 0)
+ * drops them -- a few microseconds per call that matter for small batches (K of a few thousand) */
+int ss_set_timing(ss_ctx* ctx, int enabled);
 /* number of kernel launches issued by this context since creation */
 int64_t ss_launch_count(ss_ctx* ctx);
 /* pinned host memory for end-to-end callers (bench e2e leg) */
@@ -169,7 +172,10 @@ int ss_mpc_finish(ss_ctx* ctx, int64_t* out_best_k, double* out_best_score, doub
  * without a host synchronisation (the trajectory rows of the batch are kept on the device in both
  * penalty modes, the winner's path is a gather).  Multi-GPU callers all-gather the packages and pick with
  * np.argmax ordering -- one collective and one device->host copy per decision.  want_path = 0
- * leaves the sequence / path part zero.  ss_mpc_read_package copies it to the host. */
+ * leaves the sequence / path part zero.  Phase B is ONE kernel launch (coefficients, penalties, arg-max
+ * and package); on an unsharded batch the same kernel also writes the package to mapped pinned host
+ * memory and raises a completion flag there, so ss_mpc_read_package returns it without a
+ * device->host copy or a stream synchronisation. */
 int ss_mpc_finish_package(ss_ctx* ctx, int want_path, double** package_dev, int* count);
 int ss_mpc_read_package(ss_ctx* ctx, double* out_package, int count);
 /* ---- NVLink peer-memory exchange for sharded batches (one process per GPU, one node) -------

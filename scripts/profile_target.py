@@ -10,6 +10,16 @@ import bench
 from smartstartcontinuous_b200.engine import Engine
 
 eng = Engine(0)
+if os.environ.get("SS_PROFILE_CFG") == "c3":
+    # BASELINE config 3: MountainCar, K=4096, H=20, MLP 2x500 -- the small-K decision
+    wl = bench.make_workload_mountaincar(2, 500)
+    eng.set_model(wl["w"], wl["b"], wl["norm"])
+    eng.set_plan(wl["plan"]["desired_states"], wl["plan"]["distances_left"], wl["plan"]["radii"])
+    for i in range(6):
+        r = eng.plan(wl["state"], 0, K=bench.C3_K, H=bench.C3_H, seed=i, act_low=wl["low"], act_high=wl["high"],
+                     penalty_mode="reference", precision="bf16_tc")
+    print("mpc c3", r["best_k"], r["best_score"], eng.last_timings())
+    sys.exit(0)
 wl = bench.make_workload()
 eng.set_model(wl["w"], wl["b"], wl["norm"])
 eng.set_plan(wl["plan"]["desired_states"], wl["plan"]["distances_left"], wl["plan"]["radii"])

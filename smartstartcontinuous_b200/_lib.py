@@ -37,6 +37,7 @@ SIGNATURES = {
     "ss_device_info": (C.c_int, [C.c_void_p, _c_int_p, _c_int_p, _c_int_p, _c_int_p]),
     "ss_last_timings": (C.c_int, [C.c_void_p, _c_float_p, C.POINTER(C.c_char_p), C.c_int]),
     "ss_launch_count": (C.c_int64, [C.c_void_p]),
+    "ss_set_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "ss_host_alloc": (C.c_void_p, [C.c_int64]),
     "ss_host_free": (None, [C.c_void_p]),
     "ss_device_alloc": (C.c_void_p, [C.c_int64]),

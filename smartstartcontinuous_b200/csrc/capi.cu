@@ -70,6 +70,7 @@ extern "C" int ss_destroy(ss_ctx* c) {
         for (int i = 0; i <= SS_MAX_PHASES; ++i) cudaEventDestroy(c->timer.ev[i]);
     ss_peer_close(c);
     c->mpc_package_local.release();
+    if (c->host_pkg) cudaFreeHost(c->host_pkg);
     if (c->copy_ready) {
         for (int i = 0; i <= ss_ctx::MAX_COPY_CHUNKS; ++i) cudaEventDestroy(c->copy_ev[i]);
         cudaStreamDestroy(c->copy_stream);
@@ -102,7 +103,7 @@ extern "C" int ss_device_info(ss_ctx* c, int* sm_count, int* cc_major, int* cc_m
 }
 
 extern "C" int ss_last_timings(ss_ctx* c, float* ms, const char** names, int max_phases) {
-    if (!c || !c->timer.created) return 0;
+    if (!c || !c->timer.created || !c->timing) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     int n = c->timer.n < max_phases ? c->timer.n : max_phases;
@@ -116,6 +117,13 @@ extern "C" int ss_last_timings(ss_ctx* c, float* ms, const char** names, int max
 }
 
 extern "C" int64_t ss_launch_count(ss_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" int ss_set_timing(ss_ctx* c, int enabled) {
+    if (!c) return SS_EINVAL;
+    c->timing = enabled != 0;
+    c->timer.n = 0;
+    return SS_OK;
+}
 
 extern "C" void* ss_host_alloc(int64_t bytes) {
     void* p = nullptr;

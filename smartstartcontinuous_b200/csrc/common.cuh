@@ -159,12 +159,27 @@ struct ss_ctx {
         bool finished = false;         // the reference-mode penalty pass has rewritten the scores
         bool peer_sums = false;        // the projection sums were all-reduced over peer memory
         int sum_blocks = 0;
+        // reference penalty: [2T][n_cols] partial columns of the projection sums the fused tail kernel
+        // reduces (n_cols == 1 and sums_reduced: they are final, in mpc_sums)
+        const double* sum_cols = nullptr;
+        int n_cols = 0;
+        bool sums_reduced = false;
+        bool pkg_on_host = false;      // the winner package of this decision lands in host_pkg
+        unsigned long long pkg_seq = 0;
     } run;
+    // mapped pinned host memory the tail kernel writes the winner package to: [0] completion flag
+    // (= run.pkg_seq when done), [2..] the package
+    static constexpr size_t HOST_PKG_BYTES = 64 * 1024;
+    void* host_pkg = nullptr;
+    void* host_pkg_dev = nullptr;
+    unsigned long long host_pkg_seq = 0;
+    bool timing = true;                // per-phase CUDA events (ss_last_timings); ss_set_timing(0) drops them
 };
 
 // ---- phase timing helpers (CUDA events on the context stream) -------------------------
 static inline void timer_begin(ss_ctx* c) {
     PhaseTimer& t = c->timer;
+    if (!c->timing) { t.n = 0; return; }
     if (!t.created) {
         for (int i = 0; i <= SS_MAX_PHASES; ++i) cudaEventCreate(&t.ev[i]);
         t.created = true;
@@ -174,7 +189,7 @@ static inline void timer_begin(ss_ctx* c) {
 }
 static inline void timer_mark(ss_ctx* c, const char* name) {
     PhaseTimer& t = c->timer;
-    if (t.n >= SS_MAX_PHASES) return;
+    if (!c->timing || !t.created || t.n >= SS_MAX_PHASES) return;
     t.names[t.n] = name;
     t.n++;
     cudaEventRecord(t.ev[t.n], c->stream);

@@ -5,6 +5,7 @@
 //   ss_mpc_rollout    phase A: sample/fetch actions, roll the MLP for H steps, score
 //   ss_mpc_finish     phase B (reference penalty) + arg-max
 //   ss_mpc_replay     re-roll the winner for best_sequence / best_path (NND_MB_agent.py:516-518)
+#include <atomic>
 #include <cstring>
 
 #include "mpc_kernels.cuh"
@@ -30,34 +31,6 @@ __global__ void gather_path_kernel(const float* __restrict__ rows, long long K, 
                                    int d, float* __restrict__ out) {
     const int o = blockIdx.x * blockDim.x + threadIdx.x;
     if (o < T * d) out[o] = rows[((size_t)(o / d) * K + k) * (d + 1) + (o % d)];
-}
-
-// package = [best_score, best_k, sequence (H*da), path (T*d)] of the arg-max result `res`.
-// rows: trajectory rows [T][K_rows][d + 1]; fixed_row >= 0 selects that row (re-rolled winner),
-// otherwise the winner's local row best_k - k_offset.
-__global__ void package_kernel(const MpcResult* __restrict__ res, const float* __restrict__ rows, long long K_rows,
-                               long long fixed_row, long long k_offset, int T, int d, ActionSource act, int want_path,
-                               double* __restrict__ pkg) {
-    const long long k = res->best_k;
-    const long long kl = k - k_offset;
-    const int n_seq = act.H * act.da, n_path = T * d;
-    if (threadIdx.x == 0) {
-        pkg[0] = res->best_score;
-        pkg[1] = (double)k;
-    }
-    for (int o = threadIdx.x; o < n_seq + n_path; o += blockDim.x) {
-        double v = 0.0;
-        if (want_path && k >= 0) {
-            if (o < n_seq) {
-                v = (double)fetch_action(act, kl, k, o / act.da, o % act.da);
-            } else {
-                const int q = o - n_seq;
-                const long long row = fixed_row >= 0 ? fixed_row : kl;
-                v = (double)rows[((size_t)(q / d) * K_rows + row) * (d + 1) + (q % d)];
-            }
-        }
-        pkg[2 + o] = v;
-    }
 }
 
 int fill_action_source(ss_ctx* c, ActionSource& s, int H, int da, uint64_t seed, const double* low,
@@ -348,6 +321,9 @@ extern "C" int ss_mpc_rollout(ss_ctx* c, const double* state, int wp_index, int6
         if (rc) return rc;
     }
     timer_mark(c, "mpc_rollout");
+    r.sum_cols = nullptr;
+    r.n_cols = 0;
+    r.sums_reduced = false;
     if (ref) {
         int red_blocks = tc_sums ? (int)tc_qcols : sum_blocks;
         const double* red_src = c->mpc_partial_sums.as<double>();
@@ -362,12 +338,24 @@ extern "C" int ss_mpc_rollout(ss_ctx* c, const double* state, int wp_index, int6
             if (rc) return rc;
             red_src = folded;
         }
-        // a sharded batch on a context with an open peer exchange: the reduction kernel also
-        // all-reduces the sums over NVLink peer memory (no NCCL call, no host round trip)
-        r.peer_sums = c->peer_ready && K_global != K_local;
-        rc = r.peer_sums ? peer_allreduce_sums(c, red_src, red_blocks, T, c->mpc_sums.as<double>())
-                         : mpc_reduce_sums(c, red_src, red_blocks, T, c->mpc_sums.as<double>());
-        if (rc) return rc;
+        if (K_global != K_local) {
+            // a shard of a larger batch: the sums of ALL shards are needed before the penalties.  On a
+            // context with an open peer exchange the reduction kernel also all-reduces them over NVLink
+            // peer memory (no NCCL call, no host round trip); otherwise the caller all-reduces the
+            // buffer ss_mpc_projection_sums returns.
+            r.peer_sums = c->peer_ready;
+            rc = r.peer_sums ? peer_allreduce_sums(c, red_src, red_blocks, T, c->mpc_sums.as<double>())
+                             : mpc_reduce_sums(c, red_src, red_blocks, T, c->mpc_sums.as<double>());
+            if (rc) return rc;
+            r.sum_cols = c->mpc_sums.as<double>();
+            r.n_cols = 1;
+            r.sums_reduced = true;
+        } else {
+            // the whole batch is here: the fused tail kernel reduces the (<= 256) columns itself
+            r.peer_sums = false;
+            r.sum_cols = red_src;
+            r.n_cols = red_blocks;
+        }
         r.sum_blocks = red_blocks;
         timer_mark(c, "mpc_sums_pass1");
     }
@@ -383,45 +371,57 @@ extern "C" int ss_mpc_projection_sums(ss_ctx* c, double** sums_dev, int* count) 
         if (count) *count = 0;
         return SS_OK;
     }
+    if (!c->run.sums_reduced) {
+        // unsharded batch: the columns were left for the fused tail; reduce them now for this caller
+        SS_CUDA_CHECK(c, cudaSetDevice(c->device));
+        int rc = mpc_reduce_sums(c, c->run.sum_cols, c->run.n_cols, c->run.H + 1, c->mpc_sums.as<double>());
+        if (rc) return rc;
+        c->run.sum_cols = c->mpc_sums.as<double>();
+        c->run.n_cols = 1;
+        c->run.sums_reduced = true;
+    }
     if (sums_dev) *sums_dev = c->mpc_sums.as<double>();
     if (count) *count = 2 * (c->run.H + 1);
     return SS_OK;
 }
 
-// phase B on the device: reference-mode penalty pass + arg-max -> c->mpc_result (no host sync)
-static int finish_device(ss_ctx* c) {
+// phase B on the device, ONE launch (mpc_tail): reference-mode coefficients + penalty pass, arg-max,
+// and the local winner's package at pkg_dst (and in mapped host memory when host_pkg is given)
+static int finish_device(ss_ctx* c, int want_path, double* pkg_dst, double* host_pkg, unsigned long long seq) {
     auto& r = c->run;
     if (!r.valid) SS_FAIL(c, SS_ESTATE, "mpc: ss_mpc_finish without ss_mpc_rollout");
     SS_CUDA_CHECK(c, cudaSetDevice(c->device));
     const int T = r.H + 1;
     const float* gpow = c->mpc_replay.as<float>();
-    int rc;
-    if (r.penalty_mode == SS_PENALTY_REFERENCE && !r.finished) {
-        PlanView p = make_plan_view(c, gpow, r.gamma, r.hpf);
-        rc = mpc_score_reference(c, p, c->mpc_states.as<float>(), r.K_local, T, c->mpc_sums.as<double>(),
-                                 c->mpc_scores.as<float>());
-        if (rc) return rc;
-        timer_mark(c, "mpc_score_pass2");
-    }
-    r.finished = true;      // the second pass rewrites the scores in place: run it once per rollout
-    SS_CUDA_CHECK(c, c->mpc_block_best.ensure(1024 * 16));
+    const bool penalties = r.penalty_mode == SS_PENALTY_REFERENCE && !r.finished;
+    PlanView p = make_plan_view(c, gpow, r.gamma, r.hpf);
+    const int blocks = mpc_tail_blocks(r.K_local);
+    SS_CUDA_CHECK(c, c->mpc_block_best.ensure((size_t)blocks * 16 + 64));
     if (!c->mpc_result.p) {
         SS_CUDA_CHECK(c, c->mpc_result.ensure(sizeof(MpcResult)));
         SS_CUDA_CHECK(c, cudaMemsetAsync(c->mpc_result.p, 0, sizeof(MpcResult), c->stream));
     }
     double* bv = c->mpc_block_best.as<double>();
-    rc = mpc_argmax(c, c->mpc_scores.as<float>(), r.K_local, r.k_offset, bv,
-                    reinterpret_cast<long long*>(bv + 1024), c->mpc_result.p);
+    int rc = mpc_tail(c, p, c->mpc_states.as<float>(), r.K_local, T, penalties ? r.sum_cols : nullptr, r.n_cols,
+                      c->mpc_scores.as<float>(), r.k_offset, bv, reinterpret_cast<long long*>(bv + blocks),
+                      c->mpc_result.p, r.act, want_path, pkg_dst, host_pkg, seq,
+                      penalties && !r.sums_reduced ? c->mpc_sums.as<double>() : nullptr);
     if (rc) return rc;
-    timer_mark(c, "mpc_argmax");
+    r.finished = true;      // the penalty pass rewrites the scores in place: run it once per rollout
+    timer_mark(c, "mpc_tail");
     return SS_OK;
 }
+
+static int package_count(ss_ctx* c) { return 2 + c->run.H * c->da + (c->run.H + 1) * c->d; }
 
 extern "C" int ss_mpc_finish(ss_ctx* c, int64_t* out_best_k, double* out_best_score, double* out_scores) {
     if (!c) return SS_EINVAL;
     auto& r = c->run;
-    int rc = finish_device(c);
+    if (!r.valid) SS_FAIL(c, SS_ESTATE, "mpc: ss_mpc_finish without ss_mpc_rollout");
+    SS_CUDA_CHECK(c, c->mpc_package.ensure((size_t)package_count(c) * 8));
+    int rc = finish_device(c, 0, c->mpc_package.as<double>(), nullptr, 0);
     if (rc) return rc;
+    r.pkg_on_host = false;
     MpcResult h;
     SS_CUDA_CHECK(c, cudaMemcpyAsync(&h, c->mpc_result.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     std::vector<float> sc;
@@ -442,42 +442,37 @@ static int reroll_winner(ss_ctx* c, int64_t k_global, float* rows_dev);
 extern "C" int ss_mpc_finish_package(ss_ctx* c, int want_path, double** package_dev, int* count) {
     if (!c) return SS_EINVAL;
     auto& r = c->run;
-    int rc = finish_device(c);
-    if (rc) return rc;
-    const int T = r.H + 1, d = c->d, da = c->da;
-    const int n = 2 + r.H * da + T * d;
+    if (!r.valid) SS_FAIL(c, SS_ESTATE, "mpc: ss_mpc_finish_package without ss_mpc_rollout");
+    SS_CUDA_CHECK(c, cudaSetDevice(c->device));
+    const int n = package_count(c);
     SS_CUDA_CHECK(c, c->mpc_package.ensure((size_t)n * 8));
-    const float* rows = c->mpc_states.as<float>();
-    long long K_rows = r.K_local, fixed_row = -1;
-    if (want_path && !r.states_stored) {
-        // per-sample mode keeps no trajectories: fetch the winner's index and re-roll that one
-        // sequence with the kernel family that scored it
-        MpcResult h;
-        SS_CUDA_CHECK(c, cudaMemcpyAsync(&h, c->mpc_result.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-        SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-        float* rows_dev = c->mpc_replay.as<float>() + (T + SS_MAX_D + 3) / 4 * 4;
-        rc = reroll_winner(c, h.best_k, rows_dev);
-        if (rc) return rc;
-        rows = rows_dev;
-        K_rows = 1;
-        fixed_row = 0;
-    }
     const bool peer = c->peer_ready && r.K_global != r.K_local;
     double* pkg_dst = c->mpc_package.as<double>();
+    double* host_pkg = nullptr;
+    r.pkg_on_host = false;
     if (peer) {
         SS_CUDA_CHECK(c, c->mpc_package_local.ensure((size_t)n * 8));
         pkg_dst = c->mpc_package_local.as<double>();
+    } else if ((size_t)(n + 2) * 8 <= ss_ctx::HOST_PKG_BYTES) {
+        // the package also lands in mapped pinned host memory, followed by a completion flag:
+        // ss_mpc_read_package then needs no device->host copy and no stream synchronisation
+        if (!c->host_pkg) {
+            SS_CUDA_CHECK(c, cudaHostAlloc(&c->host_pkg, ss_ctx::HOST_PKG_BYTES, cudaHostAllocMapped));
+            std::memset(c->host_pkg, 0, ss_ctx::HOST_PKG_BYTES);
+            SS_CUDA_CHECK(c, cudaHostGetDevicePointer(&c->host_pkg_dev, c->host_pkg, 0));
+        }
+        host_pkg = reinterpret_cast<double*>(c->host_pkg_dev);
+        r.pkg_seq = ++c->host_pkg_seq;
+        r.pkg_on_host = true;
     }
-    package_kernel<<<1, 256, 0, c->stream>>>(reinterpret_cast<const MpcResult*>(c->mpc_result.p), rows, K_rows,
-                                             fixed_row, r.k_offset, T, d, r.act, want_path, pkg_dst);
-    c->launches++;
-    SS_CUDA_CHECK(c, cudaGetLastError());
+    int rc = finish_device(c, want_path, pkg_dst, host_pkg, r.pkg_seq);
+    if (rc) return rc;
     if (peer) {
         // every rank's package goes to every peer; the same kernel picks the global winner
         rc = peer_package_exchange(c, pkg_dst, n, c->mpc_package.as<double>());
         if (rc) return rc;
+        timer_mark(c, "mpc_package");
     }
-    timer_mark(c, "mpc_package");
     if (package_dev) *package_dev = c->mpc_package.as<double>();
     if (count) *count = n;
     return SS_OK;
@@ -488,6 +483,26 @@ extern "C" int ss_mpc_read_package(ss_ctx* c, double* out_package, int count) {
     if (!out_package || count < 2 || (size_t)count * 8 > c->mpc_package.cap)
         SS_FAIL(c, SS_EINVAL, "mpc: bad package buffer");
     SS_CUDA_CHECK(c, cudaSetDevice(c->device));
+    auto& r = c->run;
+    if (r.pkg_on_host && (size_t)(count + 2) * 8 <= ss_ctx::HOST_PKG_BYTES) {
+        // wait for the tail kernel's completion flag in mapped host memory (a spin on a cache line the
+        // GPU writes once); the stream is queried now and then so that a failed launch cannot hang us
+        volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(c->host_pkg);
+        unsigned spins = 0;
+        while (*flag != r.pkg_seq) {
+            if ((++spins & 0x3fff) == 0) {
+                cudaError_t e = cudaStreamQuery(c->stream);
+                if (e != cudaSuccess && e != cudaErrorNotReady) SS_CUDA_CHECK(c, e);
+                if (e == cudaSuccess && *flag != r.pkg_seq) {
+                    SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+                    if (*flag != r.pkg_seq) SS_FAIL(c, SS_ECUDA, "mpc: the tail kernel finished without raising its flag");
+                }
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        std::memcpy(out_package, reinterpret_cast<const double*>(c->host_pkg) + 2, (size_t)count * 8);
+        return SS_OK;
+    }
     SS_CUDA_CHECK(c, cudaMemcpyAsync(out_package, c->mpc_package.p, (size_t)count * 8, cudaMemcpyDeviceToHost, c->stream));
     SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     return SS_OK;

@@ -51,6 +51,13 @@ int mpc_score_reference(ss_ctx* c, const PlanView& plan, const float* rows, long
                         const double* sums, float* scores);
 int mpc_argmax(ss_ctx* c, const float* scores, long long K_local, long long k_offset,
                double* block_v, long long* block_i, void* result_dev);
+// the fused tail: [2T][n_cols] partial sum columns (or null) -> coefficients, penalties, arg-max, package
+// (device copy at pkg; host_pkg = mapped pinned memory [flag, -, package...] or null; flag := seq when done)
+int mpc_tail_blocks(long long K_local);
+int mpc_tail(ss_ctx* c, const PlanView& plan, const float* rows, long long K_local, int T, const double* sum_cols,
+             int n_cols, float* scores, long long k_offset, double* block_v, long long* block_i, void* result_dev,
+             const ActionSource& act, int want_path, double* pkg, double* host_pkg, unsigned long long seq,
+             double* sums_out);
 
 // peer-memory exchange (peer.cu): fused reduce + all-reduce of the projection sums, and the
 // all-gather + pick of the winner packages

@@ -7,6 +7,11 @@
 //   mpc_score_reference  second pass: subtract the penalties computed with the global projection
 //                        coefficient of every step (NND_MB_agent.py:616-622) from the progress term
 //   mpc_argmax           np.argmax-ordered arg-max over the scores (NND_MB_agent.py:625-626)
+//   mpc_tail             ONE launch for the whole tail of a decision: projection-sum columns -> global
+//                        coefficients, penalty pass, arg-max, and the winner's package (score, k, action
+//                        sequence, predicted path; NND_MB_agent.py:516-518) written to device memory and
+//                        to mapped pinned host memory with a completion flag -- the call ends without
+//                        a device->host copy
 #include "mpc_kernels.cuh"
 
 namespace {
@@ -153,6 +158,136 @@ mpc_argmax_kernel(const float* __restrict__ scores, long long K, long long k_off
     }
 }
 
+// ---- the fused tail -------------------------------------------------------------------------
+// grid = ceil(K / 256) blocks of 256 threads, one sequence per thread.
+//   sum_cols != null (reference penalty): [2T][n_cols] partial columns of a'.b' / b'.b'; every block
+//     reduces them redundantly with the lane-stride + shuffle-tree order of mpc_reduce_sums_kernel (so
+//     the coefficients are bit-identical to the separate-kernel path and to every other block's), takes
+//     lambda_t and subtracts the penalties of its sequences from the progress term;
+//   then the np.argmax-ordered block arg-max, and in the last block to finish (atomic ticket) the final
+//   arg-max and the winner's package.
+struct TailOut {
+    double* pkg;                    // device package [2 + H*da + T*d]
+    double* host_pkg;               // mapped pinned host copy: [0] = completion flag, [2..] = package; or null
+    unsigned long long seq;         // value the flag takes when the package is complete
+    double* sums_out;               // [2T] reduced sums (block 0 writes them), or null
+    float* scores_final;            // where the final scores go (== scores in place)
+};
+
+template <int DT>
+__global__ void __launch_bounds__(256)
+mpc_tail_kernel(const PlanView Pg, const float* __restrict__ rows, long long K, int T, int ds_in_smem,
+                const double* __restrict__ sum_cols, int n_cols, float* __restrict__ scores, long long k_offset,
+                double* __restrict__ block_v, long long* __restrict__ block_i, MpcResult* __restrict__ result,
+                ActionSource act, int want_path, TailOut out) {
+    extern __shared__ float s_dyn[];             // [T] lambda | [W * d] waypoints (optional)
+    __shared__ double s_v[32];
+    __shared__ long long s_i[32];
+    __shared__ bool s_last;
+    float* s_lam = s_dyn;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    PlanView P = Pg;
+    const long long k = blockIdx.x * (long long)blockDim.x + tid;
+    if (sum_cols) {
+        // the two sums of a step live in consecutive outputs 2t, 2t + 1: one warp per step takes both
+        for (int t = warp; t < T; t += 8) {
+            double s0 = 0.0, s1 = 0.0;
+            for (int b = lane; b < n_cols; b += 32) {
+                s0 += sum_cols[(size_t)(2 * t) * n_cols + b];
+                s1 += sum_cols[(size_t)(2 * t + 1) * n_cols + b];
+            }
+            for (int off = 16; off > 0; off >>= 1) {
+                s0 += __shfl_down_sync(0xffffffffu, s0, off);
+                s1 += __shfl_down_sync(0xffffffffu, s1, off);
+            }
+            if (lane == 0) {
+                s_lam[t] = (float)(s0 / s1);
+                if (out.sums_out && blockIdx.x == 0) { out.sums_out[2 * t] = s0; out.sums_out[2 * t + 1] = s1; }
+            }
+        }
+        if (ds_in_smem) {
+            float* s_ds = s_dyn + T;
+            for (int i = tid; i < Pg.W * Pg.d; i += blockDim.x) s_ds[i] = Pg.ds[i];
+            P.ds = s_ds;
+        }
+        __syncthreads();
+    }
+    double v = 0.0;
+    long long bi = -1;
+    if (k < K) {
+        float score = scores[k];
+        if (sum_cols) {
+#pragma unroll 8
+            for (int t = 0; t < T; ++t) {
+                float x[DT];
+                int idx;
+                traj_load<DT>(rows, (size_t)t * K + k, P.d, x, idx);
+                score -= penalty_with_lambda<DT>(P, idx, x, s_lam[t]);
+            }
+            scores[k] = score;
+        }
+        v = (double)score;
+        bi = k;
+    }
+    block_argmax(v, bi, s_v, s_i);
+    if (tid == 0) {
+        block_v[blockIdx.x] = v;
+        block_i[blockIdx.x] = bi;
+        __threadfence();
+        s_last = atomicAdd(&result->blocks_done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    v = 0.0;
+    bi = -1;
+    for (int b = tid; b < gridDim.x; b += blockDim.x) {
+        const double ov = __ldcg(block_v + b);
+        const long long oi = __ldcg(block_i + b);
+        if (argmax_better(ov, oi, v, bi)) { v = ov; bi = oi; }
+    }
+    block_argmax(v, bi, s_v, s_i);
+    if (tid == 0) {
+        s_v[0] = v;
+        s_i[0] = bi;
+        result->best_score = v;
+        result->best_k = bi < 0 ? -1 : bi + k_offset;
+        result->blocks_done = 0;
+    }
+    __syncthreads();
+    // ---- the winner's package: [score, k (global), sequence (H*da), path (T*d)] ----------------------
+    const double best_v = s_v[0];
+    const long long kl = s_i[0];
+    const long long kg = kl < 0 ? -1 : kl + k_offset;
+    const int n_seq = act.H * act.da, n_path = T * Pg.d;
+    double* hp = out.host_pkg ? out.host_pkg + 2 : nullptr;
+    for (int o = tid; o < 2 + n_seq + n_path; o += blockDim.x) {
+        double val = 0.0;
+        if (o == 0) val = best_v;
+        else if (o == 1) val = (double)kg;
+        else if (want_path && kl >= 0) {
+            const int q = o - 2;
+            if (q < n_seq) val = (double)fetch_action(act, kl, kg, q / act.da, q % act.da);
+            else {
+                const int r = q - n_seq;
+                // the penalty pass of other blocks may have rewritten nothing here: rows are read-only
+                val = (double)__ldcg(rows + ((size_t)(r / Pg.d) * K + kl) * (Pg.d + 1) + (r % Pg.d));
+            }
+        }
+        out.pkg[o] = val;
+        if (hp) hp[o] = val;
+    }
+    if (out.host_pkg) {
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long*>(out.host_pkg)),
+                         "l"(out.seq)
+                         : "memory");
+        }
+    }
+}
+
 }  // namespace
 
 int mpc_reduce_sums(ss_ctx* c, const double* partial, int blocks, int T, double* sums) {
@@ -218,6 +353,35 @@ int mpc_argmax(ss_ctx* c, const float* scores, long long K_local, long long k_of
     const int grid = (int)(want < 1 ? 1 : (want > 1024 ? 1024 : want));
     mpc_argmax_kernel<<<grid, 256, 0, c->stream>>>(scores, K_local, k_offset, block_v, block_i,
                                                    reinterpret_cast<MpcResult*>(result_dev));
+    c->launches++;
+    SS_CUDA_CHECK(c, cudaGetLastError());
+    return SS_OK;
+}
+
+int mpc_tail_blocks(long long K_local) { return (int)((K_local + 255) / 256); }
+
+// sum_cols may be null (per-sample penalty: the scores are final already); out_pkg / host_pkg as TailOut
+int mpc_tail(ss_ctx* c, const PlanView& plan, const float* rows, long long K_local, int T, const double* sum_cols,
+             int n_cols, float* scores, long long k_offset, double* block_v, long long* block_i, void* result_dev,
+             const ActionSource& act, int want_path, double* pkg, double* host_pkg, unsigned long long seq,
+             double* sums_out) {
+    const unsigned grid = (unsigned)mpc_tail_blocks(K_local);
+    const size_t ds_bytes = (size_t)plan.W * plan.d * 4;
+    const int in_smem = sum_cols && ds_bytes + (size_t)T * 4 <= 40 * 1024;
+    const size_t smem = (size_t)T * sizeof(float) + (in_smem ? ds_bytes : 0);
+    TailOut out;
+    out.pkg = pkg; out.host_pkg = host_pkg; out.seq = seq; out.sums_out = sums_out; out.scores_final = scores;
+    MpcResult* res = reinterpret_cast<MpcResult*>(result_dev);
+    if (plan.d <= 4)
+        mpc_tail_kernel<4><<<grid, 256, smem, c->stream>>>(plan, rows, K_local, T, in_smem, sum_cols, n_cols, scores,
+                                                          k_offset, block_v, block_i, res, act, want_path, out);
+    else if (plan.d <= 8)
+        mpc_tail_kernel<8><<<grid, 256, smem, c->stream>>>(plan, rows, K_local, T, in_smem, sum_cols, n_cols, scores,
+                                                          k_offset, block_v, block_i, res, act, want_path, out);
+    else
+        mpc_tail_kernel<SS_MAX_D><<<grid, 256, smem, c->stream>>>(plan, rows, K_local, T, in_smem, sum_cols, n_cols,
+                                                                  scores, k_offset, block_v, block_i, res, act,
+                                                                  want_path, out);
     c->launches++;
     SS_CUDA_CHECK(c, cudaGetLastError());
     return SS_OK;

@@ -130,6 +130,14 @@ class ShardedPlanner:
         k_offset, k_local = shard_bounds(K, self.world, self.rank)
         if local_actions is None and actions is not None:
             local_actions = actions[k_offset:k_offset + k_local]
+        if self.world == 1 and isinstance(self.tensors, EngineTensors):
+            # nothing to merge: the single-call form (one trip through the C ABI, ss_mpc_plan)
+            res = self.engine.plan(state, wp_index, actions=local_actions, K=K, H=H, seed=seed, act_low=act_low,
+                                   act_high=act_high, gamma=gamma,
+                                   horizontal_penalty_factor=horizontal_penalty_factor, penalty_mode=penalty_mode,
+                                   precision=precision, want_path=want_path)
+            res.update(owner=0, k_offset=0, k_local=k_local)
+            return res
         self.engine.rollout(state, wp_index, actions=local_actions, K=k_local, H=H, seed=seed,
                             act_low=act_low, act_high=act_high, gamma=gamma,
                             horizontal_penalty_factor=horizontal_penalty_factor,

@@ -166,8 +166,15 @@ def test_c3_size_fp32_properties(engine):
 # sample sitting on a waypoint-switch boundary, dc <= 1 or dn <= dc, can flip and jump), and the
 # chosen index must EQUAL the oracle's whenever the oracle's top-2 gap exceeds 2x the bound;
 # otherwise the chosen sample's oracle score must be within 2x the bound of the oracle's best.
-TC_SCORE_ATOL = 5e-2       # absolute, every configuration incl. H = 50
-TC_STATE_RTOL = 2e-3       # of the per-dimension state scale
+TC_SCORE_ATOL = 5e-2       # absolute, every configuration (largest measured: 3.3e-2, golden MountainCar)
+TC_SCORE_ATOL_BENCH = 1.5e-2   # configs 3 and 4 (measured max outside switch flips: 4.2e-3 / 4.3e-3 at p99.9)
+TC_STATE_RTOL = 2e-3       # of the per-dimension state scale (measured: <= 7e-4)
+
+
+def _state_scale(states, norm):
+    """Per-dimension scale of a trajectory error: the larger of the trajectories' magnitude and the
+    training-data spread of that dimension (a MountainCar velocity of 1e-4 is not a scale)."""
+    return np.maximum(np.abs(states).max(axis=(0, 1)), np.asarray(norm["std_x"], dtype=np.float64))
 
 
 def _score_close_abs(got, want, atol, max_outlier_frac=0.01):
@@ -305,7 +312,8 @@ def test_tc_config4_shard_properties(engine):
     np.testing.assert_allclose(ref["best_path"][0], start, rtol=0, atol=1e-6)
 
 
-def _assert_tc_matches_oracle(engine, start, acts, w, b, norm, plan, mode="reference"):
+def _assert_tc_matches_oracle(engine, start, acts, w, b, norm, plan, mode="reference", atol=TC_SCORE_ATOL_BENCH,
+                              max_outlier_frac=0.01):
     """Whole-batch comparison of the tcgen05 decision with the float64 oracle: every trajectory,
     every score (absolute bound, <= 1 % switch-boundary outliers), the arg-best, the returned
     sequence and path."""
@@ -313,10 +321,10 @@ def _assert_tc_matches_oracle(engine, start, acts, w, b, norm, plan, mode="refer
     states = engine.get_states()
     o = mpc_oracle.plan(start, acts, w, b, norm, plan["desired_states"], plan["distances_left"], plan["radii"],
                         0, .75, .5, penalty_mode=0 if mode == "reference" else 1)
-    scale = np.abs(o["states"]).max(axis=(0, 1))
+    scale = _state_scale(o["states"], norm)
     assert np.all(np.abs(states - o["states"]).max(axis=(0, 1)) <= TC_STATE_RTOL * scale)
-    _score_close_abs(res["scores"], o["scores"], TC_SCORE_ATOL)
-    _check_best_abs(res["best_k"], o["scores"], TC_SCORE_ATOL)
+    _score_close_abs(res["scores"], o["scores"], atol, max_outlier_frac)
+    _check_best_abs(res["best_k"], o["scores"], atol)
     assert res["best_k"] == int(np.argmax(res["scores"]))
     np.testing.assert_array_equal(res["best_sequence"], acts[res["best_k"]].astype(np.float32).astype(np.float64))
     np.testing.assert_allclose(res["best_path"], o["states"][:, res["best_k"]], rtol=0, atol=TC_STATE_RTOL * scale.max())
@@ -353,7 +361,9 @@ def test_tc_config4_shard_vs_oracle(engine):
     engine.set_plan(wl["plan"]["desired_states"], wl["plan"]["distances_left"], wl["plan"]["radii"])
     K, H, seed = bench.K_PER_GPU, bench.HORIZON, 1001
     acts = philox.sample_actions(K, H, 1, seed, wl["low"], wl["high"])
-    res, o = _assert_tc_matches_oracle(engine, wl["state"], acts, wl["w"], wl["b"], wl["norm"], wl["plan"])
+    # measured: 0.08 % of the 131072 scores off by more than 1e-2 (waypoint-switch flips, up to 0.37)
+    res, o = _assert_tc_matches_oracle(engine, wl["state"], acts, wl["w"], wl["b"], wl["norm"], wl["plan"],
+                                       max_outlier_frac=0.003)
     # the same decision with the samples drawn on the device (what the bench times) is bit-identical
     dev = engine.plan(wl["state"], 0, K=K, H=H, seed=seed, act_low=wl["low"], act_high=wl["high"],
                       penalty_mode="reference", precision="bf16_tc", want_scores=True)
