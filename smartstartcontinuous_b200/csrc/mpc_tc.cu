@@ -108,6 +108,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
         if (++spins > SPIN_LIMIT) asm volatile("trap;");   // never hang the GPU on a protocol bug
     }
 }
+// waits for TWO barriers whose try_waits are issued back to back (one round trip to the barrier unit
+// instead of two: a try_wait on an already completed phase still costs ~100 clk on the issuing thread)
+__device__ __forceinline__ void mbar_wait2(uint64_t* a, uint32_t pa, uint64_t* b, uint32_t pb) {
+    uint32_t done = 0;
+    int spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n.reg .pred p, q;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\nand.pred p, p, q;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(smem_u32(a)), "r"(pa), "r"(smem_u32(b)), "r"(pb)
+            : "memory");
+        if (done) break;
+        if (++spins > SPIN_LIMIT) asm volatile("trap;");
+    }
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
                      "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -292,6 +308,11 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
     unsigned long long* trace_s = reinterpret_cast<unsigned long long*>(smem + Smem::TRACE);
     if (p.prof && blockIdx.x == 0)
         for (int i = tid; i < 3 * 256; i += THREADS) trace_s[i] = 0;
+    unsigned long long trace_clk0 = 0, trace_ns0 = 0;
+    if (p.prof && blockIdx.x == 0 && tid == 0) {
+        trace_clk0 = (unsigned long long)clock64();
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace_ns0));
+    }
     const int nch = p.hp / NC;          // accumulator chunks per layer
     const int nslab = p.hp / KSLAB;     // W2 K-slabs (stages) per chunk
     static_assert(KSLAB % NC == 0, "a K-slab covers whole layer-1 chunks");
@@ -429,8 +450,11 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                 for (int c0 = 0; c0 < nch; c0 += 2) {          // one K-slab of layer 2 per iteration
                     const uint32_t slot_i = (uint32_t)(c0 >> 1);
                     uint32_t v0[32], v1[32], pk0[16], pk1[16];
-                    // even chunk: FP32 in the dead H1 columns, converted in place
-                    mbar_wait<false>(&l1_full[c0], step_it & 1);
+                    // even chunk: FP32 in the dead H1 columns, converted in place.  Only chunk 0 has a
+                    // completion barrier of its own (an mbarrier wait costs ~100 clk even when the phase
+                    // is long complete, and four of them sat on the per-step critical path); the other
+                    // chunks share l1_full[1].
+                    if (c0 == 0) mbar_wait<false>(&l1_full[0], step_it & 1);
                     TC_TRACE(tb + 2 + c0);
                     tc_fence_after();
                     tmem_ld32(lane_addr + COL_H1 + slot_i * NC + ch * CPT, v0);
@@ -445,12 +469,20 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                     tmem_st16(lane_addr + COL_H1 + c0 * (NC / 2) + ch * (CPT / 2), pk0);
                     tmem_st16(lane_addr + COL_H1 + c0 * (NC / 2) + ch * (CPT / 2) + 16, pk1);
                     TC_TRACE(tb + 6 + c0);
-                    // odd chunk: FP32 in accumulator slot c0 / 2 (its stores overlap the even chunk's)
-                    mbar_wait<false>(&l1_full[c0 + 1], step_it & 1);
+                    // odd chunk: FP32 in accumulator slot c0 / 2; its loads are in flight while the even
+                    // chunk's stores drain
+                    if (c0 == 0) {
+                        mbar_wait<false>(&l1_full[1], step_it & 1);
+                        tc_fence_after();
+                    }
                     TC_TRACE(tb + 3 + c0);
-                    tc_fence_after();
                     tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * CPT, v0);
                     tmem_ld32(lane_addr + COL_ACC + slot_i * NC + ch * CPT + 32, v1);
+                    // the even chunk is an A operand now: layer 2 may start on this K half right away
+                    tmem_wait_st();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&h1_ready[c0]);
                     tmem_wait_ld();
                     tc_fence_before();
                     __syncwarp();
@@ -465,7 +497,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                     tmem_wait_st();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) { mbar_arrive_leader(&h1_ready[c0]); mbar_arrive_leader(&h1_ready[c0 + 1]); }
+                    if (lane == 0) mbar_arrive_leader(&h1_ready[c0 + 1]);
                     TC_TRACE(tb + 7 + c0);
                 }
                 // ---- off the critical path (the tensor pipe is busy with layer 2 now) ----------
@@ -519,7 +551,8 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
 #pragma unroll
                 for (int j = 0; j < DZ; ++j) zx[(j * TPR + ch) * TM + row] = zacc[j].x + zacc[j].y;
                 TC_TRACE(tb + 62);
-                asm volatile("bar.sync 1, %0;" ::"n"(ROW_THREADS) : "memory");
+                // only the two warps that share these rows have to meet (warp q and q + 4)
+                asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
                 TC_TRACE(tb + 63);
 #pragma unroll
                 for (int j = 0; j < DZ; ++j) {
@@ -581,9 +614,14 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                     // accumulator slots (once the previous step's layer-2 epilogue drained them --
                     // long before x_ready, so these ~90-cycle waits are taken off the critical path),
                     // even chunks to the dead H1 columns -- all issued back to back
-#pragma unroll
-                    for (int sl = 0; sl < ACC_SLOTS; ++sl)
-                        if (l1_use[sl]) mbar_wait<true>(&acc_free[sl], ((step_it * use_per_step[sl]) & 1) ^ 1);
+                    // (all of these completed long before x_ready: polled together, off the critical path;
+                    // the first W2 stage of the step is taken here as well)
+                    if (l1_use[1])
+                        mbar_wait2(&acc_free[0], ((step_it * use_per_step[0]) & 1) ^ 1, &acc_free[1],
+                                   ((step_it * use_per_step[1]) & 1) ^ 1);
+                    else if (l1_use[0])
+                        mbar_wait<true>(&acc_free[0], ((step_it * use_per_step[0]) & 1) ^ 1);
+                    mbar_wait<true>(&w2_full[w2_it % NSTAGE], (w2_it / NSTAGE) & 1);
                     mbar_wait<true>(x_ready, step_it & 1);
                     TC_TRACE(20);
                     tc_fence_after();
@@ -593,7 +631,10 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                             if (c < nch) {
 #pragma unroll
                                 for (int ks = 0; ks < K1T / 16; ++ks) umma2_ss(l1_d[c], l1_a[ks], l1_b[c][ks], IDESC, ks);
-                                tc_commit_pair_addr(l1_bar[c]);
+                                // chunk 0 completes on its own barrier (the row warps start converting
+                                // it at once), all the others on l1_full[1]
+                                if (c == 0) tc_commit_pair_addr(l1_bar[0]);
+                                else if (c == nch - 1) tc_commit_pair_addr(l1_bar[1]);
                             }
                     }
                     __syncwarp();
@@ -603,26 +644,57 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
                         const uint32_t slot_i = (uint32_t)(n & 1);
                         const uint32_t free_k = slot_i ? step_it * use_per_step[1] + l1_use[1] + (uint32_t)(n >> 1)
                                                        : step_it * use_per_step[0] + l1_use[0] + (uint32_t)(n >> 1);
-                        mbar_wait<true>(&acc_free[slot_i], (free_k & 1) ^ 1);
+                        // accumulator slot drained by its previous user.  For n == 0 that user is layer-1
+                        // chunk 1: every row warp arrives here AFTER it arrived on h1_ready[0] (program
+                        // order, both release), so this one wait also covers "H1 chunk 0 is converted".
+                        // For n >= 1 the wait is polled together with the first W2 stage of the chunk.
+                        if (n == 0 || nslab < 1) mbar_wait<true>(&acc_free[slot_i], (free_k & 1) ^ 1);
+                        else mbar_wait2(&acc_free[slot_i], (free_k & 1) ^ 1, &w2_full[w2_it % NSTAGE], (w2_it / NSTAGE) & 1);
                         TC_TRACE(41 + n);
                         for (int ksl = 0; ksl < nslab; ++ksl, ++w2_it) {
                             const uint32_t st = w2_it % NSTAGE;
+                            const uint32_t d_tmem = tmem + COL_ACC + slot_i * NC;
+                            const uint32_t a_tmem = tmem + COL_H1 + ksl * (KSLAB / 2);
+                            const uint64_t b0 = make_desc(ring_addr + st * STAGE_BYTES, NH);
                             if (n == 0) {
+                                // first chunk of the step: the A operand is still being converted -- issue
+                                // each 128-wide K half as soon as ITS layer-1 chunk is ready.  The W2 stage of
+                                // K-slab 0 was taken before x_ready; later slabs poll it together with h1_ready.
+                                static_assert(CPS == 2, "two layer-1 chunks per K-slab");
+                                if (ksl > 0)
+                                    mbar_wait2(&w2_full[st], (w2_it / NSTAGE) & 1, &h1_ready[ksl * CPS], step_it & 1);
+                                else if (l1_use[0] == 0)
+                                    mbar_wait<true>(&h1_ready[0], step_it & 1);     // (no layer-1 chunk in slot 0)
+                                TC_TRACE(45 + 2 * ksl);
+                                tc_fence_after();
+                                if (elect_one()) {
 #pragma unroll
-                                for (int i = 0; i < CPS; ++i) mbar_wait<true>(&h1_ready[ksl * CPS + i], step_it & 1);
-                            }
-                            mbar_wait<true>(&w2_full[st], (w2_it / NSTAGE) & 1);    // both halves have landed
-                            tc_fence_after();
-                            if (elect_one()) {
-                                const uint32_t d_tmem = tmem + COL_ACC + slot_i * NC;
-                                const uint32_t a_tmem = tmem + COL_H1 + ksl * (KSLAB / 2);
-                                const uint64_t b0 = make_desc(ring_addr + st * STAGE_BYTES, NH);
+                                    for (int ks = 0; ks < KSLAB / 32; ++ks)
+                                        umma2_ts(d_tmem, a_tmem + ks * 8, b0 + (uint64_t)((ks * 2 * (NH * 16)) >> 4), IDESC,
+                                                 (ksl | ks) != 0);
+                                }
+                                __syncwarp();
+                                mbar_wait<true>(&h1_ready[ksl * CPS + 1], step_it & 1);
+                                TC_TRACE(46 + 2 * ksl);
+                                tc_fence_after();
+                                if (elect_one()) {
 #pragma unroll
-                                for (int ks = 0; ks < KSLAB / 16; ++ks)
-                                    umma2_ts(d_tmem, a_tmem + ks * 8, b0 + (uint64_t)((ks * 2 * (NH * 16)) >> 4), IDESC,
-                                             (ksl | ks) != 0);
-                                tc_commit_pair(&w2_empty[st]);
-                                if (ksl == nslab - 1) tc_commit_pair(&acc_full[slot_i]);
+                                    for (int ks = KSLAB / 32; ks < KSLAB / 16; ++ks)
+                                        umma2_ts(d_tmem, a_tmem + ks * 8, b0 + (uint64_t)((ks * 2 * (NH * 16)) >> 4), IDESC, 1u);
+                                    tc_commit_pair(&w2_empty[st]);
+                                    if (ksl == nslab - 1) tc_commit_pair(&acc_full[slot_i]);
+                                }
+                            } else {
+                                if (ksl > 0) mbar_wait<true>(&w2_full[st], (w2_it / NSTAGE) & 1);    // both halves have landed
+                                tc_fence_after();
+                                if (elect_one()) {
+#pragma unroll
+                                    for (int ks = 0; ks < KSLAB / 16; ++ks)
+                                        umma2_ts(d_tmem, a_tmem + ks * 8, b0 + (uint64_t)((ks * 2 * (NH * 16)) >> 4), IDESC,
+                                                 (ksl | ks) != 0);
+                                    tc_commit_pair(&w2_empty[st]);
+                                    if (ksl == nslab - 1) tc_commit_pair(&acc_full[slot_i]);
+                                }
                             }
                             __syncwarp();
                             TC_TRACE(25 + n * 4 + ksl);
@@ -667,8 +739,16 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
     __syncthreads();
     cluster_sync_all();                  // no CTA leaves while its peer may still read / signal it
     tc_fence_after();
-    if (p.prof && blockIdx.x == 0)
+    if (p.prof && blockIdx.x == 0) {
         for (int i = tid; i < 3 * 256; i += THREADS) p.prof[i] = trace_s[i];
+        if (tid == 0) {
+            // SM clock actually delivered over the kernel: cycles / globaltimer nanoseconds
+            unsigned long long ns1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+            p.prof[3 * 256] = (unsigned long long)clock64() - trace_clk0;
+            p.prof[3 * 256 + 1] = ns1 - trace_ns0;
+        }
+    }
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
 }
@@ -794,8 +874,8 @@ int mpc_tc_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out, long lo
     p.tile_end = tile_begin + tile_count;
     p.prof = nullptr;
     if (getenv("SS_TC_TRACE")) {
-        SS_CUDA_CHECK(c, c->tc_misc.ensure(3 * 256 * 8));
-        SS_CUDA_CHECK(c, cudaMemsetAsync(c->tc_misc.p, 0, 3 * 256 * 8, c->stream));
+        SS_CUDA_CHECK(c, c->tc_misc.ensure((3 * 256 + 2) * 8));
+        SS_CUDA_CHECK(c, cudaMemsetAsync(c->tc_misc.p, 0, (3 * 256 + 2) * 8, c->stream));
         p.prof = c->tc_misc.as<unsigned long long>();
     }
     const int grid = mpc_tc_grid(c, tile_count);
@@ -832,9 +912,11 @@ int mpc_tc_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out, long lo
     c->launches++;
     SS_CUDA_CHECK(c, e);
     if (p.prof) {
-        std::vector<unsigned long long> h(3 * 256);
+        std::vector<unsigned long long> h(3 * 256 + 2);
         SS_CUDA_CHECK(c, cudaMemcpyAsync(h.data(), p.prof, h.size() * 8, cudaMemcpyDeviceToHost, c->stream));
         SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        fprintf(stderr, "[trace] block 0: %llu clk in %llu ns = %.0f MHz delivered SM clock\n", h[3 * 256], h[3 * 256 + 1],
+                h[3 * 256 + 1] ? 1e3 * (double)h[3 * 256] / (double)h[3 * 256 + 1] : 0.0);
         for (int st2 = 0; st2 < 3; ++st2) {
             const unsigned long long* ev = &h[st2 * 256];
             const unsigned long long t0 = ev[0];
@@ -855,6 +937,8 @@ int mpc_tc_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out, long lo
             for (int c2 = 0; c2 < 16; ++c2) fprintf(stderr, " %llu", ev[25 + c2] - t0);
             fprintf(stderr, " | acc_free seen");
             for (int c2 = 0; c2 < 4; ++c2) fprintf(stderr, " %llu", ev[41 + c2] - t0);
+            fprintf(stderr, " | n=0: h1_ready chunk0 %llu chunk1 %llu chunk2 %llu chunk3 %llu", ev[45] - t0, ev[46] - t0,
+                    ev[47] - t0, ev[48] - t0);
             fprintf(stderr, "\n[trace step %d] ch1: L1 epi_done %llu | score_done %llu | L2 full", 10 + st2, ev[109] - t0, ev[119] - t0);
             for (int c2 = 0; c2 < 4; ++c2) fprintf(stderr, " %llu", ev[110 + c2] - t0);
             fprintf(stderr, " | L2 epi_done");
