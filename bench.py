@@ -250,6 +250,46 @@ def cpu_reference_kde_pool(kw, m, procs, reps):
     return float(np.mean(times))
 
 
+def dyn_train_workload(seed=0):
+    """Row f1: the training call of NND_MB_agent.train_dynamics_model at the BASELINE shapes --
+    25 x 333 random-policy Pendulum transitions as the initial data (NND_MB_agent.py:75-76), 3000
+    aggregated transitions, MLP 2x500, batch 512 (90 % new), lr 1e-3."""
+    from smartstartcontinuous_b200 import synthetic as syn
+    rng = np.random.default_rng(seed)
+    obs, act = syn.pendulum_rollouts(rng, 34, 333)
+    xs = np.concatenate([o[:-1] for o in obs]); ys = np.concatenate(list(act))
+    zs = np.concatenate([o[1:] - o[:-1] for o in obs])
+    st = dict(mean_x=xs.mean(0), std_x=xs.std(0), mean_y=ys.mean(0), std_y=ys.std(0), mean_z=zs.mean(0), std_z=zs.std(0))
+    X = np.concatenate([(xs - st["mean_x"]) / st["std_x"], (ys - st["mean_y"]) / st["std_y"]], axis=1)
+    Z = (zs - st["mean_z"]) / st["std_z"]
+    n_old = 25 * 333
+    w, b = syn.xavier_mlp(rng, 3, 1, 2, 500)
+    return dict(X_old=X[:n_old], Z_old=Z[:n_old], X_new=X[n_old:n_old + 2997], Z_new=Z[n_old:n_old + 2997], w=w, b=b,
+                norm=st, batch=512, frac=0.9, lr=1e-3, epochs=30)
+
+
+DYN_FLOP_PER_STEP = 2 * 512 * (4 * 500 + 500 * 500 + 500 * 3) * 3      # forward + two backward products per layer
+
+
+def cpu_dyn_train(cores):
+    """One Adam step of Dyn_Model.train on the CPU: float64 numpy restatement (oracle/dyn_train_oracle.py;
+    TensorFlow cannot run here), BLAS on all cores.  Returns ms per step over 20 steps."""
+    from oracle import dyn_train_oracle as dto
+    tw = dyn_train_workload()
+    w, b = [a.copy() for a in tw["w"]], [a.copy() for a in tw["b"]]
+    state = dto.AdamState(w, b)
+    np.random.seed(0)
+    io, inw = dto.epoch_batches(len(tw["X_old"]), len(tw["X_new"]), tw["batch"], tw["frac"])
+    dto.train_batches(w, b, state, tw["X_old"], tw["Z_old"], tw["X_new"], tw["Z_new"], io[:3], inw[:3], tw["lr"])
+    t0 = time.perf_counter()
+    dto.train_batches(w, b, state, tw["X_old"], tw["Z_old"], tw["X_new"], tw["Z_new"], io[3:23], inw[3:23], tw["lr"])
+    ms = 1e3 * (time.perf_counter() - t0) / 20
+    steps_per_training = tw["epochs"] * len(io)
+    return {"ms_per_adam_step": ms, "steps_per_training": steps_per_training, "training_s_scaled": ms * steps_per_training / 1e3,
+            "kind": "port (float64 numpy restatement of the TF graph + AdamOptimizer)", "cores": cores,
+            "sample": "20 Adam steps of batch 512 on the 2x500 network"}
+
+
 def pin_blas_threads():
     """All host cores for the BLAS behind numpy, whatever OMP_NUM_THREADS says (torch.distributed.run
     exports OMP_NUM_THREADS=1 to its workers).  Returns (controller to keep alive, threads in use)."""
@@ -298,6 +338,7 @@ def run_reference(args, guard):
         ts = [cp.decide(i) for i in range(3)]
         small[name] = {"ms_per_decision": 1e3 * float(np.mean(ts)), "rollout_steps_per_s": K * H / float(np.mean(ts)),
                        "K": K, "H": H, "mlp": "%dx%d" % (L, h), "kind": cp.kind, "cores": cores}
+    small["dyn_train"] = cpu_dyn_train(cores)
     procs = os.cpu_count() or 1
     m_pool = min(KDE_M, 256 * procs)
     reps = max(1, min(args.steps, 5))
@@ -663,6 +704,45 @@ def main():
     eng.set_model(wl["w"], wl["b"], wl["norm"])
     eng.set_plan(wl["plan"]["desired_states"], wl["plan"]["distances_left"], wl["plan"]["radii"])
 
+    # ---- row f1: dynamics-model training on the device (Dyn_Model.train, 30 epochs) -----------------
+    dyn = None
+    if rank == 0:
+        from smartstartcontinuous_b200.dynamics_model import Dyn_Model
+        tw = dyn_train_workload()
+        nm = tw["norm"]
+        model = Dyn_Model(4, 3, None, tw["lr"], tw["batch"], 2, 500, nm["mean_x"], nm["mean_y"], nm["mean_z"], nm["std_x"],
+                          nm["std_y"], nm["std_z"], "float64", False, engine=eng, seed=0)
+        model.set_weights(tw["w"], tw["b"])
+        eng.dyn_reset_optimizer()
+        np.random.seed(0)
+        model.train(tw["X_old"], tw["Z_old"], tw["X_new"], tw["Z_new"], 1, None, tw["frac"], save_results=False)   # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tr_loss, old_loss, new_loss = model.train(tw["X_old"], tw["Z_old"], tw["X_new"], tw["Z_new"], tw["epochs"], None,
+                                                  tw["frac"], save_results=False)
+        torch.cuda.synchronize()
+        train_s = time.perf_counter() - t0
+        from oracle import dyn_train_oracle as dto_
+        io, inw = dto_.epoch_batches(len(tw["X_old"]), len(tw["X_new"]), tw["batch"], tw["frac"])
+        eng.dyn_train_batches(io, inw, tw["lr"], want_losses=False)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        eng.dyn_train_batches(io, inw, tw["lr"], want_losses=False)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        step_ms = e0.elapsed_time(e1) / len(io)
+        fp32_peak = 148 * 128 * 2 * measured_peaks()["sm_max_mhz"] * 1e6 / 1e12
+        dyn = {"workload": "Dyn_Model.train: %d old + %d new rows, MLP 2x500, batch 512 (52 old + 460 new), %d epochs x %d "
+                           "Adam steps" % (len(tw["X_old"]), len(tw["X_new"]), tw["epochs"], len(io)),
+               "training_s": train_s, "adam_steps": tw["epochs"] * len(io), "ms_per_adam_step_wall": 1e3 * train_s / (tw["epochs"] * len(io)),
+               "ms_per_adam_step_device": step_ms, "final_training_loss": tr_loss, "old_loss": old_loss, "new_loss": new_loss,
+               "roofline": {"bound": "fp32 (FFMA)", "achieved": DYN_FLOP_PER_STEP / (step_ms * 1e-3) / 1e12,
+                            "peak": fp32_peak, "unit": "TFLOP/s", "frac": DYN_FLOP_PER_STEP / (step_ms * 1e-3) / 1e12 / fp32_peak,
+                            "note": "0.77 GFLOP per step in 9 launches: latency-bound, not throughput-bound"}}
+        eng.set_model(wl["w"], wl["b"], wl["norm"])
+        eng.set_plan(wl["plan"]["desired_states"], wl["plan"]["distances_left"], wl["plan"]["radii"])
+
     # ---- multi-GPU self-check: the sharded decision equals the unsharded one ----------------------
     multi = None
     if world > 1:
@@ -790,6 +870,7 @@ def main():
                              "traffic": NCU_TRAFFIC["kde_pairs_tc_kernel"],
                              "traffic_source": NCU_TRAFFIC_SOURCE}},
         "small_k": small,
+        "dyn_train": dyn,
     }
     if multi is not None:
         out["multi_gpu_check"] = multi
@@ -835,6 +916,8 @@ def main():
             out["kde"]["cpu_baseline"] = {k: r["kde"][k] for k in ("value", "unit", "cores", "kind", "sample", "single_core")}
             for name in small:
                 small[name]["cpu_baseline"] = r["small_k"].get(name)
+            if dyn is not None:
+                dyn["cpu_baseline"] = r["small_k"].get("dyn_train")
         except Exception as exc:                                     # never lose the GPU line
             out["cpu_baseline"] = {"value": None, "unit": "rollout-steps/s", "cores": 0, "kind": "port",
                                    "sample": "failed: %r" % (exc,)}

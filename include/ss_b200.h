@@ -205,6 +205,31 @@ int ss_mpc_sample_actions(ss_ctx* ctx, int64_t K_local, int64_t k_offset, int H,
 /* 1 when ss_mpc_set_model's shape can run on the tcgen05 kernel */
 int ss_mpc_tc_supported(ss_ctx* ctx);
 
+/* ---- dynamics-model training on the device ------------------------------
+ * Replaces Dyn_Model.train (dynamics_model.py:52-171) as NND_MB_agent.train_dynamics_model calls it
+ * (NND_MB_agent.py:437-480): mini-batch Adam (tf.train.AdamOptimizer defaults) on
+ * reduce_mean(square(z - f(x))) for the network set with ss_mpc_set_model.  Data sets, FP32 master
+ * parameters and Adam moments stay on the device across calls.
+ *   ss_dyn_set_data       which = 0: the initial ("old") data set, 1: the aggregated ("new") one;
+ *                         X [n, d + da] normalised inputs, Z [n, d] normalised state deltas
+ *   ss_dyn_train_batches  n_batches Adam steps; batch i = old rows idx_old[i*n_old ..] followed by
+ *                         new rows idx_new[i*n_new ..] (the reference's batching rule: the caller draws
+ *                         the indices with the reference's numpy calls); out_losses [n_batches] = the
+ *                         batch MSE before each update (what sess.run returns), nullable
+ *   ss_dyn_eval_loss      mean batch MSE over the consecutive full batches of a data set
+ *                         (old_loss / new_loss :139-166, run_validation :174-197)
+ *   ss_dyn_commit         re-pack the trained parameters for the rollout kernels on the device (no
+ *                         host round trip); ss_mpc_plan uses them from then on
+ *   ss_dyn_get_params     export as float64 [in, out] / [out] (checkpoints, tests)
+ *   ss_dyn_reset_optimizer  forget the Adam moments and step count */
+int ss_dyn_set_data(ss_ctx* ctx, int which, const double* X, const double* Z, int64_t n_rows);
+int ss_dyn_train_batches(ss_ctx* ctx, const int32_t* idx_old, const int32_t* idx_new, int n_batches, int n_old,
+                         int n_new, double lr, double* out_losses);
+int ss_dyn_eval_loss(ss_ctx* ctx, int which, int batchsize, double* out_mean_loss, int* out_batches);
+int ss_dyn_commit(ss_ctx* ctx);
+int ss_dyn_get_params(ss_ctx* ctx, double* const* out_weights, double* const* out_biases);
+int ss_dyn_reset_optimizer(ss_ctx* ctx);
+
 /* ---- critic value batch in front of the UCB --------------------------
  * V_j = critic(q_j, actor(q_j)) of the DDPG base agent (agent.get_state_value,
  * smartexplorationcontinuous.py:274 -> ddpg_editted.py:274-279; graph :106-131; networks

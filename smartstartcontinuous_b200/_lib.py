@@ -72,6 +72,13 @@ SIGNATURES = {
     "ss_peer_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "ss_peer_close": (C.c_int, [C.c_void_p]),
     "ss_peer_ready": (C.c_int, [C.c_void_p]),
+    "ss_dyn_set_data": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]),
+    "ss_dyn_train_batches": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double,
+                                       C.c_void_p]),
+    "ss_dyn_eval_loss": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _c_double_p, _c_int_p]),
+    "ss_dyn_commit": (C.c_int, [C.c_void_p]),
+    "ss_dyn_get_params": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "ss_dyn_reset_optimizer": (C.c_int, [C.c_void_p]),
     "ss_value_net_set": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ss_value_net_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "ss_mirror_write": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_void_p]),

@@ -62,7 +62,9 @@ extern "C" int ss_destroy(ss_ctx* c) {
                       &c->tc_misc, &c->plan_ds, &c->plan_dl, &c->mpc_actions64, &c->mpc_states,
                       &c->mpc_scores, &c->mpc_partial_sums, &c->mpc_sums, &c->mpc_block_best,
                       &c->mpc_result, &c->mpc_replay, &c->mpc_sampled, &c->mpc_package,
-                      &c->geom_in, &c->geom_rows, &c->geom_pairs, &c->mirror_s, &c->mirror_s2, &c->mirror_idx, &c->value_net_params};
+                      &c->geom_in, &c->geom_rows, &c->geom_pairs, &c->mirror_s, &c->mirror_s2, &c->mirror_idx, &c->value_net_params,
+                      &c->tc_b3, &c->dyn_params, &c->dyn_m, &c->dyn_v, &c->dyn_x[0], &c->dyn_x[1], &c->dyn_z[0], &c->dyn_z[1],
+                      &c->dyn_act, &c->dyn_scratch, &c->dyn_idx, &c->dyn_losses};
     for (DevBuf* b : bufs) b->release();
     for (auto& b : c->w32) b.release();
     for (auto& b : c->b32) b.release();

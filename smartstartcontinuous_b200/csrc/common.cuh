@@ -134,10 +134,19 @@ struct ss_ctx {
     std::vector<DevBuf> w32, b32;      // padded fp32 weights [in_pad][out_pad], biases [out_pad]
     MpcNorm norm;
     // tcgen05 images (built lazily by mpc_tc.cu)
-    DevBuf tc_w1, tc_w2, tc_w3, tc_misc;
+    DevBuf tc_w1, tc_w2, tc_w3, tc_misc, tc_b3;
     bool tc_ready = false;
     int tc_hp = 0;
     std::vector<std::vector<double>> hw, hb;   // host copies of the float64 parameters
+    // ---- dynamics-model training on the device (dyn_train.cu): FP32 master parameters, Adam moments,
+    // both training sets, per-batch activations
+    DevBuf dyn_params, dyn_m, dyn_v, dyn_x[2], dyn_z[2], dyn_act, dyn_scratch, dyn_idx, dyn_losses;
+    int64_t dyn_rows[2] = {0, 0};
+    long long dyn_t = 0;               // Adam step counter (persists across training calls like TF's slots)
+    bool dyn_adam_valid = false;       // moments / counter belong to the current model shape
+    bool dyn_params_valid = false;     // dyn_params mirrors (or is ahead of) the model
+    bool dyn_dirty = false;            // trained since the last ss_dyn_commit
+    bool host_params_stale = false;    // hw / hb are older than the device parameters
     // ---- MPC plan
     bool plan_set = false;
     int W = 0;

@@ -99,6 +99,12 @@ extern "C" int ss_mpc_set_model(ss_ctx* c, int d, int da, int num_fc_layers, int
         SS_FAIL(c, SS_EINVAL, "mpc: null model pointer");
     SS_CUDA_CHECK(c, cudaSetDevice(c->device));
     if (d != c->d) c->plan_set = false;   // a plan refers to the state dimension
+    // the trainer's master copy follows the host parameters again; the Adam moments outlive a weight
+    // assignment of the same shape (like the optimizer slots of the reference's TF graph)
+    if (d != c->d || da != c->da || num_fc_layers != c->L || depth != c->h) c->dyn_adam_valid = false;
+    c->dyn_params_valid = false;
+    c->dyn_dirty = false;
+    c->host_params_stale = false;
     c->d = d; c->da = da; c->L = num_fc_layers; c->h = depth;
     c->din_pad = round_up(d + da, 16);
     c->h_pad = round_up(depth, 16);

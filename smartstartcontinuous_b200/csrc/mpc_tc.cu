@@ -73,7 +73,7 @@ struct Params {
     const __nv_bfloat16* w1_img;        // [2 (cta)][HP/128][4][64][8]
     const __nv_bfloat16* w2_img;        // [HP/128 (n)][HP/128 (k-slab)][2 (cta)][16][64][8]
     const float* w3;                    // [HP/2 (unit pairs)][DZP][2]: packed for FFMA2
-    float b3[SS_MAX_D];
+    const float* b3;                    // [SS_MAX_D] output-layer bias (device memory: ss_dyn_commit rewrites it)
     int hp;                             // padded hidden width (multiple of 128)
     int din;
     long long tile_begin, tile_end;     // this launch rolls the tiles [tile_begin, tile_end) of the batch
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const Rollou
 #pragma unroll
         for (int j = 0; j < DZ; ++j) {
             upd_s[j] = j < a.d ? a.norm.std_z[j] : 0.f;
-            upd_c[j] = j < a.d ? fmaf(p.b3[j], a.norm.std_z[j], a.norm.mean_z[j]) : 0.f;
+            upd_c[j] = j < a.d ? fmaf(__ldg(p.b3 + j), a.norm.std_z[j], a.norm.mean_z[j]) : 0.f;
             asm volatile("" : "+f"(upd_s[j]), "+f"(upd_c[j]));
         }
         for (int it = 0; it < p.iters; ++it) {
@@ -837,6 +837,10 @@ int mpc_tc_prepare(ss_ctx* c) {
     SS_CUDA_CHECK(c, c->tc_w1.ensure(w1.size() * 2));
     SS_CUDA_CHECK(c, c->tc_w2.ensure(w2.size() * 2));
     SS_CUDA_CHECK(c, c->tc_w3.ensure(w3.size() * 4));
+    float b3[SS_MAX_D] = {};
+    for (int j = 0; j < d; ++j) b3[j] = (float)c->hb[2][j];
+    SS_CUDA_CHECK(c, c->tc_b3.ensure(SS_MAX_D * 4));
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(c->tc_b3.p, b3, SS_MAX_D * 4, cudaMemcpyHostToDevice, c->stream));
     SS_CUDA_CHECK(c, cudaMemcpyAsync(c->tc_w1.p, w1.data(), w1.size() * 2, cudaMemcpyHostToDevice, c->stream));
     SS_CUDA_CHECK(c, cudaMemcpyAsync(c->tc_w2.p, w2.data(), w2.size() * 2, cudaMemcpyHostToDevice, c->stream));
     SS_CUDA_CHECK(c, cudaMemcpyAsync(c->tc_w3.p, w3.data(), w3.size() * 4, cudaMemcpyHostToDevice, c->stream));
@@ -847,6 +851,16 @@ int mpc_tc_prepare(ss_ctx* c) {
 }
 
 int mpc_tc_tile_rows() { return tc::TM; }
+
+// geometry of the operand images for ss_dyn_commit (dyn_train.cu), which re-packs them on the device
+void mpc_tc_geometry(const ss_ctx* c, int* k1, int* dz, int* hp, int* NC_, int* NH_, int* KSLAB_, int* CLUSTER_,
+                     int* dzp) {
+    *k1 = tc::k1_slots(c->d, c->da);
+    *dz = tc::dz_of(c->d);
+    *hp = c->tc_hp;
+    *NC_ = tc::NC; *NH_ = tc::NH; *KSLAB_ = tc::KSLAB; *CLUSTER_ = tc::CLUSTER;
+    *dzp = tc::w3_pair_floats(tc::dz_of(c->d)) / 2;
+}
 
 int mpc_tc_grid(const ss_ctx* c, long long tiles) {
     // a multiple of the pair size; at most one CTA per SM (TMEM: 512 columns per CTA)
@@ -863,7 +877,7 @@ int mpc_tc_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out, long lo
     p.w1_img = c->tc_w1.as<__nv_bfloat16>();
     p.w2_img = c->tc_w2.as<__nv_bfloat16>();
     p.w3 = c->tc_w3.as<float>();
-    for (int j = 0; j < c->d; ++j) p.b3[j] = (float)c->hb[2][j];
+    p.b3 = c->tc_b3.as<float>();
     p.hp = c->tc_hp;
     p.din = c->d + c->da;
     const long long all_tiles = (a.K_local + TM - 1) / TM;

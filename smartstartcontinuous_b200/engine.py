@@ -321,6 +321,54 @@ class Engine:
             self._plan_set = False
         self._model_shape = (d, da, L, h)
 
+    # ------------------------------------------------------------------ dynamics-model training (row f1)
+    def dyn_set_data(self, which, X, Z):
+        """Upload a training set (which = 0: initial / "old", 1: aggregated / "new"): X [n, d + da]
+        normalised inputs, Z [n, d] normalised state deltas."""
+        X, Z = _f64(X), _f64(Z)
+        n = X.shape[0] if X.ndim == 2 else 0
+        if n and (X.ndim != 2 or Z.ndim != 2 or Z.shape[0] != n):
+            raise ValueError("X [n, d + da] and Z [n, d] expected")
+        self._check(self._lib.ss_dyn_set_data(self._h, int(which), _ptr(X) if n else None, _ptr(Z) if n else None, n))
+
+    def dyn_train_batches(self, idx_old, idx_new, lr, want_losses=True):
+        """Adam steps over explicit batches (row i of idx_old / idx_new = one batch); returns the
+        per-batch losses (before each update) or None."""
+        io = np.ascontiguousarray(idx_old, dtype=np.int32)
+        inw = np.ascontiguousarray(idx_new, dtype=np.int32)
+        nb = io.shape[0] if io.size else inw.shape[0]
+        n_old = io.shape[1] if io.size else 0
+        n_new = inw.shape[1] if inw.size else 0
+        losses = np.empty(nb) if want_losses else None
+        self._check(self._lib.ss_dyn_train_batches(self._h, _ptr(io) if io.size else None, _ptr(inw) if inw.size else None,
+                                                   int(nb), int(n_old), int(n_new), float(lr), _ptr(losses)))
+        return losses
+
+    def dyn_eval_loss(self, which, batchsize):
+        """(mean batch MSE over the consecutive full batches of data set `which`, number of batches)."""
+        out = C.c_double(0.0)
+        nb = C.c_int(0)
+        self._check(self._lib.ss_dyn_eval_loss(self._h, int(which), int(batchsize), C.byref(out), C.byref(nb)))
+        return float(out.value), int(nb.value)
+
+    def dyn_commit(self):
+        """Hand the trained parameters to the rollout kernels (device-side re-packing)."""
+        self._check(self._lib.ss_dyn_commit(self._h))
+
+    def dyn_reset_optimizer(self):
+        self._check(self._lib.ss_dyn_reset_optimizer(self._h))
+
+    def dyn_get_params(self):
+        """(weights, biases) of the model as float64 numpy ([in, out] / [out])."""
+        d, da, L, h = self._model_shape
+        sizes = [d + da] + [h] * L + [d]
+        ws = [np.empty((i, o)) for i, o in zip(sizes[:-1], sizes[1:])]
+        bs = [np.empty(o) for o in sizes[1:]]
+        wp = (C.c_void_p * len(ws))(*[w.ctypes.data for w in ws])
+        bp = (C.c_void_p * len(bs))(*[b.ctypes.data for b in bs])
+        self._check(self._lib.ss_dyn_get_params(self._h, wp, bp))
+        return ws, bs
+
     def tc_supported(self):
         return bool(self._lib.ss_mpc_tc_supported(self._h))
 
