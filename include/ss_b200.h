@@ -191,6 +191,10 @@ int ss_peer_init(ss_ctx* ctx, int rank, int world, void* out_ipc_handle_64_bytes
 int ss_peer_open(ss_ctx* ctx, const void* all_handles_world_x_64_bytes, int world);
 int ss_peer_close(ss_ctx* ctx);
 int ss_peer_ready(ss_ctx* ctx);
+/* merge of per-rank (value, global index) pairs over the same exchange: every rank gets the
+ * np.argmax-ordered winner (NaN first, then the larger value, then the lower index; index < 0 = this
+ * rank has nothing).  Used for the KDE query shards: (ucb, j) of smartexplorationcontinuous.py:280. */
+int ss_peer_argmax_merge(ss_ctx* ctx, double value, int64_t index, double* out_value, int64_t* out_index);
 /* roll out ONE sequence of the last ss_mpc_rollout batch again (the global winner) in FP32 and
  * return its actions [H, da] and predicted path [H+1, d] (NND_MB_agent.py:516-518) */
 int ss_mpc_replay(ss_ctx* ctx, int64_t k_global, double* out_sequence, double* out_path);

@@ -72,6 +72,7 @@ SIGNATURES = {
     "ss_peer_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "ss_peer_close": (C.c_int, [C.c_void_p]),
     "ss_peer_ready": (C.c_int, [C.c_void_p]),
+    "ss_peer_argmax_merge": (C.c_int, [C.c_void_p, C.c_double, C.c_int64, _c_double_p, _c_int64_p]),
     "ss_dyn_set_data": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64]),
     "ss_dyn_train_batches": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double,
                                        C.c_void_p]),

@@ -73,6 +73,7 @@ extern "C" int ss_destroy(ss_ctx* c) {
     ss_peer_close(c);
     c->mpc_package_local.release();
     if (c->host_pkg) cudaFreeHost(c->host_pkg);
+    if (c->host_kde) cudaFreeHost(c->host_kde);
     if (c->copy_ready) {
         for (int i = 0; i <= ss_ctx::MAX_COPY_CHUNKS; ++i) cudaEventDestroy(c->copy_ev[i]);
         cudaStreamDestroy(c->copy_stream);

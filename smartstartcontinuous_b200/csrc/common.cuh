@@ -109,6 +109,10 @@ struct ss_ctx {
     DevBuf kde_data64, kde_q64, kde_vals, kde_pts, kde_qw, kde_partial, kde_fit, kde_moments;
     DevBuf kde_density, kde_ucb, kde_block_best, kde_result;
     bool kde_tc_attr_set = false;
+    // mapped pinned host memory the finish kernel writes the selection result to (+ completion flag)
+    void* host_kde = nullptr;
+    void* host_kde_dev = nullptr;
+    unsigned long long host_kde_seq = 0;
     // ---- plan set-up geometry scratch (plan_geom.cu)
     DevBuf geom_in, geom_rows, geom_pairs;
     // ---- peer-memory exchange of the sharded planner (peer.cu)

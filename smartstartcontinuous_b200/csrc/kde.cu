@@ -29,6 +29,7 @@
 // Roofline: SFU (MUFU.EX2, 16 / clk / SM) and FP32 pipes, co-limited; see DESIGN.md.
 #include <cuda_bf16.h>
 
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
 
@@ -424,6 +425,16 @@ struct KdeResult {
     int pad;
 };
 
+// what a selection hands back to the host, written by the last block of kde_finish_kernel straight
+// into mapped pinned host memory (flag last, release at system scope): the call ends without a
+// device->host copy and without a stream synchronisation
+struct KdeHostOut {
+    unsigned long long flag;          // == seq of the call when the fields below are valid
+    double best_ucb;
+    long long best_j;
+    int status, max_norm2_bits;       // copies of KdeFit::status / max_norm2_bits
+};
+
 __global__ void __launch_bounds__(256)
 kde_finish_kernel(const float* __restrict__ partial, int n_slices, long long m, long long m_pad,
                   const double* __restrict__ data, long long n, int d,
@@ -431,7 +442,7 @@ kde_finish_kernel(const float* __restrict__ partial, int n_slices, long long m, 
                   const KdeFit* __restrict__ fit, double n_transitions, double volume, double alpha,
                   double beta, double* __restrict__ density, double* __restrict__ ucb_out,
                   double* __restrict__ block_v, long long* __restrict__ block_i,
-                  KdeResult* __restrict__ result) {
+                  KdeResult* __restrict__ result, KdeHostOut* __restrict__ host_out, unsigned long long seq) {
     __shared__ double s_v[32];
     __shared__ long long s_i[32];
     __shared__ int s_list[256];
@@ -522,6 +533,14 @@ kde_finish_kernel(const float* __restrict__ partial, int n_slices, long long m, 
             result->best_ucb = v;
             result->best_j = bi;
             result->blocks_done = 0;
+            if (host_out) {
+                host_out->best_ucb = v;
+                host_out->best_j = bi;
+                host_out->status = fit->status;
+                host_out->max_norm2_bits = fit->max_norm2_bits;
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&host_out->flag), "l"(seq) : "memory");
+            }
         }
     }
 }
@@ -690,18 +709,39 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
 
         double* bv = c->kde_block_best.as<double>();
         long long* bi = reinterpret_cast<long long*>(bv + fin_blocks);
+        if (!c->host_kde) {
+            SS_CUDA_CHECK(c, cudaHostAlloc(&c->host_kde, 4096, cudaHostAllocMapped));
+            std::memset(c->host_kde, 0, 4096);
+            SS_CUDA_CHECK(c, cudaHostGetDevicePointer(&c->host_kde_dev, c->host_kde, 0));
+        }
+        const unsigned long long seq = ++c->host_kde_seq;
         kde_finish_kernel<<<fin_blocks, 256, 0, c->stream>>>(
             c->kde_partial.as<float>(), n_slices, m, m_pad, data_dev, n, d, queries_dev, values_dev, fit,
-            (double)n_transitions, volume, alpha, beta, density_dev, ucb_dev, bv, bi, res);
+            (double)n_transitions, volume, alpha, beta, density_dev, ucb_dev, bv, bi, res,
+            reinterpret_cast<KdeHostOut*>(c->host_kde_dev), seq);
         c->launches++;
         SS_CUDA_CHECK(c, cudaGetLastError());
         timer_mark(c, "kde_finish");
 
+        // wait for the completion flag in mapped host memory (the stream is queried now and then so
+        // that a failed launch cannot hang the caller)
+        volatile KdeHostOut* ho = reinterpret_cast<volatile KdeHostOut*>(c->host_kde);
+        unsigned spins = 0;
+        while (ho->flag != seq) {
+            if ((++spins & 0x3fff) == 0) {
+                cudaError_t qe = cudaStreamQuery(c->stream);
+                if (qe != cudaSuccess && qe != cudaErrorNotReady) SS_CUDA_CHECK(c, qe);
+                if (qe == cudaSuccess && ho->flag != seq) {
+                    SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+                    if (ho->flag != seq) SS_FAIL(c, SS_ECUDA, "kde: the finish kernel ended without raising its flag");
+                }
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
         KdeResult hres;
-        int hstat[2] = {0, 0};     // fit->status, fit->max_norm2_bits (adjacent ints)
-        SS_CUDA_CHECK(c, cudaMemcpyAsync(&hres, res, sizeof(KdeResult), cudaMemcpyDeviceToHost, c->stream));
-        SS_CUDA_CHECK(c, cudaMemcpyAsync(hstat, &fit->status, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        hres.best_ucb = ho->best_ucb;
+        hres.best_j = ho->best_j;
+        int hstat[2] = {ho->status, ho->max_norm2_bits};
         if (hstat[0] != 0)
             SS_FAIL(c, SS_ESINGULAR, "kde: data covariance is not positive definite (singular matrix)");
         float max_norm2;

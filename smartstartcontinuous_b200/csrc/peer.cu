@@ -15,6 +15,7 @@
 // memory are followed by __threadfence_system() and a release-scope flag store; readers poll the
 // flag with acquire scope and read the payload past L1 (ld.global.cg).  A missing peer traps after
 // PEER_TIMEOUT_NS instead of hanging the GPU.
+#include <atomic>
 #include <cstring>
 
 #include "mpc_kernels.cuh"
@@ -131,7 +132,82 @@ mpc_package_exchange_kernel(const double* __restrict__ pkg_local, int n, double*
     for (int o = tid; o < n; o += blockDim.x) pkg_out[o] = __ldcg(src + o);
 }
 
+// ---- 3. (value, global index) pairs -> all peers -> np.argmax-ordered pick (KDE query shards) ---------
+// the pair travels as kernel arguments; the result lands in mapped pinned host memory with a flag
+struct PeerPickOut {
+    unsigned long long flag;
+    double value;
+    long long index;
+};
+__global__ void __launch_bounds__(32)
+peer_argmax_exchange_kernel(double value, long long index, PeerView pv, unsigned long long epoch,
+                            PeerPickOut* __restrict__ host_out, unsigned long long seq) {
+    const int tid = threadIdx.x;
+    const int par = (int)(epoch & 1);
+    if (tid < pv.world) {
+        double* dst = peer_slot(pv.base[tid], PEER_CH_PKG, par, pv.rank);
+        dst[0] = value;
+        dst[1] = (double)index;
+        __threadfence_system();
+        st_release_sys(peer_flag(pv.base[tid], PEER_CH_PKG, par, pv.rank), epoch);
+        peer_wait(pv.base[pv.rank], PEER_CH_PKG, par, tid, epoch);
+    }
+    __syncwarp();
+    if (tid == 0) {
+        double* mine = pv.base[pv.rank];
+        double bv = 0.0;
+        long long bk = -1;
+        for (int r = 0; r < pv.world; ++r) {
+            const double v = __ldcg(peer_slot(mine, PEER_CH_PKG, par, r));
+            const long long k = (long long)__ldcg(peer_slot(mine, PEER_CH_PKG, par, r) + 1);
+            if (argmax_better(v, k, bv, bk)) { bv = v; bk = k; }
+        }
+        host_out->value = bv;
+        host_out->index = bk;
+        __threadfence_system();
+        st_release_sys(&host_out->flag, seq);
+    }
+}
+
 }  // namespace
+
+// every rank contributes (value, global index; index < 0 = nothing); every rank gets the np.argmax-ordered
+// winner (NaN first, larger value, lower index).  Shares the package channel (same epoch sequence on every rank).
+extern "C" int ss_peer_argmax_merge(ss_ctx* c, double value, int64_t index, double* out_value, int64_t* out_index) {
+    if (!c) return SS_EINVAL;
+    if (!c->peer_ready) SS_FAIL(c, SS_ESTATE, "peer exchange: not open (ss_peer_init / ss_peer_open)");
+    if (!out_value || !out_index) SS_FAIL(c, SS_EINVAL, "peer exchange: null output");
+    SS_CUDA_CHECK(c, cudaSetDevice(c->device));
+    if (!c->host_kde) {
+        SS_CUDA_CHECK(c, cudaHostAlloc(&c->host_kde, 4096, cudaHostAllocMapped));
+        std::memset(c->host_kde, 0, 4096);
+        SS_CUDA_CHECK(c, cudaHostGetDevicePointer(&c->host_kde_dev, c->host_kde, 0));
+    }
+    // the pick result uses the second half of the mapped page (the first holds the KDE result)
+    PeerPickOut* dev_out = reinterpret_cast<PeerPickOut*>(reinterpret_cast<char*>(c->host_kde_dev) + 2048);
+    volatile PeerPickOut* ho = reinterpret_cast<volatile PeerPickOut*>(reinterpret_cast<char*>(c->host_kde) + 2048);
+    const unsigned long long seq = ++c->host_kde_seq;
+    c->peer_epoch[PEER_CH_PKG]++;
+    peer_argmax_exchange_kernel<<<1, 32, 0, c->stream>>>(value, (long long)index, c->peer_view, c->peer_epoch[PEER_CH_PKG],
+                                                         dev_out, seq);
+    c->launches++;
+    SS_CUDA_CHECK(c, cudaGetLastError());
+    unsigned spins = 0;
+    while (ho->flag != seq) {
+        if ((++spins & 0x3fff) == 0) {
+            cudaError_t qe = cudaStreamQuery(c->stream);
+            if (qe != cudaSuccess && qe != cudaErrorNotReady) SS_CUDA_CHECK(c, qe);
+            if (qe == cudaSuccess && ho->flag != seq) {
+                SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+                if (ho->flag != seq) SS_FAIL(c, SS_ECUDA, "peer exchange: the pick kernel ended without raising its flag");
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    *out_value = ho->value;
+    *out_index = (int64_t)ho->index;
+    return SS_OK;
+}
 
 int peer_allreduce_sums(ss_ctx* c, const double* partial, int blocks, int T, double* sums) {
     if (2 * T > 2048 || 2 * T > SS_PEER_SLOT_DOUBLES)

@@ -192,6 +192,11 @@ class ShardedSelector:
         dist = _dist()
         if self.world == 1:
             return j, ucb
+        if bool(getattr(self.engine, "peer_ready", False)):
+            # one small kernel over NVLink peer memory, result through mapped host memory: no NCCL
+            # call and no stream synchronisation
+            v, k = self.engine.peer_argmax_merge(ucb, j)
+            return k, v
         mine = torch.tensor([ucb, float(j)], dtype=torch.float64, device=self.device)
         gathered = torch.empty(2 * self.world, dtype=torch.float64, device=self.device)
         dist.all_gather_into_tensor(gathered, mine, group=self.group)

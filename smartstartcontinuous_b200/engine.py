@@ -140,6 +140,12 @@ class Engine:
     def peer_ready(self):
         return bool(self._lib.ss_peer_ready(self._h))
 
+    def peer_argmax_merge(self, value, index):
+        """np.argmax-ordered pick over every rank's (value, global index) through the peer exchange."""
+        v, k = C.c_double(0.0), C.c_int64(-1)
+        self._check(self._lib.ss_peer_argmax_merge(self._h, float(value), int(index), C.byref(v), C.byref(k)))
+        return float(v.value), int(k.value)
+
     def peer_close(self):
         self._check(self._lib.ss_peer_close(self._h))
 

@@ -59,6 +59,30 @@ def test_random_dims_vs_oracle(engine, d, n, m):
     _check_choice(best, oucb)
 
 
+@pytest.mark.parametrize("d,n,m,no_tc", [(24, 5000, 300, False), (32, 4000, 200, False), (3, 20001, 2049, True),
+                                         (8, 3000, 100, True)])
+def test_cuda_core_expanded_variant_vs_oracle(engine, monkeypatch, d, n, m, no_tc):
+    """kde_pairs_kernel<D, EXPANDED>: the pair kernel on the CUDA cores -- taken for 20 < d <= 32,
+    and for any d with SS_KDE_NO_TC=1 (the library reads the variable at every call)."""
+    if no_tc:
+        monkeypatch.setenv("SS_KDE_NO_TC", "1")
+    rng = np.random.default_rng(d * 77 + n)
+    A = rng.normal(size=(d, d)) / np.sqrt(d) + 2 * np.eye(d)
+    data = rng.normal(size=(n, d)) @ A + rng.normal(size=d) * 3
+    q = data[rng.choice(n, m, replace=False)] + 0.05 * rng.normal(size=(m, d))
+    vals = rng.normal(size=m).astype(np.float32)
+    best, _, dens, ucb = engine.select_start(data, q, vals, n - 1, 0.37, 1.0, 2.0, want_density=True, want_ucb=True)
+    assert dict(engine.last_timings()).get("kde_pairs") is not None
+    obest, odens, oucb = kde_oracle.select_start(data, q, vals, n - 1, 0.37, 1.0, 2.0)
+    np.testing.assert_allclose(dens, odens, rtol=RTOL)
+    _ucb_close(ucb, oucb, vals)
+    _check_choice(best, oucb)
+    if no_tc:
+        monkeypatch.delenv("SS_KDE_NO_TC")
+        _, _, dens_tc, _ = engine.select_start(data, q, vals, n - 1, 0.37, 1.0, 2.0, want_density=True)
+        np.testing.assert_allclose(dens_tc, dens, rtol=5e-5)       # tcgen05 and CUDA-core variants agree
+
+
 def test_far_queries_are_rescued_in_fp64(engine):
     """Queries far from every data point underflow the fp32 sum; the kernel recomputes them in
     fp64 exactly like scipy so the (huge) exploration bonus still ranks them correctly."""
@@ -130,9 +154,11 @@ def test_full_size_c2_properties(engine):
     vals = syn.critic_like_values(q)
     best, best_ucb, dens, ucb = engine.select_start(all_states, q, vals, 100_000, 1e-3, 1.0, 2.0,
                                                     want_density=True, want_ucb=True)
-    sub = rng.choice(16_384, 256, replace=False)
-    odens = kde_oracle.kde_density(all_states, q[sub])
-    np.testing.assert_allclose(dens[sub], odens, rtol=RTOL)
+    # the float64 oracle on ALL 16 384 queries (~15 s of numpy): densities, UCB and the choice
+    obest, odens, oucb = kde_oracle.select_start(all_states, q, vals, 100_000, 1e-3, 1.0, 2.0)
+    np.testing.assert_allclose(dens, odens, rtol=RTOL)
+    _ucb_close(ucb, oucb, vals)
+    _check_choice(best, oucb)
     assert best == int(np.argmax(ucb)) and best_ucb == ucb[best]
     perm = rng.permutation(len(all_states))
     best2, _, dens2, _ = engine.select_start(all_states[perm], q, vals, 100_000, 1e-3, 1.0, 2.0,
@@ -154,9 +180,14 @@ def test_full_size_c5_properties(engine):
     vals = syn.critic_like_values(q)
     best, best_ucb, dens, ucb = engine.select_start(all_states, q, vals, 1_000_000, 1e-3, 1.0, 2.0,
                                                     want_density=True, want_ucb=True)
-    sub = rng.choice(16_384, 64, replace=False)
-    odens = kde_oracle.kde_density(all_states, q[sub])
+    # the float64 oracle on a 1 536-query subset (~15 s of numpy at 1 M points); the selection among
+    # exactly those queries must be the oracle's
+    sub = np.sort(rng.choice(16_384, 1536, replace=False))
+    obest, odens, oucb = kde_oracle.select_start(all_states, q[sub], vals[sub], 1_000_000, 1e-3, 1.0, 2.0)
     np.testing.assert_allclose(dens[sub], odens, rtol=RTOL)
+    _ucb_close(ucb[sub], oucb, vals[sub])
+    best_sub, _, _, _ = engine.select_start(all_states, q[sub], vals[sub], 1_000_000, 1e-3, 1.0, 2.0)
+    _check_choice(best_sub, oucb)
     assert best == int(np.argmax(ucb)) and best_ucb == ucb[best]
     part = slice(5000, 5000 + 777)
     _, _, dens_part, _ = engine.select_start(all_states, q[part], vals[part], 1_000_000, 1e-3, 1.0, 2.0,
@@ -191,6 +222,12 @@ def test_device_mirror_selection_matches_host_path(engine):
             np.testing.assert_allclose(got[2], want[2], rtol=1e-5)      # same points, other summation order
             _ucb_close(got[3], want[3], vals)
             _check_choice(got[0], want[3])
+            # and directly against the float64 oracle on the buffer's contents
+            obest, odens, oucb = kde_oracle.select_start(rb.get_all_states(), rb.states_s2(idx), vals, len(rb), 0.5,
+                                                         1.0, 2.0)
+            np.testing.assert_allclose(got[2], odens, rtol=RTOL)
+            _ucb_close(got[3], oucb, vals)
+            _check_choice(got[0], oucb)
     assert added > 3000                                    # the ring did wrap
     rb._rebuild_mirror()                                   # new ring object: uploaded whole again
     ring = rb.state_ring()

@@ -553,6 +553,12 @@ def test_peer_exchange_kernels_single_rank(engine, prec):
         assert engine.peer_ready
         for (m, s), want in plain.items():
             np.testing.assert_array_equal(shard(m, s), want)
+        # the (value, index) merge of the KDE query shards over the same channel
+        assert engine.peer_argmax_merge(3.5, 17) == (3.5, 17)
+        v, k = engine.peer_argmax_merge(float("nan"), 4)
+        assert np.isnan(v) and k == 4
+        assert engine.peer_argmax_merge(0.0, -1)[1] == -1
+        np.testing.assert_array_equal(shard("reference", 2), plain[("reference", 2)])   # the channel's epochs stay in step
     finally:
         engine.peer_close()
     assert not engine.peer_ready
