@@ -20,6 +20,19 @@ if os.environ.get("SS_PROFILE_CFG") == "c3":
                      penalty_mode="reference", precision="bf16_tc")
     print("mpc c3", r["best_k"], r["best_score"], eng.last_timings())
     sys.exit(0)
+if os.environ.get("SS_PROFILE_CFG") == "dyn":
+    # row f1: a few Adam steps of the device trainer at the BASELINE shapes (2x500, batch 512)
+    from oracle import dyn_train_oracle as dto
+    tw = bench.dyn_train_workload()
+    eng.set_model(tw["w"], tw["b"], tw["norm"])
+    eng.dyn_set_data(0, tw["X_old"], tw["Z_old"])
+    eng.dyn_set_data(1, tw["X_new"], tw["Z_new"])
+    np.random.seed(0)
+    io, inw = dto.epoch_batches(len(tw["X_old"]), len(tw["X_new"]), tw["batch"], tw["frac"])
+    losses = eng.dyn_train_batches(io[:6], inw[:6], tw["lr"])
+    eng.dyn_commit()
+    print("dyn losses", losses)
+    sys.exit(0)
 wl = bench.make_workload()
 eng.set_model(wl["w"], wl["b"], wl["norm"])
 eng.set_plan(wl["plan"]["desired_states"], wl["plan"]["distances_left"], wl["plan"]["radii"])

@@ -89,7 +89,12 @@ dyn_first_layer_kernel(const float* __restrict__ x_old, const float* __restrict_
 // EPI 0: C = relu(acc + bias[j])                      (forward hidden layer)
 // EPI 1: C = acc * (mask[i][j] > 0)                   (dH = dY W^T (.) relu')
 // EPI 2: Adam on W[i][j] with gradient acc            (dW = H^T dY; C unused)
-constexpr int GT_M = 32, GT_N = 64, GT_P = 16, GT_THREADS = 256;
+#ifndef SS_DYN_GT_N
+#define SS_DYN_GT_N 32
+#endif
+constexpr int GT_M = 64, GT_N = SS_DYN_GT_N, GT_P = 16, GT_THREADS = 256;
+constexpr int GT_CN = GT_N / 16;           // output columns per thread (4 rows x GT_CN columns)
+constexpr int GT_BL = GT_P * GT_N / GT_THREADS;   // B-tile elements staged per thread
 struct GemmEpi {
     const float* bias;
     const float* mask;
@@ -99,61 +104,83 @@ struct GemmEpi {
     AdamArgs adam;
 };
 
+// 64 x GT_N output tile, 16-deep reduction steps, 256 threads with 4 x GT_CN register micro-tiles; both
+// operand tiles are stored reduction-major in shared memory ([p][i], [p][j]) so the inner loop reads
+// one float4 of A and one of B per 16 FFMA; the next step's global loads are issued into registers
+// before the current step's FMAs (software double buffering).
 template <int TA, int TB, int EPI>
 __global__ void __launch_bounds__(GT_THREADS)
 dyn_gemm_kernel(int M, int N, int P, const float* __restrict__ A, int lda, const float* __restrict__ Bm, int ldb,
                 float* __restrict__ C, int ldc, GemmEpi e) {
-    __shared__ float As[GT_P][GT_M + 4];
-    __shared__ float Bs[GT_P][GT_N + 4];
+    __shared__ __align__(16) float As[2][GT_P][GT_M + 4];
+    __shared__ __align__(16) float Bs[2][GT_P][GT_N + 4];
     const int tid = threadIdx.x;
     const int i0 = blockIdx.y * GT_M, j0 = blockIdx.x * GT_N;
-    // micro-tile: 2 rows x 4 columns per thread (16 x 16 threads)
-    const int ti = tid / 16, tj = tid % 16;
-    float acc[2][4] = {};
-    for (int p0 = 0; p0 < P; p0 += GT_P) {
-        // A tile: GT_M x GT_P = 512 elements, 2 per thread
+    const int ti = tid / 16, tj = tid % 16;          // rows ti*4.., columns tj*GT_CN..
+    // global -> register staging: 4 elements of A and GT_BL of B per thread and step
+    int a_i[4], a_p[4], b_j[GT_BL], b_p[GT_BL];
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const int o = tid + r * GT_THREADS;
-            int ii, pp;
-            if (TA == 0) { ii = o / GT_P; pp = o % GT_P; }      // p contiguous in memory
-            else { pp = o / GT_M; ii = o % GT_M; }              // i contiguous in memory
-            const int gi = i0 + ii, gp = p0 + pp;
-            float val = 0.f;
-            if (gi < M && gp < P) val = TA == 0 ? A[(size_t)gi * lda + gp] : A[(size_t)gp * lda + gi];
-            As[pp][ii] = val;
-        }
-        // B tile: GT_P x GT_N = 1024 elements, 4 per thread
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int o = tid + r * GT_THREADS;
-            int jj, pp;
-            if (TB == 0) { pp = o / GT_N; jj = o % GT_N; }      // j contiguous
-            else { jj = o / GT_P; pp = o % GT_P; }              // p contiguous
-            const int gj = j0 + jj, gp = p0 + pp;
-            float val = 0.f;
-            if (gj < N && gp < P) val = TB == 0 ? Bm[(size_t)gp * ldb + gj] : Bm[(size_t)gj * ldb + gp];
-            Bs[pp][jj] = val;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int pp = 0; pp < GT_P; ++pp) {
-            const float a0 = As[pp][ti * 2], a1 = As[pp][ti * 2 + 1];
-            const float4 bv = *reinterpret_cast<const float4*>(&Bs[pp][tj * 4]);
-            acc[0][0] = fmaf(a0, bv.x, acc[0][0]); acc[0][1] = fmaf(a0, bv.y, acc[0][1]);
-            acc[0][2] = fmaf(a0, bv.z, acc[0][2]); acc[0][3] = fmaf(a0, bv.w, acc[0][3]);
-            acc[1][0] = fmaf(a1, bv.x, acc[1][0]); acc[1][1] = fmaf(a1, bv.y, acc[1][1]);
-            acc[1][2] = fmaf(a1, bv.z, acc[1][2]); acc[1][3] = fmaf(a1, bv.w, acc[1][3]);
-        }
-        __syncthreads();
+    for (int r = 0; r < 4; ++r) {
+        const int o = tid + r * GT_THREADS;
+        if (TA == 0) { a_i[r] = o / GT_P; a_p[r] = o % GT_P; } else { a_p[r] = o / GT_M; a_i[r] = o % GT_M; }
     }
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int gi = i0 + ti * 2 + r;
+    for (int r = 0; r < GT_BL; ++r) {
+        const int o = tid + r * GT_THREADS;
+        if (TB == 0) { b_p[r] = o / GT_N; b_j[r] = o % GT_N; } else { b_j[r] = o / GT_P; b_p[r] = o % GT_P; }
+    }
+    float ra[4], rb[GT_BL];
+    auto fetch = [&](int p0) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int gi = i0 + a_i[r], gp = p0 + a_p[r];
+            ra[r] = (gi < M && gp < P) ? (TA == 0 ? __ldg(A + (size_t)gi * lda + gp) : __ldg(A + (size_t)gp * lda + gi)) : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < GT_BL; ++r) {
+            const int gj = j0 + b_j[r], gq = p0 + b_p[r];
+            rb[r] = (gj < N && gq < P) ? (TB == 0 ? __ldg(Bm + (size_t)gq * ldb + gj) : __ldg(Bm + (size_t)gj * ldb + gq)) : 0.f;
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) As[buf][a_p[r]][a_i[r]] = ra[r];
+#pragma unroll
+        for (int r = 0; r < GT_BL; ++r) Bs[buf][b_p[r]][b_j[r]] = rb[r];
+    };
+    float acc[4][GT_CN] = {};
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    int buf = 0;
+    for (int p0 = 0; p0 < P; p0 += GT_P) {
+        const bool more = p0 + GT_P < P;
+        if (more) fetch(p0 + GT_P);
+#pragma unroll
+        for (int pp = 0; pp < GT_P; ++pp) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[buf][pp][ti * 4]);
+            const float a4[4] = {av.x, av.y, av.z, av.w};
+            float b4[GT_CN];
+#pragma unroll
+            for (int cidx = 0; cidx < GT_CN; ++cidx) b4[cidx] = Bs[buf][pp][tj * GT_CN + cidx];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int cidx = 0; cidx < GT_CN; ++cidx) acc[r][cidx] = fmaf(a4[r], b4[cidx], acc[r][cidx]);
+        }
+        if (more) {
+            stash(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int gi = i0 + ti * 4 + r;
         if (gi >= M) continue;
 #pragma unroll
-        for (int cidx = 0; cidx < 4; ++cidx) {
-            const int gj = j0 + tj * 4 + cidx;
+        for (int cidx = 0; cidx < GT_CN; ++cidx) {
+            const int gj = j0 + tj * GT_CN + cidx;
             if (gj >= N) continue;
             const float a = acc[r][cidx];
             if (EPI == 0) {
