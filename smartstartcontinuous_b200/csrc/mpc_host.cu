@@ -344,24 +344,17 @@ extern "C" int ss_mpc_rollout(ss_ctx* c, const double* state, int wp_index, int6
             if (rc) return rc;
             red_src = folded;
         }
-        if (K_global != K_local) {
-            // a shard of a larger batch: the sums of ALL shards are needed before the penalties.  On a
-            // context with an open peer exchange the reduction kernel also all-reduces them over NVLink
-            // peer memory (no NCCL call, no host round trip); otherwise the caller all-reduces the
-            // buffer ss_mpc_projection_sums returns.
-            r.peer_sums = c->peer_ready;
-            rc = r.peer_sums ? peer_allreduce_sums(c, red_src, red_blocks, T, c->mpc_sums.as<double>())
-                             : mpc_reduce_sums(c, red_src, red_blocks, T, c->mpc_sums.as<double>());
-            if (rc) return rc;
-            r.sum_cols = c->mpc_sums.as<double>();
-            r.n_cols = 1;
-            r.sums_reduced = true;
-        } else {
-            // the whole batch is here: the fused tail kernel reduces the (<= 256) columns itself
-            r.peer_sums = false;
-            r.sum_cols = red_src;
-            r.n_cols = red_blocks;
-        }
+        // On a shard of a larger batch the sums of ALL shards are needed before the penalties: with an
+        // open peer exchange the reduction kernel also all-reduces them over NVLink peer memory (no
+        // NCCL call, no host round trip); otherwise the caller all-reduces the buffer
+        // ss_mpc_projection_sums returns.
+        r.peer_sums = c->peer_ready && K_global != K_local;
+        rc = r.peer_sums ? peer_allreduce_sums(c, red_src, red_blocks, T, c->mpc_sums.as<double>())
+                         : mpc_reduce_sums(c, red_src, red_blocks, T, c->mpc_sums.as<double>());
+        if (rc) return rc;
+        r.sum_cols = c->mpc_sums.as<double>();
+        r.n_cols = 1;
+        r.sums_reduced = true;
         r.sum_blocks = red_blocks;
         timer_mark(c, "mpc_sums_pass1");
     }

@@ -160,10 +160,10 @@ mpc_argmax_kernel(const float* __restrict__ scores, long long K, long long k_off
 
 // ---- the fused tail -------------------------------------------------------------------------
 // grid = ceil(K / 256) blocks of 256 threads, one sequence per thread.
-//   sum_cols != null (reference penalty): [2T][n_cols] partial columns of a'.b' / b'.b'; every block
-//     reduces them redundantly with the lane-stride + shuffle-tree order of mpc_reduce_sums_kernel (so
-//     the coefficients are bit-identical to the separate-kernel path and to every other block's), takes
-//     lambda_t and subtracts the penalties of its sequences from the progress term;
+//   sum_cols != null (reference penalty): the final per-step sums of a'.b' / b'.b' [2T]; every block
+//     takes lambda_t = sum a'.b' / sum b'.b' and subtracts the penalties of its sequences from the
+//     progress term (a per-block reduction of the partial columns was measured: 4-13 us of dependent
+//     loads in front of every block, more than the extra 3 us launch of mpc_reduce_sums);
 //   then the np.argmax-ordered block arg-max, and in the last block to finish (atomic ticket) the final
 //   arg-max and the winner's package.
 struct TailOut {
@@ -174,8 +174,44 @@ struct TailOut {
     float* scores_final;            // where the final scores go (== scores in place)
 };
 
+// the winner's package: [score, k (global), sequence (H*da), path (T*d)] -- kept out of line so that its
+// Philox / float64 code does not inflate the register count of the bandwidth-bound penalty loop
+__device__ __noinline__ void tail_write_package(double best_v, long long kl, long long k_offset, const float* rows,
+                                                long long K, int T, int d, const ActionSource* actp, int want_path,
+                                                TailOut out) {
+    const ActionSource& act = *actp;
+    const int tid = threadIdx.x;
+    const long long kg = kl < 0 ? -1 : kl + k_offset;
+    const int n_seq = act.H * act.da, n_path = T * d;
+    double* hp = out.host_pkg ? out.host_pkg + 2 : nullptr;
+    for (int o = tid; o < 2 + n_seq + n_path; o += blockDim.x) {
+        double val = 0.0;
+        if (o == 0) val = best_v;
+        else if (o == 1) val = (double)kg;
+        else if (want_path && kl >= 0) {
+            const int q = o - 2;
+            if (q < n_seq) val = (double)fetch_action(act, kl, kg, q / act.da, q % act.da);
+            else {
+                const int r = q - n_seq;
+                val = (double)__ldcg(rows + ((size_t)(r / d) * K + kl) * (d + 1) + (r % d));
+            }
+        }
+        out.pkg[o] = val;
+        if (hp) hp[o] = val;
+    }
+    if (out.host_pkg) {
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long*>(out.host_pkg)),
+                         "l"(out.seq)
+                         : "memory");
+        }
+    }
+}
+
 template <int DT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, DT <= 4 ? 3 : 2)
 mpc_tail_kernel(const PlanView Pg, const float* __restrict__ rows, long long K, int T, int ds_in_smem,
                 const double* __restrict__ sum_cols, int n_cols, float* __restrict__ scores, long long k_offset,
                 double* __restrict__ block_v, long long* __restrict__ block_i, MpcResult* __restrict__ result,
@@ -189,22 +225,9 @@ mpc_tail_kernel(const PlanView Pg, const float* __restrict__ rows, long long K, 
     PlanView P = Pg;
     const long long k = blockIdx.x * (long long)blockDim.x + tid;
     if (sum_cols) {
-        // the two sums of a step live in consecutive outputs 2t, 2t + 1: one warp per step takes both
-        for (int t = warp; t < T; t += 8) {
-            double s0 = 0.0, s1 = 0.0;
-            for (int b = lane; b < n_cols; b += 32) {
-                s0 += sum_cols[(size_t)(2 * t) * n_cols + b];
-                s1 += sum_cols[(size_t)(2 * t + 1) * n_cols + b];
-            }
-            for (int off = 16; off > 0; off >>= 1) {
-                s0 += __shfl_down_sync(0xffffffffu, s0, off);
-                s1 += __shfl_down_sync(0xffffffffu, s1, off);
-            }
-            if (lane == 0) {
-                s_lam[t] = (float)(s0 / s1);
-                if (out.sums_out && blockIdx.x == 0) { out.sums_out[2 * t] = s0; out.sums_out[2 * t + 1] = s1; }
-            }
-        }
+        // sum_cols = the final per-step sums [2T] (n_cols == 1; reduced -- and, on a sharded batch,
+        // all-reduced -- by the kernel in front of this one)
+        for (int t = tid; t < T; t += blockDim.x) s_lam[t] = (float)(sum_cols[2 * t] / sum_cols[2 * t + 1]);
         if (ds_in_smem) {
             float* s_ds = s_dyn + T;
             for (int i = tid; i < Pg.W * Pg.d; i += blockDim.x) s_ds[i] = Pg.ds[i];
@@ -217,12 +240,20 @@ mpc_tail_kernel(const PlanView Pg, const float* __restrict__ rows, long long K, 
     if (k < K) {
         float score = scores[k];
         if (sum_cols) {
-#pragma unroll 8
-            for (int t = 0; t < T; ++t) {
-                float x[DT];
-                int idx;
-                traj_load<DT>(rows, (size_t)t * K + k, P.d, x, idx);
-                score -= penalty_with_lambda<DT>(P, idx, x, s_lam[t]);
+            // the H + 1 trajectory rows of a sequence are independent loads: issue them eight at a time
+            // (a plain loop serialises one L2 / DRAM round trip per step, which is all a small batch does)
+            constexpr int TB = 8;
+            for (int t0 = 0; t0 < T; t0 += TB) {
+                float xs[TB][DT];
+                int idxs[TB];
+#pragma unroll
+                for (int i = 0; i < TB; ++i) {
+                    const int t = t0 + i < T ? t0 + i : T - 1;
+                    traj_load<DT>(rows, (size_t)t * K + k, P.d, xs[i], idxs[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < TB; ++i)
+                    if (t0 + i < T) score -= penalty_with_lambda<DT>(P, idxs[i], xs[i], s_lam[t0 + i]);
             }
             scores[k] = score;
         }
@@ -255,37 +286,7 @@ mpc_tail_kernel(const PlanView Pg, const float* __restrict__ rows, long long K, 
         result->blocks_done = 0;
     }
     __syncthreads();
-    // ---- the winner's package: [score, k (global), sequence (H*da), path (T*d)] ----------------------
-    const double best_v = s_v[0];
-    const long long kl = s_i[0];
-    const long long kg = kl < 0 ? -1 : kl + k_offset;
-    const int n_seq = act.H * act.da, n_path = T * Pg.d;
-    double* hp = out.host_pkg ? out.host_pkg + 2 : nullptr;
-    for (int o = tid; o < 2 + n_seq + n_path; o += blockDim.x) {
-        double val = 0.0;
-        if (o == 0) val = best_v;
-        else if (o == 1) val = (double)kg;
-        else if (want_path && kl >= 0) {
-            const int q = o - 2;
-            if (q < n_seq) val = (double)fetch_action(act, kl, kg, q / act.da, q % act.da);
-            else {
-                const int r = q - n_seq;
-                // the penalty pass of other blocks may have rewritten nothing here: rows are read-only
-                val = (double)__ldcg(rows + ((size_t)(r / Pg.d) * K + kl) * (Pg.d + 1) + (r % Pg.d));
-            }
-        }
-        out.pkg[o] = val;
-        if (hp) hp[o] = val;
-    }
-    if (out.host_pkg) {
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long*>(out.host_pkg)),
-                         "l"(out.seq)
-                         : "memory");
-        }
-    }
+    tail_write_package(s_v[0], s_i[0], k_offset, rows, K, T, Pg.d, &act, want_path, out);
 }
 
 }  // namespace
@@ -358,7 +359,12 @@ int mpc_argmax(ss_ctx* c, const float* scores, long long K_local, long long k_of
     return SS_OK;
 }
 
-int mpc_tail_blocks(long long K_local) { return (int)((K_local + 255) / 256); }
+// small batches: 64-thread blocks, four times as many of them (the pass is latency-bound there)
+static int mpc_tail_threads(long long K_local) { return K_local <= 16384 ? 64 : 256; }
+int mpc_tail_blocks(long long K_local) {
+    const int t = mpc_tail_threads(K_local);
+    return (int)((K_local + t - 1) / t);
+}
 
 // sum_cols may be null (per-sample penalty: the scores are final already); out_pkg / host_pkg as TailOut
 int mpc_tail(ss_ctx* c, const PlanView& plan, const float* rows, long long K_local, int T, const double* sum_cols,
@@ -366,6 +372,7 @@ int mpc_tail(ss_ctx* c, const PlanView& plan, const float* rows, long long K_loc
              const ActionSource& act, int want_path, double* pkg, double* host_pkg, unsigned long long seq,
              double* sums_out) {
     const unsigned grid = (unsigned)mpc_tail_blocks(K_local);
+    const unsigned threads = (unsigned)mpc_tail_threads(K_local);
     const size_t ds_bytes = (size_t)plan.W * plan.d * 4;
     const int in_smem = sum_cols && ds_bytes + (size_t)T * 4 <= 40 * 1024;
     const size_t smem = (size_t)T * sizeof(float) + (in_smem ? ds_bytes : 0);
@@ -373,13 +380,13 @@ int mpc_tail(ss_ctx* c, const PlanView& plan, const float* rows, long long K_loc
     out.pkg = pkg; out.host_pkg = host_pkg; out.seq = seq; out.sums_out = sums_out; out.scores_final = scores;
     MpcResult* res = reinterpret_cast<MpcResult*>(result_dev);
     if (plan.d <= 4)
-        mpc_tail_kernel<4><<<grid, 256, smem, c->stream>>>(plan, rows, K_local, T, in_smem, sum_cols, n_cols, scores,
+        mpc_tail_kernel<4><<<grid, threads, smem, c->stream>>>(plan, rows, K_local, T, in_smem, sum_cols, n_cols, scores,
                                                           k_offset, block_v, block_i, res, act, want_path, out);
     else if (plan.d <= 8)
-        mpc_tail_kernel<8><<<grid, 256, smem, c->stream>>>(plan, rows, K_local, T, in_smem, sum_cols, n_cols, scores,
+        mpc_tail_kernel<8><<<grid, threads, smem, c->stream>>>(plan, rows, K_local, T, in_smem, sum_cols, n_cols, scores,
                                                           k_offset, block_v, block_i, res, act, want_path, out);
     else
-        mpc_tail_kernel<SS_MAX_D><<<grid, 256, smem, c->stream>>>(plan, rows, K_local, T, in_smem, sum_cols, n_cols,
+        mpc_tail_kernel<SS_MAX_D><<<grid, threads, smem, c->stream>>>(plan, rows, K_local, T, in_smem, sum_cols, n_cols,
                                                                   scores, k_offset, block_v, block_i, res, act,
                                                                   want_path, out);
     c->launches++;
