@@ -746,6 +746,8 @@ def main():
     # ---- multi-GPU self-check: the sharded decision equals the unsharded one ----------------------
     multi = None
     if world > 1:
+        barrier()          # rank 0 comes from the training leg: nobody may spin in an exchange kernel waiting for it
+
         def same_decision(route):
             ok = True
             for mode in ("reference", "per_sample"):
