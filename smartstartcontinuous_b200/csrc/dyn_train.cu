@@ -14,11 +14,11 @@
 //
 //   first layer  gather the batch rows + Linear(din -> h) + ReLU              (K = din is tiny)
 //   hidden       H_{l+1} = relu(H_l W_l + b_l)                 tiled FP32 GEMM (NN)
-//   output+loss  out = H_L W_L + b_L; dOut = 2 (out - z) / (B dout); loss     (N = dout is tiny)
-//   backward     dH_L = dOut W_L^T (.) [H_L > 0];  dW_L, Adam
-//                per hidden layer: dH_l = dY_{l+1} W_l^T (.) [H_l > 0]  (NT GEMM, old W_l),
+//   output+loss  out = H_L W_L + b_L; dOut = 2 (out - z) / (B dout); loss; dH_L = dOut W_L^T (.) [H_L > 0]
+//   backward     per hidden layer: dH_l = dY_{l+1} W_l^T (.) [H_l > 0]  (NT GEMM, old W_l),
 //                                  dW_l = H_l^T dY_{l+1} + Adam           (TN GEMM, update fused)
-//                dW_0 = X^T dY_1 + Adam; all bias gradients (column sums) + Adam in one launch
+//   thin updates dW_L, dW_0 and all bias gradients (column sums) + Adam in one launch
+// (6 launches per step for the 2-hidden-layer network)
 //
 // No host synchronisation inside an epoch; the per-step losses come back in one copy.  After
 // training, ss_dyn_commit re-packs the parameters for the rollout kernels ON THE DEVICE (FP32
@@ -197,14 +197,17 @@ dyn_gemm_kernel(int M, int N, int P, const float* __restrict__ A, int lda, const
     }
 }
 
-// ---- output layer + loss --------------------------------------------------------------------
-// out[b][j] = H[b] . W[:, j] + bias[j]; dOut = 2 (out - z) / (B dout); loss = mean (out - z)^2
+// ---- output layer + loss (+ the first backward product) -----------------------------------------
+// out[b][j] = H[b] . W[:, j] + bias[j]; dOut = 2 (out - z) / (B dout); loss = mean (out - z)^2;
+// when training also dH[b][k] = (sum_j dOut[b][j] W[k][j]) * [H[b][k] > 0] (N = dout is tiny).
 // one warp per batch row; per-block partial loss -> last block (ticket) sums them in fixed order
 __global__ void __launch_bounds__(256)
 dyn_out_loss_kernel(const float* __restrict__ H, int h, const float* __restrict__ W, const float* __restrict__ bias,
-                    const float* __restrict__ Z, int B, int dout, float* __restrict__ dOut, double* __restrict__ partial,
-                    unsigned int* __restrict__ ticket, double* __restrict__ loss_out, int train) {
+                    const float* __restrict__ Z, int B, int dout, float* __restrict__ dOut, float* __restrict__ dH,
+                    double* __restrict__ partial, unsigned int* __restrict__ ticket, double* __restrict__ loss_out,
+                    int train) {
     __shared__ double s_part[8];
+    __shared__ float s_dout[8][SS_MAX_D];
     __shared__ bool s_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * 8 + warp;
@@ -218,8 +221,18 @@ dyn_out_loss_kernel(const float* __restrict__ H, int h, const float* __restrict_
             const float out = acc + bias[j];
             const float diff = out - Z[(size_t)b * dout + j];
             if (lane == 0) {
-                if (train) dOut[(size_t)b * dout + j] = 2.f * diff / (float)(B * dout);
+                const float g = 2.f * diff / (float)(B * dout);
+                if (train) dOut[(size_t)b * dout + j] = g;
+                s_dout[warp][j] = g;
                 sq += (double)diff * (double)diff;
+            }
+        }
+        if (train) {
+            __syncwarp();
+            for (int k = lane; k < h; k += 32) {
+                float acc = 0.f;
+                for (int j = 0; j < dout; ++j) acc = fmaf(s_dout[warp][j], W[(size_t)k * dout + j], acc);
+                dH[(size_t)b * h + k] = hb[k] > 0.f ? acc : 0.f;
             }
         }
     }
@@ -242,63 +255,43 @@ dyn_out_loss_kernel(const float* __restrict__ H, int h, const float* __restrict_
     }
 }
 
-// dH[b][k] = (sum_j dOut[b][j] W[k][j]) * [H[b][k] > 0]      (N = dout is tiny)
-__global__ void __launch_bounds__(256)
-dyn_back_out_kernel(const float* __restrict__ dOut, const float* __restrict__ W, const float* __restrict__ H, int B,
-                    int h, int dout, float* __restrict__ dH) {
-    const long long o = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (o >= (long long)B * h) return;
-    const int b = (int)(o / h), k = (int)(o % h);
-    float acc = 0.f;
-    for (int j = 0; j < dout; ++j) acc = fmaf(dOut[(size_t)b * dout + j], W[(size_t)k * dout + j], acc);
-    dH[o] = H[o] > 0.f ? acc : 0.f;
-}
-
-// dW[k][j] = sum_b A[b][k] dY[b][j] for a SMALL dimension on one side (first / last layer) + Adam.
-// one warp per (k, j): lanes stride over the batch, shuffle tree (fixed order)
-__global__ void __launch_bounds__(256)
-dyn_small_dw_adam_kernel(const float* __restrict__ A, int lda, const float* __restrict__ dY, int ldy, int B, int K,
-                         int N, float* __restrict__ W, float* __restrict__ Mo, float* __restrict__ Vo, AdamArgs adam) {
-    const long long wid = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (wid >= (long long)K * N) return;
-    const int k = (int)(wid / N), j = (int)(wid % N);
-    float acc = 0.f;
-    for (int b = lane; b < B; b += 32) acc = fmaf(A[(size_t)b * lda + k], dY[(size_t)b * ldy + j], acc);
-    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-    if (lane == 0) {
-        const size_t o = (size_t)k * N + j;
-        float w = W[o], m = Mo[o], v = Vo[o];
-        adam_update(acc, w, m, v, adam);
-        W[o] = w; Mo[o] = m; Vo[o] = v;
-    }
-}
-
-// all bias gradients of a step (column sums of the layers' dY) + Adam, one launch
-struct BiasJob {
-    const float* dY[DYN_MAX_LAYERS];
-    float* b[DYN_MAX_LAYERS];
-    float* m[DYN_MAX_LAYERS];
-    float* v[DYN_MAX_LAYERS];
-    int width[DYN_MAX_LAYERS];
-    int start[DYN_MAX_LAYERS + 1];     // prefix sums of width
-    int layers;
+// every "thin" parameter update of a step in ONE launch: the first and the last layer's matrices
+// (dW[k][j] = sum_b A[b][k] dY[b][j] with a tiny K or N) and all bias vectors (column sums of dY),
+// each followed by its Adam update.  One warp per parameter: lanes stride over the batch, shuffle
+// tree (fixed order).
+struct SmallSeg {
+    const float* A;      // [B][lda] activations, or null for a bias (A = 1)
+    const float* dY;     // [B][ldy]
+    float* w;
+    float* m;
+    float* v;
+    int lda, ldy, N;     // parameter o of the segment: k = o / N, j = o % N
+    int start;           // first warp of the segment
+};
+struct SmallJob {
+    SmallSeg seg[DYN_MAX_LAYERS + 3];
+    int n_seg, total;
 };
 __global__ void __launch_bounds__(256)
-dyn_bias_adam_kernel(BiasJob job, int B, AdamArgs adam) {
+dyn_small_updates_kernel(SmallJob job, int B, AdamArgs adam) {
     const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (wid >= job.start[job.layers]) return;
-    int l = 0;
-    while (wid >= job.start[l + 1]) ++l;
-    const int n = wid - job.start[l], width = job.width[l];
+    if (wid >= job.total) return;
+    int si = 0;
+    while (si + 1 < job.n_seg && wid >= job.seg[si + 1].start) ++si;
+    const SmallSeg& g = job.seg[si];
+    const int o = wid - g.start, k = o / g.N, j = o % g.N;
     float acc = 0.f;
-    for (int b = lane; b < B; b += 32) acc += job.dY[l][(size_t)b * width + n];
+    if (g.A) {
+        for (int b = lane; b < B; b += 32) acc = fmaf(g.A[(size_t)b * g.lda + k], g.dY[(size_t)b * g.ldy + j], acc);
+    } else {
+        for (int b = lane; b < B; b += 32) acc += g.dY[(size_t)b * g.ldy + j];
+    }
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
     if (lane == 0) {
-        float w = job.b[l][n], m = job.m[l][n], v = job.v[l][n];
+        float w = g.w[o], m = g.m[o], v = g.v[o];
         adam_update(acc, w, m, v, adam);
-        job.b[l][n] = w; job.m[l][n] = m; job.v[l][n] = v;
+        g.w[o] = w; g.m[o] = m; g.v[o] = v;
     }
 }
 
@@ -497,7 +490,8 @@ static int dyn_step(ss_ctx* c, const DynLayout& y, const int* idx_old, const int
         launch_gemm<0, 0, 0>(c, B, h, h, H + (size_t)(l - 1) * B * h, h, P + y.w_off[l], h, H + (size_t)l * B * h, h, e);
     }
     const float* HL = H + (size_t)(L - 1) * B * h;
-    dyn_out_loss_kernel<<<(B + 7) / 8, 256, 0, c->stream>>>(HL, h, P + y.w_off[L], P + y.b_off[L], Z, B, dout, dOut,
+    float* dHL = dH + (size_t)(L - 1) * B * h;
+    dyn_out_loss_kernel<<<(B + 7) / 8, 256, 0, c->stream>>>(HL, h, P + y.w_off[L], P + y.b_off[L], Z, B, dout, dOut, dHL,
                                                             partial, ticket, loss_out, train);
     c->launches++;
     if (!train) {
@@ -505,14 +499,7 @@ static int dyn_step(ss_ctx* c, const DynLayout& y, const int* idx_old, const int
         return SS_OK;
     }
     // ---- backward.  Every dH uses the weights of the forward pass: it is computed BEFORE the Adam
-    // update of the same layer's matrix.
-    float* dHL = dH + (size_t)(L - 1) * B * h;
-    dyn_back_out_kernel<<<(unsigned)(((long long)B * h + 255) / 256), 256, 0, c->stream>>>(dOut, P + y.w_off[L], HL, B, h,
-                                                                                         dout, dHL);
-    c->launches++;
-    dyn_small_dw_adam_kernel<<<(unsigned)(((long long)h * dout + 7) / 8), 256, 0, c->stream>>>(
-        HL, h, dOut, dout, B, h, dout, P + y.w_off[L], Mo + y.w_off[L], Vo + y.w_off[L], adam);
-    c->launches++;
+    // update of the same layer's matrix (dH_L came out of the loss kernel; W_L is updated last).
     for (int l = L - 1; l >= 1; --l) {
         // dH_l [B][h] = dH_{l+1} [B][h] W_l^T (W_l stored [in = h][out = h]) (.) [H_l > 0]
         e.mask = H + (size_t)(l - 1) * B * h;
@@ -521,22 +508,24 @@ static int dyn_step(ss_ctx* c, const DynLayout& y, const int* idx_old, const int
         e.w = P + y.w_off[l]; e.m = Mo + y.w_off[l]; e.v = Vo + y.w_off[l]; e.adam = adam;
         launch_gemm<1, 0, 2>(c, h, h, B, H + (size_t)(l - 1) * B * h, h, dH + (size_t)l * B * h, h, nullptr, h, e);
     }
-    dyn_small_dw_adam_kernel<<<(unsigned)(((long long)din * h + 7) / 8), 256, 0, c->stream>>>(
-        X, din, dH, h, B, din, h, P + y.w_off[0], Mo + y.w_off[0], Vo + y.w_off[0], adam);
-    c->launches++;
-    BiasJob job;
+    // first / last layer matrices and every bias vector: one launch
+    SmallJob job;
     std::memset(&job, 0, sizeof(job));
-    job.layers = L + 1;
-    int start = 0;
-    for (int l = 0; l <= L; ++l) {
-        job.dY[l] = l == L ? dOut : dH + (size_t)l * B * h;
-        job.b[l] = P + y.b_off[l]; job.m[l] = Mo + y.b_off[l]; job.v[l] = Vo + y.b_off[l];
-        job.width[l] = y.out[l];
-        job.start[l] = start;
-        start += y.out[l];
-    }
-    job.start[L + 1] = start;
-    dyn_bias_adam_kernel<<<(start + 7) / 8, 256, 0, c->stream>>>(job, B, adam);
+    int ns = 0, start = 0;
+    auto add_seg = [&](const float* A, int lda, const float* dY, int ldy, int K, int N, size_t off) {
+        SmallSeg& g = job.seg[ns++];
+        g.A = A; g.lda = lda; g.dY = dY; g.ldy = ldy; g.N = N;
+        g.w = P + off; g.m = Mo + off; g.v = Vo + off;
+        g.start = start;
+        start += K * N;
+    };
+    add_seg(HL, h, dOut, dout, h, dout, y.w_off[L]);                 // dW_L = H_L^T dOut
+    add_seg(X, din, dH, h, din, h, y.w_off[0]);                      // dW_0 = X^T dH_1
+    for (int l = 0; l <= L; ++l)                                     // db_l = column sums of dY_l
+        add_seg(nullptr, 0, l == L ? dOut : dH + (size_t)l * B * h, y.out[l], 1, y.out[l], y.b_off[l]);
+    job.n_seg = ns;
+    job.total = start;
+    dyn_small_updates_kernel<<<(start + 7) / 8, 256, 0, c->stream>>>(job, B, adam);
     c->launches++;
     SS_CUDA_CHECK(c, cudaGetLastError());
     return SS_OK;
