@@ -12,11 +12,13 @@ BASELINE.json's metric, KDE kernel-evals/s, is reported in the same line under "
             (= BASELINE config 4's K=1M / 8), H=50 -- at N=8 this is exactly config 4.
   value     K_total * H / device time, inputs resident (actions sampled on the device, Philox)
   e2e       the same decision through the drop-in plugin call NND_MB_agent.get_best_sim_actions
-            (NND_MB_agent.py:498-520) in its DEFAULT configuration: K*H*da float64 action samples
-            drawn on the host with numpy's legacy MT19937 stream exactly like :500-501 (inside the
-            timer), uploaded inside the call, winner package read back.  e2e_device_sampling is the
-            same call with device_sampling=True (Philox on the GPU), e2e_host_samples the C-ABI call
-            on pre-drawn pinned samples (no host RNG in the timer).
+            (NND_MB_agent.py:498-520) in its DEFAULT configuration: the K*H*da float64 samples of
+            npr.uniform (:500-501) come from numpy's global MT19937 stream, generated on the GPU from
+            np.random.get_state() bit for bit (csrc/mt19937.cu) and the advanced state set back; inputs
+            per call = the state + the generator key, outputs = winner package + key.  e2e_host_rng is
+            the same call with host_rng=True (samples drawn on the host inside the timer, uploaded),
+            e2e_device_sampling the call with device_sampling=True (Philox on the GPU), e2e_host_samples
+            the C-ABI call on pre-drawn pinned samples (52 MB H2D per step, no host RNG in the timer).
   kde       BASELINE config 2: 100 001 Pendulum states x 16 384 candidate queries per GPU; its e2e
             goes through SmartStartContinuous.get_smart_start_path (smartexplorationcontinuous.py:223-305)
   small_k   BASELINE configs 3 (MountainCar, K=4096, H=20, 2x500) and 1 (the example's shapes:
@@ -402,7 +404,7 @@ class _Env:
         self.action_space = _Box(low, high)
 
 
-def make_nav_agent(eng, wl, K, H, device_sampling, planner=None):
+def make_nav_agent(eng, wl, K, H, device_sampling, planner=None, host_rng=None):
     """The drop-in NND_MB_agent carrying the benchmark's network and plan (no environment: the
     constructor gets a tiny synthetic training set, the weights are set afterwards)."""
     from smartstartcontinuous_b200.nnd_mb_agent import NND_MB_agent
@@ -411,7 +413,8 @@ def make_nav_agent(eng, wl, K, H, device_sampling, planner=None):
     td = dict(dataX=rng.normal(size=(64, d)), dataY=rng.normal(size=(64, da)), dataZ=rng.normal(size=(64, d)))
     ag = NND_MB_agent(_Env(wl["low"], wl["high"]), None, horizon=H, num_control_samples=K, num_fc_layers=wl["L"],
                       depth_fc_layers=wl["h"], verbose=False, engine=eng, training_data=td,
-                      device_sampling=device_sampling, precision="auto", penalty_mode="reference", planner=planner)
+                      device_sampling=device_sampling, host_rng=host_rng, precision="auto", penalty_mode="reference",
+                      planner=planner)
     for k in ("mean_x", "std_x", "mean_y", "std_y", "mean_z", "std_z"):
         setattr(ag, k, np.asarray(wl["norm"][k], dtype=np.float64))
         setattr(ag.dyn_model, k, getattr(ag, k))
@@ -548,19 +551,36 @@ def main():
 
     # ---- e2e through the plugin call: NND_MB_agent.get_best_sim_actions -------------------------
     np.random.seed(1234)                      # identical on every rank (lock-step agents)
-    nav_host = make_nav_agent(eng, wl, K_total, HORIZON, device_sampling=False, planner=planner if world > 1 else None)
+    nav_default = make_nav_agent(eng, wl, K_total, HORIZON, device_sampling=False, planner=planner if world > 1 else None)
+    nav_host = make_nav_agent(eng, wl, K_total, HORIZON, device_sampling=False, host_rng=True,
+                              planner=planner if world > 1 else None)
     nav_dev = make_nav_agent(eng, wl, K_total, HORIZON, device_sampling=True, planner=planner if world > 1 else None)
-    rng_s = []
 
     def e2e_agent_step(i):
+        nav_default.get_best_sim_actions(wl["state"])
+
+    def e2e_agent_host_rng_step(i):
         nav_host.get_best_sim_actions(wl["state"])
 
     def e2e_agent_dev_step(i):
         nav_dev.get_best_sim_actions(wl["state"])
 
-    e2e_steps = max(3, min(half, 6))
-    e2e_ms = timed(e2e_agent_step, e2e_steps, 2) / e2e_steps
+    # the default call and the host_rng=True call make the same decision from the same generator state
+    st_check = np.random.get_state()
+    r_default = nav_default.get_best_sim_actions(wl["state"])
+    st_after = np.random.get_state()
+    np.random.set_state(st_check)
+    r_host = nav_host.get_best_sim_actions(wl["state"])
+    st_after_host = np.random.get_state()
+    mt_same = bool(r_default[1] == r_host[1] and np.array_equal(r_default[2], r_host[2]) and
+                   st_after[2] == st_after_host[2] and np.array_equal(st_after[1], st_after_host[1]))
+    if world > 1:
+        mt_same = None          # with host_rng a rank draws only its own K/world sequences: a different draw
+
+    e2e_ms = timed(e2e_agent_step, half, 3) / half
     e2e_value = K_total * HORIZON / (e2e_ms * 1e-3)
+    e2e_steps = max(3, min(half, 6))
+    e2e_host_rng_ms = timed(e2e_agent_host_rng_step, e2e_steps, 2) / e2e_steps
     t0 = time.perf_counter()
     for _ in range(3):
         np.random.random_sample((K_PER_GPU, HORIZON, 1))
@@ -664,6 +684,8 @@ def main():
         wls = make_workload_mountaincar(L, h)
         np.random.seed(4321)
         ag_host = make_nav_agent(eng, wls, K, H, device_sampling=False, planner=planner if world > 1 else None)
+        ag_hrng = make_nav_agent(eng, wls, K, H, device_sampling=False, host_rng=True,
+                                 planner=planner if world > 1 else None)
         ag_dev = make_nav_agent(eng, wls, K, H, device_sampling=True, planner=planner if world > 1 else None)
         prec_s = "bf16_tc" if eng.tc_supported() else "fp32"
         k_ms = []
@@ -680,6 +702,7 @@ def main():
         eng.set_timing(False)                                  # the lean path a latency-sensitive caller uses
         fast_ms = timed(resident, n_s, 3) / n_s
         host_ms = timed(lambda i: ag_host.get_best_sim_actions(wls["state"]), n_s, 3) / n_s
+        hrng_ms = timed(lambda i: ag_hrng.get_best_sim_actions(wls["state"]), n_s, 3) / n_s
         devs_ms = timed(lambda i: ag_dev.get_best_sim_actions(wls["state"]), n_s, 3) / n_s
         torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -698,6 +721,7 @@ def main():
             "decision_over_rollout_kernel": (fast_ms / kern) if kern else None,
             "rollout_steps_per_s_resident": K * H / (fast_ms * 1e-3),
             "ms_per_decision_agent_default": host_ms, "rollout_steps_per_s_agent_default": K * H / (host_ms * 1e-3),
+            "ms_per_decision_agent_host_rng": hrng_ms,
             "ms_per_decision_agent_device_sampling": devs_ms, "wall_ms_agent_device_sampling": wall_ms,
             "tensor_frac_of_burst_peak": (FLOP_PER_STEP[2] * K * H / (kern * 1e-3) / 1e12 / measured_peaks()["bf16_burst"])
             if (kern and prec_s == "bf16_tc") else None}
@@ -760,6 +784,19 @@ def main():
                 ok &= abs(sh["best_score"] - one["best_score"]) <= 1e-5 * max(1.0, abs(one["best_score"]))
                 ok &= bool(np.array_equal(sh["best_sequence"], one["best_sequence"]))
                 ok &= bool(np.allclose(sh["best_path"], one["best_path"], rtol=1e-5, atol=1e-6))
+            # numpy's MT19937 stream: every rank generates its slice of the one global draw on its GPU
+            rs = np.random.RandomState(99)
+            rs.random_sample(321)
+            st0 = rs.get_state()
+            kwm = dict(K=20000, H=12, act_low=wl["low"], act_high=wl["high"], penalty_mode="reference",
+                       precision=precision, rng_state=st0)
+            sh = planner.plan(wl["state"], 0, **kwm)
+            torch.cuda.synchronize()
+            one = eng.plan(wl["state"], 0, **kwm)
+            rs.uniform(wl["low"], wl["high"], (20000, 12, 1))
+            ok &= sh["best_k"] == one["best_k"] and bool(np.array_equal(sh["best_sequence"], one["best_sequence"]))
+            for res in (sh, one):
+                ok &= res["rng_state"][2] == rs.get_state()[2] and bool(np.array_equal(res["rng_state"][1], rs.get_state()[1]))
             return ok
 
         peer_was = eng.peer_ready
@@ -781,8 +818,9 @@ def main():
                  "sharded_equals_single_peer_memory": bool(flags[0].item() == 1.0) if peer_was else None,
                  "sharded_equals_single_nccl": bool(flags[1].item() == 1.0),
                  "kde_sharded_equals_single": bool(flags[2].item() == 1.0),
-                 "check": "K=20000, H=12, reference and per-sample penalty, %s: best_k and sequence identical, score "
-                          "within 1e-5 relative, path within 1e-5; KDE n=20000, m=4096: same index, ucb within 1e-9"
+                 "check": "K=20000, H=12, reference and per-sample penalty (Philox) and numpy's MT19937 stream with every "
+                          "rank generating its slice, %s: best_k and sequence identical, score "
+                          "within 1e-5 relative, path within 1e-5, generator state after the draw = numpy's; KDE n=20000, m=4096: same index, ucb within 1e-9"
                           % precision}
     clocks = sampler.stop() if rank == 0 else None
 
@@ -808,7 +846,7 @@ def main():
         "dtype": "bf16 (tcgen05, fp32 accumulate; first/last layer, state, scoring fp32)" if precision == "bf16_tc" else "f32",
         "data": "synthetic",
         "config": cfg,
-        "run": {"actions": "device Philox4x32-10 for `value`; host MT19937 (npr) for `e2e`",
+        "run": {"actions": "device Philox4x32-10 for `value`; numpy's MT19937 stream generated on the device for `e2e`",
                 "l2": "flushed between timed steps (256 MiB memset, outside the event-timed region)",
                 "collective": ("peer-memory" if eng.peer_ready else ("nccl" if world > 1 else "none")),
                 "parallelism": "K sharded over %d GPU(s); all-reduce of %d float64 + all-gather of the winner packages, %s"
@@ -817,12 +855,18 @@ def main():
                                   else ("NCCL" if world > 1 else "none at N=1"))},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "rollout-steps/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(n_act * 8 + 3 * 8), "d2h_bytes_per_step": pkg_bytes,
-                "host_rng_ms": rng_ms,
-                "path": "NND_MB_agent.get_best_sim_actions, default device_sampling=False: K*H float64 samples drawn on the "
-                        "host from numpy's legacy MT19937 stream (bit-identical to npr.uniform of NND_MB_agent.py:500-501, "
-                        "inside the timer: host_rng_ms of the step) -> ss_mpc_plan / ShardedPlanner with host buffers "
-                        "(H2D inside the call) -> D2H of the winner package"},
+                "h2d_bytes_per_step": int(3 * 8 + 624 * 4 + 8), "d2h_bytes_per_step": int(pkg_bytes + 624 * 4 + 8),
+                "same_decision_and_rng_state_as_host_draw": mt_same,
+                "path": "NND_MB_agent.get_best_sim_actions in its default configuration: the K*H*da samples of "
+                        "npr.uniform(low, high, (K, H, da)) (NND_MB_agent.py:500-501) are generated ON THE GPU from "
+                        "np.random.get_state() -- numpy's MT19937 stream bit for bit, polynomial jump-ahead over the SMs "
+                        "(csrc/mt19937.cu) -- and the advanced generator state is handed back with np.random.set_state; "
+                        "inputs per decision: the state and the 2.5 KB generator key; outputs: winner package + key"},
+        "e2e_host_rng": {"value": K_total * HORIZON / (e2e_host_rng_ms * 1e-3), "unit": "rollout-steps/s",
+                         "ms_per_step": e2e_host_rng_ms, "h2d_bytes_per_step": int(n_act * 8 + 3 * 8),
+                         "d2h_bytes_per_step": pkg_bytes, "host_rng_ms": rng_ms,
+                         "path": "the same call with host_rng=True: the samples drawn on the host from the same stream "
+                                 "(host_rng_ms of the step, inside the timer), uploaded inside the call"},
         "e2e_device_sampling": {"value": K_total * HORIZON / (e2e_dev_ms * 1e-3), "unit": "rollout-steps/s",
                                 "ms_per_step": e2e_dev_ms, "h2d_bytes_per_step": 24, "d2h_bytes_per_step": pkg_bytes,
                                 "path": "NND_MB_agent(device_sampling=True).get_best_sim_actions: state in, Philox on the "

@@ -80,6 +80,7 @@ void ss_host_free(void* p);
 void* ss_device_alloc(int64_t bytes);
 void ss_device_free(void* p);
 int ss_memcpy_h2d(ss_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes);
+int ss_memcpy_d2h(ss_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes);
 
 /* ---- stage 1: Gaussian KDE + UCB + argmax --------------------------------------------
  * Replaces smartexplorationcontinuous.py:260 (scipy.stats.gaussian_kde(all_states.T,
@@ -135,7 +136,8 @@ int ss_mpc_set_plan(ss_ctx* ctx, const double* desired_states, int W,
  *   K_local sequences are evaluated by this context; they are sequences
  *   [k_offset, k_offset + K_local) of a global batch of K_global (multi-GPU sharding;
  *   single GPU: k_offset = 0, K_global = K_local).
- *   actions             host [K_local, H, da] float64 action samples (parity mode), or NULL:
+ *   actions             [K_local, H, da] float64 action samples in host memory (uploaded) or in device
+ *                       memory (used in place, e.g. ss_mt19937_uniform's buffer), or NULL:
  *                       sampled on the device with Philox4x32-10(seed) indexed by the GLOBAL
  *                       sequence number, uniform in [act_low, act_high) like npr.uniform.
  *   out_best_k          GLOBAL index of the first maximum score on this shard
@@ -206,6 +208,29 @@ int ss_mpc_get_states(ss_ctx* ctx, double* out_states);
 int ss_mpc_sample_actions(ss_ctx* ctx, int64_t K_local, int64_t k_offset, int H, int da,
                           uint64_t seed, const double* act_low, const double* act_high,
                           double* out_actions);
+/* ---- numpy's legacy RandomState stream on the device ---------------------------------------
+ * The reference draws the action samples of every decision from numpy's global Mersenne Twister:
+ *     all_samples = npr.uniform(self.low, self.high, (self.N, self.horizon, da))   NND_MB_agent.py:500-501
+ * (element i = low[i % da] + (high - low)[i % da] * random_sample(), in C order).  ss_mt19937_uniform
+ * produces elements [first, first + count) of that draw of n_total doubles bit for bit on the GPU
+ * (MT19937 with polynomial jump-ahead, csrc/mt19937.cu) from the generator state
+ * np.random.get_state() returns -- key[624], pos (0..624) -- and leaves them in device memory:
+ * *out_dev is valid until the next ss_mt19937_uniform / host-sample ss_mpc_rollout on this context and
+ * can be passed as `actions` to ss_mpc_rollout / ss_mpc_plan (device pointers are rolled in place).
+ * A rank of a sharded batch passes its own [first, first + count) and gets the same numbers the
+ * single-process draw would have put there.  ss_mt19937_state returns the generator state AFTER the
+ * whole n_total draw (what np.random.set_state needs so that the host stream continues exactly as if
+ * the host had drawn); it waits for the kernel.  period = da. */
+int ss_mt19937_uniform(ss_ctx* ctx, const uint32_t* key, int pos, int64_t n_total, int64_t first,
+                       int64_t count, int period, const double* low, const double* high,
+                       double** out_dev);
+int ss_mt19937_state(ss_ctx* ctx, uint32_t* out_key, int* out_pos);
+/* host-only helpers behind the jump-ahead (no GPU work; used by the CPU tests): the coefficient words
+ * of x^J mod phi (624 x uint32, bit i of word w = x^(32 w + i)), and the exponents of phi, MT19937's
+ * characteristic polynomial (returns their number, 135). */
+int ss_mt19937_jump_poly(uint64_t J, uint32_t* out_words);
+int ss_mt19937_phi_exponents(int* out, int cap);
+
 /* 1 when ss_mpc_set_model's shape can run on the tcgen05 kernel */
 int ss_mpc_tc_supported(ss_ctx* ctx);
 

@@ -43,6 +43,7 @@ SIGNATURES = {
     "ss_device_alloc": (C.c_void_p, [C.c_int64]),
     "ss_device_free": (None, [C.c_void_p]),
     "ss_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "ss_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "ss_kde_ucb_argmax": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double,
                                     C.c_void_p, C.c_void_p, _c_int64_p, _c_double_p]),
@@ -68,6 +69,11 @@ SIGNATURES = {
     "ss_mpc_sample_actions": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_uint64,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),
     "ss_mpc_tc_supported": (C.c_int, [C.c_void_p]),
+    "ss_mt19937_uniform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "ss_mt19937_state": (C.c_int, [C.c_void_p, C.c_void_p, _c_int_p]),
+    "ss_mt19937_jump_poly": (C.c_int, [C.c_uint64, C.c_void_p]),
+    "ss_mt19937_phi_exponents": (C.c_int, [_c_int_p, C.c_int]),
     "ss_peer_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "ss_peer_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "ss_peer_close": (C.c_int, [C.c_void_p]),

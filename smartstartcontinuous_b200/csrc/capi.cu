@@ -9,6 +9,7 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
             double* out_best_ucb);
 
 int value_net_eval_dev(ss_ctx* c, const double* queries_dev, long long m, float* values_dev);
+void mt19937_release(ss_ctx* c);
 
 static std::string g_create_error;
 
@@ -72,6 +73,7 @@ extern "C" int ss_destroy(ss_ctx* c) {
         for (int i = 0; i <= SS_MAX_PHASES; ++i) cudaEventDestroy(c->timer.ev[i]);
     ss_peer_close(c);
     c->mpc_package_local.release();
+    mt19937_release(c);
     if (c->host_pkg) cudaFreeHost(c->host_pkg);
     if (c->host_kde) cudaFreeHost(c->host_kde);
     if (c->copy_ready) {
@@ -148,6 +150,14 @@ extern "C" int ss_memcpy_h2d(ss_ctx* c, void* dst, const void* src, int64_t byte
     if (!c) return SS_EINVAL;
     SS_CUDA_CHECK(c, cudaSetDevice(c->device));
     SS_CUDA_CHECK(c, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, c->stream));
+    SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return SS_OK;
+}
+
+extern "C" int ss_memcpy_d2h(ss_ctx* c, void* dst, const void* src, int64_t bytes) {
+    if (!c) return SS_EINVAL;
+    SS_CUDA_CHECK(c, cudaSetDevice(c->device));
+    SS_CUDA_CHECK(c, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
     SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     return SS_OK;
 }

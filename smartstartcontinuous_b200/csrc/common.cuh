@@ -186,6 +186,7 @@ struct ss_ctx {
     void* host_pkg = nullptr;
     void* host_pkg_dev = nullptr;
     unsigned long long host_pkg_seq = 0;
+    void* mt_cache = nullptr;          // MT19937 jump-ahead plans + state read-back buffer (mt19937.cu)
     bool timing = true;                // per-phase CUDA events (ss_last_timings); ss_set_timing(0) drops them
 };
 

@@ -236,7 +236,19 @@ extern "C" int ss_mpc_rollout(ss_ctx* c, const double* state, int wp_index, int6
     // no launch ends on a partial wave except the last one.
     int n_chunks = 0;
     long long chunk_tile[ss_ctx::MAX_COPY_CHUNKS + 1] = {0};
+    bool actions_on_device = false;
     if (actions) {
+        // samples already in device memory (ss_mt19937_uniform's buffer, or any device allocation of
+        // the caller's) are rolled in place
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, actions) == cudaSuccess && pa.type == cudaMemoryTypeDevice)
+            actions_on_device = true;
+        else
+            (void)cudaGetLastError();
+    }
+    if (actions_on_device) {
+        r.act.host_actions = actions;
+    } else if (actions) {
         const size_t n = (size_t)K_local * H * c->da;
         SS_CUDA_CHECK(c, c->mpc_actions64.ensure(n * 8));
         r.act.host_actions = c->mpc_actions64.as<double>();

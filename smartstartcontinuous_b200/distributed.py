@@ -114,9 +114,12 @@ class ShardedPlanner:
 
     def plan(self, state, wp_index, *, K, H, seed=0, act_low=None, act_high=None, actions=None,
              gamma=.75, horizontal_penalty_factor=.5, penalty_mode="reference", precision="auto",
-             want_path=True, local_actions=None):
+             want_path=True, local_actions=None, rng_state=None):
         """actions: the GLOBAL [K, H, da] host samples (every rank passes the same array), or
-        local_actions: this rank's own [K/world, H, da] slice, or neither (device Philox)."""
+        local_actions: this rank's own [K/world, H, da] slice, or rng_state: numpy's legacy generator
+        state (identical on every rank) -- each rank then generates its slice of the reference's
+        npr.uniform(low, high, (K, H, da)) draw on its GPU (MT19937 jump-ahead) and the result carries
+        the advanced state -- or none of them (device Philox)."""
         import torch
         dist = _dist()
         if K < self.world:
@@ -135,14 +138,14 @@ class ShardedPlanner:
             res = self.engine.plan(state, wp_index, actions=local_actions, K=K, H=H, seed=seed, act_low=act_low,
                                    act_high=act_high, gamma=gamma,
                                    horizontal_penalty_factor=horizontal_penalty_factor, penalty_mode=penalty_mode,
-                                   precision=precision, want_path=want_path)
+                                   precision=precision, want_path=want_path, rng_state=rng_state)
             res.update(owner=0, k_offset=0, k_local=k_local)
             return res
         self.engine.rollout(state, wp_index, actions=local_actions, K=k_local, H=H, seed=seed,
                             act_low=act_low, act_high=act_high, gamma=gamma,
                             horizontal_penalty_factor=horizontal_penalty_factor,
                             penalty_mode=penalty_mode, precision=precision, k_offset=k_offset,
-                            K_global=K)
+                            K_global=K, **({} if rng_state is None else dict(rng_state=rng_state)))
         # with an open peer exchange (Engine.peer_setup) both merges already happened inside the
         # kernels over NVLink peer memory; otherwise they are two small collectives
         peer = self.world > 1 and bool(getattr(self.engine, "peer_ready", False))
@@ -172,8 +175,11 @@ class ShardedPlanner:
         if want_path:
             seq = pk[row, 2:2 + H * da].reshape(H, da).copy()
             path = pk[row, 2 + H * da:2 + H * da + (H + 1) * d].reshape(H + 1, d).copy()
-        return dict(best_k=best_k, best_score=best_score, best_sequence=seq, best_path=path,
-                    owner=w, k_offset=k_offset, k_local=k_local)
+        res = dict(best_k=best_k, best_score=best_score, best_sequence=seq, best_path=path,
+                   owner=w, k_offset=k_offset, k_local=k_local)
+        if rng_state is not None:
+            res["rng_state"] = self.engine.mt19937_state()
+        return res
 
 
 class ShardedSelector:

@@ -30,8 +30,16 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+class _DevicePointer(int):
+    """A device address handed to the library in place of a host array."""
+
+
 def _ptr(a):
-    return None if a is None else a.ctypes.data_as(C.c_void_p)
+    if a is None:
+        return None
+    if isinstance(a, _DevicePointer):
+        return C.c_void_p(int(a))
+    return a.ctypes.data_as(C.c_void_p)
 
 
 class Engine:
@@ -393,7 +401,9 @@ class Engine:
         st = _f64(state).reshape(-1)
         if st.size != d:
             raise ValueError("state has %d entries, model expects %d" % (st.size, d))
-        if actions is not None:
+        if isinstance(actions, _DevicePointer):
+            pass                                   # [K, H, da] float64 already on the device
+        elif actions is not None:
             actions = _f64(actions)
             if actions.ndim != 3 or actions.shape[2] != da:
                 raise ValueError("actions must be [K, H, da]")
@@ -404,12 +414,22 @@ class Engine:
 
     def plan(self, state, wp_index, *, actions=None, K=None, H=None, seed=0, act_low=None,
              act_high=None, gamma=.75, horizontal_penalty_factor=.5, penalty_mode="reference",
-             precision="auto", want_scores=False, want_path=True, k_offset=0, K_global=None):
+             precision="auto", want_scores=False, want_path=True, k_offset=0, K_global=None, actions_dev=None,
+             rng_state=None):
         """One MPC decision on this GPU.  Returns dict(best_k, best_score, best_sequence [H,da],
-        best_path [H+1,d], scores [K] | None)."""
+        best_path [H+1,d], scores [K] | None).  actions_dev: device address of [K, H, da] float64
+        samples (mt19937_uniform) instead of a host array; K and H must then be given."""
         if self._model_shape is None:
             raise RuntimeError("set_model() first")
         d, da, _, _ = self._model_shape
+        if rng_state is not None:
+            # the reference's draw, npr.uniform(low, high, (K, H, da)) of NND_MB_agent.py:500-501, made on
+            # the device from the host generator's state; the advanced state comes back in the result
+            K_global = int(K) if K_global is None else int(K_global)
+            actions_dev = self.mt19937_uniform(rng_state, K_global * int(H) * da, act_low, act_high,
+                                               first=int(k_offset) * int(H) * da, count=int(K) * int(H) * da)
+        if actions_dev is not None:
+            actions = _DevicePointer(actions_dev)
         st, actions, K, H, lo, hi = self._plan_args(state, actions, K, H, act_low, act_high)
         K_global = K if K_global is None else int(K_global)
         scores = np.empty(K) if want_scores else None
@@ -423,13 +443,23 @@ class Engine:
             C.c_uint64(int(seed)), _ptr(lo), _ptr(hi), float(gamma),
             float(horizontal_penalty_factor), _PENALTY[penalty_mode], _PRECISION[precision],
             C.byref(best), C.byref(best_score), _ptr(seq), _ptr(path), _ptr(scores)))
-        return dict(best_k=int(best.value), best_score=float(best_score.value), best_sequence=seq,
-                    best_path=path, scores=scores)
+        res = dict(best_k=int(best.value), best_score=float(best_score.value), best_sequence=seq,
+                   best_path=path, scores=scores)
+        if rng_state is not None:
+            res["rng_state"] = self.mt19937_state()
+        return res
 
     # three-call form (multi-GPU reference penalty): rollout -> all-reduce sums -> finish
     def rollout(self, state, wp_index, *, actions=None, K=None, H=None, seed=0, act_low=None,
                 act_high=None, gamma=.75, horizontal_penalty_factor=.5, penalty_mode="reference",
-                precision="auto", k_offset=0, K_global=None):
+                precision="auto", k_offset=0, K_global=None, actions_dev=None, rng_state=None):
+        if rng_state is not None:
+            da = self._model_shape[1]
+            Kg = int(K) if K_global is None else int(K_global)
+            actions_dev = self.mt19937_uniform(rng_state, Kg * int(H) * da, act_low, act_high,
+                                               first=int(k_offset) * int(H) * da, count=int(K) * int(H) * da)
+        if actions_dev is not None:
+            actions = _DevicePointer(actions_dev)
         st, actions, K, H, lo, hi = self._plan_args(state, actions, K, H, act_low, act_high)
         K_global = K if K_global is None else int(K_global)
         self._check(self._lib.ss_mpc_rollout(
@@ -489,6 +519,37 @@ class Engine:
         path = np.empty((H + 1, d))
         self._check(self._lib.ss_mpc_replay(self._h, int(k_global), _ptr(seq), _ptr(path)))
         return seq, path
+
+    # numpy's legacy RandomState stream on the device (csrc/mt19937.cu)
+    def mt19937_uniform(self, rng_state, n_total, low, high, first=0, count=None):
+        """Elements [first, first + count) of what np.random.uniform(low, high, (n_total // da, da))
+        would draw from ``rng_state`` (np.random.get_state() / RandomState.get_state()), generated on
+        the GPU bit for bit and left there: returns the device pointer (pass it to plan / rollout as
+        ``actions_dev``).  The state after the whole draw comes from mt19937_state()."""
+        if rng_state[0] != "MT19937":
+            raise ValueError("legacy MT19937 state expected")
+        key = np.ascontiguousarray(rng_state[1], dtype=np.uint32)
+        lo = _f64(np.asarray(low, dtype=np.float64).reshape(-1))
+        hi = _f64(np.asarray(high, dtype=np.float64).reshape(-1))
+        count = int(n_total) - int(first) if count is None else int(count)
+        out = C.c_void_p()
+        self._check(self._lib.ss_mt19937_uniform(self._h, _ptr(key), int(rng_state[2]), int(n_total), int(first),
+                                                 count, lo.shape[0], _ptr(lo), _ptr(hi), C.byref(out)))
+        self._mt_rest = tuple(rng_state[3:])
+        return out.value
+
+    def mt19937_state(self):
+        """Generator state after the last mt19937_uniform draw, in np.random.set_state's format."""
+        key = np.empty(624, dtype=np.uint32)
+        pos = C.c_int(0)
+        self._check(self._lib.ss_mt19937_state(self._h, _ptr(key), C.byref(pos)))
+        return ("MT19937", key, int(pos.value)) + self._mt_rest
+
+    def read_device_doubles(self, dev_ptr, count):
+        """Copy ``count`` float64 from device memory (tests / debugging)."""
+        out = np.empty(int(count))
+        self._check(self._lib.ss_memcpy_d2h(self._h, _ptr(out), C.c_void_p(int(dev_ptr)), int(count) * 8))
+        return out
 
     def sample_actions(self, K, H, da, seed, act_low, act_high, k_offset=0):
         lo = _f64(np.broadcast_to(np.asarray(act_low, dtype=np.float64), (da,)))

@@ -15,12 +15,17 @@ Extra keyword-only options (all default to the reference behaviour):
   engine / device     share an Engine or create one on cuda:<device>
   penalty_mode        "reference" (global projection coefficient, Q1) | "per_sample"
   precision           "auto" | "fp32" | "bf16_tc"
-  device_sampling     False: actions from numpy.random.uniform exactly like :500-501;
-                      True: Philox on the GPU (no K*H*da host RNG + H2D copy)
+  device_sampling     False: the actions of numpy.random.uniform exactly like :500-501 -- the global
+                      MT19937 stream, generated on the GPU from np.random.get_state() and advanced with
+                      set_state (host_rng=True draws them on the host and uploads them instead, False
+                      always uses the GPU; the default None draws batches of up to HOST_DRAW_MAX samples
+                      on the host, where that is faster -- the numbers are the same either way);
+                      True: Philox on the GPU (a different, shard-invariant stream)
   planner             a distributed.ShardedPlanner: the K sequences of every decision are sharded
                       over the ranks of its torch.distributed group (all ranks run the agent in
-                      lock-step with identical numpy seeds; with host sampling every rank draws only
-                      its own K/world sequences)
+                      lock-step with identical numpy seeds; every rank generates its own slice of the
+                      one global draw, so the sharded decision equals the single-GPU one; with
+                      host_rng=True every rank draws only its own K/world sequences)
 """
 from __future__ import annotations
 
@@ -82,6 +87,7 @@ class NND_MB_agent(NavigationRLAgent):
     tf_datatype = "float64"
     noiseToSignal = 0.01
     actions_ag = 'nc'
+    HOST_DRAW_MAX = 32768       # K*H*da up to which the host draws the action samples itself (host_rng=None)
 
     def __init__(self, env, sess,
 
@@ -108,7 +114,8 @@ class NND_MB_agent(NavigationRLAgent):
                  steps_per_rollout_train=333, steps_per_rollout_val=333,
 
                  *, engine=None, device=0, penalty_mode="reference", precision="auto",
-                 device_sampling=False, training_data=None, model_root=None, seed=None, planner=None):
+                 device_sampling=False, host_rng=None, training_data=None, model_root=None, seed=None,
+                 planner=None):
         self.theta = 1            # distance function is scaled instead (NND_MB_agent.py:135-138)
         self.final_steps = final_steps
         self.gamma = gamma
@@ -143,6 +150,7 @@ class NND_MB_agent(NavigationRLAgent):
         self.penalty_mode = penalty_mode
         self.precision = precision
         self.device_sampling = device_sampling
+        self.host_rng = host_rng
         self.planner = planner
         self._plan_calls = 0
 
@@ -254,15 +262,27 @@ class NND_MB_agent(NavigationRLAgent):
             seed = int(npr.randint(0, 2 ** 31 - 1)) * 4099 + self._plan_calls
             res = plan(curr_nn_state, self.current_desired_state_index, K=self.N,
                        H=self.horizon, seed=seed, act_low=low, act_high=high, **common)
+        elif self.host_rng is False or (self.host_rng is None and self.N * self.horizon * da > self.HOST_DRAW_MAX):
+            # npr.uniform(low, high, (N, H, da)) of :500-501, bit for bit, but generated on the GPU from
+            # numpy's own generator state (MT19937 jump-ahead, csrc/mt19937.cu): the global stream
+            # advances exactly as if the host had drawn, no K*H*da host RNG and no upload.  A sharded
+            # planner generates each rank's slice of the SAME draw.
+            res = plan(curr_nn_state, self.current_desired_state_index, K=self.N, H=self.horizon,
+                       act_low=low, act_high=high, rng_state=npr.get_state(), **common)
+            npr.set_state(res["rng_state"])
         else:
-            # npr.uniform(low, high, (N, H, da)) of :500-501, bit for bit (legacy uniform =
-            # low + (high - low) * random_sample in draw order) without its slow broadcast path
-            all_samples = npr.random_sample((K_draw, self.horizon, da))
+            # the same draw on the host (legacy uniform = low + (high - low) * random_sample in draw
+            # order, without npr.uniform's slow broadcast path).  host_rng=True under a sharded planner:
+            # every rank draws only its own K/world sequences (a different, cheaper draw); the automatic
+            # choice for small batches draws the whole array so that the decision does not depend on it
+            local_only = self.planner is not None and self.host_rng is True
+            all_samples = npr.random_sample((K_draw if local_only else self.N, self.horizon, da))
             all_samples *= np.asarray(high, dtype=np.float64) - np.asarray(low, dtype=np.float64)
             all_samples += np.asarray(low, dtype=np.float64)
             if self.planner is not None:
+                key = "local_actions" if local_only else "actions"
                 res = plan(curr_nn_state, self.current_desired_state_index, K=self.N, H=self.horizon,
-                           local_actions=all_samples, **common)
+                           **{key: all_samples}, **common)
             else:
                 res = plan(curr_nn_state, self.current_desired_state_index, actions=all_samples, **common)
         best_sequence = res["best_sequence"]
