@@ -425,8 +425,26 @@ def make_nav_agent(eng, wl, K, H, device_sampling, planner=None, host_rng=None):
     return ag
 
 
+def ddpg_like_nets(d, seed=11):
+    """Actor / critic of the example's DDPG agent (models_editted.py:22-100: dense-relu 64, dense-relu 32,
+    dense; the action enters the critic's second layer), random weights, in Engine.set_value_net's format."""
+    rng = np.random.default_rng(seed)
+
+    def lin(i, o, scale=None):
+        sc = scale if scale is not None else 1.0 / np.sqrt(i)
+        return rng.uniform(-sc, sc, (i, o)).astype(np.float32), rng.uniform(-sc, sc, o).astype(np.float32)
+    return dict(actor=[lin(d, 64), lin(64, 32), lin(32, 1, 3e-3)], critic=[lin(d, 64), lin(64 + 1, 32), lin(32, 1, 3e-3)],
+                last_layer_tanh=True, obs_clip=(-5.0, 5.0))
+
+
 class _ValueBase:
-    """Base agent of the selection e2e: get_state_value like DDPG_Baselines_agent.py:197-204."""
+    """Base agent of the selection e2e: get_state_value like DDPG_Baselines_agent.py:197-204, i.e.
+    critic(obs, actor(obs)) of `net`, evaluated on the host in float32 numpy (the stand-in for the
+    user's TensorFlow session; its time is reported as host_value_fn_ms)."""
+
+    def __init__(self, net):
+        self.net = net
+        self.seconds = 0.0
 
     def get_action(self, s): return np.zeros(1)
     def observe(self, *a): pass
@@ -435,21 +453,30 @@ class _ValueBase:
     def get_param_dict(self): return {}
 
     def get_state_value(self, states):
-        from smartstartcontinuous_b200 import synthetic as syn
-        return syn.critic_like_values(np.asarray(states)).reshape(-1, 1)
+        t0 = time.perf_counter()
+        x = np.clip(np.asarray(states, dtype=np.float32), *self.net["obs_clip"])
+        (aw1, ab1), (aw2, ab2), (aw3, ab3) = self.net["actor"]
+        (cw1, cb1), (cw2, cb2), (cw3, cb3) = self.net["critic"]
+        a = np.tanh(np.maximum(np.maximum(x @ aw1 + ab1, 0) @ aw2 + ab2, 0) @ aw3 + ab3)
+        h = np.maximum(x @ cw1 + cb1, 0)
+        v = np.maximum(np.concatenate([h, a], axis=1) @ cw2 + cb2, 0) @ cw3 + cb3
+        self.seconds += time.perf_counter() - t0
+        return v.reshape(-1, 1)
 
 
-def make_smart_start(eng, kw, n_ss):
+def make_smart_start(eng, kw, n_ss, device_values=False):
     """SmartStartContinuous over a replay buffer filled (through its own add / start_new_episode API)
-    with the KDE workload's transitions."""
+    with the KDE workload's transitions.  device_values: the base agent's nets are handed over as
+    value_net (row f4), so the candidates' values are computed on the device."""
     from smartstartcontinuous_b200.smart_start import SmartStartContinuous
     d = kw["all_states"].shape[1]
     rng = np.random.default_rng(0)
     td = dict(dataX=rng.normal(size=(64, d)), dataY=rng.normal(size=(64, 1)), dataZ=rng.normal(size=(64, d)))
     n = kw["n"]
-    ss = SmartStartContinuous(_ValueBase(), _Env([-2.0], [2.0]), None, buffer_size=n, n_ss=n_ss, print_ss_stuff=False,
+    net = ddpg_like_nets(d)
+    ss = SmartStartContinuous(_ValueBase(net), _Env([-2.0], [2.0]), None, buffer_size=n, n_ss=n_ss, print_ss_stuff=False,
                               nnd_mb_num_fc_layers=1, nnd_mb_depth_fc_layers=32, nnd_mb_verbose=False, engine=eng,
-                              nnd_mb_extra=dict(training_data=td))
+                              nnd_mb_extra=dict(training_data=td), value_net=net if device_values else None)
     rb = ss.replay_buffer
     s_all = kw["all_states"]
     a0 = np.zeros(1)
@@ -639,6 +666,14 @@ def main():
         ss.get_smart_start_path()
 
     kde_agent_ms = timed(kde_agent_step, half, 2) / half
+    ss.agent.seconds = 0.0
+    for _ in range(3):
+        ss.get_smart_start_path()
+    kde_value_fn_ms = 1e3 * ss.agent.seconds / 3
+    ss_dev = make_smart_start(eng, kw, KDE_M, device_values=True)
+    kde_agent_dev_ms = timed(lambda i: ss_dev.get_smart_start_path(), half, 2) / half
+    eng.set_value_net(None)
+    del ss_dev
     ss2k = make_smart_start(eng, kde_workload(seed=2, n=KDE_N, m=C1_NSS), C1_NSS)
     d2k = kde_workload(seed=2, n=KDE_N, m=C1_NSS)
     t_data = torch.as_tensor(d2k["all_states"], device=dev)
@@ -895,9 +930,18 @@ def main():
                                        % (KDE_N + 1, KDE_M)},
                 "e2e": {"value": evals / (kde_agent_ms * 1e-3), "unit": "kernel-evals/s", "ms_per_step": kde_agent_ms,
                         "h2d_bytes_per_step": int(12 * KDE_M), "d2h_bytes_per_step": 16,
+                        "host_value_fn_ms": kde_value_fn_ms,
                         "path": "SmartStartContinuous.get_smart_start_path (smartexplorationcontinuous.py:223-305): "
-                                "random.sample of the candidates, host value function, selection from the device mirror "
+                                "random.sample of the candidates (the interpreter's stream, drawn in C++: "
+                                "csrc/py_random.cu), the base agent's get_state_value on the host (host_value_fn_ms, a "
+                                "numpy stand-in for the user's TF critic), selection from the device mirror "
                                 "of the replay buffer (row indices + values uploaded), episodic path extraction"},
+                "e2e_device_values": {"value": evals / (kde_agent_dev_ms * 1e-3), "unit": "kernel-evals/s",
+                                      "ms_per_step": kde_agent_dev_ms, "h2d_bytes_per_step": int(8 * KDE_M),
+                                      "d2h_bytes_per_step": 16,
+                                      "path": "the same call with value_net= the agent's actor / critic parameters: "
+                                              "V = critic(q, actor(q)) evaluated on the device in front of the UCB "
+                                              "(row f4), only the candidate row indices are uploaded"},
                 "e2e_full_upload": {"value": evals / (kde_e2e_ms * 1e-3), "unit": "kernel-evals/s", "ms_per_step": kde_e2e_ms,
                                     "h2d_bytes_per_step": int(8 * 3 * (KDE_N + 1 + KDE_M) + 4 * KDE_M), "d2h_bytes_per_step": 16,
                                     "path": "ss_kde_ucb_argmax with host float64 buffers (whole data set uploaded)"},

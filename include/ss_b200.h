@@ -231,6 +231,13 @@ int ss_mt19937_state(ss_ctx* ctx, uint32_t* out_key, int* out_pos);
 int ss_mt19937_jump_poly(uint64_t J, uint32_t* out_words);
 int ss_mt19937_phi_exponents(int* out, int cap);
 
+/* CPython's random.sample(range(first, first + n), k) in C++ on the generator state random.getstate()
+ * exposes (mt_state[624], *mt_index = the 625th entry): replaces the candidate draw of
+ * ReplayBuffer.get_possible_smart_start_indices (replay_buffer.py:145-152), ~0.6 us per index in the
+ * interpreter, with the same indices in the same order; state and index are advanced in place.
+ * Host only (csrc/py_random.cu); n < 2^31. */
+int ss_py_random_sample(uint32_t* mt_state, int* mt_index, int64_t first, int64_t n, int64_t k, int64_t* out);
+
 /* 1 when ss_mpc_set_model's shape can run on the tcgen05 kernel */
 int ss_mpc_tc_supported(ss_ctx* ctx);
 

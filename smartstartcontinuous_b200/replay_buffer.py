@@ -19,6 +19,57 @@ from collections import deque
 import numpy as np
 
 
+# --------------------------------------------------------------------------- candidate draw
+_FAST_SAMPLE = None      # None: not probed yet; False: use the interpreter; else the library handle
+
+
+def _sample_with(lib, rnd, first, n, k):
+    """random.sample(range(first, first + n), k) of generator ``rnd`` through csrc/py_random.cu."""
+    import ctypes as C
+    version, internal, gauss = rnd.getstate()
+    state = np.array(internal, dtype=np.uint32)                # 624 words + the index
+    index = C.c_int(int(state[624]))
+    out = np.empty(k, dtype=np.int64)
+    rc = lib.ss_py_random_sample(state.ctypes.data_as(C.c_void_p), C.byref(index), int(first), int(n), int(k),
+                                 out.ctypes.data_as(C.c_void_p))
+    if rc != 0:
+        return None
+    state[624] = index.value
+    rnd.setstate((version, tuple(state.tolist()), gauss))
+    return out
+
+
+def _probe_fast_sample():
+    """The C++ restatement is used only if it reproduces this interpreter's random.sample -- indices,
+    order and the generator state afterwards -- on both of Random.sample's branches."""
+    global _FAST_SAMPLE
+    _FAST_SAMPLE = False
+    try:
+        from . import _lib
+        lib = _lib.load()
+        for first, n, k in ((7, 5000, 900), (3, 57, 25), (0, 1, 1), (11, 300000, 4000)):
+            a, b = random.Random(987654321), random.Random(987654321)
+            want = a.sample(range(first, first + n), k)
+            got = _sample_with(lib, b, first, n, k)
+            if got is None or got.tolist() != want or a.getstate() != b.getstate():
+                return
+        _FAST_SAMPLE = lib
+    except Exception:
+        _FAST_SAMPLE = False
+
+
+def sample_range(first, stop, k):
+    """np.array(random.sample(range(first, stop), k)) on the global generator (replay_buffer.py:152)."""
+    if _FAST_SAMPLE is None:
+        _probe_fast_sample()
+    n = stop - first
+    if _FAST_SAMPLE and k > 64 and 0 < n < 2 ** 31:
+        out = _sample_with(_FAST_SAMPLE, random._inst, first, n, k)
+        if out is not None:
+            return out
+    return np.array(random.sample(range(first, stop), k))
+
+
 class _StateRing:
     """Contiguous mirror of (s, s2) rows in buffer order."""
 
@@ -192,7 +243,7 @@ class ReplayBuffer(object):
             return None
         first = self.episode_number_to_buffer_index(self.episode_starting_indices[0])
         n = min(n_ss, len(self.buffer) - first)
-        return np.array(random.sample(range(first, len(self.buffer)), n))
+        return sample_range(first, len(self.buffer), n)
 
     def get_episodic_path_to_buffer_index(self, buffer_index):
         """States of the episode containing ``buffer_index`` from its start up to and

@@ -70,9 +70,10 @@ class SmartStartContinuous(RLAgent):
                  nnd_mb_steps_per_rollout_train=333,
                  nnd_mb_steps_per_rollout_val=333,
 
-                 *, engine=None, device=0, nnd_mb_extra=None, device_mirror=True):
+                 *, engine=None, device=0, nnd_mb_extra=None, device_mirror=True, value_net=None):
         self.param_dict = {k: v for k, v in locals().items()
-                           if k not in ("self", "sess", "env", "agent", "engine", "nnd_mb_extra", "device_mirror", "__class__")}
+                           if k not in ("self", "sess", "env", "agent", "engine", "nnd_mb_extra", "device_mirror", "value_net",
+                                        "__class__")}
         for name in ("self", "sess", "env", "__class__"):
             self.param_dict[name] = "Not serializable"
         self.param_dict["agent"] = agent.get_param_dict()
@@ -103,6 +104,11 @@ class SmartStartContinuous(RLAgent):
         # select from the device-resident mirror of the replay buffer's state ring
         # whenever the buffer keeps one; False = upload the whole buffer at every selection
         self.device_mirror = bool(device_mirror)
+        # with the critic / actor parameters of the base agent given (the dict
+        # Engine.set_value_net takes, or a callable returning it -- called at every selection, so it can
+        # export the weights the agent has NOW), V = critic(q, actor(q)) is evaluated on the device in
+        # front of the UCB and agent.get_state_value is not called for the candidates
+        self.value_net = value_net
 
         self.nnd_mb_agent = NND_MB_agent(
             env, sess, replay_buffer=self.replay_buffer,
@@ -167,21 +173,30 @@ class SmartStartContinuous(RLAgent):
             one_radii_volume = volume_of_n_dimensional_hyperellipsoid(self.nnd_mb_agent.radii)
         else:
             one_radii_volume = 1
-        possible_ss_states = self._candidate_states(possible_start_indices)
-        ss_state_values = np.asarray(self.agent.get_state_value(possible_ss_states)).T   # 1 x m
         ring = self.replay_buffer.state_ring() if hasattr(self.replay_buffer, "state_ring") else None
-        if ring is not None and self.device_mirror:
+        mirror = ring is not None and self.device_mirror
+        values = None
+        if self.value_net is not None:
+            net = self.value_net() if callable(self.value_net) else self.value_net
+            if net is not getattr(self, "_value_net_on_device", None):
+                self.engine.set_value_net(net)
+                self._value_net_on_device = net
+        if self.value_net is None or not mirror:
+            possible_ss_states = self._candidate_states(possible_start_indices)
+        if self.value_net is None:
+            values = np.asarray(self.agent.get_state_value(possible_ss_states)).T.reshape(-1)   # 1 x m
+        if mirror:
             # the buffer's states already live on the device (incremental mirror): only the m candidate
-            # indices and values are uploaded
+            # indices (and the values, unless the device computes them) are uploaded
             best_j, best_ucb, _, _ = self.engine.select_start_mirror(
-                ring, possible_start_indices, ss_state_values.reshape(-1), len(self.replay_buffer),
+                ring, possible_start_indices, values, len(self.replay_buffer),
                 one_radii_volume, self.exploitation_param, self.exploration_param)
         else:
             all_states = np.asarray(self.replay_buffer.get_all_states(), dtype=np.float64)
             if all_states.ndim == 1:
                 all_states = all_states[:, None]
             best_j, best_ucb, _, _ = self.engine.select_start(
-                all_states, possible_ss_states, ss_state_values.reshape(-1), len(self.replay_buffer),
+                all_states, possible_ss_states, values, len(self.replay_buffer),
                 one_radii_volume, self.exploitation_param, self.exploration_param)
         smart_start_index = int(possible_start_indices[best_j])
         self.last_selection = (smart_start_index, best_ucb)

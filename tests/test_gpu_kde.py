@@ -281,3 +281,59 @@ def test_value_net_matches_oracle_and_feeds_the_ucb(engine, cfg):
         engine.set_value_net(None)
     with pytest.raises(ValueError):
         engine.select_start(data, q, None, 5999, 0.3, 1.0, 2.0)
+
+
+def test_smart_start_with_device_value_net_equals_host_values(engine):
+    """SmartStartContinuous(value_net=...): the candidates' values come from the device critic in front
+    of the UCB (row f4) and agent.get_state_value is not called; the choice equals the one made with the
+    same values evaluated on the host by the numpy restatement of the nets."""
+    import random
+
+    from oracle import value_oracle
+    from smartstartcontinuous_b200.smart_start import SmartStartContinuous
+
+    rng = np.random.default_rng(77)
+    net = _random_value_net(rng, 3, 1, 64, 32, False, True, True)
+
+    class Box:
+        low, high, shape = np.array([-2.0]), np.array([2.0]), (1,)
+
+    class Env:
+        action_space = Box()
+
+    class Base:
+        calls = 0
+
+        def get_action(self, s): return np.zeros(1)
+        def observe(self, *a): pass
+        def start_new_episode(self, s): pass
+        def end_episode(self): pass
+        def get_param_dict(self): return {}
+
+        def get_state_value(self, states):
+            Base.calls += 1
+            return value_oracle.state_values(np.asarray(states), net).reshape(-1, 1)
+
+    td = dict(dataX=rng.normal(size=(64, 3)), dataY=rng.normal(size=(64, 1)), dataZ=rng.normal(size=(64, 3)))
+    s_all, _, _ = syn.pendulum_buffer(6000, seed=5)
+    picks = []
+    try:
+        for value_net in (None, net, lambda: net):
+            ss = SmartStartContinuous(Base(), Env(), None, buffer_size=6000, n_ss=900, print_ss_stuff=False,
+                                      nnd_mb_num_fc_layers=1, nnd_mb_depth_fc_layers=32, nnd_mb_verbose=False,
+                                      engine=engine, nnd_mb_extra=dict(training_data=td), value_net=value_net)
+            rb = ss.replay_buffer
+            for i in range(6000):
+                if i % 200 == 0:
+                    rb.start_new_episode(ss)
+                rb.add(ss, s_all[i], np.zeros(1), 0.0, (i % 200) == 199, s_all[i + 1])
+            random.seed(11)
+            before = Base.calls
+            path = ss.get_smart_start_path()
+            assert (Base.calls == before) == (value_net is not None)
+            picks.append((ss.last_selection, np.asarray(path[-1])))
+    finally:
+        engine.set_value_net(None)
+    (i0, u0), p0 = picks[0]
+    for (i1, u1), p1 in picks[1:]:
+        assert i1 == i0 and abs(u1 - u0) <= 1e-4 * abs(u0) and np.array_equal(p0, p1)

@@ -125,3 +125,30 @@ def test_no_episode_errors():
     rb.add(0, 1.0, 0.0, 0.0, False, 2.0)
     with pytest.raises(ValueError):
         rb.get_episodic_path_to_buffer_index(0)
+
+
+def test_candidate_draw_in_cxx_equals_random_sample():
+    """csrc/py_random.cu restates random.sample(range(first, stop), k): same indices in the same order
+    and the same global generator state afterwards, on both of Random.sample's branches."""
+    import random
+
+    from smartstartcontinuous_b200 import replay_buffer as rbm
+    rbm._probe_fast_sample()
+    assert rbm._FAST_SAMPLE, "the library's restatement disagrees with this interpreter's random.sample"
+    for seed, (first, stop, k) in enumerate([(0, 100, 100), (5, 70, 65), (200, 100001, 16384), (0, 2001, 2000),
+                                             (17, 5000, 4000), (3, 1000003, 65536), (0, 300, 65), (9, 4200, 1400)]):
+        random.seed(seed)
+        random.random()
+        want = np.array(random.sample(range(first, stop), k))
+        tail_want = [random.random(), random.getrandbits(40), random.gauss(0, 1)]
+        random.seed(seed)
+        random.random()
+        got = rbm.sample_range(first, stop, k)
+        tail_got = [random.random(), random.getrandbits(40), random.gauss(0, 1)]
+        assert got.dtype == want.dtype and np.array_equal(got, want), (first, stop, k)
+        assert tail_got == tail_want
+    # the buffer method goes through it
+    random.seed(3)
+    a = random.sample(range(0, 500), 120)
+    random.seed(3)
+    assert rbm.sample_range(0, 500, 120).tolist() == a
