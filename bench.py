@@ -745,12 +745,14 @@ def main():
             ag_dev.get_best_sim_actions(wls["state"])
         wall_ms = 1e3 * (time.perf_counter() - t0) / n_s
         eng.set_timing(True)
+        resident(0)
+        kernel_name = eng.last_rollout_kernel()
         k_ms = kern_ms
         kern = float(np.mean(k_ms)) if k_ms else None
         small[name] = {
             "workload": "MountainCar d=2 da=1, K=%d (strong-scaled over %d GPU(s)), H=%d, MLP %dx%d, reference penalty"
                         % (K, world, H, L, h),
-            "kernel": "mpc_rollout_tc_kernel" if prec_s == "bf16_tc" else "mpc_rollout_simt_kernel",
+            "kernel": kernel_name,
             "ms_per_decision_resident": fast_ms, "ms_per_decision_resident_with_phase_events": res_ms,
             "rollout_kernel_ms": kern,
             "decision_over_rollout_kernel": (fast_ms / kern) if kern else None,

@@ -141,6 +141,7 @@ struct ss_ctx {
     DevBuf tc_w1, tc_w2, tc_w3, tc_misc, tc_b3;
     bool tc_ready = false;
     int tc_hp = 0;
+    int tc_quad_clusters = -1;         // co-resident 4-CTA clusters of the small-batch kernel (-1: not probed)
     std::vector<std::vector<double>> hw, hb;   // host copies of the float64 parameters
     // ---- dynamics-model training on the device (dyn_train.cu): FP32 master parameters, Adam moments,
     // both training sets, per-batch activations
@@ -169,6 +170,7 @@ struct ss_ctx {
         float state[SS_MAX_D];
         ActionSource act;
         bool states_stored = false;
+        int kernel = 0;                // rollout kernel of this decision: 0 FP32 SIMT, 1 tcgen05 CTA pairs, 2 tcgen05 4-CTA clusters
         bool finished = false;         // the reference-mode penalty pass has rewritten the scores
         bool peer_sums = false;        // the projection sums were all-reduced over peer memory
         int sum_blocks = 0;

@@ -6,6 +6,7 @@
 //   ss_mpc_finish     phase B (reference penalty) + arg-max
 //   ss_mpc_replay     re-roll the winner for best_sequence / best_path (NND_MB_agent.py:516-518)
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "mpc_kernels.cuh"
@@ -153,6 +154,7 @@ extern "C" int ss_mpc_set_model(ss_ctx* c, int d, int da, int num_fc_layers, int
 }
 
 extern "C" int ss_mpc_tc_supported(ss_ctx* c) { return c && c->model_set && c->tc_ready ? 1 : 0; }
+extern "C" int ss_mpc_last_kernel(ss_ctx* c) { return c && c->run.valid ? c->run.kernel : -1; }
 
 extern "C" int ss_mpc_set_plan(ss_ctx* c, const double* desired_states, int W,
                                const double* distances_left, const double* radii, int d) {
@@ -334,9 +336,24 @@ extern "C" int ss_mpc_rollout(ss_ctx* c, const double* state, int wp_index, int6
             rc = mpc_tc_launch(c, a, &grid, chunk_tile[i], chunk_tile[i + 1] - chunk_tile[i]);
             if (rc) return rc;
         }
-    } else {
-        rc = precision == SS_PRECISION_BF16_TC ? mpc_tc_launch(c, a, &grid) : mpc_simt_launch(c, a, &grid);
+        r.kernel = 1;
+    } else if (precision == SS_PRECISION_BF16_TC) {
+        // small batches: one tile per 4-CTA cluster with the hidden layer split over the cluster
+        // (mpc_tc_quad.cu).  The choice follows the GLOBAL batch, so every shard of a batch runs the same
+        // kernel as the unsharded decision would.  SS_TC_QUAD = 0 / 1 forces the pair / quad kernel.
+        bool quad = false;
+        if (mpc_tc_quad_supported(c)) {
+            const char* env = std::getenv("SS_TC_QUAD");
+            const long long global_tiles = (K_global + mpc_tc_tile_rows() - 1) / mpc_tc_tile_rows();
+            quad = env ? std::atoi(env) != 0 : global_tiles <= mpc_tc_quad_clusters(c);
+        }
+        rc = quad ? mpc_tc_quad_launch(c, a, &grid) : mpc_tc_launch(c, a, &grid);
         if (rc) return rc;
+        r.kernel = quad ? 2 : 1;
+    } else {
+        rc = mpc_simt_launch(c, a, &grid);
+        if (rc) return rc;
+        r.kernel = 0;
     }
     timer_mark(c, "mpc_rollout");
     r.sum_cols = nullptr;

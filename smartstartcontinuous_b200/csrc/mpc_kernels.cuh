@@ -40,6 +40,10 @@ int mpc_tc_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out, long lo
                   long long tile_count = -1);
 int mpc_tc_grid(const ss_ctx* c, long long tiles);
 int mpc_tc_tile_rows();
+// small batches (mpc_tc_quad.cu): one tile per 4-CTA cluster, the hidden layer split over the cluster
+bool mpc_tc_quad_supported(const ss_ctx* c);
+int mpc_tc_quad_clusters(ss_ctx* c);
+int mpc_tc_quad_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out);
 
 // scoring tail (mpc_score.cu)
 int mpc_reduce_sums(ss_ctx* c, const double* partial, int blocks, int T, double* sums);

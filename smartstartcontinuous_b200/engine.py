@@ -386,6 +386,11 @@ class Engine:
     def tc_supported(self):
         return bool(self._lib.ss_mpc_tc_supported(self._h))
 
+    def last_rollout_kernel(self):
+        """Name of the rollout kernel the last decision ran on."""
+        return {0: "mpc_rollout_simt_kernel", 1: "mpc_rollout_tc_kernel", 2: "mpc_rollout_tc_quad_kernel"}.get(
+            int(self._lib.ss_mpc_last_kernel(self._h)))
+
     def set_plan(self, desired_states, distances_left, radii):
         ds = _f64(desired_states)
         dl = _f64(distances_left).reshape(-1)

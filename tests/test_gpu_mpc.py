@@ -1,4 +1,6 @@
 """Stage 2 on the B200 through the C ABI vs the oracle / the reference's golden vectors."""
+import os
+
 import numpy as np
 import pytest
 
@@ -563,3 +565,67 @@ def test_peer_exchange_kernels_single_rank(engine, prec):
         engine.peer_close()
     assert not engine.peer_ready
     np.testing.assert_array_equal(shard("reference", 1), plain[("reference", 1)])
+
+
+def _with_env(name, value, fn):
+    old = os.environ.get(name)
+    if value is None:
+        os.environ.pop(name, None)
+    else:
+        os.environ[name] = value
+    try:
+        return fn()
+    finally:
+        if old is None:
+            os.environ.pop(name, None)
+        else:
+            os.environ[name] = old
+
+
+@pytest.mark.parametrize("env_name,d", [("mountaincar", 2), ("pendulum", 3)])
+def test_tc_quad_kernel_vs_oracle_and_pair_kernel(engine, env_name, d):
+    """The small-batch kernel (one tile per 4-CTA cluster, hidden layer split over the cluster,
+    csrc/mpc_tc_quad.cu) against the float64 oracle and against the pair kernel on the same batch:
+    ragged K, several tile iterations per cluster (forced), both penalty modes, sharded = unsharded."""
+    rng = np.random.default_rng(30 + d)
+    if env_name == "mountaincar":
+        roll = [syn.mountaincar_rollout(rng, 200) for _ in range(6)]
+        states = np.concatenate([r[0] for r in roll])
+        acts_all = np.concatenate([np.concatenate([r[1], r[1][-1:]]) for r in roll])
+        path, lo, hi, start = list(roll[0][0][:50]), -1.0, 1.0, roll[0][0][0]
+    else:
+        obs, act = syn.pendulum_rollouts(rng, 6, 200)
+        states = obs.reshape(-1, 3)
+        acts_all = np.concatenate([act, act[:, -1:]], axis=1).reshape(-1, 1)
+        path, lo, hi, start = list(obs[0, :50]), -2.0, 2.0, obs[0, 0]
+    norm = syn.normalisation_stats(states, acts_all)
+    w, b = syn.xavier_mlp(rng, d, 1, 2, 500, scale=0.5)
+    from smartstartcontinuous_b200.nnd_mb_agent import plan_from_path
+    plan = plan_from_path(path, mean_per_stepsize=1, std_per_stepsize=1, stepsizes_in_waypoint_radii=1,
+                          path_shortcutting=True, theta=1, steps_per_waypoint=1)
+    engine.set_model(w, b, norm)
+    engine.set_plan(plan["desired_states"], plan["distances_left"], plan["radii"])
+    assert engine.tc_supported()
+    for K, H in ((700, 9), (4096, 20)):
+        acts = np.random.RandomState(K).uniform(lo, hi, (K, H, 1))
+        for mode in ("reference", "per_sample"):
+            quad, o = _with_env("SS_TC_QUAD", "1", lambda: _assert_tc_matches_oracle(engine, start, acts, w, b, norm, plan, mode))
+            pair = _with_env("SS_TC_QUAD", "0", lambda: engine.plan(start, 0, actions=acts, penalty_mode=mode,
+                                                                    precision="bf16_tc", want_scores=True))
+            # two roundings of the same FP32 sums: the layer-3 partials are added in a different order
+            assert np.median(np.abs(quad["scores"] - pair["scores"])) < 1e-3
+            _check_best_abs(quad["best_k"], pair["scores"], TC_SCORE_ATOL_BENCH)
+    # many tiles on few clusters (forced): every cluster walks several tiles
+    K, H = 40000, 6
+    acts = np.random.RandomState(5).uniform(lo, hi, (K, H, 1))
+    _with_env("SS_TC_QUAD", "1", lambda: _assert_tc_matches_oracle(engine, start, acts, w, b, norm, plan, "reference"))
+    # shards of a small batch run the same kernel as the whole batch: bit-identical scores
+    K, H = 3000, 12
+    acts = np.random.RandomState(6).uniform(lo, hi, (K, H, 1))
+    whole = engine.plan(start, 0, actions=acts, penalty_mode="per_sample", precision="bf16_tc", want_scores=True)
+    parts = [engine.plan(start, 0, actions=acts[k0:k1], penalty_mode="per_sample", precision="bf16_tc", want_scores=True,
+                         k_offset=k0, K_global=K)["scores"] for k0, k1 in ((0, 1100), (1100, 3000))]
+    np.testing.assert_array_equal(np.concatenate(parts), whole["scores"])
+    # repeatable bit for bit
+    again = engine.plan(start, 0, actions=acts, penalty_mode="per_sample", precision="bf16_tc", want_scores=True)
+    np.testing.assert_array_equal(again["scores"], whole["scores"])
