@@ -11,12 +11,14 @@
 // double-buffered by step parity) and summed in a fixed order, so the four copies of the state stay
 // bit-identical.  Layer 2 drops to 2048 tensor clocks per step; 32 tiles use 128 SMs.
 //
-// Same operand images as the pair kernel (each CTA issues two N = 64 MMAs per K step, one per image half),
+// Same operand images in global memory as the pair kernel; the loader warp interleaves the two 64-unit halves
+// of every block into one 128-row K-major tile in shared memory (1 KB bulk copies), so one N = 128 MMA per K step,
 // same layer-1 split-bf16 scheme, same TMEM map ([0,256) H1 as bf16 A operand, [256,512) accumulators),
 // same scoring (tc_score_row.cuh; quarter q of the rows is scored by CTA q of the cluster).  Model shapes:
 // padded hidden width 512 (four chunks), d <= 4.
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "mpc_kernels.cuh"
 #include "tc_ptx.cuh"
@@ -40,8 +42,8 @@ constexpr int ROW_WARPS = 8, TPR = 2, CPT = NC / TPR;
 constexpr int THREADS = ROW_WARPS * 32 + 64;
 constexpr int DZ_MAX = 4;
 constexpr uint32_t TMEM_COLS = 512, COL_H1 = 0, COL_ACC = 256;
-// D f32, A/B bf16, K-major, N = 64, M = 128 (cta_group::1)
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NH >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+// D f32, A/B bf16, K-major, N = 128, M = 128 (cta_group::1)
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NC >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
 __host__ __device__ constexpr int dz_of(int d) { return d <= 2 ? 2 : (d <= 3 ? 3 : 4); }
 __host__ __device__ constexpr int k1_slots(int d, int da) { return 3 * (dz_of(d) + da) + 2 <= 16 ? 16 : 32; }
@@ -54,6 +56,7 @@ struct Params {
     const float* b3;
     long long tile_begin, tile_end;
     int iters;                          // tile iterations per cluster
+    unsigned long long* prof;           // SS_TC_TRACE: clock stamps of cluster 0 / CTA 0, steps 10..12
 };
 
 struct Smem {
@@ -64,10 +67,16 @@ struct Smem {
     static constexpr size_t ZX = W3 + (size_t)(HP / 2) * 8 * 4;                       // [DZ_MAX][2 halves][128] local partials
     static constexpr size_t ZQ = ZX + (size_t)DZ_MAX * TPR * TM * 4;                  // [2 parity][4 src][128 rows][4] exchanged
     static constexpr size_t BARS = ZQ + (size_t)2 * QUAD * TM * 16;
-    static constexpr int N_BARS = 2 + 2 + NCH + 2 + 1 + 1 + 2;
+    static constexpr int N_BARS = 2 + 2 + NCH + 2 + 1 + 2 + 2;
     static constexpr size_t TMEM_PTR = BARS + (size_t)N_BARS * 8;
     static constexpr size_t END = TMEM_PTR + 16;
 };
+
+#define TQ_TRACE(ev)                                                                             \
+    do {                                                                                         \
+        if (p.prof && blockIdx.x == 0 && lane == 0 && trace_on && trace_t >= 10 && trace_t < 13)  \
+            p.prof[(trace_t - 10) * 64 + (ev)] = (unsigned long long)clock64();                   \
+    } while (0)
 
 template <int DT, int DZ, int K1T>
 __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const RolloutArgs a, const Params p) {
@@ -87,8 +96,8 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
     uint64_t* h1_ready = acc_free + 2;    // [NCH] layer-1 chunk converted (an A operand now)
     uint64_t* l1_full = h1_ready + NCH;   // [2] layer-1 chunk 0 / all chunks complete (commit)
     uint64_t* x_ready = l1_full + 2;      // the layer-1 A tile is in shared memory
-    uint64_t* w_full = x_ready + 1;       // weights have landed (once)
-    uint64_t* z_full = w_full + 1;        // [2 parity] the four CTAs' partial state deltas of the step have landed (tx bytes)
+    uint64_t* w_full = x_ready + 1;       // [2] W1 / this CTA's W2 chunk have landed (once)
+    uint64_t* z_full = w_full + 2;        // [2 parity] the four CTAs' partial state deltas of the step have landed (tx bytes)
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + Smem::TMEM_PTR);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -103,7 +112,8 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
         mbar_init(&l1_full[0], 1);
         mbar_init(&l1_full[1], 1);
         mbar_init(x_ready, 4);
-        mbar_init(w_full, 1);
+        mbar_init(&w_full[0], 1);
+        mbar_init(&w_full[1], 1);
         mbar_init(&z_full[0], 1);
         mbar_init(&z_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -115,18 +125,28 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
     }
     for (int i = tid; i < (HP / 2) * (2 * DZP); i += THREADS) w3s[i] = p.w3[i];
     __syncthreads();
-    if (tid == 0) {
-        // resident operands: W1 of every chunk (both halves) and this CTA's chunk of W2
-        const uint32_t w1_bytes = (uint32_t)(NCH * W1_CHUNK_BYTES);
-        mbar_expect_tx(w_full, 2 * w1_bytes + (uint32_t)(NSLAB * 2 * BLOCK_BYTES));
-        for (int r = 0; r < 2; ++r)
-            bulk_g2s(w1s + (size_t)r * w1_bytes, reinterpret_cast<const unsigned char*>(p.w1_img) + (size_t)r * w1_bytes,
-                     w1_bytes, w_full);
-        for (int b = 0; b < NSLAB * 2; ++b)
-            bulk_g2s(w2s + (size_t)b * BLOCK_BYTES,
-                     reinterpret_cast<const unsigned char*>(p.w2_img) + ((size_t)rank * NSLAB * 2 + b) * BLOCK_BYTES,
-                     BLOCK_BYTES, w_full);
-        mbar_wait<false>(w_full, 0);
+    if (warp == ROW_WARPS + 1) {
+        // resident operands, each as 128-row K-major tiles [k/8][128 units][8]: the two 64-unit halves of the
+        // global images are interleaved k-group by k-group (1 KB bulk copies spread over the lanes).  W1 of
+        // every chunk first (the first MMAs need it), then this CTA's chunk of W2 (needed ~1000 clocks later).
+        constexpr int KG1 = K1T / 8, KG2 = KSLAB / 8;
+        if (lane == 0) {
+            mbar_expect_tx(&w_full[0], (uint32_t)(NCH * 2 * W1_CHUNK_BYTES));
+            mbar_expect_tx(&w_full[1], (uint32_t)(NSLAB * 2 * BLOCK_BYTES));
+        }
+        __syncwarp();
+        const unsigned char* g1 = reinterpret_cast<const unsigned char*>(p.w1_img);
+        for (int i = lane; i < NCH * KG1 * 2; i += 32) {
+            const int r = i & 1, kg = (i >> 1) % KG1, c = (i >> 1) / KG1;
+            bulk_g2s(w1s + (size_t)c * (2 * W1_CHUNK_BYTES) + (size_t)kg * (NC * 16) + (size_t)r * (NH * 16),
+                     g1 + ((size_t)r * NCH + c) * W1_CHUNK_BYTES + (size_t)kg * (NH * 16), NH * 16, &w_full[0]);
+        }
+        const unsigned char* g2 = reinterpret_cast<const unsigned char*>(p.w2_img) + (size_t)rank * NSLAB * 2 * BLOCK_BYTES;
+        for (int i = lane; i < NSLAB * KG2 * 2; i += 32) {
+            const int r = i & 1, kg = (i >> 1) % KG2, ksl = (i >> 1) / KG2;
+            bulk_g2s(w2s + (size_t)ksl * (2 * BLOCK_BYTES) + (size_t)kg * (NC * 16) + (size_t)r * (NH * 16),
+                     g2 + ((size_t)ksl * 2 + r) * BLOCK_BYTES + (size_t)kg * (NH * 16), NH * 16, &w_full[1]);
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -171,6 +191,9 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
             }
             for (int t = 0; t < a.H; ++t, ++step_it) {
                 const uint32_t ph = step_it & 1;
+                const bool trace_on = it == 0 && warp == 0;
+                const int trace_t = t;
+                TQ_TRACE(0);
                 // this step's exchange: 4 sources x 128 rows x 16 bytes land on z_full[ph] (its previous phase,
                 // two steps ago, completed before this thread left that step)
                 if (tid == 0) mbar_expect_tx(&z_full[ph], QUAD * TM * 16);
@@ -211,6 +234,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
                     __syncwarp();
                     if (lane == 0) mbar_arrive_local(x_ready);
                 }
+                TQ_TRACE(1);
                 // ---- layer-1 epilogue: relu, bf16, becomes the layer-2 A operand (as in mpc_tc.cu: even
                 // chunks sit in the dead H1 columns and are converted in place, odd chunks in the two
                 // accumulator slots)
@@ -218,6 +242,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
                     const uint32_t slot_i = (uint32_t)(c0 >> 1);
                     uint32_t v0[32], v1[32], pk0[16], pk1[16];
                     if (c0 == 0) mbar_wait<false>(&l1_full[0], ph);
+                    TQ_TRACE(2 + c0);
                     tc_fence_after();
                     tmem_ld32(lane_addr + COL_H1 + slot_i * NC + ch * CPT, v0);
                     tmem_ld32(lane_addr + COL_H1 + slot_i * NC + ch * CPT + 32, v1);
@@ -255,6 +280,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive_local(&h1_ready[c0 + 1]);
+                    TQ_TRACE(3 + c0);
                 }
                 // ---- in the shadow of the layer-2 MMAs
                 if (scorer) {
@@ -269,7 +295,9 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
 #pragma unroll
                 for (int j = 0; j < DZ; ++j) zacc[j] = make_float2(0.f, 0.f);
                 {
+                    TQ_TRACE(6);
                     mbar_wait<false>(&acc_full[0], ph);
+                    TQ_TRACE(7);
                     tc_fence_after();
                     uint32_t v0[32], v1[32];
                     tmem_ld32(lane_addr + COL_ACC + ch * CPT, v0);
@@ -294,6 +322,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
                         }
                     }
                 }
+                TQ_TRACE(8);
                 // ---- all-reduce of the partial deltas over the cluster.  The two column halves of a row meet
                 // through local shared memory; the ch-0 thread then sends the row's partial (one 16-byte
                 // st.async per destination, completing transaction bytes on the destination's barrier of this
@@ -319,7 +348,9 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
                                 : "memory");
                         }
                     }
+                    TQ_TRACE(9);
                     mbar_wait_cluster(&z_full[ph], (step_it >> 1) & 1);
+                    TQ_TRACE(10);
                     // fixed order (CTA 0, 1, 2, 3): the four copies of the state stay bit-identical
                     const float4 p0 = zbuf[row], p1 = zbuf[TM + row], p2 = zbuf[2 * TM + row], p3 = zbuf[3 * TM + row];
                     const float zz[4] = {((p0.x + p1.x) + p2.x) + p3.x, ((p0.y + p1.y) + p2.y) + p3.y,
@@ -327,6 +358,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
 #pragma unroll
                     for (int j = 0; j < DZ; ++j) x[j] += fmaf(zz[j], upd_s[j], upd_c[j]);
                 }
+                TQ_TRACE(11);
             }
             if (scorer) {
                 score_row<DT>(a, a.H, x, sc, live, k_local, qcol, n_qcols, lane);
@@ -340,51 +372,53 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
         const long long steps = (long long)p.iters * a.H;
         for (long long s = 0; s < steps; ++s, ++step_it) {
             const uint32_t ph = step_it & 1;
+            const bool trace_on = s < a.H;
+            const int trace_t = (int)s;
             // layer 1 overwrites both accumulator slots: slot 0 was last used by the previous step's layer-2
             // chunk (second drain of that step), slot 1 by its layer-1 chunk 3
             mbar_wait2(&acc_free[0], 1u, &acc_free[1], ph ^ 1u);
+            if (s == 0) mbar_wait<false>(&w_full[0], 0);
             mbar_wait<false>(x_ready, ph);
+            TQ_TRACE(20);
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
                     const uint32_t d0 = tmem + ((c & 1) ? COL_ACC : COL_H1) + (uint32_t)(c >> 1) * NC;
 #pragma unroll
-                    for (int r = 0; r < 2; ++r) {
-#pragma unroll
-                        for (int ks = 0; ks < K1T / 16; ++ks)
-                            umma1_ss(d0 + r * NH, make_desc(a1_addr + ks * 2 * (TM * 16), TM),
-                                     make_desc(w1_addr + (r * NCH + c) * W1_CHUNK_BYTES + ks * 2 * (NH * 16), NH), IDESC, ks);
-                    }
+                    for (int ks = 0; ks < K1T / 16; ++ks)
+                        umma1_ss(d0, make_desc(a1_addr + ks * 2 * (TM * 16), TM),
+                                 make_desc(w1_addr + c * (2 * W1_CHUNK_BYTES) + ks * 2 * (NC * 16), NC), IDESC, ks);
                     if (c == 0) tc_commit_one(&l1_full[0]);
                     else if (c == NCH - 1) tc_commit_one(&l1_full[1]);
                 }
             }
             __syncwarp();
+            TQ_TRACE(21);
             // layer 2, this CTA's chunk: D = acc slot 0 (its layer-1 occupant, chunk 1, must be drained: the
             // first drain of this step; every row warp arrives there after h1_ready[0], so the wait also
             // covers "H1 chunk 0 is converted"), K streamed in 128-wide halves as their layer-1 chunks finish
+            if (s == 0) mbar_wait<false>(&w_full[1], 0);
             mbar_wait<false>(&acc_free[0], 0u);
+            TQ_TRACE(22);
             const uint32_t d_tmem = tmem + COL_ACC;
 #pragma unroll
             for (int c = 0; c < NCH; ++c) {
                 if (c > 0) mbar_wait<false>(&h1_ready[c], ph);
+                TQ_TRACE(23 + c);
                 tc_fence_after();
                 if (elect_one()) {
                     const int ksl = c >> 1;
 #pragma unroll
                     for (int k8 = 0; k8 < NC / 16; ++k8) {
                         const int ks = (c & 1) * (NC / 16) + k8;                 // K step inside the 256-wide block
-                        const uint32_t a_tmem = tmem + COL_H1 + ksl * (KSLAB / 2) + ks * 8;
-#pragma unroll
-                        for (int r = 0; r < 2; ++r)
-                            umma1_ts(d_tmem + r * NH, a_tmem,
-                                     make_desc(w2_addr + (ksl * 2 + r) * BLOCK_BYTES + ks * 2 * (NH * 16), NH), IDESC,
-                                     (c | k8) != 0);
+                        umma1_ts(d_tmem, tmem + COL_H1 + ksl * (KSLAB / 2) + ks * 8,
+                                 make_desc(w2_addr + ksl * (2 * BLOCK_BYTES) + ks * 2 * (NC * 16), NC), IDESC, (c | k8) != 0);
                     }
                     if (c == NCH - 1) tc_commit_one(&acc_full[0]);
                 }
                 __syncwarp();
+                TQ_TRACE(27 + c);
             }
         }
     }
@@ -446,6 +480,12 @@ int mpc_tc_quad_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out) {
     const long long tiles = (a.K_local + TM - 1) / TM;
     p.tile_begin = 0;
     p.tile_end = tiles;
+    p.prof = nullptr;
+    if (getenv("SS_TC_TRACE")) {
+        SS_CUDA_CHECK(c, c->tc_misc.ensure((3 * 256 + 2) * 8));
+        SS_CUDA_CHECK(c, cudaMemsetAsync(c->tc_misc.p, 0, (3 * 256 + 2) * 8, c->stream));
+        p.prof = c->tc_misc.as<unsigned long long>();
+    }
     const int max_clusters = mpc_tc_quad_clusters(c);
     if (max_clusters < 1) SS_FAIL(c, SS_EUNSUPPORTED, "mpc: no 4-CTA cluster fits on this device");
     const int clusters = (int)std::min<long long>(tiles, max_clusters);
@@ -480,5 +520,18 @@ int mpc_tc_quad_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out) {
     if (e == cudaSuccess) e = cudaGetLastError();
     c->launches++;
     SS_CUDA_CHECK(c, e);
+    if (p.prof) {
+        std::vector<unsigned long long> h(3 * 64);
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(h.data(), p.prof, h.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+        SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        for (int st = 0; st < 3; ++st) {
+            const unsigned long long* ev = &h[st * 64];
+            const unsigned long long t0 = ev[0];
+            fprintf(stderr, "[quad trace step %d, %d clusters] row: xsplit %llu | l1_full0 %llu epi01 %llu | c2 %llu epi23 %llu | wait acc_full %llu got %llu | l3 done %llu | sent %llu z_full %llu | end %llu\n",
+                    10 + st, clusters, ev[1] - t0, ev[2] - t0, ev[3] - t0, ev[4] - t0, ev[5] - t0, ev[6] - t0, ev[7] - t0, ev[8] - t0, ev[9] - t0, ev[10] - t0, ev[11] - t0);
+            fprintf(stderr, "[quad trace step %d] mma: x_ready %llu | L1 issued %llu | acc_free0 %llu | h1 %llu %llu %llu %llu | L2 issued %llu %llu %llu %llu\n",
+                    10 + st, ev[20] - t0, ev[21] - t0, ev[22] - t0, ev[23] - t0, ev[24] - t0, ev[25] - t0, ev[26] - t0, ev[27] - t0, ev[28] - t0, ev[29] - t0, ev[30] - t0);
+        }
+    }
     return SS_OK;
 }
