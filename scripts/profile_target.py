@@ -20,6 +20,16 @@ if os.environ.get("SS_PROFILE_CFG") == "c3":
                      penalty_mode="reference", precision="bf16_tc")
     print("mpc c3", r["best_k"], r["best_score"], eng.last_timings())
     sys.exit(0)
+if os.environ.get("SS_PROFILE_CFG") == "mt":
+    # numpy's MT19937 stream on the device at the bench shape (K = 131072, H = 50) and at config 3's
+    rs = np.random.RandomState(1)
+    rs.random_sample(100)
+    for n in (bench.K_PER_GPU * bench.HORIZON, bench.C3_K * bench.C3_H):
+        for i in range(2):
+            eng.mt19937_uniform(rs.get_state(), n, [-2.0], [2.0])
+            st = eng.mt19937_state()
+    print("mt19937 pos", st[2])
+    sys.exit(0)
 if os.environ.get("SS_PROFILE_CFG") == "dyn":
     # row f1: a few Adam steps of the device trainer at the BASELINE shapes (2x500, batch 512)
     from oracle import dyn_train_oracle as dto
