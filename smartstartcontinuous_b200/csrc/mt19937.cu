@@ -175,7 +175,10 @@ struct MtSegment {
     int poly;                  // row of the polynomial table (jump to 624 * first_block - 1), -1: no jump
     int emit;                  // 0: state-only segment
     int write_state;           // this segment may write the final state
-    int pad;
+    // a jump shared by `share_n` CTAs: CTA `share_r` correlates the coefficient words m with m % share_n ==
+    // share_r (in units of 20 words), XORs its 625 partial outputs into window `window` in global memory and
+    // counts itself in; share_r == 0 waits for everybody and goes on to generate the segment, the others exit
+    int share_r, share_n, window;
 };
 
 struct MtArgs {
@@ -187,6 +190,8 @@ struct MtArgs {
     int pos;                   // numpy's pos: words of the key block already consumed (0..624)
     uint32_t* state_out;       // mapped host memory: [0..1] flag (u64), [2] pos, [4 .. 4 + 624) key
     unsigned long long seq;
+    uint32_t* windows;         // [n_windows][640] partial jump results (zero between calls) ...
+    unsigned int* counters;    // ... and how many CTAs have contributed to each
 };
 
 // raw words -> doubles: element e of the shard = words (w, w + 1), w = word_base + 2 e, of the raw buffer
@@ -299,7 +304,7 @@ mt19937_raw_kernel(const __grid_constant__ MtKey key, const __grid_constant__ Mt
 #pragma unroll
             for (int r = 0; r < CONV_PER_LANE; ++r) o[r] = 0u;
             const uint32_t* sp = seq + CONV_PER_LANE * lane;
-            for (int w = warp; w < MT_N; w += CONV_WARPS) {
+            for (int w = warp + CONV_WARPS * seg.share_r; w < MT_N; w += CONV_WARPS * seg.share_n) {
                 const uint32_t gw = g_s[w];
                 if (gw == 0u) continue;
                 uint32_t s[52];
@@ -317,13 +322,37 @@ mt19937_raw_kernel(const __grid_constant__ MtKey key, const __grid_constant__ Mt
         }
         __syncthreads();
         // conv word j = x[J + j], J = 624 * first_block - 1: the block is words 1 .. 624
+        uint32_t v = 0;
         if (tid < MT_N) {
             const int j = tid + 1;
-            uint32_t v = 0;
 #pragma unroll
             for (int p = 0; p < CONV_WARPS; ++p) v ^= part[p * CONV_OUT + j];
-            ring[tid] = v;
         }
+        if (seg.share_n > 1) {
+            // several CTAs share this jump: combine through global memory (XOR is order-free), count in, and
+            // let share 0 carry on once everybody has contributed (all CTAs of the grid are co-resident:
+            // cooperative launch)
+            uint32_t* win = args.windows + (size_t)seg.window * CONV_OUT;
+            unsigned int* cnt = args.counters + seg.window;
+            if (tid < MT_N) atomicXor(win + tid, v);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicAdd(cnt, 1u);
+            if (seg.share_r != 0) return;
+            if (tid == 0) {
+                int spins = 0;
+                while (*reinterpret_cast<volatile unsigned int*>(cnt) < (unsigned int)seg.share_n)
+                    if (++spins > (1 << 26)) asm volatile("trap;");
+                __threadfence();
+            }
+            __syncthreads();
+            if (tid < MT_N) {
+                v = __ldcg(win + tid);
+                win[tid] = 0u;                       // zero again for the next call
+            }
+            if (tid == 0) *cnt = 0u;
+        }
+        if (tid < MT_N) ring[tid] = v;
         __syncthreads();
     }
 
@@ -400,13 +429,15 @@ mt19937_convert_kernel(const __grid_constant__ MtConvertArgs a) {
 struct MtPlan {
     long long off_w = -1, n_w = 0, total_w = 0;
     long long b_lo = 0, n_blocks = 0;
-    int n_segments = 0;
+    int n_segments = 0, n_windows = 0;
+    bool cooperative = false;      // jumps shared between CTAs: the grid must be co-resident
     DevBuf segs, polys;
 };
 
 struct MtCache {
     std::vector<MtPlan> plans;
-    DevBuf raw;
+    DevBuf raw, windows;           // windows: [n][640] partial jump results + [n] counters, zero between calls
+    size_t windows_n = 0;
     void* host_state = nullptr;
     void* host_state_dev = nullptr;
     unsigned long long seq = 0;
@@ -418,17 +449,29 @@ MtCache* cache_of(ss_ctx* c) {
     return static_cast<MtCache*>(c->mt_cache);
 }
 
-// one way to cut the blocks [b_lo, b_hi] into P segments: descriptors, polynomials and the modelled time
+// one way to cut the blocks [b_lo, b_hi] into P segments: CTA descriptors, polynomials and the modelled time
 struct MtLayout {
-    std::vector<MtSegment> segs;
+    std::vector<MtSegment> segs;       // one entry per CTA
     std::vector<uint32_t> words;
+    int n_windows = 0;
+    bool shared_jumps = false;
     double cost_us = 0.0;
 };
 
-MtLayout make_layout(long long b_lo, long long b_hi, long long total_w, int P) {
+// measured on B200: 0.19 us per regenerated block, 5.7 us for the 34 raw blocks a jump reads, 56 us for the
+// correlation with a dense polynomial (~10 000 set bits; zero coefficients are skipped, and x^J mod phi stays
+// sparse for J up to a few times 19937 because phi has only 135 terms), ~1.5 us for the hand-off of a shared jump
+double layout_cost(long long per, int n_jumps, int shares, int max_weight) {
+    if (n_jumps == 0) return 0.19 * (double)per;
+    return 0.19 * (double)per + 5.7 + 56.0 * max_weight / 10000.0 / shares + (shares > 1 ? 1.5 : 0.0);
+}
+
+// with_polys = false: shape and cost only (dense polynomials assumed)
+MtLayout make_layout(long long b_lo, long long b_hi, long long total_w, int P, int sm_count, bool with_polys) {
     MtLayout L;
     const long long n_blocks = b_hi - b_lo + 1;
     const long long per = (n_blocks + P - 1) / P;
+    std::vector<MtSegment> logical;
     std::vector<uint64_t> jumps;
     for (long long b = b_lo; b <= b_hi; b += per) {
         MtSegment s{};
@@ -438,12 +481,12 @@ MtLayout make_layout(long long b_lo, long long b_hi, long long total_w, int P) {
         s.write_state = 1;
         s.poly = -1;
         if (b > 0) { s.poly = (int)jumps.size(); jumps.push_back((uint64_t)b * MT_N - 1); }
-        L.segs.push_back(s);
+        logical.push_back(s);
     }
     // the block that holds the state after the WHOLE draw (all shards): one of two, depending on pos
     const long long f0 = (total_w - 1) / MT_N;
     if (!(b_lo <= f0 && f0 + 1 <= b_hi)) {
-        for (auto& s : L.segs) s.write_state = 0;
+        for (auto& s : logical) s.write_state = 0;
         MtSegment s{};
         s.first_block = f0;
         s.end_block = f0 + 2;
@@ -451,33 +494,50 @@ MtLayout make_layout(long long b_lo, long long b_hi, long long total_w, int P) {
         s.write_state = 1;
         s.poly = -1;
         if (f0 > 0) { s.poly = (int)jumps.size(); jumps.push_back((uint64_t)f0 * MT_N - 1); }
-        L.segs.push_back(s);
+        logical.push_back(s);
     }
     // polynomials: the regular segments are `per` blocks apart -> one power, then a chain of products
-    L.words.resize(jumps.size() * (size_t)MT_N);
-    Poly step{}, g{};
-    bool have_step = false;
-    int max_weight = 0;
-    for (size_t i = 0; i < jumps.size(); ++i) {
-        const bool chain = i > 0 && jumps[i] - jumps[i - 1] == (uint64_t)per * MT_N;
-        if (chain) {
-            if (!have_step) { step = poly_pow_x((uint64_t)per * MT_N); have_step = true; }
-            g = poly_mul(g, step);
-        } else {
-            g = poly_pow_x(jumps[i]);
+    int max_weight = jumps.empty() ? 0 : 10000;
+    if (with_polys) {
+        L.words.resize(jumps.size() * (size_t)MT_N);
+        Poly step{}, g{};
+        bool have_step = false;
+        max_weight = 0;
+        for (size_t i = 0; i < jumps.size(); ++i) {
+            const bool chain = i > 0 && jumps[i] - jumps[i - 1] == (uint64_t)per * MT_N;
+            if (chain) {
+                if (!have_step) { step = poly_pow_x((uint64_t)per * MT_N); have_step = true; }
+                g = poly_mul(g, step);
+            } else {
+                g = poly_pow_x(jumps[i]);
+            }
+            int weight = 0;
+            for (int k = 0; k < POLY_W64; ++k) {
+                L.words[i * MT_N + 2 * k] = (uint32_t)g[k];
+                L.words[i * MT_N + 2 * k + 1] = (uint32_t)(g[k] >> 32);
+                weight += __builtin_popcountll(g[k]);
+            }
+            max_weight = std::max(max_weight, weight);
         }
-        int weight = 0;
-        for (int k = 0; k < POLY_W64; ++k) {
-            L.words[i * MT_N + 2 * k] = (uint32_t)g[k];
-            L.words[i * MT_N + 2 * k + 1] = (uint32_t)(g[k] >> 32);
-            weight += __builtin_popcountll(g[k]);
-        }
-        max_weight = std::max(max_weight, weight);
     }
-    // measured on B200: 0.19 us per regenerated block, 5.7 us for the 34 raw blocks a jump reads, and
-    // 56 us for the correlation with a dense polynomial (~10 000 set bits; zero coefficients are skipped,
-    // and x^J mod phi stays sparse for J up to a few times 19937 because phi has only 135 terms)
-    L.cost_us = 0.19 * (double)per + (jumps.empty() ? 0.0 : 5.7 + 56.0 * max_weight / 10000.0);
+    // spare SMs share the jumps: every jump gets `shares` CTAs, each correlating a part of the polynomial
+    const int n_jumps = (int)jumps.size(), n_plain = (int)logical.size() - n_jumps;
+    int shares = 1;
+    if (n_jumps > 0) shares = std::max(1, std::min(MT_N / CONV_WARPS, (sm_count - n_plain) / n_jumps));
+    if (n_jumps > 0 && 56.0 * max_weight / 10000.0 < 4.0) shares = 1;          // not worth a hand-off
+    for (const MtSegment& lg : logical) {
+        const int n = lg.poly >= 0 ? shares : 1;
+        for (int r = 0; r < n; ++r) {
+            MtSegment s = lg;
+            s.share_r = r;
+            s.share_n = n;
+            s.window = lg.poly >= 0 ? lg.poly : 0;
+            L.segs.push_back(s);
+        }
+    }
+    L.n_windows = n_jumps;
+    L.shared_jumps = shares > 1;
+    L.cost_us = layout_cost(per, n_jumps, shares, max_weight);
     return L;
 }
 
@@ -490,21 +550,31 @@ int build_plan(ss_ctx* c, MtPlan& p, long long off_w, long long n_w, long long t
     p.n_blocks = n_blocks;
     MtLayout best;
     if (std::getenv("SS_MT_FORCE_P")) {
-        best = make_layout(b_lo, b_hi, total_w, std::max(1, std::atoi(std::getenv("SS_MT_FORCE_P"))));
-    } else if (n_blocks >= 4096) {
-        // long streams: one segment per SM, dense polynomials either way
-        best = make_layout(b_lo, b_hi, total_w, (int)std::min<long long>(c->sm_count, n_blocks / 4));
+        best = make_layout(b_lo, b_hi, total_w, std::max(1, std::atoi(std::getenv("SS_MT_FORCE_P"))), c->sm_count, true);
     } else {
-        // short and medium streams: a few candidates, scored with the actual polynomial weights
-        const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32};
-        bool have = false;
+        // candidates: few segments (cheap sparse jumps, each shared by many SMs) ... one segment per SM (dense
+        // jumps, nothing to share).  Small P are scored with their actual polynomial weights, the large ones
+        // as dense; the winner's polynomials are computed last.
+        const int cand[] = {1, 2, 3, 4, 6, 8, 12, 16, 24, 32, 48, 74, 148};
+        int best_P = 1;
+        bool have = false, best_has_polys = false;
         for (int P : cand) {
-            if (P > 1 && n_blocks / P < 8) break;
-            MtLayout L = make_layout(b_lo, b_hi, total_w, P);
-            if (!have || L.cost_us < best.cost_us) { best = std::move(L); have = true; }
+            if (P > c->sm_count || (P > 1 && n_blocks / P < 4)) break;
+            if (n_blocks >= 4096 && P < 48) continue;                      // long streams: dense either way
+            const bool exact = P <= 32;
+            MtLayout L = make_layout(b_lo, b_hi, total_w, P, c->sm_count, exact);
+            if (!have || L.cost_us < best.cost_us) {
+                best = std::move(L);
+                best_P = P;
+                best_has_polys = exact;
+                have = true;
+            }
         }
+        if (!best_has_polys) best = make_layout(b_lo, b_hi, total_w, best_P, c->sm_count, true);
     }
     p.n_segments = (int)best.segs.size();
+    p.cooperative = best.shared_jumps;
+    p.n_windows = best.n_windows;
     SS_CUDA_CHECK(c, p.segs.ensure(best.segs.size() * sizeof(MtSegment)));
     SS_CUDA_CHECK(c, cudaMemcpyAsync(p.segs.p, best.segs.data(), best.segs.size() * sizeof(MtSegment), cudaMemcpyHostToDevice, c->stream));
     if (!best.words.empty()) {
@@ -522,6 +592,7 @@ void mt19937_release(ss_ctx* c) {
     MtCache* m = static_cast<MtCache*>(c->mt_cache);
     for (auto& p : m->plans) { p.segs.release(); p.polys.release(); }
     m->raw.release();
+    m->windows.release();
     if (m->host_state) cudaFreeHost(m->host_state);
     delete m;
     c->mt_cache = nullptr;
@@ -591,7 +662,28 @@ extern "C" int ss_mt19937_uniform(ss_ctx* c, const uint32_t* key, int pos, int64
     a.pos = pos;
     a.state_out = reinterpret_cast<uint32_t*>(m->host_state_dev);
     a.seq = ++m->seq;
-    mt19937_raw_kernel<<<plan->n_segments, MT_THREADS, SMEM_WORDS * 4, c->stream>>>(k, a);
+    if ((size_t)plan->n_windows > m->windows_n) {
+        const size_t n = (size_t)plan->n_windows;
+        SS_CUDA_CHECK(c, m->windows.ensure(n * (CONV_OUT + 1) * 4));
+        SS_CUDA_CHECK(c, cudaMemsetAsync(m->windows.p, 0, n * (CONV_OUT + 1) * 4, c->stream));
+        m->windows_n = n;
+    }
+    a.windows = m->windows.as<uint32_t>();
+    a.counters = reinterpret_cast<unsigned int*>(m->windows.as<uint32_t>() + m->windows_n * CONV_OUT);
+    {
+        cudaLaunchConfig_t cfg;
+        std::memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(plan->n_segments);
+        cfg.blockDim = dim3(MT_THREADS);
+        cfg.dynamicSmemBytes = SMEM_WORDS * 4;
+        cfg.stream = c->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = plan->cooperative ? 1 : 0;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        SS_CUDA_CHECK(c, cudaLaunchKernelEx(&cfg, mt19937_raw_kernel, k, a));
+    }
     c->launches++;
     SS_CUDA_CHECK(c, cudaGetLastError());
     MtConvertArgs cv{};
