@@ -177,7 +177,9 @@ class ShardedPlanner:
             path = pk[row, 2 + H * da:2 + H * da + (H + 1) * d].reshape(H + 1, d).copy()
         res = dict(best_k=best_k, best_score=best_score, best_sequence=seq, best_path=path,
                    owner=w, k_offset=k_offset, k_local=k_local)
-        if rng_state is not None:
+        if isinstance(rng_state, int):
+            self.engine.mt19937_state_into(rng_state)   # numpy's generator advanced in place
+        elif rng_state is not None:
             res["rng_state"] = self.engine.mt19937_state()
         return res
 

@@ -30,6 +30,38 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+class _NumpyGlobalMT:
+    """Direct access to the MT19937 state struct of numpy's global legacy generator (the one behind
+    np.random.uniform): BitGenerator.ctypes.state_address points at {uint32 key[624]; int pos}.  The library
+    then reads and advances numpy's state in place -- np.random.get_state() / set_state() cost 50-150 us per
+    round trip, more than a small decision.  Verified against get_state() once per generator object; any
+    surprise (another bit generator, another layout) disables it and the caller uses get_state / set_state."""
+
+    _checked = {}
+
+    @classmethod
+    def address(cls):
+        try:
+            bg = np.random.mtrand._rand._bit_generator
+            ok = cls._checked.get(id(bg))
+            if ok is None:
+                ok = False
+                if type(bg).__name__ == "MT19937":
+                    addr = bg.ctypes.state_address
+                    addr = addr if isinstance(addr, int) else C.cast(addr, C.c_void_p).value
+                    st = np.random.get_state()
+                    key = np.ctypeslib.as_array((C.c_uint32 * 624).from_address(addr))
+                    if st[0] == "MT19937" and np.array_equal(key, st[1]) and \
+                            C.c_int.from_address(addr + 2496).value == st[2]:
+                        ok = (bg, addr)                 # keep the object alive with its address
+                cls._checked[id(bg)] = ok
+            if not ok or ok[0] is not bg:
+                return None
+            return ok[1]
+        except Exception:
+            return None
+
+
 class _DevicePointer(int):
     """A device address handed to the library in place of a host array."""
 
@@ -450,9 +482,16 @@ class Engine:
             C.byref(best), C.byref(best_score), _ptr(seq), _ptr(path), _ptr(scores)))
         res = dict(best_k=int(best.value), best_score=float(best_score.value), best_sequence=seq,
                    best_path=path, scores=scores)
-        if rng_state is not None:
+        if isinstance(rng_state, int):
+            self.mt19937_state_into(rng_state)          # numpy's generator advanced in place
+        elif rng_state is not None:
             res["rng_state"] = self.mt19937_state()
         return res
+
+    @staticmethod
+    def global_rng_address():
+        """Address of the state struct of numpy's global legacy generator, or None (then use get_state())."""
+        return _NumpyGlobalMT.address()
 
     # three-call form (multi-GPU reference penalty): rollout -> all-reduce sums -> finish
     def rollout(self, state, wp_index, *, actions=None, K=None, H=None, seed=0, act_low=None,
@@ -528,20 +567,32 @@ class Engine:
     # numpy's legacy RandomState stream on the device (csrc/mt19937.cu)
     def mt19937_uniform(self, rng_state, n_total, low, high, first=0, count=None):
         """Elements [first, first + count) of what np.random.uniform(low, high, (n_total // da, da))
-        would draw from ``rng_state`` (np.random.get_state() / RandomState.get_state()), generated on
+        would draw from ``rng_state`` (np.random.get_state() / RandomState.get_state(), or the address of
+        numpy's global state struct, see global_rng_address), generated on
         the GPU bit for bit and left there: returns the device pointer (pass it to plan / rollout as
         ``actions_dev``).  The state after the whole draw comes from mt19937_state()."""
-        if rng_state[0] != "MT19937":
-            raise ValueError("legacy MT19937 state expected")
-        key = np.ascontiguousarray(rng_state[1], dtype=np.uint32)
         lo = _f64(np.asarray(low, dtype=np.float64).reshape(-1))
         hi = _f64(np.asarray(high, dtype=np.float64).reshape(-1))
         count = int(n_total) - int(first) if count is None else int(count)
         out = C.c_void_p()
-        self._check(self._lib.ss_mt19937_uniform(self._h, _ptr(key), int(rng_state[2]), int(n_total), int(first),
+        if isinstance(rng_state, int):
+            # address of numpy's own state struct {uint32 key[624]; int pos} (_NumpyGlobalMT): read in place
+            key_ptr, pos = C.c_void_p(rng_state), C.c_int.from_address(rng_state + 2496).value
+            self._mt_rest = None
+        else:
+            if rng_state[0] != "MT19937":
+                raise ValueError("legacy MT19937 state expected")
+            key = np.ascontiguousarray(rng_state[1], dtype=np.uint32)
+            key_ptr, pos = _ptr(key), int(rng_state[2])
+            self._mt_rest = tuple(rng_state[3:])
+        self._check(self._lib.ss_mt19937_uniform(self._h, key_ptr, pos, int(n_total), int(first),
                                                  count, lo.shape[0], _ptr(lo), _ptr(hi), C.byref(out)))
-        self._mt_rest = tuple(rng_state[3:])
         return out.value
+
+    def mt19937_state_into(self, address):
+        """Write the generator state after the last mt19937_uniform draw straight into numpy's state struct."""
+        self._check(self._lib.ss_mt19937_state(self._h, C.c_void_p(address),
+                                               C.cast(C.c_void_p(address + 2496), C.POINTER(C.c_int))))
 
     def mt19937_state(self):
         """Generator state after the last mt19937_uniform draw, in np.random.set_state's format."""

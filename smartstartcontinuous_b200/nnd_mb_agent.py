@@ -87,7 +87,7 @@ class NND_MB_agent(NavigationRLAgent):
     tf_datatype = "float64"
     noiseToSignal = 0.01
     actions_ag = 'nc'
-    HOST_DRAW_MAX = 32768       # K*H*da up to which the host draws the action samples itself (host_rng=None)
+    HOST_DRAW_MAX = 4096        # K*H*da up to which the host draws the action samples itself (host_rng=None)
 
     def __init__(self, env, sess,
 
@@ -267,9 +267,13 @@ class NND_MB_agent(NavigationRLAgent):
             # numpy's own generator state (MT19937 jump-ahead, csrc/mt19937.cu): the global stream
             # advances exactly as if the host had drawn, no K*H*da host RNG and no upload.  A sharded
             # planner generates each rank's slice of the SAME draw.
+            # (the library reads and advances numpy's state struct in place when it can be reached:
+            # np.random.get_state() + set_state() cost 50-150 us per decision)
+            addr = self.engine.global_rng_address()
             res = plan(curr_nn_state, self.current_desired_state_index, K=self.N, H=self.horizon,
-                       act_low=low, act_high=high, rng_state=npr.get_state(), **common)
-            npr.set_state(res["rng_state"])
+                       act_low=low, act_high=high, rng_state=addr if addr is not None else npr.get_state(), **common)
+            if addr is None:
+                npr.set_state(res["rng_state"])
         else:
             # the same draw on the host (legacy uniform = low + (high - low) * random_sample in draw
             # order, without npr.uniform's slow broadcast path).  host_rng=True under a sharded planner:

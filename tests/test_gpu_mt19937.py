@@ -140,6 +140,8 @@ def test_agent_default_path_draws_numpys_stream_on_the_device(engine):
     rng = np.random.default_rng(4)
     s, a = syn.mountaincar_rollout(rng, 900)
     data = dict(dataX=s[:-1], dataY=a, dataZ=s[1:] - s[:-1])
+    # the library reaches numpy's global state struct directly (no get_state / set_state round trip)
+    assert engine.global_rng_address() is not None
     outs = []
     for host_rng in (True, False, None):
         np.random.seed(77)
@@ -151,7 +153,7 @@ def test_agent_default_path_draws_numpys_stream_on_the_device(engine):
         for t in range(3):
             act, k, seq, path = ag.get_best_sim_actions(s[t])
             res.append((act.copy(), k, seq.copy(), path.copy()))
-        outs.append((res, np.random.random_sample(5)))
+        outs.append((res, np.concatenate([np.random.random_sample(5), np.random.normal(size=3), np.random.randint(0, 1000, 4)])))
     for other in (1, 2):
         for (a0, k0, s0, p0), (a1, k1, s1, p1) in zip(outs[0][0], outs[other][0]):
             # (every agent trains its own model: the device trainer's Adam slots persist across agents of one
