@@ -67,11 +67,21 @@ class _DevicePointer(int):
 
 
 def _ptr(a):
+    """Address for a c_void_p argument (an int: ndarray.ctypes.data_as costs twice as much per argument)."""
     if a is None:
         return None
     if isinstance(a, _DevicePointer):
-        return C.c_void_p(int(a))
-    return a.ctypes.data_as(C.c_void_p)
+        return int(a)
+    return a.ctypes.data
+
+
+def _bounds(v, da):
+    """Action bound as contiguous float64 [da] (no copy when it already is one)."""
+    if v is None:
+        return None
+    if isinstance(v, np.ndarray) and v.dtype == np.float64 and v.shape == (da,) and v.flags.c_contiguous:
+        return v
+    return _f64(np.broadcast_to(np.asarray(v, dtype=np.float64), (da,)))
 
 
 class Engine:
@@ -445,9 +455,7 @@ class Engine:
             if actions.ndim != 3 or actions.shape[2] != da:
                 raise ValueError("actions must be [K, H, da]")
             K, H = actions.shape[0], actions.shape[1]
-        lo = None if act_low is None else _f64(np.broadcast_to(np.asarray(act_low, dtype=np.float64), (da,)))
-        hi = None if act_high is None else _f64(np.broadcast_to(np.asarray(act_high, dtype=np.float64), (da,)))
-        return st, actions, int(K), int(H), lo, hi
+        return st, actions, int(K), int(H), _bounds(act_low, da), _bounds(act_high, da)
 
     def plan(self, state, wp_index, *, actions=None, K=None, H=None, seed=0, act_low=None,
              act_high=None, gamma=.75, horizontal_penalty_factor=.5, penalty_mode="reference",
@@ -571,13 +579,15 @@ class Engine:
         numpy's global state struct, see global_rng_address), generated on
         the GPU bit for bit and left there: returns the device pointer (pass it to plan / rollout as
         ``actions_dev``).  The state after the whole draw comes from mt19937_state()."""
-        lo = _f64(np.asarray(low, dtype=np.float64).reshape(-1))
-        hi = _f64(np.asarray(high, dtype=np.float64).reshape(-1))
+        lo = low if isinstance(low, np.ndarray) and low.dtype == np.float64 and low.ndim == 1 and low.flags.c_contiguous \
+            else _f64(np.asarray(low, dtype=np.float64).reshape(-1))
+        hi = high if isinstance(high, np.ndarray) and high.dtype == np.float64 and high.ndim == 1 and high.flags.c_contiguous \
+            else _f64(np.asarray(high, dtype=np.float64).reshape(-1))
         count = int(n_total) - int(first) if count is None else int(count)
         out = C.c_void_p()
         if isinstance(rng_state, int):
             # address of numpy's own state struct {uint32 key[624]; int pos} (_NumpyGlobalMT): read in place
-            key_ptr, pos = C.c_void_p(rng_state), C.c_int.from_address(rng_state + 2496).value
+            key_ptr, pos = rng_state, C.c_int.from_address(rng_state + 2496).value
             self._mt_rest = None
         else:
             if rng_state[0] != "MT19937":

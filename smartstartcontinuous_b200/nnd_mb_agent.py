@@ -248,8 +248,14 @@ class NND_MB_agent(NavigationRLAgent):
 
     def get_best_sim_actions(self, curr_nn_state):
         """(best_action [da], best_sim_number, best_sequence [H, da], best_path [H+1, d])."""
-        low, high = self.env.action_space.low, self.env.action_space.high
-        da = int(np.prod(self.env.action_space.shape))
+        space = self.env.action_space
+        cached = getattr(self, "_bounds_cache", None)
+        if cached is None or cached[0] is not space.low or cached[1] is not space.high:
+            # contiguous float64 copies of the bounds, redone only when the environment hands out new arrays
+            cached = (space.low, space.high, np.ascontiguousarray(space.low, dtype=np.float64).reshape(-1),
+                      np.ascontiguousarray(space.high, dtype=np.float64).reshape(-1), int(np.prod(space.shape)))
+            self._bounds_cache = cached
+        low, high, da = cached[2], cached[3], cached[4]
         common = dict(gamma=self.gamma, horizontal_penalty_factor=self.horizontal_penalty_factor,
                       penalty_mode=self.penalty_mode, precision=self.precision)
         K_draw, plan = self.N, self.engine.plan
