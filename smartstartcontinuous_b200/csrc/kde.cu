@@ -76,6 +76,7 @@ __host__ __device__ constexpr int kde_queries_per_thread(int D) {
 // ---- 1. moments ------------------------------------------------------------------------
 // partial[b] = { sum (x - x0) [d], sum (x - x0)(x - x0)^T lower-tri [d(d+1)/2] }, x0 = data[0]
 // (shifted by the first data point so the fp64 one-pass covariance does not cancel)
+template <int DF>
 __device__ void kde_fit_block(const double* __restrict__ data, long long n, int d, const double* __restrict__ partial,
                               int nblocks, KdeFit* __restrict__ fit);
 
@@ -130,12 +131,17 @@ kde_moments_kernel(const double* __restrict__ data, long long n, int d, double* 
     __syncthreads();
     if (s_last) {
         __threadfence();
-        kde_fit_block(data, n, d, partial, (int)gridDim.x, fit);
+        // (matrix scratch sized for the dimension at hand: with d <= 4 the serial fit runs out of registers
+        // instead of a 24 KB local-memory frame -- ~8 us of the call at d = 3)
+        if (d <= 4) kde_fit_block<4>(data, n, d, partial, (int)gridDim.x, fit);
+        else if (d <= 8) kde_fit_block<8>(data, n, d, partial, (int)gridDim.x, fit);
+        else kde_fit_block<SS_MAX_D>(data, n, d, partial, (int)gridDim.x, fit);
         if (threadIdx.x == 0) *ticket = 0;
     }
 }
 
 // ---- 2. fit ----------------------------------------------------------------------------
+template <int DF>
 __device__ void kde_fit_block(const double* __restrict__ data, long long n, int d, const double* __restrict__ partial,
                               int nblocks, KdeFit* __restrict__ fit) {
     __shared__ double mom[SS_MAX_D + SS_MAX_D * (SS_MAX_D + 1) / 2];
@@ -151,48 +157,89 @@ __device__ void kde_fit_block(const double* __restrict__ data, long long n, int 
     if (threadIdx.x != 0) return;
     const double N = (double)n;
     const double factor = pow(N, -1.0 / (d + 4));          // scotts_factor
-    double cov[SS_MAX_D * SS_MAX_D];
-    int p = d;
-    for (int j = 0; j < d; ++j) {
-        fit->mean[j] = data[j] + mom[j] / N;
-        for (int k = 0; k <= j; ++k) {
-            double c = (mom[p++] - mom[j] * mom[k] / N) / (N - 1.0);   // ddof = 1
-            cov[j * d + k] = c * factor * factor;
-            cov[k * d + j] = cov[j * d + k];
-        }
-    }
-    // Cholesky (lower), in place in l[]
-    double l[SS_MAX_D * SS_MAX_D];
-    int status = 0;
-    for (int j = 0; j < d; ++j) {
-        for (int k = 0; k <= j; ++k) {
-            double s = cov[j * d + k];
-            for (int q = 0; q < k; ++q) s -= l[j * d + q] * l[k * d + q];
-            if (j == k) {
-                if (!(s > 0.0)) { status = 1; s = 1.0; }
-                l[j * d + j] = sqrt(s);
-            } else {
-                l[j * d + k] = s / l[k * d + k];
+    // DF x DF scratch with compile-time strides; for DF <= 4 the loops unroll and the matrices stay in registers
+    constexpr bool UNROLL = DF <= 4;
+    double cov[DF * DF], l[DF * DF], inv[DF * DF];
+    {
+        int p = d;
+#pragma unroll(DF <= 4 ? DF * DF : 1)
+        for (int j = 0; j < DF; ++j) {
+            if (j < d) {
+                fit->mean[j] = data[j] + mom[j] / N;
+#pragma unroll(DF <= 4 ? DF * DF : 1)
+                for (int k = 0; k < DF; ++k) {
+                    if (k <= j) {
+                        const double c = (mom[p + k] - mom[j] * mom[k] / N) / (N - 1.0);   // ddof = 1
+                        cov[j * DF + k] = c * factor * factor;
+                        cov[k * DF + j] = cov[j * DF + k];
+                    }
+                }
+                p += j + 1;
             }
         }
-        for (int k = j + 1; k < d; ++k) l[j * d + k] = 0.0;
+    }
+    // Cholesky (lower)
+    int status = 0;
+#pragma unroll(DF <= 4 ? DF * DF : 1)
+    for (int j = 0; j < DF; ++j) {
+        if (!UNROLL && j >= d) break;
+#pragma unroll(DF <= 4 ? DF * DF : 1)
+        for (int k = 0; k < DF; ++k) {
+            if (!UNROLL && k >= d) break;
+            if (j < d && k < d) {
+                if (k <= j) {
+                    double s = cov[j * DF + k];
+#pragma unroll(DF <= 4 ? DF * DF : 1)
+                    for (int q = 0; q < DF; ++q)
+                        if (q < k) s -= l[j * DF + q] * l[k * DF + q];
+                    if (j == k) {
+                        if (!(s > 0.0)) { status = 1; s = 1.0; }
+                        l[j * DF + j] = sqrt(s);
+                    } else {
+                        l[j * DF + k] = s / l[k * DF + k];
+                    }
+                } else {
+                    l[j * DF + k] = 0.0;
+                }
+            }
+        }
     }
     // inverse of the lower-triangular factor
-    double inv[SS_MAX_D * SS_MAX_D];
-    for (int j = 0; j < d * d; ++j) inv[j] = 0.0;
-    for (int c = 0; c < d; ++c) {
-        inv[c * d + c] = 1.0 / l[c * d + c];
-        for (int r = c + 1; r < d; ++r) {
-            double s = 0.0;
-            for (int q = c; q < r; ++q) s -= l[r * d + q] * inv[q * d + c];
-            inv[r * d + c] = s / l[r * d + r];
+#pragma unroll(DF <= 4 ? DF * DF : 1)
+    for (int j = 0; j < DF * DF; ++j) inv[j] = 0.0;
+#pragma unroll(DF <= 4 ? DF * DF : 1)
+    for (int c = 0; c < DF; ++c) {
+        if (!UNROLL && c >= d) break;
+        if (c < d) {
+            inv[c * DF + c] = 1.0 / l[c * DF + c];
+#pragma unroll(DF <= 4 ? DF * DF : 1)
+            for (int r = 0; r < DF; ++r) {
+                if (!UNROLL && r >= d) break;
+                if (r > c && r < d) {
+                    double s = 0.0;
+#pragma unroll(DF <= 4 ? DF * DF : 1)
+                    for (int q = 0; q < DF; ++q)
+                        if (q >= c && q < r) s -= l[r * DF + q] * inv[q * DF + c];
+                    inv[r * DF + c] = s / l[r * DF + r];
+                }
+            }
         }
     }
     // exp(-e/2) = exp2(-(sqrt(log2(e)/2) |L^-1 (q-x)|)^2)
     const double scale = sqrt(0.5 * 1.4426950408889634074);
     double det = 1.0;
-    for (int j = 0; j < d; ++j) det *= l[j * d + j];
-    for (int j = 0; j < d * d; ++j) fit->wm[j] = inv[j] * scale;
+#pragma unroll(DF <= 4 ? DF * DF : 1)
+    for (int j = 0; j < DF; ++j)
+        if (j < d) det *= l[j * DF + j];
+#pragma unroll(DF <= 4 ? DF * DF : 1)
+    for (int j = 0; j < DF; ++j) {
+        if (!UNROLL && j >= d) break;
+#pragma unroll(DF <= 4 ? DF * DF : 1)
+        for (int k = 0; k < DF; ++k) {
+            if (!UNROLL && k >= d) break;
+            if (j < d && k < d) fit->wm[j * d + k] = inv[j * DF + k] * scale;
+        }
+    }
     fit->norm = N * pow(2.0 * 3.14159265358979323846, 0.5 * d) * det;
     fit->status = status;
     fit->max_norm2_bits = 0;

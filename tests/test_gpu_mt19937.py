@@ -161,3 +161,24 @@ def test_agent_default_path_draws_numpys_stream_on_the_device(engine):
             assert k0 == k1 and np.array_equal(a0, a1) and np.array_equal(s0, s1)
             assert np.allclose(p0, p1, rtol=1e-4, atol=1e-6)
         assert np.array_equal(outs[0][1], outs[other][1])
+
+
+@pytest.mark.parametrize("force_p", [2, 5, 9, 40, 148])
+def test_forced_segment_layouts(engine, force_p):
+    """Every layout the planner can pick -- few segments whose jumps are shared by many CTAs, many segments
+    with one CTA each -- produces numpy's stream (SS_MT_FORCE_P overrides the cost model; a fresh stream
+    length per layout keeps the plan cache from answering)."""
+    import os
+    old = os.environ.get("SS_MT_FORCE_P")
+    os.environ["SS_MT_FORCE_P"] = str(force_p)
+    try:
+        n_rows = 150000 + 1000 * force_p
+        _check(engine, _rs(40 + force_p, 321), n_rows, [-2.0], [2.0])
+        rs = np.random.RandomState(force_p)
+        rs.randint(0, 2 ** 31, size=5)
+        _check(engine, rs, n_rows + 7, [-2.0, 0.5], [2.0, 0.75], shards=2)
+    finally:
+        if old is None:
+            os.environ.pop("SS_MT_FORCE_P", None)
+        else:
+            os.environ["SS_MT_FORCE_P"] = old
