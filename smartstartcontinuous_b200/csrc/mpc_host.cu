@@ -310,23 +310,24 @@ extern "C" int ss_mpc_rollout(ss_ctx* c, const double* state, int wp_index, int6
     SS_CUDA_CHECK(c, c->mpc_scores.ensure((size_t)K_local * 4));
     a.scores_out = c->mpc_scores.as<float>();
     const bool ref = penalty_mode == SS_PENALTY_REFERENCE;
-    const int sum_blocks = mpc_sums_reference_blocks(K_local);
     // The trajectory rows (state, waypoint index) are spilled in both penalty modes: the stores
     // hide behind the layer-2 MMAs (no measurable cost), the reference-mode passes need them, and the
     // winner's predicted path (NND_MB_agent.py:517) is then a gather instead of a re-roll.
     r.states_stored = true;
     SS_CUDA_CHECK(c, c->mpc_states.ensure((size_t)T * K_local * traj_row_stride(c->d) * 4));
     a.states_out = c->mpc_states.as<float>();
-    const long long tc_qcols = 4 * ((K_local + mpc_tc_tile_rows() - 1) / mpc_tc_tile_rows());
-    const bool tc_sums = ref && precision == SS_PRECISION_BF16_TC;   // projection sums inside the rollout kernel
+    // projection sums come out of the rollout kernel: one table column per (tile, row warp) of the tcgen05
+    // kernels, one per 32-sequence CTA of the FP32 kernel
+    RolloutArgs probe;
+    probe.K_local = K_local;
+    const long long tc_qcols = precision == SS_PRECISION_BF16_TC
+                                   ? 4 * ((K_local + mpc_tc_tile_rows() - 1) / mpc_tc_tile_rows())
+                                   : (long long)mpc_simt_grid(probe);
     if (ref) {
-        // reference penalty: the projection sums come out of the tcgen05 kernel (one table column per
-        // tile and row warp) or, on the FP32 path, from a pass over the rows; the penalties from a
-        // second light pass (mpc_score.cu)
-        const size_t cols = tc_sums ? (size_t)tc_qcols : (size_t)sum_blocks;
-        SS_CUDA_CHECK(c, c->mpc_partial_sums.ensure((cols + 64) * T * 2 * 8));     // + room for the folded columns
+        // reference penalty: the penalties themselves come from the tail's pass over the rows (mpc_score.cu)
+        SS_CUDA_CHECK(c, c->mpc_partial_sums.ensure(((size_t)tc_qcols + 64) * T * 2 * 8));     // + room for the folded columns
         SS_CUDA_CHECK(c, c->mpc_sums.ensure((size_t)T * 2 * 8));
-        if (tc_sums) a.qsums = c->mpc_partial_sums.as<double>();
+        a.qsums = c->mpc_partial_sums.as<double>();
     }
     timer_mark(c, "mpc_setup");
     int grid = 0;
@@ -360,12 +361,8 @@ extern "C" int ss_mpc_rollout(ss_ctx* c, const double* state, int wp_index, int6
     r.n_cols = 0;
     r.sums_reduced = false;
     if (ref) {
-        int red_blocks = tc_sums ? (int)tc_qcols : sum_blocks;
+        int red_blocks = (int)tc_qcols;
         const double* red_src = c->mpc_partial_sums.as<double>();
-        if (!tc_sums) {
-            rc = mpc_sums_reference(c, a.plan, c->mpc_states.as<float>(), K_local, T, c->mpc_partial_sums.as<double>());
-            if (rc) return rc;
-        }
         if (red_blocks > 256) {
             // thousands of columns (one per tile and row warp): fold them to 16 per output first
             double* folded = c->mpc_partial_sums.as<double>() + (size_t)red_blocks * T * 2;

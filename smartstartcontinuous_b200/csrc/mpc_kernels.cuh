@@ -24,7 +24,7 @@ struct RolloutArgs {
     float* states_out;       // [H+1][K_local][d + 1] trajectory rows (score.cuh) or null
     float* scores_out;       // [K_local] (per-sample mode: final; reference mode: progress term)
     double* qsums;           // tcgen05 kernel, reference mode: [H+1][2][4 * tiles] a'.b' and b'.b' summed over the
-                             // 32 rows of every (tile, row warp), or null (then mpc_sums_reference computes them)
+                             // 32 rows of every (tile, row warp), or null (per-sample penalty)
 };
 
 // fp32 SIMT rollout (mpc_simt.cu)
@@ -48,13 +48,6 @@ int mpc_tc_quad_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out);
 // scoring tail (mpc_score.cu)
 int mpc_reduce_sums(ss_ctx* c, const double* partial, int blocks, int T, double* sums);
 int mpc_fold_partials(ss_ctx* c, const double* partial, int blocks, int T, double* folded, int* blocks_out);
-int mpc_sums_reference_blocks(long long K_local);
-int mpc_sums_reference(ss_ctx* c, const PlanView& plan, const float* rows, long long K_local, int T,
-                       double* partial);
-int mpc_score_reference(ss_ctx* c, const PlanView& plan, const float* rows, long long K_local, int T,
-                        const double* sums, float* scores);
-int mpc_argmax(ss_ctx* c, const float* scores, long long K_local, long long k_offset,
-               double* block_v, long long* block_i, void* result_dev);
 // the fused tail: [2T][n_cols] partial sum columns (or null) -> coefficients, penalties, arg-max, package
 // (device copy at pkg; host_pkg = mapped pinned memory [flag, -, package...] or null; flag := seq when done)
 int mpc_tail_blocks(long long K_local);

@@ -1,12 +1,8 @@
 // mpc_score.cu -- the scoring tail of the MPC planner.
 //
-//   mpc_sums_reference   SS_PENALTY_REFERENCE first pass over the spilled (state, waypoint index)
-//                        rows: per-block partial sums of a'.b' and b'.b' for every time step
-//   mpc_reduce_sums      deterministic reduction of those partials
-//                        (sum_k a'.b', sum_k b'.b' per time step; numerical.py:89-93)
-//   mpc_score_reference  second pass: subtract the penalties computed with the global projection
-//                        coefficient of every step (NND_MB_agent.py:616-622) from the progress term
-//   mpc_argmax           np.argmax-ordered arg-max over the scores (NND_MB_agent.py:625-626)
+//   mpc_fold_partials    the rollout kernels leave the projection terms a'.b' and b'.b' of every time step
+//   mpc_reduce_sums      (numerical.py:89-93) as one float64 table column per (tile, row warp) / 32-sequence
+//                        CTA: deterministic fold + reduction to the 2 (H + 1) sums of the batch
 //   mpc_tail             ONE launch for the whole tail of a decision: projection-sum columns -> global
 //                        coefficients, penalty pass, arg-max, and the winner's package (score, k, action
 //                        sequence, predicted path; NND_MB_agent.py:516-518) written to device memory and
@@ -15,8 +11,6 @@
 #include "mpc_kernels.cuh"
 
 namespace {
-
-constexpr int SUMS_KPT = 4;   // sequences per thread in the projection-sum pass
 
 // sums[2t + w] = sum over the blocks' partials, one warp per output, fixed order (lanes stride over
 // the blocks, then a shuffle tree): deterministic for a given K_local
@@ -45,117 +39,6 @@ mpc_fold_partials_kernel(const double* __restrict__ partial, int blocks, int n_o
     for (int b = b0 + lane; b < b1; b += 32) s += partial[(size_t)o * blocks + b];
     for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
     if (lane == 0) folded[(size_t)o * SUMS_FOLD + f] = s;
-}
-
-// first pass over the spilled rows: a'.b' and b'.b' (numerical.py:89-93) of every (t, k), summed
-// over k per time step.  grid = (k blocks, T); partial[t][2][block].
-template <int DT>
-__global__ void __launch_bounds__(256)
-mpc_sums_reference_kernel(const PlanView Pg, const float* __restrict__ rows, long long K, int ds_in_smem,
-                          double* __restrict__ partial) {
-    __shared__ double s_part[8][2];
-    extern __shared__ float s_dyn[];
-    PlanView P = Pg;
-    if (ds_in_smem) {          // waypoints in shared memory: the lookups depend on the loaded index
-        for (int i = threadIdx.x; i < Pg.W * Pg.d; i += blockDim.x) s_dyn[i] = Pg.ds[i];
-        P.ds = s_dyn;
-        __syncthreads();
-    }
-    const int t = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double dab = 0.0, dbb = 0.0;
-#pragma unroll
-    for (int i = 0; i < SUMS_KPT; ++i) {
-        const long long k = ((long long)blockIdx.x * SUMS_KPT + i) * blockDim.x + threadIdx.x;
-        if (k < K) {
-            float x[DT];
-            int idx;
-            traj_load<DT>(rows, (size_t)t * K + k, P.d, x, idx);
-            float ab, bb;
-            proj_terms<DT>(P, idx, x, ab, bb);
-            dab += (double)ab;
-            dbb += (double)bb;
-        }
-    }
-    for (int off = 16; off > 0; off >>= 1) {
-        dab += __shfl_down_sync(0xffffffffu, dab, off);
-        dbb += __shfl_down_sync(0xffffffffu, dbb, off);
-    }
-    if (lane == 0) { s_part[warp][0] = dab; s_part[warp][1] = dbb; }
-    __syncthreads();
-    if (threadIdx.x < 2) {
-        double tot = 0.0;
-        for (int w = 0; w < 8; ++w) tot += s_part[w][threadIdx.x];
-        partial[((size_t)t * 2 + threadIdx.x) * gridDim.x + blockIdx.x] = tot;
-    }
-}
-
-// second pass: scores[k] (the progress term from the rollout kernel) minus the penalties of the
-// H+1 trajectory points with the global projection coefficient of each step, in step order
-template <int DT>
-__global__ void __launch_bounds__(256)
-mpc_score_reference_kernel(const PlanView Pg, const float* __restrict__ rows, long long K, int T, int ds_in_smem,
-                           const double* __restrict__ sums, float* __restrict__ scores) {
-    extern __shared__ float s_lam[];
-    for (int t = threadIdx.x; t < T; t += blockDim.x) s_lam[t] = (float)(sums[2 * t] / sums[2 * t + 1]);
-    PlanView P = Pg;
-    if (ds_in_smem) {
-        float* s_ds = s_lam + T;
-        for (int i = threadIdx.x; i < Pg.W * Pg.d; i += blockDim.x) s_ds[i] = Pg.ds[i];
-        P.ds = s_ds;
-    }
-    __syncthreads();
-    const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (k >= K) return;
-    float score = scores[k];
-#pragma unroll 8
-    for (int t = 0; t < T; ++t) {
-        float x[DT];
-        int idx;
-        traj_load<DT>(rows, (size_t)t * K + k, P.d, x, idx);
-        score -= penalty_with_lambda<DT>(P, idx, x, s_lam[t]);
-    }
-    scores[k] = score;
-}
-
-__global__ void __launch_bounds__(256)
-mpc_argmax_kernel(const float* __restrict__ scores, long long K, long long k_offset,
-                  double* __restrict__ block_v, long long* __restrict__ block_i,
-                  MpcResult* __restrict__ result) {
-    __shared__ double s_v[32];
-    __shared__ long long s_i[32];
-    __shared__ bool s_last;
-    double v = 0.0;
-    long long bi = -1;
-    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < K;
-         k += (long long)gridDim.x * blockDim.x) {
-        double ov = (double)scores[k];
-        if (argmax_better(ov, k, v, bi)) { v = ov; bi = k; }
-    }
-    block_argmax(v, bi, s_v, s_i);
-    if (threadIdx.x == 0) {
-        block_v[blockIdx.x] = v;
-        block_i[blockIdx.x] = bi;
-        __threadfence();
-        s_last = atomicAdd(&result->blocks_done, 1u) == gridDim.x - 1;
-    }
-    __syncthreads();
-    if (s_last) {
-        __threadfence();
-        v = 0.0;
-        bi = -1;
-        for (int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
-            double ov = block_v[b];
-            long long oi = block_i[b];
-            if (argmax_better(ov, oi, v, bi)) { v = ov; bi = oi; }
-        }
-        block_argmax(v, bi, s_v, s_i);
-        if (threadIdx.x == 0) {
-            result->best_score = v;
-            result->best_k = bi < 0 ? -1 : bi + k_offset;
-            result->blocks_done = 0;
-        }
-    }
 }
 
 // ---- the fused tail -------------------------------------------------------------------------
@@ -306,56 +189,6 @@ int mpc_fold_partials(ss_ctx* c, const double* partial, int blocks, int T, doubl
     c->launches++;
     SS_CUDA_CHECK(c, cudaGetLastError());
     *blocks_out = SUMS_FOLD;
-    return SS_OK;
-}
-
-int mpc_sums_reference_blocks(long long K_local) {
-    return (int)((K_local + 256 * SUMS_KPT - 1) / (256 * SUMS_KPT));
-}
-
-int mpc_sums_reference(ss_ctx* c, const PlanView& plan, const float* rows, long long K_local, int T,
-                       double* partial) {
-    const dim3 grid((unsigned)mpc_sums_reference_blocks(K_local), (unsigned)T);
-    const size_t ds_bytes = (size_t)plan.W * plan.d * 4;
-    const int in_smem = ds_bytes <= 40 * 1024;
-    const size_t smem = in_smem ? ds_bytes : 0;
-    if (plan.d <= 4)
-        mpc_sums_reference_kernel<4><<<grid, 256, smem, c->stream>>>(plan, rows, K_local, in_smem, partial);
-    else if (plan.d <= 8)
-        mpc_sums_reference_kernel<8><<<grid, 256, smem, c->stream>>>(plan, rows, K_local, in_smem, partial);
-    else
-        mpc_sums_reference_kernel<SS_MAX_D><<<grid, 256, smem, c->stream>>>(plan, rows, K_local, in_smem, partial);
-    c->launches++;
-    SS_CUDA_CHECK(c, cudaGetLastError());
-    return SS_OK;
-}
-
-int mpc_score_reference(ss_ctx* c, const PlanView& plan, const float* rows, long long K_local, int T,
-                        const double* sums, float* scores) {
-    const unsigned grid = (unsigned)((K_local + 255) / 256);
-    const size_t ds_bytes = (size_t)plan.W * plan.d * 4;
-    const int in_smem = ds_bytes + (size_t)T * 4 <= 40 * 1024;
-    const size_t smem = (size_t)T * sizeof(float) + (in_smem ? ds_bytes : 0);
-    if (plan.d <= 4)
-        mpc_score_reference_kernel<4><<<grid, 256, smem, c->stream>>>(plan, rows, K_local, T, in_smem, sums, scores);
-    else if (plan.d <= 8)
-        mpc_score_reference_kernel<8><<<grid, 256, smem, c->stream>>>(plan, rows, K_local, T, in_smem, sums, scores);
-    else
-        mpc_score_reference_kernel<SS_MAX_D><<<grid, 256, smem, c->stream>>>(plan, rows, K_local, T, in_smem, sums,
-                                                                         scores);
-    c->launches++;
-    SS_CUDA_CHECK(c, cudaGetLastError());
-    return SS_OK;
-}
-
-int mpc_argmax(ss_ctx* c, const float* scores, long long K_local, long long k_offset, double* block_v,
-               long long* block_i, void* result_dev) {
-    long long want = (K_local + 255) / 256;
-    const int grid = (int)(want < 1 ? 1 : (want > 1024 ? 1024 : want));
-    mpc_argmax_kernel<<<grid, 256, 0, c->stream>>>(scores, K_local, k_offset, block_v, block_i,
-                                                   reinterpret_cast<MpcResult*>(result_dev));
-    c->launches++;
-    SS_CUDA_CHECK(c, cudaGetLastError());
     return SS_OK;
 }
 

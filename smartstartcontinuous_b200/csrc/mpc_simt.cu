@@ -10,6 +10,7 @@
 //   act[k][row] (unit-major) ping/pong buffers, weights streamed from L2 through a
 //   double-buffered cp.async stage, 4 rows x 8 units register tile per thread.
 #include "mpc_kernels.cuh"
+#include "tc_score_row.cuh"
 
 namespace {
 
@@ -166,11 +167,9 @@ __global__ void __launch_bounds__(ST) mpc_rollout_simt_kernel(const RolloutArgs 
 
     for (int t = 0; t < T; ++t) {
         // ---- score the current point (row owners) -------------------------------------
-        if (owner) {
-            score_point<DT>(a.plan, t, x, sc, a.per_sample != 0);
-            if (a.states_out && live)
-                traj_store<DT>(a.states_out, (size_t)t * a.K_local + k_local, a.d, x, sc.idx);
-        }
+        // (reference penalty: the step's projection terms summed over the CTA's 32 sequences, one column
+        // of a.qsums per CTA -- the same scheme as the tcgen05 kernels, no pass over the spilled rows)
+        if (owner) tc::score_row<DT>(a, t, x, sc, live, k_local, (long long)blockIdx.x, (long long)gridDim.x, tid);
         if (t == a.H) break;
         // ---- network input: normalised state and action (dynamics_model.py:228-230) ------
         if (owner) {
