@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();         // = the layer-2 chunk this CTA computes
     const long long cluster_id = blockIdx.x / QUAD, n_clusters = gridDim.x / QUAD;
+    if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[192] = (unsigned long long)clock64();
 
     if (tid == 0) {
         mbar_init(&acc_full[0], 1);
@@ -117,21 +118,26 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
         mbar_init(&z_full[0], 1);
         mbar_init(&z_full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (p.prof && blockIdx.x == 0) p.prof[196] = (unsigned long long)clock64();
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
                      "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[197] = (unsigned long long)clock64();
     }
-    for (int i = tid; i < (HP / 2) * (2 * DZP); i += THREADS) w3s[i] = p.w3[i];
     __syncthreads();
+    if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[198] = (unsigned long long)clock64();
     if (warp == ROW_WARPS + 1) {
         // resident operands, each as 128-row K-major tiles [k/8][128 units][8]: the two 64-unit halves of the
         // global images are interleaved k-group by k-group (1 KB bulk copies spread over the lanes).  W1 of
         // every chunk first (the first MMAs need it), then this CTA's chunk of W2 (needed ~1000 clocks later).
         constexpr int KG1 = K1T / 8, KG2 = KSLAB / 8;
         if (lane == 0) {
-            mbar_expect_tx(&w_full[0], (uint32_t)(NCH * 2 * W1_CHUNK_BYTES));
+            // (layer-3 weights ride on the first barrier: a 320-thread global-load loop here cost ~4000 clocks of
+            // every launch)
+            mbar_expect_tx(&w_full[0], (uint32_t)(NCH * 2 * W1_CHUNK_BYTES) + (uint32_t)((HP / 2) * (2 * DZP) * 4));
+            bulk_g2s(w3s, p.w3, (uint32_t)((HP / 2) * (2 * DZP) * 4), &w_full[0]);
             mbar_expect_tx(&w_full[1], (uint32_t)(NSLAB * 2 * BLOCK_BYTES));
         }
         __syncwarp();
@@ -153,6 +159,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
     cluster_sync_all();                  // every CTA's barriers exist before anybody arrives remotely
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
+    if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[193] = (unsigned long long)clock64();
 
     if (warp < ROW_WARPS) {
         // =============================== ROW WARPS ========================================
@@ -168,6 +175,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
             upd_c[j] = j < a.d ? fmaf(__ldg(p.b3 + j), a.norm.std_z[j], a.norm.mean_z[j]) : 0.f;
             asm volatile("" : "+f"(upd_s[j]), "+f"(upd_c[j]));
         }
+        mbar_wait<false>(&w_full[0], 0);             // W3 (read by these warps) has landed
         for (int it = 0; it < p.iters; ++it) {
             const long long tile = p.tile_begin + (long long)it * n_clusters + cluster_id;   // >= tile_end: padding
             const long long k_local = tile * TM + row;
@@ -360,6 +368,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
                 }
                 TQ_TRACE(11);
             }
+            if (p.prof && blockIdx.x == 0 && tid == 0 && it == 0) p.prof[194] = (unsigned long long)clock64();
             if (scorer) {
                 score_row<DT>(a, a.H, x, sc, live, k_local, qcol, n_qcols, lane);
                 if (live && a.scores_out) a.scores_out[k_local] = sc.score;
@@ -427,6 +436,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
     __syncthreads();
     cluster_sync_all();                  // nobody leaves while a peer may still write into its buffers
     tc_fence_after();
+    if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[195] = (unsigned long long)clock64();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(TMEM_COLS));
 }
@@ -521,9 +531,12 @@ int mpc_tc_quad_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out) {
     c->launches++;
     SS_CUDA_CHECK(c, e);
     if (p.prof) {
-        std::vector<unsigned long long> h(3 * 64);
+        std::vector<unsigned long long> h(3 * 64 + 8);
         SS_CUDA_CHECK(c, cudaMemcpyAsync(h.data(), p.prof, h.size() * 8, cudaMemcpyDeviceToHost, c->stream));
         SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+        fprintf(stderr, "[quad trace] entry: barriers %llu tmem alloc %llu first sync %llu\n", h[196] - h[192], h[197] - h[192], h[198] - h[192]);
+        fprintf(stderr, "[quad trace] entry->setup done %llu clk | setup->last step end %llu | ->teardown done %llu | step 10 starts %llu after entry\n",
+                h[193] - h[192], h[194] - h[193], h[195] - h[194], h[0] - h[192]);
         for (int st = 0; st < 3; ++st) {
             const unsigned long long* ev = &h[st * 64];
             const unsigned long long t0 = ev[0];

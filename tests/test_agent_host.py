@@ -44,3 +44,39 @@ def test_reference_harness_sources():
     ref = rh.load_reference()
     assert hasattr(ref.nnd.NND_MB_agent, "get_best_sim_actions")
     assert hasattr(ref.ssc.SmartStartContinuous, "get_smart_start_path")
+
+
+def test_numpy_global_generator_state_is_reachable_in_place():
+    """The default agent path hands the library the address of numpy's global MT19937 state struct
+    ({uint32 key[624]; int pos}, BitGenerator.ctypes.state_address) instead of paying get_state() +
+    set_state() per decision: what is read there is what get_state() reports, through draws, re-seeding and
+    set_state, and a state written there is what numpy continues from."""
+    import ctypes as C
+
+    from smartstartcontinuous_b200.engine import _NumpyGlobalMT
+
+    addr = _NumpyGlobalMT.address()
+    assert addr is not None
+
+    def view():
+        return np.ctypeslib.as_array((C.c_uint32 * 624).from_address(addr)), C.c_int.from_address(addr + 2496)
+
+    saved = np.random.get_state()
+    try:
+        for prepare in (lambda: np.random.seed(123), lambda: np.random.random_sample(777),
+                        lambda: np.random.set_state(saved), lambda: np.random.randint(0, 10, 3)):
+            prepare()
+            assert _NumpyGlobalMT.address() == addr
+            key, pos = view()
+            st = np.random.get_state()
+            assert np.array_equal(key, st[1]) and pos.value == st[2]
+        # advance a private generator, write its state into the struct: the global stream continues from there
+        rs = np.random.RandomState(5)
+        rs.random_sample(1000)
+        st = rs.get_state()
+        key, pos = view()
+        key[:] = st[1]
+        pos.value = st[2]
+        assert np.array_equal(np.random.random_sample(10), rs.random_sample(10))
+    finally:
+        np.random.set_state(saved)
