@@ -64,9 +64,11 @@ def sample_range(first, stop, k):
         _probe_fast_sample()
     n = stop - first
     if _FAST_SAMPLE and k > 64 and 0 < n < 2 ** 31:
-        out = _sample_with(_FAST_SAMPLE, random._inst, first, n, k)
-        if out is not None:
-            return out
+        rnd = getattr(random.sample, "__self__", None)       # the module-level generator random.sample is bound to
+        if type(rnd) is random.Random:
+            out = _sample_with(_FAST_SAMPLE, rnd, first, n, k)
+            if out is not None:
+                return out
     return np.array(random.sample(range(first, stop), k))
 
 
