@@ -211,6 +211,32 @@ static inline void timer_mark(ss_ctx* c, const char* name) {
     cudaEventRecord(t.ev[t.n], c->stream);
 }
 
+// ---- programmatic dependent launch (the small kernels behind a rollout) -------------------------
+// A kernel launched with launch_dependent() may be scheduled while its predecessor in the stream still runs
+// (once every CTA of the predecessor has executed pdl_trigger() or exited); it must execute pdl_wait() before it
+// touches anything the predecessor writes -- the wait returns when the predecessor has completed and its
+// memory operations are visible.  This takes the launch latency of the reduce / tail kernels (2-3 us each) off
+// a small decision's critical path.  Both instructions are no-ops in a normally launched kernel.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                           cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // ---- device helpers --------------------------------------------------------------------
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;

@@ -16,6 +16,8 @@ namespace {
 // the blocks, then a shuffle tree): deterministic for a given K_local
 __global__ void __launch_bounds__(256)
 mpc_reduce_sums_kernel(const double* __restrict__ partial, int blocks, int T, double* __restrict__ sums) {
+    pdl_trigger();
+    pdl_wait();
     const int o = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (o >= 2 * T) return;
     const int t = o >> 1, w = o & 1, lane = threadIdx.x & 31;
@@ -30,6 +32,8 @@ mpc_reduce_sums_kernel(const double* __restrict__ partial, int blocks, int T, do
 constexpr int SUMS_FOLD = 16;
 __global__ void __launch_bounds__(256)
 mpc_fold_partials_kernel(const double* __restrict__ partial, int blocks, int n_out, double* __restrict__ folded) {
+    pdl_trigger();
+    pdl_wait();
     const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (wid >= n_out * SUMS_FOLD) return;
     const int o = wid / SUMS_FOLD, f = wid % SUMS_FOLD, lane = threadIdx.x & 31;
@@ -100,6 +104,7 @@ mpc_tail_kernel(const PlanView Pg, const float* __restrict__ rows, long long K, 
                 double* __restrict__ block_v, long long* __restrict__ block_i, MpcResult* __restrict__ result,
                 ActionSource act, int want_path, TailOut out) {
     extern __shared__ float s_dyn[];             // [T] lambda | [W * d] waypoints (optional)
+    pdl_wait();                                  // (launched as a programmatic dependent of the kernel in front)
     __shared__ double s_v[32];
     __shared__ long long s_i[32];
     __shared__ bool s_last;
@@ -175,7 +180,7 @@ mpc_tail_kernel(const PlanView Pg, const float* __restrict__ rows, long long K, 
 }  // namespace
 
 int mpc_reduce_sums(ss_ctx* c, const double* partial, int blocks, int T, double* sums) {
-    mpc_reduce_sums_kernel<<<(2 * T + 7) / 8, 256, 0, c->stream>>>(partial, blocks, T, sums);
+    SS_CUDA_CHECK(c, launch_dependent(mpc_reduce_sums_kernel, dim3((2 * T + 7) / 8), dim3(256), 0, c->stream, partial, blocks, T, sums));
     c->launches++;
     SS_CUDA_CHECK(c, cudaGetLastError());
     return SS_OK;
@@ -185,7 +190,7 @@ int mpc_reduce_sums(ss_ctx* c, const double* partial, int blocks, int T, double*
 // (blocks > SUMS_FOLD); returns the new column count through *blocks_out
 int mpc_fold_partials(ss_ctx* c, const double* partial, int blocks, int T, double* folded, int* blocks_out) {
     const int warps = 2 * T * SUMS_FOLD;
-    mpc_fold_partials_kernel<<<(warps + 7) / 8, 256, 0, c->stream>>>(partial, blocks, 2 * T, folded);
+    SS_CUDA_CHECK(c, launch_dependent(mpc_fold_partials_kernel, dim3((warps + 7) / 8), dim3(256), 0, c->stream, partial, blocks, 2 * T, folded));
     c->launches++;
     SS_CUDA_CHECK(c, cudaGetLastError());
     *blocks_out = SUMS_FOLD;
@@ -212,16 +217,18 @@ int mpc_tail(ss_ctx* c, const PlanView& plan, const float* rows, long long K_loc
     TailOut out;
     out.pkg = pkg; out.host_pkg = host_pkg; out.seq = seq; out.sums_out = sums_out; out.scores_final = scores;
     MpcResult* res = reinterpret_cast<MpcResult*>(result_dev);
-    if (plan.d <= 4)
-        mpc_tail_kernel<4><<<grid, threads, smem, c->stream>>>(plan, rows, K_local, T, in_smem, sum_cols, n_cols, scores,
-                                                          k_offset, block_v, block_i, res, act, want_path, out);
-    else if (plan.d <= 8)
-        mpc_tail_kernel<8><<<grid, threads, smem, c->stream>>>(plan, rows, K_local, T, in_smem, sum_cols, n_cols, scores,
-                                                          k_offset, block_v, block_i, res, act, want_path, out);
-    else
-        mpc_tail_kernel<SS_MAX_D><<<grid, threads, smem, c->stream>>>(plan, rows, K_local, T, in_smem, sum_cols, n_cols,
-                                                                  scores, k_offset, block_v, block_i, res, act,
-                                                                  want_path, out);
+    // after a peer-memory exchange kernel (sharded batch) the tail is an ordinary launch: those kernels do not
+    // release their dependents early; after the reduce kernel of an unsharded batch it is a programmatic one
+    cudaError_t e;
+    const dim3 g(grid), b(threads);
+#define TAIL_LAUNCH(DT_)                                                                                            \
+    e = launch_dependent(mpc_tail_kernel<DT_>, g, b, smem, c->stream, plan, rows, K_local, T, in_smem, sum_cols, n_cols, \
+                         scores, k_offset, block_v, block_i, res, act, want_path, out)
+    if (plan.d <= 4) TAIL_LAUNCH(4);
+    else if (plan.d <= 8) TAIL_LAUNCH(8);
+    else TAIL_LAUNCH(SS_MAX_D);
+#undef TAIL_LAUNCH
+    SS_CUDA_CHECK(c, e);
     c->launches++;
     SS_CUDA_CHECK(c, cudaGetLastError());
     return SS_OK;

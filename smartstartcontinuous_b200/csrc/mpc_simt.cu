@@ -138,6 +138,7 @@ __device__ void output_layer(const float* __restrict__ in, int K_pad, const floa
 
 template <int DT>
 __global__ void __launch_bounds__(ST) mpc_rollout_simt_kernel(const RolloutArgs a) {
+    pdl_trigger();      // the reduce / tail kernels behind this launch may be scheduled (they wait for its completion)
     extern __shared__ __align__(16) float sm[];
     const int act_elems = (a.h_pad > a.din_pad ? a.h_pad : a.din_pad) * SR;
     float* actA = sm;

@@ -110,6 +110,7 @@ struct SmemT {
 // K1T: K slots of the layer-1 MMA (16 when 3 (d + da) + 2 <= 16, else 32)
 template <int DT, int DZ, int K1T>
 __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_kernel(const RolloutArgs a, const Params p) {
+    pdl_trigger();      // the reduce / tail kernels behind this launch may be scheduled (they wait for its completion)
     extern __shared__ __align__(128) unsigned char smem[];
     using Smem = SmemT<DZ>;
     constexpr int MAXIN = (K1T - 2) / 3;            // network inputs the A tile has slots for

@@ -80,6 +80,7 @@ struct Smem {
 
 template <int DT, int DZ, int K1T>
 __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const RolloutArgs a, const Params p) {
+    pdl_trigger();      // the reduce / tail kernels behind this launch may be scheduled (they wait for its completion)
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int MAXIN = (K1T - 2) / 3;
     constexpr int W1_CHUNK_BYTES = NH * K1T * 2;
