@@ -43,8 +43,17 @@ class OracleEngine:
                              self.w[0].shape[1])
 
     def rollout(self, state, wp_index, *, actions, K, H, seed, act_low, act_high, gamma,
-                horizontal_penalty_factor, penalty_mode, precision, k_offset, K_global):
+                horizontal_penalty_factor, penalty_mode, precision, k_offset, K_global, rng_state=None):
         self.sampler = None
+        if rng_state is not None:
+            # what Engine.rollout(rng_state=...) does on the GPU: this rank's slice of the ONE global
+            # npr.uniform(low, high, (K_global, H, da)) draw, and the generator state after the whole draw
+            rs = np.random.RandomState()
+            rs.set_state(rng_state)
+            full = rs.uniform(np.asarray(act_low, dtype=np.float64), np.asarray(act_high, dtype=np.float64),
+                              (K_global, H, 1))
+            actions = full[k_offset:k_offset + K]
+            self._rng_after = rs.get_state()
         if actions is None:
             self.sampler = (H, seed, act_low, act_high)
             actions = philox.sample_actions(K, H, 1, seed, act_low, act_high, k_offset=k_offset)
@@ -57,6 +66,9 @@ class OracleEngine:
         mpc_oracle.score_add_delta(self.states, *self.args, penalty_mode=0, lambdas_out=lam)
         self.sums = torch.tensor(np.array(lam).reshape(-1), dtype=torch.float64)
         self.state = state
+
+    def mt19937_state(self):
+        return self._rng_after
 
     def projection_sums_tensor(self):
         return self.sums
@@ -124,12 +136,18 @@ def _worker(rank, world, port, mode, out):
                            penalty_mode=mode)
         res_host = planner.plan(g["in_start_state"], 0, K=len(g["in_actions"]), H=g["in_actions"].shape[1],
                                 actions=g["in_actions"], penalty_mode=mode)
+        # the default agent route: every rank takes its slice of one draw from numpy's legacy generator
+        rs = np.random.RandomState(2024)
+        rs.random_sample(77)
+        res_mt = planner.plan(g["in_start_state"], 0, K=97, H=5, act_low=[-1.0], act_high=[1.0], penalty_mode=mode,
+                              rng_state=rs.get_state())
         k = load_golden("kde_pendulum.npz")
         sel = ShardedSelector(eng, device="cpu").select_start(
             k["in_all_states"], k["in_queries"], k["in_values"], int(k["in_n_transitions"]),
             float(k["in_volume"]), 1.0, 2.0)
         out[rank] = (res["best_k"], res["best_score"], res["best_path"], res_host["best_k"],
-                     res_host["best_sequence"], res_host["best_path"], sel)
+                     res_host["best_sequence"], res_host["best_path"], sel,
+                     (res_mt["best_k"], res_mt["best_sequence"], res_mt["rng_state"][1], res_mt["rng_state"][2]))
     finally:
         dist.destroy_process_group()
 
@@ -149,12 +167,19 @@ def test_two_rank_plan_matches_single_process(mode):
     single = mpc_oracle.plan(g["in_start_state"], acts, w, b, norm, *args, penalty_mode=0 if mode == "reference" else 1)
     single_host = mpc_oracle.plan(g["in_start_state"], g["in_actions"], w, b, norm, *args,
                                   penalty_mode=0 if mode == "reference" else 1)
+    rs = np.random.RandomState(2024)
+    rs.random_sample(77)
+    acts_mt = rs.uniform(np.array([-1.0]), np.array([1.0]), (97, 5, 1))
+    single_mt = mpc_oracle.plan(g["in_start_state"], acts_mt, w, b, norm, *args, penalty_mode=0 if mode == "reference" else 1)
     k = load_golden("kde_pendulum.npz")
     with mp.Manager() as mgr:
         out = mgr.dict()
         mp.spawn(_worker, args=(2, _free_port(), mode, out), nprocs=2, join=True)
         for rank in (0, 1):
-            best_k, best_score, path, hk, hseq, hpath, sel = out[rank]
+            best_k, best_score, path, hk, hseq, hpath, sel, mt = out[rank]
+            assert mt[0] == single_mt["best_k"]
+            np.testing.assert_array_equal(mt[1], acts_mt[single_mt["best_k"]])
+            assert mt[3] == rs.get_state()[2] and np.array_equal(mt[2], rs.get_state()[1])
             assert best_k == single["best_k"]
             assert best_score == pytest.approx(single["best_score"], rel=1e-12)
             np.testing.assert_allclose(path, single["best_path"], rtol=1e-12)
