@@ -317,6 +317,15 @@ __device__ __forceinline__ float fetch_action(const ActionSource& src, long long
     return (float)(src.low[j] + u * src.range[j]);
 }
 
+// The sample as the caller gets it back (best_sequence, NND_MB_agent.py:516-518): host-provided / MT19937
+// samples are float64 and are returned bit for bit (the rollout itself consumes them rounded to FP32); the
+// Philox sampler is defined in FP32 (oracle/philox.py).
+__device__ __forceinline__ double fetch_action_f64(const ActionSource& src, long long k_local, long long k_global,
+                                                   int t, int j) {
+    if (src.host_actions) return src.host_actions[((size_t)k_local * src.H + t) * src.da + j];
+    return (double)fetch_action(src, k_local, k_global, t, j);
+}
+
 // Same values as fetch_action() for a thread that walks t = 0, 1, 2, ... of ONE sequence: the
 // Philox block of four samples is kept in registers and recomputed only when (t * da + j) / 4
 // changes; the affine map runs in FP32 when that is bit-identical (ActionSource::fp32_exact).

@@ -23,7 +23,7 @@ __global__ void sample_actions_kernel(ActionSource src, long long K, long long k
         const long long k = o / (src.H * src.da);
         const int rem = (int)(o - k * (src.H * src.da));
         const int t = rem / src.da, j = rem - t * src.da;
-        out[o] = (double)fetch_action(src, k, k_offset + k, t, j);
+        out[o] = fetch_action_f64(src, k, k_offset + k, t, j);
     }
 }
 

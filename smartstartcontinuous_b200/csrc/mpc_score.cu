@@ -77,7 +77,7 @@ __device__ __noinline__ void tail_write_package(double best_v, long long kl, lon
         else if (o == 1) val = (double)kg;
         else if (want_path && kl >= 0) {
             const int q = o - 2;
-            if (q < n_seq) val = (double)fetch_action(act, kl, kg, q / act.da, q % act.da);
+            if (q < n_seq) val = fetch_action_f64(act, kl, kg, q / act.da, q % act.da);
             else {
                 const int r = q - n_seq;
                 val = (double)__ldcg(rows + ((size_t)(r / d) * K + kl) * (d + 1) + (r % d));

@@ -182,3 +182,56 @@ def test_forced_segment_layouts(engine, force_p):
             os.environ.pop("SS_MT_FORCE_P", None)
         else:
             os.environ["SS_MT_FORCE_P"] = old
+
+
+@pytest.mark.parametrize("name,seed", [("mpc_pendulum_2x500.npz", 4), ("mpc_mountaincar_L2.npz", 1)])
+def test_default_agent_reproduces_the_reference_decision_from_the_seed(engine, name, seed):
+    """The goldens were produced by the reference's own get_best_sim_actions under np.random.seed(seed)
+    (oracle/make_golden.py): from the same seed the drop-in agent -- samples generated on the GPU from
+    numpy's generator state -- draws the very same K x H samples (the returned sequence is the golden's
+    row, bit for bit), picks the same sequence wherever the fp32 tolerance allows, returns the reference's
+    first action, and leaves numpy's generator where the reference's draw leaves it."""
+    from conftest import golden_model, load_golden
+    from smartstartcontinuous_b200.nnd_mb_agent import NND_MB_agent
+
+    g = load_golden(name)
+    w, b, norm = golden_model(g)
+    K, H, _ = g["in_actions"].shape
+    d = w[-1].shape[1]
+
+    class Box:
+        low, high, shape = g["in_act_low"], g["in_act_high"], (1,)
+
+    class Env:
+        action_space = Box()
+
+    rng = np.random.default_rng(0)
+    td = dict(dataX=rng.normal(size=(64, d)), dataY=rng.normal(size=(64, 1)), dataZ=rng.normal(size=(64, d)))
+    ag = NND_MB_agent(Env(), None, horizon=H, num_control_samples=K, num_fc_layers=len(w) - 1,
+                      depth_fc_layers=w[0].shape[1], gamma=float(g["in_gamma"]),
+                      horizontal_penalty_factor=float(g["in_hpf"]), verbose=False, training_data=td, engine=engine,
+                      precision="fp32", host_rng=False)
+    for k in ("mean_x", "std_x", "mean_y", "std_y", "mean_z", "std_z"):
+        setattr(ag, k, np.asarray(g["in_" + k], dtype=np.float64))
+        setattr(ag.dyn_model, k, getattr(ag, k))
+    ag.dyn_model.set_weights(w, b)
+    engine.set_plan(g["out_desired_states"], g["out_distances_left"], g["out_radii"])
+    ag.desired_states, ag.distances_left, ag.radii = g["out_desired_states"], g["out_distances_left"], g["out_radii"]
+    ag.current_desired_state_index = int(g["in_wp_index"])
+
+    np.random.seed(seed)
+    best_action, best_k, best_seq, best_path = ag.get_best_sim_actions(g["in_start_state"])
+    after = np.random.get_state()
+    np.random.seed(seed)
+    np.random.uniform(g["in_act_low"], g["in_act_high"], (K, H, 1))
+    want_after = np.random.get_state()
+    assert after[2] == want_after[2] and np.array_equal(after[1], want_after[1])
+    np.testing.assert_array_equal(best_seq, g["in_actions"][best_k])          # the reference's own draw
+    scores = g["out_scores"]
+    top2 = np.sort(scores)[-2:]
+    if top2[1] - top2[0] > 2e-4 * max(1.0, abs(top2[1])):
+        assert best_k == int(g["out_best_k"])
+        np.testing.assert_array_equal(best_action, g["out_best_action"])
+        np.testing.assert_allclose(best_path, g["out_best_path"], rtol=1e-4, atol=1e-4 * np.abs(g["out_best_path"]).max())
+    else:
+        assert scores[best_k] >= top2[1] - 2e-4 * max(1.0, abs(top2[1]))
