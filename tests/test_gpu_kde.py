@@ -337,3 +337,50 @@ def test_smart_start_with_device_value_net_equals_host_values(engine):
     (i0, u0), p0 = picks[0]
     for (i1, u1), p1 in picks[1:]:
         assert i1 == i0 and abs(u1 - u0) <= 1e-4 * abs(u0) and np.array_equal(p0, p1)
+
+
+@pytest.mark.parametrize("name,env,n,n_ss,seed", [("kde_pendulum.npz", "pendulum", 3000, 300, 0),
+                                                  ("kde_mountaincar.npz", "mountaincar", 2000, 5000, 1)])
+def test_smart_start_path_equals_the_references_from_the_seed(engine, name, env, n, n_ss, seed):
+    """The selection goldens come from the reference's own get_smart_start_path under random.seed(seed): the
+    drop-in class over the same (rebuilt) buffer, from the same seed, chooses the same buffer index and returns
+    the same path -- candidate draw, device-mirror selection and episodic path extraction end to end."""
+    import random
+
+    from smartstartcontinuous_b200.smart_start import SmartStartContinuous
+    from test_replay_buffer import _golden_buffer
+
+    g = load_golden(name)
+    rb, episodes = _golden_buffer(name, env, n, seed)
+    d = episodes[0][0].shape[1]
+
+    class Box:
+        low, high, shape = np.array([-2.0]), np.array([2.0]), (1,)
+
+    class Env:
+        action_space = Box()
+
+    class Base:
+        replay_buffer = rb
+
+        def set_replay_buffer_main_agent(self, main): pass
+        def get_action(self, s): return np.zeros(1)
+        def observe(self, *a): pass
+        def start_new_episode(self, s): pass
+        def end_episode(self): pass
+        def get_param_dict(self): return {}
+        def get_state_value(self, states): return syn.critic_like_values(np.asarray(states), seed + 7).reshape(-1, 1)
+
+    rng = np.random.default_rng(0)
+    td = dict(dataX=rng.normal(size=(64, d)), dataY=rng.normal(size=(64, 1)), dataZ=rng.normal(size=(64, d)))
+    ss = SmartStartContinuous(Base(), Env(), None, n_ss=n_ss, print_ss_stuff=False, nnd_mb_num_fc_layers=1,
+                              nnd_mb_depth_fc_layers=8, nnd_mb_verbose=False, engine=engine,
+                              nnd_mb_extra=dict(training_data=td))
+    assert ss.replay_buffer is rb
+    ss.nnd_mb_agent.radii = g["in_radii"] if len(g["in_radii"]) else None
+    random.seed(seed)
+    path = ss.get_smart_start_path()
+    chosen, ucb = ss.last_selection
+    assert chosen == int(g["out_chosen_buffer_index"])
+    assert ucb == pytest.approx(float(g["out_ucb"][int(g["out_best_j"])]), rel=1e-4)
+    np.testing.assert_array_equal(np.asarray(path), g["out_path"])

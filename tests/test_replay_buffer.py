@@ -152,3 +152,43 @@ def test_candidate_draw_in_cxx_equals_random_sample():
     a = random.sample(range(0, 500), 120)
     random.seed(3)
     assert rbm.sample_range(0, 500, 120).tolist() == a
+
+
+def _golden_buffer(name, env, n_transitions, seed):
+    """The replay buffer of oracle/make_golden.golden_kde rebuilt through OUR ReplayBuffer API (same seeded
+    synthetic episodes, same capacity, so the same FIFO evictions)."""
+    from smartstartcontinuous_b200 import synthetic as syn
+    from smartstartcontinuous_b200.replay_buffer import ReplayBuffer
+    rng = np.random.default_rng(seed)
+    steps = 100
+    if env == "pendulum":
+        obs, act = syn.pendulum_rollouts(rng, n_transitions // steps, steps)
+        episodes = [(obs[e], act[e]) for e in range(len(obs))]
+    else:
+        episodes = [syn.mountaincar_rollout(rng, steps) for _ in range(n_transitions // steps)]
+    main = object()
+    rb = ReplayBuffer(main, n_transitions - 37)
+    for states, actions in episodes:
+        rb.start_new_episode(main)
+        T = len(actions)
+        for t in range(T):
+            rb.add(main, np.array(states[t]), np.array(actions[t]), 0.0, t == T - 1, np.array(states[t + 1]))
+    return rb, episodes
+
+
+@pytest.mark.parametrize("name,env,n,n_ss,seed", [("kde_pendulum.npz", "pendulum", 3000, 300, 0),
+                                                  ("kde_mountaincar.npz", "mountaincar", 2000, 5000, 1)])
+def test_candidate_indices_equal_the_references_from_the_seed(name, env, n, n_ss, seed):
+    """From random.seed(seed) our buffer (ring + C++ restatement of random.sample) hands out the candidate
+    indices the REFERENCE's buffer handed out when the golden was made, and the same data set."""
+    import random
+
+    from conftest import load_golden
+    g = load_golden(name)
+    rb, _ = _golden_buffer(name, env, n, seed)
+    assert len(rb) == int(g["in_n_transitions"])
+    np.testing.assert_array_equal(np.asarray(rb.get_all_states()), g["in_all_states"])
+    random.seed(seed)
+    idx = rb.get_possible_smart_start_indices(n_ss)
+    np.testing.assert_array_equal(idx, g["in_indices"])
+    np.testing.assert_array_equal(np.asarray(rb.states_s2(idx)), g["in_queries"])
