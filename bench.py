@@ -647,7 +647,12 @@ def main():
         if i > 0:
             pairs_ms.append(dict(eng.last_timings()).get("kde_pairs", 0.0))
 
-    kde_ms = timed(kde_step, args.steps, args.warmup) / args.steps
+    # the call is timed without the per-phase CUDA events (ss_set_timing(0): what a caller gets); a second short
+    # pass with them gives the pair kernel's own time for the roofline
+    eng.set_timing(False)
+    kde_ms = timed(lambda i: kde_step(0), args.steps, args.warmup) / args.steps
+    eng.set_timing(True)
+    timed(kde_step, max(4, half // 2), 1)
     evals = KDE_M * (KDE_N + 1) * world
     kde_value = evals / (kde_ms * 1e-3)
 
@@ -687,7 +692,10 @@ def main():
         if i > 0:
             pairs2k_ms.append(dict(eng.last_timings()).get("kde_pairs", 0.0))
 
-    kde2k_ms = timed(kde2k_step, args.steps, args.warmup) / args.steps
+    eng.set_timing(False)
+    kde2k_ms = timed(lambda i: kde2k_step(0), args.steps, args.warmup) / args.steps
+    eng.set_timing(True)
+    timed(kde2k_step, max(4, half // 2), 1)
     kde2k_agent_ms = timed(lambda i: ss2k.get_smart_start_path(), half, 2) / half
     del ss, ss2k
 

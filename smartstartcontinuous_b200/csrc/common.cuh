@@ -109,6 +109,7 @@ struct ss_ctx {
     DevBuf kde_data64, kde_q64, kde_vals, kde_pts, kde_qw, kde_partial, kde_fit, kde_moments;
     DevBuf kde_density, kde_ucb, kde_block_best, kde_result;
     bool kde_tc_attr_set = false;
+    bool kde_result_clean = false;     // the counters in kde_result are zero (left so by the last completed call)
     // mapped pinned host memory the finish kernel writes the selection result to (+ completion flag)
     void* host_kde = nullptr;
     void* host_kde_dev = nullptr;

@@ -88,6 +88,7 @@ kde_moments_kernel(const double* __restrict__ data, long long n, int d, double* 
                    unsigned int* __restrict__ ticket, KdeFit* __restrict__ fit) {
     __shared__ double sm[8];
     __shared__ bool s_last;
+    pdl_trigger();       // the whitening kernel may be scheduled (it waits for the fit)
     constexpr int NM = DM + DM * (DM + 1) / 2;
     const int nm = d + d * (d + 1) / 2;
     double loc[NM];
@@ -496,6 +497,7 @@ kde_finish_kernel(const float* __restrict__ partial, int n_slices, long long m, 
     __shared__ int s_nlist;
     __shared__ double s_red[8];
     __shared__ bool s_last;
+    pdl_wait();          // programmatic dependent of the pair kernel
     if (threadIdx.x == 0) s_nlist = 0;
     __syncthreads();
 
@@ -580,6 +582,7 @@ kde_finish_kernel(const float* __restrict__ partial, int n_slices, long long m, 
             result->best_ucb = v;
             result->best_j = bi;
             result->blocks_done = 0;
+            result->n_rescued = 0;
             if (host_out) {
                 host_out->best_ucb = v;
                 host_out->best_j = bi;
@@ -641,7 +644,9 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
     KdeFit* fit = c->kde_fit.as<KdeFit>();
     KdeResult* res = c->kde_result.as<KdeResult>();
 
-    SS_CUDA_CHECK(c, cudaMemsetAsync(res, 0, sizeof(KdeResult), c->stream));
+    // the kernels leave every counter of `res` at zero when a call completes: cleared only after a failure
+    if (!c->kde_result_clean) SS_CUDA_CHECK(c, cudaMemsetAsync(res, 0, sizeof(KdeResult), c->stream));
+    c->kde_result_clean = false;
     if (d <= 8)
         kde_moments_kernel<8><<<mom_blocks, 256, 0, c->stream>>>(data_dev, n, d, c->kde_moments.as<double>(),
                                                                  &res->moments_ticket, fit);
@@ -687,16 +692,17 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
             cudaError_t e = cudaSuccess;
 #define KDE_TC_CASE(KS_)                                                                                          \
     do {                                                                                                          \
-        kde_whiten_tc_kernel<KS_><<<pblocks + qblocks, 256, 0, c->stream>>>(                                      \
-            data_dev, n, n_pad, c->kde_pts.as<__nv_bfloat16>(), queries_dev, m, m_pad,                            \
-            c->kde_qw.as<__nv_bfloat16>(), d, fit, pblocks);                                                      \
+        e = launch_dependent(kde_whiten_tc_kernel<KS_>, dim3(pblocks + qblocks), dim3(256), 0, c->stream, data_dev, n,  \
+                             n_pad, c->kde_pts.as<__nv_bfloat16>(), queries_dev, m, m_pad,                         \
+                             c->kde_qw.as<__nv_bfloat16>(), d, fit, pblocks);                                      \
         timer_mark(c, "kde_fit_whiten");                                                                         \
-        e = cudaFuncSetAttribute(kde_pairs_tc_kernel<KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
-                                 (int)smem_bytes(KS_));                                                           \
         if (e == cudaSuccess)                                                                                     \
-            kde_pairs_tc_kernel<KS_><<<grid, THREADS, smem_bytes(KS_), c->stream>>>(                              \
-                c->kde_qw.as<__nv_bfloat16>(), c->kde_pts.as<__nv_bfloat16>(), n_tiles, (int)q_tiles, (int)slices, \
-                m_pad, fit, c->kde_partial.as<float>());                                                          \
+            e = cudaFuncSetAttribute(kde_pairs_tc_kernel<KS_>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                     (int)smem_bytes(KS_));                                                       \
+        if (e == cudaSuccess)                                                                                     \
+            e = launch_dependent(kde_pairs_tc_kernel<KS_>, dim3(grid), dim3(THREADS), smem_bytes(KS_), c->stream,  \
+                                 c->kde_qw.as<__nv_bfloat16>(), c->kde_pts.as<__nv_bfloat16>(), n_tiles,           \
+                                 (int)q_tiles, (int)slices, m_pad, fit, c->kde_partial.as<float>());               \
     } while (0)
             if (ks == 32) KDE_TC_CASE(32);
             else if (ks == 64) KDE_TC_CASE(64);
@@ -762,10 +768,10 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
             SS_CUDA_CHECK(c, cudaHostGetDevicePointer(&c->host_kde_dev, c->host_kde, 0));
         }
         const unsigned long long seq = ++c->host_kde_seq;
-        kde_finish_kernel<<<fin_blocks, 256, 0, c->stream>>>(
-            c->kde_partial.as<float>(), n_slices, m, m_pad, data_dev, n, d, queries_dev, values_dev, fit,
-            (double)n_transitions, volume, alpha, beta, density_dev, ucb_dev, bv, bi, res,
-            reinterpret_cast<KdeHostOut*>(c->host_kde_dev), seq);
+        SS_CUDA_CHECK(c, launch_dependent(kde_finish_kernel, dim3(fin_blocks), dim3(256), 0, c->stream,
+                                          c->kde_partial.as<float>(), n_slices, m, m_pad, data_dev, n, d, queries_dev,
+                                          values_dev, fit, (double)n_transitions, volume, alpha, beta, density_dev,
+                                          ucb_dev, bv, bi, res, reinterpret_cast<KdeHostOut*>(c->host_kde_dev), seq));
         c->launches++;
         SS_CUDA_CHECK(c, cudaGetLastError());
         timer_mark(c, "kde_finish");
@@ -797,11 +803,11 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
             // the expanded exponent would cancel too much for this data: redo the pair stage with
             // exact differences (rare: some |y|^2 above KDE_EXPAND_LIMIT, e.g. a far outlier query)
             variant = KDE_DIFFERENCE;
-            SS_CUDA_CHECK(c, cudaMemsetAsync(res, 0, sizeof(KdeResult), c->stream));
             continue;
         }
         *out_best_j = hres.best_j;
         *out_best_ucb = hres.best_ucb;
+        c->kde_result_clean = true;
         return SS_OK;
     }
     SS_FAIL(c, SS_ECUDA, "kde: pair stage did not settle");

@@ -216,6 +216,8 @@ __global__ void __launch_bounds__(256)
 kde_whiten_tc_kernel(const double* __restrict__ data, long long n, long long n_pad, __nv_bfloat16* __restrict__ p_img,
                      const double* __restrict__ queries, long long m, long long m_pad,
                      __nv_bfloat16* __restrict__ q_img, int d, KdeFit* __restrict__ fit, unsigned point_blocks) {
+    pdl_trigger();       // the pair kernel may set itself up
+    pdl_wait();          // the fit comes from the moments kernel in front
     if (blockIdx.x < point_blocks)
         whiten_tc_rows<true, KS>(blockIdx.x, data, n, n_pad, d, fit, p_img);
     else
@@ -245,6 +247,7 @@ kde_pairs_tc_kernel(const __nv_bfloat16* __restrict__ q_img, const __nv_bfloat16
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long long items = (long long)q_tiles * slices;
+    pdl_trigger();                           // the finish kernel may be scheduled (it waits for this grid)
     // the guard is evaluated by the caller after the call (optimistic launch); nothing to do here
     (void)fit;
 
@@ -264,6 +267,9 @@ kde_pairs_tc_kernel(const __nv_bfloat16* __restrict__ q_img, const __nv_bfloat16
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_ptr;
+    // launched as a programmatic dependent of the whitening kernel: barriers and TMEM are set up while it still
+    // runs; nothing it writes (operand images) and nothing the previous consumers read (partial) is touched before
+    pdl_wait();
 
     if (warp < EPI_WARPS) {
         // ================================ EPILOGUE =======================================
