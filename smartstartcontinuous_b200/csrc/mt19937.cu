@@ -272,6 +272,7 @@ mt19937_raw_kernel(const __grid_constant__ MtKey key, const __grid_constant__ Mt
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const MtSegment seg = args.segs[blockIdx.x];
+    pdl_trigger();       // the conversion kernel may be scheduled (it waits for this grid to complete)
 
     if (seg.poly < 0) {
         // the segment starts at the key block itself
@@ -401,6 +402,7 @@ mt19937_raw_kernel(const __grid_constant__ MtKey key, const __grid_constant__ Mt
 // exact bit constructions: 2^25 + a 2^-27 and 1/2 + b 2^-53 have a and b as their low mantissa words.
 __global__ void __launch_bounds__(256)
 mt19937_convert_kernel(const __grid_constant__ MtConvertArgs a) {
+    pdl_wait();          // programmatic dependent of the generator kernel
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < a.count; e += stride) {
         const uint32_t* w = a.raw + a.word_base + 2 * e;
@@ -686,7 +688,7 @@ extern "C" int ss_mt19937_uniform(ss_ctx* c, const uint32_t* key, int pos, int64
     }
     const long long want_blocks = (count + 255) / 256;
     const int grid = (int)std::min<long long>(want_blocks, (long long)c->sm_count * 8);
-    mt19937_convert_kernel<<<grid, 256, 0, c->stream>>>(cv);
+    SS_CUDA_CHECK(c, launch_dependent(mt19937_convert_kernel, dim3(grid), dim3(256), 0, c->stream, cv));
     c->launches++;
     SS_CUDA_CHECK(c, cudaGetLastError());
     *out_dev = cv.out;
