@@ -217,7 +217,9 @@ static inline void timer_mark(ss_ctx* c, const char* name) {
 // (once every CTA of the predecessor has executed pdl_trigger() or exited); it must execute pdl_wait() before it
 // touches anything the predecessor writes -- the wait returns when the predecessor has completed and its
 // memory operations are visible.  This takes the launch latency of the reduce / tail kernels (2-3 us each) off
-// a small decision's critical path.  Both instructions are no-ops in a normally launched kernel.
+// a small decision's critical path.  Both instructions are no-ops in a normally launched kernel.  (Not for long
+// launch trains: the attributed launch costs the host more than a plain one -- the trainer's 960 launches per
+// epoch became host-bound with it, 174 instead of 104 us per Adam step.)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
