@@ -98,7 +98,10 @@ __device__ __noinline__ void tail_write_package(double best_v, long long kl, lon
 }
 
 template <int DT>
-__global__ void __launch_bounds__(256, DT <= 4 ? 3 : 2)
+// (128-thread blocks, seven per SM for d <= 4: 896 x 148 = 132 608 resident threads hold the whole bench batch of
+// 131 072 sequences in ONE wave; with 256-thread blocks at three per SM 15 % of the blocks ran in a second wave and
+// doubled the kernel's time)
+__global__ void __launch_bounds__(128, DT <= 4 ? 7 : 4)
 mpc_tail_kernel(const PlanView Pg, const float* __restrict__ rows, long long K, int T, int ds_in_smem,
                 const double* __restrict__ sum_cols, int n_cols, float* __restrict__ scores, long long k_offset,
                 double* __restrict__ block_v, long long* __restrict__ block_i, MpcResult* __restrict__ result,
@@ -198,7 +201,7 @@ int mpc_fold_partials(ss_ctx* c, const double* partial, int blocks, int T, doubl
 }
 
 // small batches: 64-thread blocks, four times as many of them (the pass is latency-bound there)
-static int mpc_tail_threads(long long K_local) { return K_local <= 16384 ? 64 : 256; }
+static int mpc_tail_threads(long long K_local) { return K_local <= 16384 ? 64 : 128; }
 int mpc_tail_blocks(long long K_local) {
     const int t = mpc_tail_threads(K_local);
     return (int)((K_local + t - 1) / t);
