@@ -225,6 +225,19 @@ int ss_mt19937_uniform(ss_ctx* ctx, const uint32_t* key, int pos, int64_t n_tota
                        int64_t count, int period, const double* low, const double* high,
                        double** out_dev);
 int ss_mt19937_state(ss_ctx* ctx, uint32_t* out_key, int* out_pos);
+/* get_best_sim_actions (NND_MB_agent.py:498-520) INCLUDING its draw (:500-501), in one call: the samples come
+ * from the generator state (mt_key[624], *mt_pos) as ss_mt19937_uniform produces them, the decision is ss_mpc_plan's,
+ * and the state after the draw is written back through the same two pointers -- which may be the address of numpy's
+ * own state struct {uint32 key[624]; int pos} (BitGenerator.ctypes.state_address): the host generator then continues
+ * exactly as if npr.uniform had run, without a get_state / set_state round trip. */
+int ss_mpc_plan_mt19937(ss_ctx* ctx, const double* state, int wp_index,
+                        int64_t K_local, int64_t k_offset, int64_t K_global, int H,
+                        uint32_t* mt_key, int* mt_pos,
+                        const double* act_low, const double* act_high,
+                        double gamma, double horizontal_penalty_factor,
+                        int penalty_mode, int precision,
+                        int64_t* out_best_k, double* out_best_score,
+                        double* out_best_sequence, double* out_best_path, double* out_scores);
 /* host-only helpers behind the jump-ahead (no GPU work; used by the CPU tests): the coefficient words
  * of x^J mod phi (624 x uint32, bit i of word w = x^(32 w + i)), and the exponents of phi, MT19937's
  * characteristic polynomial (returns their number, 135). */

@@ -73,6 +73,9 @@ SIGNATURES = {
     "ss_mt19937_uniform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int,
                                      C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "ss_mt19937_state": (C.c_int, [C.c_void_p, C.c_void_p, _c_int_p]),
+    "ss_mpc_plan_mt19937": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
+                                      C.c_int, C.c_int, _c_int64_p, _c_double_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ss_mt19937_jump_poly": (C.c_int, [C.c_uint64, C.c_void_p]),
     "ss_mt19937_phi_exponents": (C.c_int, [_c_int_p, C.c_int]),
     "ss_py_random_sample": (C.c_int, [C.c_void_p, _c_int_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),

@@ -719,3 +719,26 @@ extern "C" int ss_mt19937_state(ss_ctx* c, uint32_t* out_key, int* out_pos) {
     std::memcpy(out_key, h + 4, MT_N * 4);
     return SS_OK;
 }
+
+// get_best_sim_actions with the reference's own draw in ONE call: the samples of npr.uniform(low, high,
+// (K_global, H, da)) (NND_MB_agent.py:500-501) generated on the device from numpy's generator state, the decision
+// on them (ss_mpc_plan), and the generator state after the draw written back through mt_key / mt_pos -- which may
+// point straight at numpy's own state struct.
+extern "C" int ss_mpc_plan_mt19937(ss_ctx* c, const double* state, int wp_index, int64_t K_local, int64_t k_offset,
+                                   int64_t K_global, int H, uint32_t* mt_key, int* mt_pos, const double* act_low,
+                                   const double* act_high, double gamma, double hpf, int penalty_mode, int precision,
+                                   int64_t* out_best_k, double* out_best_score, double* out_best_sequence,
+                                   double* out_best_path, double* out_scores) {
+    if (!c) return SS_EINVAL;
+    if (!mt_key || !mt_pos) SS_FAIL(c, SS_EINVAL, "mt19937: null generator state");
+    if (!c->model_set) SS_FAIL(c, SS_ESTATE, "mpc: model and plan must be set before planning");
+    const int64_t per_seq = (int64_t)H * c->da;
+    double* dev = nullptr;
+    int rc = ss_mt19937_uniform(c, mt_key, *mt_pos, K_global * per_seq, k_offset * per_seq, K_local * per_seq, c->da,
+                                act_low, act_high, &dev);
+    if (rc) return rc;
+    rc = ss_mpc_plan(c, state, wp_index, K_local, k_offset, K_global, H, dev, 0, act_low, act_high, gamma, hpf,
+                     penalty_mode, precision, out_best_k, out_best_score, out_best_sequence, out_best_path, out_scores);
+    if (rc) return rc;
+    return ss_mt19937_state(c, mt_key, mt_pos);
+}

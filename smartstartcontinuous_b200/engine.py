@@ -467,6 +467,27 @@ class Engine:
         if self._model_shape is None:
             raise RuntimeError("set_model() first")
         d, da, _, _ = self._model_shape
+        if isinstance(rng_state, int):
+            # the reference's draw + the decision + the generator state written back in place, in one call
+            # (rng_state = the address of numpy's state struct, global_rng_address())
+            st = _f64(state).reshape(-1)
+            if st.size != d:
+                raise ValueError("state has %d entries, model expects %d" % (st.size, d))
+            K, H = int(K), int(H)
+            Kg = K if K_global is None else int(K_global)
+            scores = np.empty(K) if want_scores else None
+            seq = np.empty((H, da)) if want_path else None
+            path = np.empty((H + 1, d)) if want_path else None
+            best = C.c_int64(-1)
+            best_score = C.c_double(0.0)
+            self._last = (K, H)
+            self._check(self._lib.ss_mpc_plan_mt19937(
+                self._h, _ptr(st), int(wp_index), K, int(k_offset), Kg, H, rng_state, rng_state + 2496,
+                _ptr(_bounds(act_low, da)), _ptr(_bounds(act_high, da)), float(gamma), float(horizontal_penalty_factor),
+                _PENALTY[penalty_mode], _PRECISION[precision], C.byref(best), C.byref(best_score), _ptr(seq), _ptr(path),
+                _ptr(scores)))
+            return dict(best_k=int(best.value), best_score=float(best_score.value), best_sequence=seq,
+                        best_path=path, scores=scores)
         if rng_state is not None:
             # the reference's draw, npr.uniform(low, high, (K, H, da)) of NND_MB_agent.py:500-501, made on
             # the device from the host generator's state; the advanced state comes back in the result
@@ -490,9 +511,7 @@ class Engine:
             C.byref(best), C.byref(best_score), _ptr(seq), _ptr(path), _ptr(scores)))
         res = dict(best_k=int(best.value), best_score=float(best_score.value), best_sequence=seq,
                    best_path=path, scores=scores)
-        if isinstance(rng_state, int):
-            self.mt19937_state_into(rng_state)          # numpy's generator advanced in place
-        elif rng_state is not None:
+        if rng_state is not None:
             res["rng_state"] = self.mt19937_state()
         return res
 
