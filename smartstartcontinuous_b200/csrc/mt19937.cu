@@ -13,10 +13,13 @@
 // phi of degree 19937, so the window J steps ahead is
 //     window_J[j] = XOR_{i : g_i = 1} x[i + j],        g = x^J mod phi,
 // a GF(2) correlation of the next 19937 + 624 raw words with the bits of g.  The stream is cut into
-// P segments of whole 624-word blocks; CTA c evaluates its own jump (g depends on the segment start
-// only, so the polynomials are computed once per batch shape on the host and cached on the device),
-// then regenerates its blocks exactly like genrand does, tempers, and converts pairs of words into
-// doubles ((a >> 5) * 2^26 + (b >> 6)) / 2^53, randomkit's rk_double.
+// P segments of whole 624-word blocks; a segment's jump is evaluated by one CTA or -- medium streams, few
+// segments, spare SMs -- by several CTAs that each take a slice of g and combine through global memory (g
+// depends on the segment start only, so the polynomials are computed once per batch shape on the host and
+// cached on the device; the layout is chosen by a cost model, make_layout).  The segment's CTA then regenerates
+// its blocks exactly like genrand does and hands the raw words to the TMA engine; a second, fully parallel
+// kernel tempers them and converts pairs of words into doubles ((a >> 5) * 2^26 + (b >> 6)) / 2^53
+// (randomkit's rk_double) and applies low + (high - low) * u with the reference's two roundings.
 //
 // phi is held as its 135 exponents (derived by Berlekamp-Massey from numpy's own output:
 // oracle/mt19937_poly.py; tests/test_mt19937_poly.py re-derives it and checks the table).
