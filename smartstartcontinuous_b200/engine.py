@@ -618,6 +618,13 @@ class Engine:
                                                  count, lo.shape[0], _ptr(lo), _ptr(hi), C.byref(out)))
         return out.value
 
+    def mt19937_warm(self, n_total, low, high, first=0, count=None):
+        """Build (and cache) the jump-ahead plan of a draw shape ahead of time: the polynomials of a large shape
+        take ~0.1 s of host arithmetic, which would otherwise land in the first decision."""
+        st = np.random.RandomState(0).get_state()
+        self.mt19937_uniform(st, n_total, low, high, first=first, count=count)
+        self.mt19937_state()
+
     def mt19937_state_into(self, address):
         """Write the generator state after the last mt19937_uniform draw straight into numpy's state struct."""
         self._check(self._lib.ss_mt19937_state(self._h, C.c_void_p(address),

@@ -220,6 +220,21 @@ class NND_MB_agent(NavigationRLAgent):
                                    self.std_x, self.std_y, self.std_z, self.tf_datatype, verbose,
                                    engine=self.engine, seed=seed)
         self.dyn_model.push_to_engine()
+        # the default decision path draws numpy's stream on the GPU: build its jump-ahead plan now, not in the
+        # first decision
+        try:
+            da = int(np.prod(env.action_space.shape))
+            n_total = self.N * self.horizon * da
+            if not device_sampling and host_rng is not True and n_total > self.HOST_DRAW_MAX:
+                first, count = 0, n_total
+                if planner is not None:
+                    from .distributed import shard_bounds
+                    k0, kl = shard_bounds(self.N, planner.world, planner.rank)
+                    first, count = k0 * self.horizon * da, kl * self.horizon * da
+                self.engine.mt19937_warm(n_total, np.asarray(env.action_space.low, dtype=np.float64).reshape(-1),
+                                         np.asarray(env.action_space.high, dtype=np.float64).reshape(-1), first, count)
+        except AttributeError:
+            pass            # an environment without a Box-like action space: nothing to prepare
 
     def _add_noise(self, data):
         """helper_funcs.add_noise (helper_funcs.py:10-16): per-column gaussian noise with
