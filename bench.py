@@ -58,9 +58,9 @@ C3_K, C3_H = 4096, 20                          # BASELINE config 3
 C1_K, C1_H, C1_NSS = 5000, 4, 2000             # BASELINE config 1 (the example's hyper-parameters)
 SFU_PER_CLK_PER_SM = 16                        # MUFU.EX2 lanes per SM per clock (sm_100)
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full
-# captures of exactly these workloads (profiles/r02f_ncu_summary.md); not measurable live
-NCU_TRAFFIC = {"mpc_rollout_tc_kernel": 642_816 + 52_761_856, "kde_pairs_tc_kernel": 7_491_072}
-NCU_TRAFFIC_SOURCE = "profiles/r02f_ncu_summary.md (ncu --set full, same workload)"
+# captures of exactly these workloads (profiles/r02k_ncu_summary.md); not measurable live
+NCU_TRAFFIC = {"mpc_rollout_tc_kernel": 623_872 + 53_846_784, "kde_pairs_tc_kernel": 7_491_584}
+NCU_TRAFFIC_SOURCE = "profiles/r02k_ncu_summary.md (ncu --set full, same workload)"
 
 
 def measured_peaks():
