@@ -313,6 +313,8 @@ int ss_value_net_eval(ss_ctx* ctx, const double* queries, int64_t m, int d, floa
  * rows of the candidates.  Everything else as ss_kde_ucb_argmax. */
 int ss_mirror_write(ss_ctx* ctx, int which, int64_t capacity, int d, int64_t row0, int64_t n_rows,
                     const double* rows);
+/* forget the mirror's contents (a new ring object on the host side); the next writes start from row 0 */
+int ss_mirror_reset(ss_ctx* ctx);
 int ss_kde_ucb_argmax_mirror(ss_ctx* ctx, int64_t count, int64_t last_row, const int64_t* query_rows, int64_t m,
                              const float* values, int64_t n_transitions, double volume, double alpha, double beta,
                              double* out_density, double* out_ucb, int64_t* out_best_j, double* out_best_ucb);

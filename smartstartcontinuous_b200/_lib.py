@@ -94,6 +94,7 @@ SIGNATURES = {
     "ss_value_net_set": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ss_value_net_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "ss_mirror_write": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_int64, C.c_void_p]),
+    "ss_mirror_reset": (C.c_int, [C.c_void_p]),
     "ss_kde_ucb_argmax_mirror": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                            C.c_int64, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
                                            _c_int64_p, _c_double_p]),

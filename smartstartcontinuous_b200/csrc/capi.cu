@@ -1,4 +1,5 @@
 // capi.cu -- context management and the stage-1 entry points of the C ABI (include/ss_b200.h).
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -6,7 +7,8 @@
 int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double* queries_dev,
             long long m, const float* values_dev, long long n_transitions, double volume,
             double alpha, double beta, double* density_dev, double* ucb_dev, int64_t* out_best_j,
-            double* out_best_ucb);
+            double* out_best_ucb, const double* running_sums = nullptr);
+int kde_exact_sums(ss_ctx* c, const double* data_dev, long long n, int d, double* sums_dev);
 
 int value_net_eval_dev(ss_ctx* c, const double* queries_dev, long long m, float* values_dev);
 void mt19937_release(ss_ctx* c);
@@ -63,7 +65,8 @@ extern "C" int ss_destroy(ss_ctx* c) {
                       &c->tc_misc, &c->plan_ds, &c->plan_dl, &c->mpc_actions64, &c->mpc_states,
                       &c->mpc_scores, &c->mpc_partial_sums, &c->mpc_sums, &c->mpc_block_best,
                       &c->mpc_result, &c->mpc_replay, &c->mpc_sampled, &c->mpc_package,
-                      &c->geom_in, &c->geom_rows, &c->geom_pairs, &c->mirror_s, &c->mirror_s2, &c->mirror_idx, &c->value_net_params,
+                      &c->geom_in, &c->geom_rows, &c->geom_pairs, &c->mirror_s, &c->mirror_s2, &c->mirror_idx, &c->mirror_mom,
+                      &c->mirror_stage, &c->value_net_params,
                       &c->tc_b3, &c->dyn_params, &c->dyn_m, &c->dyn_v, &c->dyn_x[0], &c->dyn_x[1], &c->dyn_z[0], &c->dyn_z[1],
                       &c->dyn_act, &c->dyn_scratch, &c->dyn_idx, &c->dyn_losses};
     for (DevBuf* b : bufs) b->release();
@@ -244,6 +247,58 @@ extern "C" int ss_kde_ucb_argmax(ss_ctx* c, const double* data, int64_t n_pts, i
 // ---- device-resident mirror of the replay buffer's state ring --------------
 // rows: [capacity + 1][d] float64 for `s` (the extra row receives the newest s2 at selection time,
 // replay_buffer.py:102) and [capacity][d] for `s2`; row index = physical ring row.
+constexpr int64_t MIRROR_INCREMENTAL_MAX = 8192;     // rows per write handled incrementally (one block)
+
+// mirror[row0 + i] <- stage[i]; sums += f(stage[i]) - (row0 + i < filled ? f(old row) : 0), f = shifted first and
+// second moments (shift x0 = sums[nm .. nm + d)); one block, fixed reduction order
+__global__ void __launch_bounds__(256)
+mirror_update_kernel(double* __restrict__ mirror, const double* __restrict__ stage, int d, long long row0,
+                     long long n_rows, long long filled, double* __restrict__ sums) {
+    __shared__ double red[8];
+    const int nm = d + d * (d + 1) / 2;
+    const double* x0 = sums + nm;
+    for (int q0 = 0; q0 < nm; q0 += 8) {
+        // eight moments per pass over the rows (registers), so any d <= 32 works with a fixed footprint
+        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (long long i = threadIdx.x; i < n_rows; i += blockDim.x) {
+            const double* nw = stage + i * d;
+            const double* od = mirror + (row0 + i) * d;
+            const bool had = row0 + i < filled;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int q = q0 + u;
+                if (q >= nm) break;
+                int j, k = -1;
+                if (q < d) j = q;
+                else {
+                    int r = q - d;
+                    j = 0;
+                    while (r > j) { r -= j + 1; ++j; }
+                    k = r;
+                }
+                double vn = nw[j] - x0[j], vo = had ? od[j] - x0[j] : 0.0;
+                if (k >= 0) { vn *= nw[k] - x0[k]; if (had) vo *= od[k] - x0[k]; }
+                acc[u] += vn - vo;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            double v = acc[u];
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+            __syncthreads();
+            if (threadIdx.x == 0 && q0 + u < nm) {
+                double t = 0.0;
+                for (int w = 0; w < 8; ++w) t += red[w];
+                sums[q0 + u] += t;
+            }
+            __syncthreads();
+        }
+    }
+    // only now overwrite the rows (every pass above read the old ones)
+    for (long long i = threadIdx.x; i < n_rows * d; i += blockDim.x) mirror[row0 * d + i] = stage[i];
+}
+
 extern "C" int ss_mirror_write(ss_ctx* c, int which, int64_t capacity, int d, int64_t row0, int64_t n_rows,
                                const double* rows) {
     if (!c) return SS_EINVAL;
@@ -257,6 +312,8 @@ extern "C" int ss_mirror_write(ss_ctx* c, int which, int64_t capacity, int d, in
         c->mirror_s2.release();
         c->mirror_capacity = capacity;
         c->mirror_d = d;
+        c->mirror_filled = 0;
+        c->mirror_mom_valid = false;
     }
     // allocate geometrically up to capacity + 1 rows, keeping what is there
     DevBuf& buf = which == 0 ? c->mirror_s : c->mirror_s2;
@@ -276,9 +333,34 @@ extern "C" int ss_mirror_write(ss_ctx* c, int which, int64_t capacity, int d, in
         buf.p = np_;
         buf.cap = want;
     }
-    if (n_rows > 0)
+    if (n_rows > 0 && which == 0 && c->mirror_mom_valid && n_rows <= MIRROR_INCREMENTAL_MAX && row0 <= c->mirror_filled) {
+        // keep the running moments of the `s` rows current: the new rows go through a staging buffer and one
+        // block adds them to the sums, subtracts the rows they overwrite (ring wrap) and stores them
+        SS_CUDA_CHECK(c, c->mirror_stage.ensure((size_t)n_rows * d * 8));
+        SS_CUDA_CHECK(c, cudaMemcpyAsync(c->mirror_stage.p, rows, (size_t)n_rows * d * 8, cudaMemcpyHostToDevice, c->stream));
+        mirror_update_kernel<<<1, 256, 0, c->stream>>>(buf.as<double>(), c->mirror_stage.as<double>(), d, row0, n_rows,
+                                                       c->mirror_filled, c->mirror_mom.as<double>());
+        c->launches++;
+        SS_CUDA_CHECK(c, cudaGetLastError());
+        c->mirror_mom_age += n_rows;
+        if (c->mirror_mom_age > capacity) c->mirror_mom_valid = false;      // exact recompute once per buffer turnover
+    } else if (n_rows > 0) {
         SS_CUDA_CHECK(c, cudaMemcpyAsync(buf.as<double>() + (size_t)row0 * d, rows, (size_t)n_rows * d * 8,
                                          cudaMemcpyHostToDevice, c->stream));
+        if (which == 0) c->mirror_mom_valid = false;                         // bulk upload: recomputed at the next selection
+    }
+    if (which == 0 && n_rows > 0) {
+        if (row0 > c->mirror_filled) c->mirror_mom_valid = false;            // a gap: not a ring any more
+        c->mirror_filled = std::max<int64_t>(c->mirror_filled, row0 + n_rows);
+    }
+    return SS_OK;
+}
+
+extern "C" int ss_mirror_reset(ss_ctx* c) {
+    if (!c) return SS_EINVAL;
+    c->mirror_filled = 0;
+    c->mirror_mom_valid = false;
+    c->mirror_mom_age = 0;
     return SS_OK;
 }
 
@@ -331,9 +413,23 @@ extern "C" int ss_kde_ucb_argmax_mirror(ss_ctx* c, int64_t count, int64_t last_r
         SS_CUDA_CHECK(c, c->kde_ucb.ensure((size_t)m * 8));
         ucb_dev = c->kde_ucb.as<double>();
     }
+    // the estimator is fitted from the running moments of the buffer rows; they are recomputed exactly after a
+    // bulk upload and once per buffer turnover
+    const double* sums = nullptr;
+    if (c->mirror_filled == count && !getenv("SS_MIRROR_NO_RUNNING_MOMENTS")) {
+        const int nm = d + d * (d + 1) / 2;
+        if (!c->mirror_mom_valid) {
+            SS_CUDA_CHECK(c, c->mirror_mom.ensure((size_t)(nm + d) * 8));
+            rc = kde_exact_sums(c, c->mirror_s.as<double>(), count, d, c->mirror_mom.as<double>());
+            if (rc) return rc;
+            c->mirror_mom_valid = true;
+            c->mirror_mom_age = 0;
+        }
+        sums = c->mirror_mom.as<double>();
+    }
     timer_mark(c, "kde_h2d");
     rc = kde_run(c, c->mirror_s.as<double>(), count + 1, d, c->kde_q64.as<double>(), m, c->kde_vals.as<float>(),
-                 n_transitions, volume, alpha, beta, dens_dev, ucb_dev, out_best_j, out_best_ucb);
+                 n_transitions, volume, alpha, beta, dens_dev, ucb_dev, out_best_j, out_best_ucb, sums);
     if (rc) return rc;
     if (out_density)
         SS_CUDA_CHECK(c, cudaMemcpyAsync(out_density, dens_dev, (size_t)m * 8, cudaMemcpyDeviceToHost, c->stream));

@@ -131,6 +131,13 @@ struct ss_ctx {
     DevBuf mirror_s, mirror_s2, mirror_idx;
     int64_t mirror_capacity = 0;
     int mirror_d = 0;
+    // running first / second moments of the `s` rows in the mirror (shifted by mirror_mom[nm .. nm + d) = x0), kept
+    // up to date by ss_mirror_write (new rows added, overwritten rows subtracted): a selection from the mirror
+    // fits the estimator from them instead of re-reducing the whole buffer
+    DevBuf mirror_mom, mirror_stage;
+    int64_t mirror_filled = 0;         // rows [0, mirror_filled) of mirror_s are valid and included in the sums
+    int64_t mirror_mom_age = 0;        // rows added / replaced since the sums were last computed exactly
+    bool mirror_mom_valid = false;
 
     // ---- MPC model
     bool model_set = false;

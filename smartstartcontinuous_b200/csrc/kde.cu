@@ -85,7 +85,7 @@ __device__ void kde_fit_block(const double* __restrict__ data, long long n, int 
 template <int DM>
 __global__ void __launch_bounds__(256)
 kde_moments_kernel(const double* __restrict__ data, long long n, int d, double* __restrict__ partial,
-                   unsigned int* __restrict__ ticket, KdeFit* __restrict__ fit) {
+                   unsigned int* __restrict__ ticket, KdeFit* __restrict__ fit, double* __restrict__ sums_out) {
     __shared__ double sm[8];
     __shared__ bool s_last;
     pdl_trigger();       // the whitening kernel may be scheduled (it waits for the fit)
@@ -130,6 +130,19 @@ kde_moments_kernel(const double* __restrict__ data, long long n, int d, double* 
         s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
+    if (s_last && sums_out) {
+        // running-moments mode (device mirror): leave the reduced sums and the shift x0 = data[0], no fit
+        __threadfence();
+        for (int q = threadIdx.x >> 5; q < nm; q += blockDim.x >> 5) {
+            double s = 0.0;
+            for (int b = threadIdx.x & 31; b < (int)gridDim.x; b += 32) s += partial[(size_t)b * nm + q];
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+            if ((threadIdx.x & 31) == 0) sums_out[q] = s;
+        }
+        if ((int)threadIdx.x < d) sums_out[nm + threadIdx.x] = data[threadIdx.x];
+        if (threadIdx.x == 0) *ticket = 0;
+        return;
+    }
     if (s_last) {
         __threadfence();
         // (matrix scratch sized for the dimension at hand: with d <= 4 the serial fit runs out of registers
@@ -244,6 +257,29 @@ __device__ void kde_fit_block(const double* __restrict__ data, long long n, int 
     fit->norm = N * pow(2.0 * 3.14159265358979323846, 0.5 * d) * det;
     fit->status = status;
     fit->max_norm2_bits = 0;
+}
+
+// fit from running sums (device mirror): sums[0 .. nm) over the n - 1 buffer rows, shifted by x0 = sums[nm ..),
+// plus the one extra data row `last` (the newest s2) -> the same estimator the moments kernel fits
+__global__ void __launch_bounds__(32)
+kde_fit_from_sums_kernel(const double* __restrict__ sums, const double* __restrict__ last, long long n, int d,
+                         double* __restrict__ scratch, KdeFit* __restrict__ fit) {
+    pdl_trigger();
+    const int nm = d + d * (d + 1) / 2;
+    const double* x0 = sums + nm;
+    if (threadIdx.x == 0) {
+        int p = d;
+        for (int j = 0; j < d; ++j) {
+            const double vj = last[j] - x0[j];
+            scratch[j] = sums[j] + vj;
+            for (int k = 0; k <= j; ++k) scratch[p + k] = sums[p + k] + vj * (last[k] - x0[k]);
+            p += j + 1;
+        }
+    }
+    __syncwarp();
+    if (d <= 4) kde_fit_block<4>(x0, n, d, scratch, 1, fit);
+    else if (d <= 8) kde_fit_block<8>(x0, n, d, scratch, 1, fit);
+    else kde_fit_block<SS_MAX_D>(x0, n, d, scratch, 1, fit);
 }
 
 // ---- 3. whitening ----------------------------------------------------------------------
@@ -628,10 +664,34 @@ int pad_dim(int d) {
 // only after whitening) rejects the expanded exponent.
 enum KdeVariant { KDE_TC = 0, KDE_EXPANDED = 1, KDE_DIFFERENCE = 2 };
 
+// exact running sums of the first n rows of data_dev (device mirror: after a bulk upload / periodically)
+int kde_exact_sums(ss_ctx* c, const double* data_dev, long long n, int d, double* sums_dev) {
+    const int mom_blocks = (int)std::min<long long>(c->sm_count * 2, (n + 255) / 256);
+    const int nm = d + d * (d + 1) / 2;
+    SS_CUDA_CHECK(c, c->kde_moments.ensure((size_t)mom_blocks * nm * 8));
+    SS_CUDA_CHECK(c, c->kde_fit.ensure(sizeof(KdeFit)));
+    SS_CUDA_CHECK(c, c->kde_result.ensure(sizeof(KdeResult)));
+    KdeResult* res = c->kde_result.as<KdeResult>();
+    if (!c->kde_result_clean) {
+        SS_CUDA_CHECK(c, cudaMemsetAsync(res, 0, sizeof(KdeResult), c->stream));
+        c->kde_result_clean = true;
+    }
+    if (d <= 8)
+        kde_moments_kernel<8><<<mom_blocks, 256, 0, c->stream>>>(data_dev, n, d, c->kde_moments.as<double>(),
+                                                                 &res->moments_ticket, c->kde_fit.as<KdeFit>(), sums_dev);
+    else
+        kde_moments_kernel<SS_MAX_D><<<mom_blocks, 256, 0, c->stream>>>(data_dev, n, d, c->kde_moments.as<double>(),
+                                                                        &res->moments_ticket, c->kde_fit.as<KdeFit>(),
+                                                                        sums_dev);
+    c->launches += 1;
+    SS_CUDA_CHECK(c, cudaGetLastError());
+    return SS_OK;
+}
+
 int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double* queries_dev,
             long long m, const float* values_dev, long long n_transitions, double volume,
             double alpha, double beta, double* density_dev, double* ucb_dev, int64_t* out_best_j,
-            double* out_best_ucb) {
+            double* out_best_ucb, const double* running_sums) {
     const int D = pad_dim(d);
     if (D < 0) SS_FAIL(c, SS_EUNSUPPORTED, "kde: state dimension > 32 is not supported");
     const int mom_blocks = (int)std::min<long long>(c->sm_count * 2, (n + 255) / 256);
@@ -647,12 +707,17 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
     // the kernels leave every counter of `res` at zero when a call completes: cleared only after a failure
     if (!c->kde_result_clean) SS_CUDA_CHECK(c, cudaMemsetAsync(res, 0, sizeof(KdeResult), c->stream));
     c->kde_result_clean = false;
-    if (d <= 8)
+    if (running_sums)
+        // device mirror: the sums of the buffer rows are maintained incrementally; add the newest s2 (the last
+        // data row) and fit -- no pass over the data
+        kde_fit_from_sums_kernel<<<1, 32, 0, c->stream>>>(running_sums, data_dev + (size_t)(n - 1) * d, n, d,
+                                                          c->kde_moments.as<double>(), fit);
+    else if (d <= 8)
         kde_moments_kernel<8><<<mom_blocks, 256, 0, c->stream>>>(data_dev, n, d, c->kde_moments.as<double>(),
-                                                                 &res->moments_ticket, fit);
+                                                                 &res->moments_ticket, fit, nullptr);
     else
         kde_moments_kernel<SS_MAX_D><<<mom_blocks, 256, 0, c->stream>>>(data_dev, n, d, c->kde_moments.as<double>(),
-                                                                        &res->moments_ticket, fit);
+                                                                        &res->moments_ticket, fit, nullptr);
     c->launches += 1;
     SS_CUDA_CHECK(c, cudaGetLastError());
 

@@ -266,6 +266,7 @@ class Engine:
         state = getattr(self, "_mirror_state", None)
         if state is None or state[0] is not ring or ring.pushes < state[1]:
             state = (ring, 0)
+            self._check(self._lib.ss_mirror_reset(self._h))
         done = state[1]
         cap, d = ring.capacity, ring.dim
         todo = ring.pushes - done

@@ -384,3 +384,34 @@ def test_smart_start_path_equals_the_references_from_the_seed(engine, name, env,
     assert chosen == int(g["out_chosen_buffer_index"])
     assert ucb == pytest.approx(float(g["out_ucb"][int(g["out_best_j"])]), rel=1e-4)
     np.testing.assert_array_equal(np.asarray(path), g["out_path"])
+
+
+def test_mirror_running_moments_track_the_buffer(engine):
+    """The estimator of a mirror selection is fitted from moments maintained incrementally by the mirror writes
+    (new rows added, overwritten rows subtracted, exact recompute after bulk uploads and once per buffer
+    turnover): through growth and many ring wraps the densities equal those of the full re-reduction
+    (SS_MIRROR_NO_RUNNING_MOMENTS) to 1e-9."""
+    import os
+
+    from smartstartcontinuous_b200.replay_buffer import ReplayBuffer
+    rng = np.random.default_rng(77)
+    agent = object()
+    rb = ReplayBuffer(agent, 1000)
+    obs, _ = syn.pendulum_rollouts(rng, 40, 150)
+    vals = rng.normal(size=300).astype(np.float32)
+    for ep, traj in enumerate(obs):
+        rb.start_new_episode(agent)
+        for t in range(len(traj) - 1):
+            rb.add(agent, traj[t], np.zeros(1), 0.0, False, traj[t + 1])
+        if ep < 1:
+            continue
+        ring = rb.state_ring()
+        idx = rb.get_possible_smart_start_indices(300)
+        got = engine.select_start_mirror(ring, idx, vals[:len(idx)], len(rb), 0.5, 1.0, 2.0, want_density=True)
+        os.environ["SS_MIRROR_NO_RUNNING_MOMENTS"] = "1"
+        try:
+            want = engine.select_start_mirror(ring, idx, vals[:len(idx)], len(rb), 0.5, 1.0, 2.0, want_density=True)
+        finally:
+            del os.environ["SS_MIRROR_NO_RUNNING_MOMENTS"]
+        np.testing.assert_allclose(got[2], want[2], rtol=1e-9, err_msg="episode %d" % ep)
+        assert got[0] == want[0]
