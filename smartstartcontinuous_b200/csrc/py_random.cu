@@ -23,28 +23,31 @@ constexpr int N = 624, M = 397;
 struct PyMt {
     uint32_t* mt;
     int index;
-    uint32_t next() {
-        if (index >= N) {
-            int kk;
-            uint32_t y;
-            for (kk = 0; kk < N - M; ++kk) {
-                y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
-                mt[kk] = mt[kk + M] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            }
-            for (; kk < N - 1; ++kk) {
-                y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
-                mt[kk] = mt[kk + (M - N)] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            }
-            y = (mt[N - 1] & 0x80000000u) | (mt[0] & 0x7fffffffu);
-            mt[N - 1] = mt[M - 1] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-            index = 0;
+    void refill() {
+        int kk;
+        uint32_t y;
+        for (kk = 0; kk < N - M; ++kk) {
+            y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+            mt[kk] = mt[kk + M] ^ (y >> 1) ^ (-(y & 1u) & 0x9908b0dfu);
         }
-        uint32_t y = mt[index++];
+        for (; kk < N - 1; ++kk) {
+            y = (mt[kk] & 0x80000000u) | (mt[kk + 1] & 0x7fffffffu);
+            mt[kk] = mt[kk + (M - N)] ^ (y >> 1) ^ (-(y & 1u) & 0x9908b0dfu);
+        }
+        y = (mt[N - 1] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+        mt[N - 1] = mt[M - 1] ^ (y >> 1) ^ (-(y & 1u) & 0x9908b0dfu);
+        index = 0;
+    }
+    static uint32_t temper(uint32_t y) {
         y ^= y >> 11;
         y ^= (y << 7) & 0x9d2c5680u;
         y ^= (y << 15) & 0xefc60000u;
         y ^= y >> 18;
         return y;
+    }
+    uint32_t next() {
+        if (index >= N) refill();
+        return temper(mt[index++]);
     }
     // Random._randbelow_with_getrandbits(n), 0 < n < 2^32
     uint32_t below(uint32_t n, int bits) {
@@ -76,14 +79,41 @@ extern "C" int ss_py_random_sample(uint32_t* mt_state, int* mt_index, int64_t fi
             pool[j] = pool[(size_t)(n - i - 1)];
         }
     } else {
+        // selected = set(); per index: j = randbelow(n) until j not in selected.  Both rejections (r >= n and
+        // "already selected") only skip generator outputs, so the result is the first k distinct values of
+        // the stream of outputs below n.  One 624-word block at a time: temper + shift (a loop the compiler
+        // vectorises), branch-free compaction of the outputs below n, then the bitmap pass -- 2 x faster than
+        // one unpredictable branch per output.
         std::vector<uint64_t> seen((size_t)((n + 63) / 64), 0);
         int bits = 0;
         while (((uint32_t)n >> bits) != 0) ++bits;
-        for (int64_t i = 0; i < k; ++i) {
-            uint32_t j = g.below((uint32_t)n, bits);
-            while (seen[j >> 6] >> (j & 63) & 1ull) j = g.below((uint32_t)n, bits);
-            seen[j >> 6] |= 1ull << (j & 63);
-            out[i] = first + j;
+        const int shift = 32 - bits;
+        const uint32_t un = (uint32_t)n;
+        uint32_t shifted[N], cand[N];
+        uint16_t at[N];
+        int64_t taken = 0;
+        while (taken < k) {
+            if (g.index >= N) g.refill();
+            for (int i = 0; i < N; ++i) shifted[i] = PyMt::temper(g.mt[i]) >> shift;
+            int c = 0;
+            for (int i = g.index; i < N; ++i) {
+                cand[c] = shifted[i];
+                at[c] = (uint16_t)i;
+                c += shifted[i] < un;
+            }
+            g.index = N;
+            for (int q = 0; q < c; ++q) {
+                const uint32_t j = cand[q];
+                uint64_t& word = seen[j >> 6];
+                const uint64_t bit = 1ull << (j & 63);
+                if (word & bit) continue;
+                word |= bit;
+                out[taken++] = first + j;
+                if (taken == k) {
+                    g.index = at[q] + 1;       // the generator stops behind the output that completed the sample
+                    break;
+                }
+            }
         }
     }
     *mt_index = g.index;

@@ -12,6 +12,7 @@ instead of Python list comprehensions over a deque / ragged object arrays
 """
 from __future__ import annotations
 
+import bisect
 import pickle
 import random
 from collections import deque
@@ -23,13 +24,31 @@ import numpy as np
 _FAST_SAMPLE = None      # None: not probed yet; False: use the interpreter; else the library handle
 
 
-def _sample_with(lib, rnd, first, n, k):
+_IN_PLACE = False        # the interpreter's generator state can be reached in place (probed)
+
+
+def _state_in_place(rnd):
+    """(address of the index, address of the 624 key words) of a ``random.Random``: CPython's
+    RandomObject is {PyObject_HEAD; int index; uint32_t state[624]} (Modules/_randommodule.c).  An
+    implementation detail, so it is only used after _probe_fast_sample has seen it agree with
+    getstate() before and after a draw in this interpreter."""
+    base = id(rnd) + object.__basicsize__
+    return base, base + 4
+
+
+def _sample_with(lib, rnd, first, n, k, in_place=False):
     """random.sample(range(first, first + n), k) of generator ``rnd`` through csrc/py_random.cu."""
     import ctypes as C
+    out = np.empty(k, dtype=np.int64)
+    if in_place:
+        # no getstate() / setstate() round trip (2 x 625 Python ints: ~55 us of a ~0.3 ms draw)
+        index_at, key_at = _state_in_place(rnd)
+        rc = lib.ss_py_random_sample(C.c_void_p(key_at), C.byref(C.c_int.from_address(index_at)), int(first), int(n), int(k),
+                                     out.ctypes.data_as(C.c_void_p))
+        return out if rc == 0 else None
     version, internal, gauss = rnd.getstate()
     state = np.array(internal, dtype=np.uint32)                # 624 words + the index
     index = C.c_int(int(state[624]))
-    out = np.empty(k, dtype=np.int64)
     rc = lib.ss_py_random_sample(state.ctypes.data_as(C.c_void_p), C.byref(index), int(first), int(n), int(k),
                                  out.ctypes.data_as(C.c_void_p))
     if rc != 0:
@@ -41,13 +60,16 @@ def _sample_with(lib, rnd, first, n, k):
 
 def _probe_fast_sample():
     """The C++ restatement is used only if it reproduces this interpreter's random.sample -- indices,
-    order and the generator state afterwards -- on both of Random.sample's branches."""
-    global _FAST_SAMPLE
+    order and the generator state afterwards -- on both of Random.sample's branches; the in-place
+    route only if, on top of that, the memory behind the object is what getstate() reports."""
+    global _FAST_SAMPLE, _IN_PLACE
     _FAST_SAMPLE = False
+    _IN_PLACE = False
     try:
         from . import _lib
         lib = _lib.load()
-        for first, n, k in ((7, 5000, 900), (3, 57, 25), (0, 1, 1), (11, 300000, 4000)):
+        cases = ((7, 5000, 900), (3, 57, 25), (0, 1, 1), (11, 300000, 4000))
+        for first, n, k in cases:
             a, b = random.Random(987654321), random.Random(987654321)
             want = a.sample(range(first, first + n), k)
             got = _sample_with(lib, b, first, n, k)
@@ -56,6 +78,27 @@ def _probe_fast_sample():
         _FAST_SAMPLE = lib
     except Exception:
         _FAST_SAMPLE = False
+        return
+    try:
+        import ctypes as C
+        import platform
+        if platform.python_implementation() != "CPython":
+            return
+        for first, n, k in cases:
+            a, b = random.Random(123456789), random.Random(123456789)
+            a.random(), b.random()                                  # index away from 624
+            index_at, key_at = _state_in_place(b)
+            internal = b.getstate()[1]
+            if C.c_int.from_address(index_at).value != internal[624] or \
+                    list((C.c_uint32 * 624).from_address(key_at)) != list(internal[:624]):
+                return
+            want = a.sample(range(first, first + n), k)
+            got = _sample_with(lib, b, first, n, k, in_place=True)
+            if got is None or got.tolist() != want or a.getstate() != b.getstate() or a.random() != b.random():
+                return
+        _IN_PLACE = True
+    except Exception:
+        _IN_PLACE = False
 
 
 def sample_range(first, stop, k):
@@ -66,7 +109,7 @@ def sample_range(first, stop, k):
     if _FAST_SAMPLE and k > 64 and 0 < n < 2 ** 31:
         rnd = getattr(random.sample, "__self__", None)       # the module-level generator random.sample is bound to
         if type(rnd) is random.Random:
-            out = _sample_with(_FAST_SAMPLE, rnd, first, n, k)
+            out = _sample_with(_FAST_SAMPLE, rnd, first, n, k, in_place=_IN_PLACE)
             if out is not None:
                 return out
     return np.array(random.sample(range(first, stop), k))
@@ -113,7 +156,11 @@ class _StateRing:
         return np.concatenate([arr[self.head:self.count], arr[:self.head]], axis=0)
 
     def physical_rows(self, buffer_indices):
-        return (np.asarray(buffer_indices, dtype=np.int64) + self.head) % max(self.count, 1)
+        """Physical rows of logical buffer indices 0 <= i < count (a fresh array)."""
+        rows = np.asarray(buffer_indices, dtype=np.int64) + self.head
+        if self.head:                                # wrapped ring: one conditional subtraction, no division
+            rows[rows >= self.count] -= self.count
+        return rows
 
     def rows(self, arr, buffer_indices):
         return arr[self.physical_rows(buffer_indices)]
@@ -254,17 +301,16 @@ class ReplayBuffer(object):
         if len(starts) == 0:
             raise ValueError(": (   -   no episodes have been recorded")
         count = self.buffer_index_to_episode_number(buffer_index)
-        start_count = None
-        for e in starts:                       # ascending; last start <= count wins
-            if e <= count:
-                start_count = e
-            else:
-                break
+        pos = bisect.bisect_right(starts, count)     # ascending; last start <= count wins
+        start_count = starts[pos - 1] if pos > 0 else None
         first = self.episode_number_to_buffer_index(start_count)
         ring = self._ring
         if ring is not None and ring.count == len(self.buffer):
-            rows = ring.rows(ring.s, np.arange(first, buffer_index + 1))
-            return [np.array(row) for row in rows] + [np.array(ring.rows(ring.s2, [buffer_index])[0])]
+            # one gather (a private copy) and a list of its rows instead of one array construction per state
+            rows = np.empty((buffer_index - first + 2, ring.dim))
+            rows[:-1] = ring.rows(ring.s, np.arange(first, buffer_index + 1))
+            rows[-1] = ring.s2[ring.physical_rows([buffer_index])[0]]
+            return list(rows)
         steps = list(self.buffer)[first:buffer_index + 1]
         return [self.step_to_s(st) for st in steps] + [self.step_to_s2(self.buffer[buffer_index])]
 

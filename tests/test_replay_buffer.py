@@ -154,6 +154,60 @@ def test_candidate_draw_in_cxx_equals_random_sample():
     assert rbm.sample_range(0, 500, 120).tolist() == a
 
 
+def test_candidate_draw_random_shapes_both_routes():
+    """Random (first, n, k, generator position): the block-wise set branch, the pool branch and the two ways
+    of reaching the interpreter's generator (in place behind the object / getstate + setstate) against
+    random.sample itself, including where the generator stops."""
+    import random
+
+    from smartstartcontinuous_b200 import replay_buffer as rbm
+    rbm._probe_fast_sample()
+    assert rbm._FAST_SAMPLE
+    assert rbm._IN_PLACE, "CPython's RandomObject layout was not recognised"
+    pick = np.random.default_rng(11)
+    for trial in range(60):
+        n = int(pick.choice([1, 2, 70, 625, 1300, 5000, 70000, 250000]))
+        k = int(pick.integers(0, min(n, 20000) + 1))
+        first = int(pick.integers(0, 1000))
+        burn = int(pick.integers(0, 1300))
+        for in_place in (True, False):
+            a, b = random.Random(trial), random.Random(trial)
+            for _ in range(burn):
+                a.getrandbits(32), b.getrandbits(32)
+            want = a.sample(range(first, first + n), k)
+            got = rbm._sample_with(rbm._FAST_SAMPLE, b, first, n, k, in_place=in_place)
+            assert got.tolist() == want, (n, k, first, burn, in_place)
+            assert a.getstate() == b.getstate(), (n, k, first, burn, in_place)
+
+
+def test_episodic_path_equals_the_per_step_construction():
+    """get_episodic_path_to_buffer_index (replay_buffer.py:154-176) from the contiguous mirror = the
+    reference's list built step by step from the deque, for every buffer index, before and after eviction."""
+    from smartstartcontinuous_b200.replay_buffer import ReplayBuffer
+    main = object()
+    rb = ReplayBuffer(main, 230)
+    rng = np.random.default_rng(5)
+    added = 0
+    for ep in range(9):
+        rb.start_new_episode(main)
+        for t in range(int(rng.integers(3, 60))):
+            rb.add(main, rng.normal(size=3), rng.normal(size=1), 0.0, False, rng.normal(size=3))
+            added += 1
+        if ep in (3, 8):
+            assert (added > 230) == (ep == 8)
+            first_ok = rb.episode_number_to_buffer_index(rb.episode_starting_indices[0])
+            for idx in range(first_ok, len(rb)):
+                got = rb.get_episodic_path_to_buffer_index(idx)
+                count = rb.buffer_index_to_episode_number(idx)
+                start = max(e for e in rb.episode_starting_indices if e <= count)
+                lo = rb.episode_number_to_buffer_index(start)
+                want = [rb.buffer[i][0] for i in range(lo, idx + 1)] + [rb.buffer[idx][4]]
+                assert len(got) == len(want)
+                assert all(isinstance(g, np.ndarray) and np.array_equal(g, w) for g, w in zip(got, want))
+            got[0][0] = 123.0                                   # a private copy, not a view of the mirror
+            assert rb.get_episodic_path_to_buffer_index(len(rb) - 1)[0][0] != 123.0
+
+
 def _golden_buffer(name, env, n_transitions, seed):
     """The replay buffer of oracle/make_golden.golden_kde rebuilt through OUR ReplayBuffer API (same seeded
     synthetic episodes, same capacity, so the same FIFO evictions)."""
