@@ -176,7 +176,7 @@ int ss_mpc_finish(ss_ctx* ctx, int64_t* out_best_k, double* out_best_score, doub
  * np.argmax ordering -- one collective and one device->host copy per decision.  want_path = 0
  * leaves the sequence / path part zero.  Phase B is ONE kernel launch (coefficients, penalties, arg-max
  * and package); on an unsharded batch the same kernel also writes the package to mapped pinned host
- * memory and raises a completion flag there, so ss_mpc_read_package returns it without a
+ * memory (self-validating tagged slots, no fence or flag), so ss_mpc_read_package returns it without a
  * device->host copy or a stream synchronisation. */
 int ss_mpc_finish_package(ss_ctx* ctx, int want_path, double** package_dev, int* count);
 int ss_mpc_read_package(ss_ctx* ctx, double* out_package, int count);

@@ -24,3 +24,18 @@ for n_ss in (16384, 2000):
         for _ in range(50): ss.get_smart_start_path()
         pr.disable()
         pstats.Stats(pr).sort_stats("cumulative").print_stats(14)
+# phases of the mirror selection (per-phase events on)
+eng.set_timing(True)
+random.seed(0)
+ss = bench.make_smart_start(eng, kw, 16384, device_values=True)
+for _ in range(3): ss.get_smart_start_path()
+print("phases (ms):", [(k, round(v, 4)) for k, v in eng.last_timings()])
+rb = ss.replay_buffer
+idx = rb.get_possible_smart_start_indices(16384)
+ring = rb.state_ring()
+eng.set_timing(False)
+for _ in range(3): eng.select_start_mirror(ring, idx, None, len(rb), 1e-3, 1.0, 2.0)
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(50): eng.select_start_mirror(ring, idx, None, len(rb), 1e-3, 1.0, 2.0)
+t1 = time.perf_counter()
+print("select_start_mirror alone: %.1f us" % ((t1 - t0) * 2e4))

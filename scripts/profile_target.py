@@ -30,6 +30,16 @@ if os.environ.get("SS_PROFILE_CFG") == "mt":
             st = eng.mt19937_state()
     print("mt19937 pos", st[2])
     sys.exit(0)
+if os.environ.get("SS_PROFILE_CFG") == "sel":
+    # the selection call with the candidates' values computed on the device (row f4) from the device mirror
+    import random
+    random.seed(0)
+    kw = bench.kde_workload()
+    ss = bench.make_smart_start(eng, kw, 16384, device_values=True)
+    for i in range(3):
+        path = ss.get_smart_start_path()
+    print("selection", ss.last_selection, len(path), eng.last_timings())
+    sys.exit(0)
 if os.environ.get("SS_PROFILE_CFG") == "dyn":
     # row f1: a few Adam steps of the device trainer at the BASELINE shapes (2x500, batch 512)
     from oracle import dyn_train_oracle as dto

@@ -135,6 +135,8 @@ struct ss_ctx {
     // up to date by ss_mirror_write (new rows added, overwritten rows subtracted): a selection from the mirror
     // fits the estimator from them instead of re-reducing the whole buffer
     DevBuf mirror_mom, mirror_stage;
+    void* host_rows = nullptr;         // pinned staging of a selection's candidate rows (+ values)
+    size_t host_rows_cap = 0;
     int64_t mirror_filled = 0;         // rows [0, mirror_filled) of mirror_s are valid and included in the sums
     int64_t mirror_mom_age = 0;        // rows added / replaced since the sums were last computed exactly
     bool mirror_mom_valid = false;
@@ -245,6 +247,51 @@ static inline cudaError_t launch_dependent(void (*kernel)(KArgs...), dim3 grid, 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---- small results through mapped pinned host memory, without a fence -------------------------------
+// A result double travels as two 8-byte units {32 payload bits | 32-bit tag of the call}, written with ONE
+// 16-byte store; the host accepts a slot once both of its tags equal the call's tag.  Every unit validates itself
+// (an aligned 8-byte write is atomic on the way to host memory, the granularity NCCL's LL protocol relies on), so
+// the payload needs no __threadfence_system() + barrier + release-store of a flag behind it.  Measured on B200
+// (scripts/dev/micro/host_flag_latency.cu): the host sees a fence-free store 8.0 us after the launch call, a
+// payload + fence + flag 11.5-13.0 us after it.
+__device__ __forceinline__ void host_slot_put(unsigned long long* slots, int slot, double v, unsigned int tag) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long t = (unsigned long long)tag << 32;
+    const unsigned long long u0 = t | (bits & 0xffffffffull), u1 = t | (bits >> 32);
+    asm volatile("st.global.v2.b64 [%0], {%1, %2};" ::"l"(slots + 2 * slot), "l"(u0), "l"(u1) : "memory");
+}
+inline unsigned int host_slot_tag(unsigned long long seq) { return (unsigned int)seq | 0x80000000u; }   // never 0
+// waits until slots [0, count) carry `tag` and copies their doubles out; the stream is queried now and then so that
+// a failed launch cannot hang the caller
+inline int host_slots_wait(ss_ctx* c, const void* mapped, int count, unsigned int tag, double* out, const char* what) {
+    const volatile unsigned long long* u = static_cast<const volatile unsigned long long*>(mapped);
+    unsigned spins = 0;
+    bool drained = false;
+    for (int o = 0; o < count;) {
+        const unsigned long long u0 = u[2 * o], u1 = u[2 * o + 1];
+        if ((unsigned int)(u0 >> 32) == tag && (unsigned int)(u1 >> 32) == tag) {
+            const unsigned long long bits = (u0 & 0xffffffffull) | (u1 << 32);
+            std::memcpy(out + o, &bits, 8);
+            ++o;
+            continue;
+        }
+        if ((++spins & 0x3fff) == 0) {
+            if (drained) {
+                c->err = std::string(what) + ": the kernel ended without delivering its result";
+                return SS_ECUDA;
+            }
+            cudaError_t e = cudaStreamQuery(c->stream);
+            if (e != cudaSuccess && e != cudaErrorNotReady) SS_CUDA_CHECK(c, e);
+            if (e == cudaSuccess) {
+                SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+                drained = true;                       // one more pass over the slot, then give up
+                spins = 0x3fff - 64;
+            }
+        }
+    }
+    return SS_OK;
 }
 
 // ---- device helpers --------------------------------------------------------------------

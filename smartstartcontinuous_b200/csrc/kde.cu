@@ -41,7 +41,7 @@ constexpr int KDE_THREADS = 128;      // threads per CTA in the pair kernel
 constexpr int KDE_TILE_FLOATS = 4096;  // 16 KB of points per shared-memory stage
 constexpr int KDE_STAGES = 2;
 constexpr double KDE_RESCUE_BELOW = 7.8886090522101181e-31;  // 2^-100
-constexpr int KDE_FIN_SPLIT = 4;           // threads per query in the finish kernel's slice reduction
+constexpr int KDE_FIN_Q = 32;              // queries per block of the finish kernel (one per lane; the warps split the slices)
 #ifndef SS_KDE_POLY_EVERY
 #define SS_KDE_POLY_EVERY 5
 #endif
@@ -512,12 +512,8 @@ struct KdeResult {
 // what a selection hands back to the host, written by the last block of kde_finish_kernel straight
 // into mapped pinned host memory (flag last, release at system scope): the call ends without a
 // device->host copy and without a stream synchronisation
-struct KdeHostOut {
-    unsigned long long flag;          // == seq of the call when the fields below are valid
-    double best_ucb;
-    long long best_j;
-    int status, max_norm2_bits;       // copies of KdeFit::status / max_norm2_bits
-};
+// the selection result in mapped pinned host memory: three tagged slots (common.cuh host_slot_put)
+constexpr int KDE_HOST_SLOTS = 3;     // best_ucb | best_j | (status, max_norm2_bits)
 
 __global__ void __launch_bounds__(256)
 kde_finish_kernel(const float* __restrict__ partial, int n_slices, long long m, long long m_pad,
@@ -526,28 +522,37 @@ kde_finish_kernel(const float* __restrict__ partial, int n_slices, long long m, 
                   const KdeFit* __restrict__ fit, double n_transitions, double volume, double alpha,
                   double beta, double* __restrict__ density, double* __restrict__ ucb_out,
                   double* __restrict__ block_v, long long* __restrict__ block_i,
-                  KdeResult* __restrict__ result, KdeHostOut* __restrict__ host_out, unsigned long long seq) {
+                  KdeResult* __restrict__ result, unsigned long long* __restrict__ host_out, unsigned long long seq) {
     __shared__ double s_v[32];
     __shared__ long long s_i[32];
     __shared__ int s_list[256];
     __shared__ int s_nlist;
     __shared__ double s_red[8];
+    __shared__ double s_part[8][KDE_FIN_Q];
     __shared__ bool s_last;
     pdl_wait();          // programmatic dependent of the pair kernel
     if (threadIdx.x == 0) s_nlist = 0;
     __syncthreads();
 
-    // four threads per query split the slice reduction (fixed order: slices sub, sub + 4, ..., then
-    // a shuffle tree); the thread with sub == 0 owns the query from here on
-    const int sub = threadIdx.x & (KDE_FIN_SPLIT - 1);
-    const long long jq0 = blockIdx.x * (long long)(blockDim.x / KDE_FIN_SPLIT) + (threadIdx.x / KDE_FIN_SPLIT);
-    const long long j = sub == 0 ? jq0 : m;          // non-owners behave like out-of-range threads
+    // slice reduction: lane = query (32 consecutive floats per load), the 8 warps take the slices warp, warp + 8, ...
+    // with 8 loads in flight each, then warp 0 adds the 8 partial sums in warp order (a fixed order) and owns
+    // the queries from here on.  [4 threads per query with 4 loads in flight each: 20 us for 148 slices, all of it
+    // load latency -- ncu r02n.]
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const long long jq0 = blockIdx.x * (long long)KDE_FIN_Q + lane;
+    const long long j = wrp == 0 ? jq0 : m;          // non-owners behave like out-of-range threads
     double sum = 0.0;
     if (jq0 < m) {
-#pragma unroll 4
-        for (int s = sub; s < n_slices; s += KDE_FIN_SPLIT) sum += (double)partial[(size_t)s * m_pad + jq0];
+#pragma unroll 8
+        for (int s = wrp; s < n_slices; s += 8) sum += (double)partial[(size_t)s * m_pad + jq0];
     }
-    for (int off = 1; off < KDE_FIN_SPLIT; off <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    s_part[wrp][lane] = sum;
+    __syncthreads();
+    if (wrp == 0) {
+        sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += s_part[w][lane];
+    }
     if (j < m && !(sum >= KDE_RESCUE_BELOW)) s_list[atomicAdd(&s_nlist, 1)] = threadIdx.x;
     __syncthreads();
     // fp64 rescue of queries whose fp32 sum underflowed (far from every data point):
@@ -555,7 +560,7 @@ kde_finish_kernel(const float* __restrict__ partial, int n_slices, long long m, 
     const int nres = s_nlist;
     for (int r = 0; r < nres; ++r) {
         const int owner = s_list[r];
-        const long long jq = blockIdx.x * (long long)(blockDim.x / KDE_FIN_SPLIT) + owner / KDE_FIN_SPLIT;
+        const long long jq = blockIdx.x * (long long)KDE_FIN_Q + owner;
         double yq[SS_MAX_D];
         for (int a = 0; a < d; ++a) {
             double y = 0.0;
@@ -620,12 +625,10 @@ kde_finish_kernel(const float* __restrict__ partial, int n_slices, long long m, 
             result->blocks_done = 0;
             result->n_rescued = 0;
             if (host_out) {
-                host_out->best_ucb = v;
-                host_out->best_j = bi;
-                host_out->status = fit->status;
-                host_out->max_norm2_bits = fit->max_norm2_bits;
-                __threadfence_system();
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(&host_out->flag), "l"(seq) : "memory");
+                const unsigned int tag = (unsigned int)seq | 0x80000000u;          // host_slot_tag
+                host_slot_put(host_out, 0, v, tag);
+                host_slot_put(host_out, 1, __longlong_as_double(bi), tag);
+                host_slot_put(host_out, 2, __hiloint2double(fit->max_norm2_bits, fit->status), tag);
             }
         }
     }
@@ -696,7 +699,7 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
     if (D < 0) SS_FAIL(c, SS_EUNSUPPORTED, "kde: state dimension > 32 is not supported");
     const int mom_blocks = (int)std::min<long long>(c->sm_count * 2, (n + 255) / 256);
     const int nm = d + d * (d + 1) / 2;
-    const int fin_blocks = (int)((m + 256 / KDE_FIN_SPLIT - 1) / (256 / KDE_FIN_SPLIT));
+    const int fin_blocks = (int)((m + KDE_FIN_Q - 1) / KDE_FIN_Q);
     SS_CUDA_CHECK(c, c->kde_moments.ensure((size_t)mom_blocks * nm * 8));
     SS_CUDA_CHECK(c, c->kde_fit.ensure(sizeof(KdeFit)));
     SS_CUDA_CHECK(c, c->kde_block_best.ensure((size_t)fin_blocks * 16));
@@ -836,30 +839,20 @@ int kde_run(ss_ctx* c, const double* data_dev, long long n, int d, const double*
         SS_CUDA_CHECK(c, launch_dependent(kde_finish_kernel, dim3(fin_blocks), dim3(256), 0, c->stream,
                                           c->kde_partial.as<float>(), n_slices, m, m_pad, data_dev, n, d, queries_dev,
                                           values_dev, fit, (double)n_transitions, volume, alpha, beta, density_dev,
-                                          ucb_dev, bv, bi, res, reinterpret_cast<KdeHostOut*>(c->host_kde_dev), seq));
+                                          ucb_dev, bv, bi, res, reinterpret_cast<unsigned long long*>(c->host_kde_dev), seq));
         c->launches++;
         SS_CUDA_CHECK(c, cudaGetLastError());
         timer_mark(c, "kde_finish");
 
-        // wait for the completion flag in mapped host memory (the stream is queried now and then so
-        // that a failed launch cannot hang the caller)
-        volatile KdeHostOut* ho = reinterpret_cast<volatile KdeHostOut*>(c->host_kde);
-        unsigned spins = 0;
-        while (ho->flag != seq) {
-            if ((++spins & 0x3fff) == 0) {
-                cudaError_t qe = cudaStreamQuery(c->stream);
-                if (qe != cudaSuccess && qe != cudaErrorNotReady) SS_CUDA_CHECK(c, qe);
-                if (qe == cudaSuccess && ho->flag != seq) {
-                    SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-                    if (ho->flag != seq) SS_FAIL(c, SS_ECUDA, "kde: the finish kernel ended without raising its flag");
-                }
-            }
-        }
-        std::atomic_thread_fence(std::memory_order_acquire);
+        // the result arrives in mapped host memory as tagged slots
+        double slots[KDE_HOST_SLOTS];
+        const int rc_wait = host_slots_wait(c, c->host_kde, KDE_HOST_SLOTS, host_slot_tag(seq), slots, "kde");
+        if (rc_wait) return rc_wait;
         KdeResult hres;
-        hres.best_ucb = ho->best_ucb;
-        hres.best_j = ho->best_j;
-        int hstat[2] = {ho->status, ho->max_norm2_bits};
+        hres.best_ucb = slots[0];
+        std::memcpy(&hres.best_j, &slots[1], 8);
+        int hstat[2];                                     // status (low word), max_norm2_bits (high word)
+        std::memcpy(hstat, &slots[2], 8);
         if (hstat[0] != 0)
             SS_FAIL(c, SS_ESINGULAR, "kde: data covariance is not positive definite (singular matrix)");
         float max_norm2;

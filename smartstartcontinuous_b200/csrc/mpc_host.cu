@@ -478,9 +478,9 @@ extern "C" int ss_mpc_finish_package(ss_ctx* c, int want_path, double** package_
     if (peer) {
         SS_CUDA_CHECK(c, c->mpc_package_local.ensure((size_t)n * 8));
         pkg_dst = c->mpc_package_local.as<double>();
-    } else if ((size_t)(n + 2) * 8 <= ss_ctx::HOST_PKG_BYTES) {
-        // the package also lands in mapped pinned host memory, followed by a completion flag:
-        // ss_mpc_read_package then needs no device->host copy and no stream synchronisation
+    } else if ((size_t)n * 16 <= ss_ctx::HOST_PKG_BYTES) {
+        // the package also lands in mapped pinned host memory as self-validating tagged slots (common.cuh
+        // host_slot_put): ss_mpc_read_package then needs no device->host copy and no stream synchronisation
         if (!c->host_pkg) {
             SS_CUDA_CHECK(c, cudaHostAlloc(&c->host_pkg, ss_ctx::HOST_PKG_BYTES, cudaHostAllocMapped));
             std::memset(c->host_pkg, 0, ss_ctx::HOST_PKG_BYTES);
@@ -509,25 +509,8 @@ extern "C" int ss_mpc_read_package(ss_ctx* c, double* out_package, int count) {
         SS_FAIL(c, SS_EINVAL, "mpc: bad package buffer");
     SS_CUDA_CHECK(c, cudaSetDevice(c->device));
     auto& r = c->run;
-    if (r.pkg_on_host && (size_t)(count + 2) * 8 <= ss_ctx::HOST_PKG_BYTES) {
-        // wait for the tail kernel's completion flag in mapped host memory (a spin on a cache line the
-        // GPU writes once); the stream is queried now and then so that a failed launch cannot hang us
-        volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(c->host_pkg);
-        unsigned spins = 0;
-        while (*flag != r.pkg_seq) {
-            if ((++spins & 0x3fff) == 0) {
-                cudaError_t e = cudaStreamQuery(c->stream);
-                if (e != cudaSuccess && e != cudaErrorNotReady) SS_CUDA_CHECK(c, e);
-                if (e == cudaSuccess && *flag != r.pkg_seq) {
-                    SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-                    if (*flag != r.pkg_seq) SS_FAIL(c, SS_ECUDA, "mpc: the tail kernel finished without raising its flag");
-                }
-            }
-        }
-        std::atomic_thread_fence(std::memory_order_acquire);
-        std::memcpy(out_package, reinterpret_cast<const double*>(c->host_pkg) + 2, (size_t)count * 8);
-        return SS_OK;
-    }
+    if (r.pkg_on_host && (size_t)count * 16 <= ss_ctx::HOST_PKG_BYTES)
+        return host_slots_wait(c, c->host_pkg, count, host_slot_tag(r.pkg_seq), out_package, "mpc");
     SS_CUDA_CHECK(c, cudaMemcpyAsync(out_package, c->mpc_package.p, (size_t)count * 8, cudaMemcpyDeviceToHost, c->stream));
     SS_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
     return SS_OK;

@@ -55,8 +55,8 @@ mpc_fold_partials_kernel(const double* __restrict__ partial, int blocks, int n_o
 //   arg-max and the winner's package.
 struct TailOut {
     double* pkg;                    // device package [2 + H*da + T*d]
-    double* host_pkg;               // mapped pinned host copy: [0] = completion flag, [2..] = package; or null
-    unsigned long long seq;         // value the flag takes when the package is complete
+    double* host_pkg;               // mapped pinned host copy as tagged slots (common.cuh host_slot_put), or null
+    unsigned long long seq;         // the call's sequence number (-> tag of the slots)
     double* sums_out;               // [2T] reduced sums (block 0 writes them), or null
     float* scores_final;            // where the final scores go (== scores in place)
 };
@@ -70,7 +70,8 @@ __device__ __noinline__ void tail_write_package(double best_v, long long kl, lon
     const int tid = threadIdx.x;
     const long long kg = kl < 0 ? -1 : kl + k_offset;
     const int n_seq = act.H * act.da, n_path = T * d;
-    double* hp = out.host_pkg ? out.host_pkg + 2 : nullptr;
+    unsigned long long* hp = reinterpret_cast<unsigned long long*>(out.host_pkg);
+    const unsigned int tag = (unsigned int)out.seq | 0x80000000u;          // host_slot_tag
     for (int o = tid; o < 2 + n_seq + n_path; o += blockDim.x) {
         double val = 0.0;
         if (o == 0) val = best_v;
@@ -84,16 +85,7 @@ __device__ __noinline__ void tail_write_package(double best_v, long long kl, lon
             }
         }
         out.pkg[o] = val;
-        if (hp) hp[o] = val;
-    }
-    if (out.host_pkg) {
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long*>(out.host_pkg)),
-                         "l"(out.seq)
-                         : "memory");
-        }
+        if (hp) host_slot_put(hp, o, val, tag);      // self-validating: no fence, barrier or flag behind it
     }
 }
 
