@@ -157,7 +157,12 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
     }
     tc_fence_before();
     __syncthreads();
-    cluster_sync_all();                  // every CTA's barriers exist before anybody arrives remotely
+    // every CTA's barriers must exist before anybody arrives on them remotely -- but the first remote operation is
+    // the exchange at the END of step 0, ~4000 clocks of purely local work away.  The four CTAs of a cluster start
+    // up to ~10 000 clocks apart (launch skew), so: arrive here, wait in front of the first exchange (row warps) /
+    // in the teardown (the others), and the early CTAs spend the skew on step 0 instead of in a barrier.
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    bool joined = false;                 // this warp has completed the wait of the start-up barrier
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
     if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[193] = (unsigned long long)clock64();
@@ -341,6 +346,10 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
                     for (int j = 0; j < DZ; ++j) zx[(j * TPR + ch) * TM + row] = zacc[j].x + zacc[j].y;
                     asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
                     float4* zbuf = zq + (size_t)ph * (QUAD * TM);
+                    if (!joined) {
+                        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+                        joined = true;
+                    }
                     if (ch == 0) {
                         float part[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -435,6 +444,7 @@ __global__ void __launch_bounds__(THREADS, 1) mpc_rollout_tc_quad_kernel(const R
     // ---- teardown ---------------------------------------------------------------------------
     tc_fence_before();
     __syncthreads();
+    if (!joined) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
     cluster_sync_all();                  // nobody leaves while a peer may still write into its buffers
     tc_fence_after();
     if (p.prof && blockIdx.x == 0 && tid == 0) p.prof[195] = (unsigned long long)clock64();
