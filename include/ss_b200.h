@@ -69,8 +69,8 @@ int ss_device_info(ss_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int
 /* device time (ms, CUDA events on the context's stream) of the most recent call, split in
  * up to 8 named phases; returns the number of phases written */
 int ss_last_timings(ss_ctx* ctx, float* ms, const char** names, int max_phases);
-/* per-phase CUDA events are recorded by default (they feed ss_last_timings); ss_set_timing(ctx, 0)
- * drops them -- a few microseconds per call that matter for small batches (K of a few thousand) */
+/* per-phase CUDA events (they feed ss_last_timings) are recorded after ss_set_timing(ctx, 1); off by
+ * default -- the events between the kernels cost ~30 us per call, a third of a K = 4096 decision */
 int ss_set_timing(ss_ctx* ctx, int enabled);
 /* number of kernel launches issued by this context since creation */
 int64_t ss_launch_count(ss_ctx* ctx);

@@ -10,6 +10,7 @@ import bench
 from smartstartcontinuous_b200.engine import Engine
 
 eng = Engine(0)
+eng.set_timing(True)
 if os.environ.get("SS_PROFILE_CFG") == "c3":
     # BASELINE config 3: MountainCar, K=4096, H=20, MLP 2x500 -- the small-K decision
     wl = bench.make_workload_mountaincar(2, 500)

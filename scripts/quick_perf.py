@@ -11,6 +11,7 @@ from smartstartcontinuous_b200.engine import Engine
 from smartstartcontinuous_b200.nnd_mb_agent import plan_from_path
 
 eng = Engine(0)
+eng.set_timing(True)
 print(eng.device_info())
 for n, m in ((100_000, 16_384), (1_000_000, 16_384), (100_000, 2_000)):
     all_states, s2, _ = syn.pendulum_buffer(n, seed=0)

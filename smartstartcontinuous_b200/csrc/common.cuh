@@ -199,7 +199,8 @@ struct ss_ctx {
     void* host_pkg_dev = nullptr;
     unsigned long long host_pkg_seq = 0;
     void* mt_cache = nullptr;          // MT19937 jump-ahead plans + state read-back buffer (mt19937.cu)
-    bool timing = true;                // per-phase CUDA events (ss_last_timings); ss_set_timing(0) drops them
+    bool timing = false;               // per-phase CUDA events (ss_last_timings) on request (ss_set_timing(1)): they
+                                       // cost ~30 us per decision, a third of a small one
 };
 
 // ---- phase timing helpers (CUDA events on the context stream) -------------------------

@@ -71,8 +71,12 @@ def test_cuda_core_expanded_variant_vs_oracle(engine, monkeypatch, d, n, m, no_t
     data = rng.normal(size=(n, d)) @ A + rng.normal(size=d) * 3
     q = data[rng.choice(n, m, replace=False)] + 0.05 * rng.normal(size=(m, d))
     vals = rng.normal(size=m).astype(np.float32)
-    best, _, dens, ucb = engine.select_start(data, q, vals, n - 1, 0.37, 1.0, 2.0, want_density=True, want_ucb=True)
-    assert dict(engine.last_timings()).get("kde_pairs") is not None
+    engine.set_timing(True)
+    try:
+        best, _, dens, ucb = engine.select_start(data, q, vals, n - 1, 0.37, 1.0, 2.0, want_density=True, want_ucb=True)
+        assert dict(engine.last_timings()).get("kde_pairs") is not None
+    finally:
+        engine.set_timing(False)
     obest, odens, oucb = kde_oracle.select_start(data, q, vals, n - 1, 0.37, 1.0, 2.0)
     np.testing.assert_allclose(dens, odens, rtol=RTOL)
     _ucb_close(ucb, oucb, vals)
