@@ -1,3 +1,4 @@
+"""Development helper: decision and rollout-kernel time of small batches (config 3 and neighbours), pair vs quad kernel (SS_TC_QUAD)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch

@@ -1,3 +1,4 @@
+"""Development helper: SS_TC_TRACE clock stamps of the quad kernel at config 3 (profiles/r02_quad_trace.md)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np

@@ -1,3 +1,4 @@
+"""Development helper: time of ss_mt19937_uniform (+ state read-back) at the benchmarked stream lengths."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import time, numpy as np, ctypes as C

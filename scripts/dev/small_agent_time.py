@@ -1,3 +1,4 @@
+"""Development helper: NND_MB_agent.get_best_sim_actions at configs 3 and 1 -- host draw / device MT19937 / Philox -- and a cProfile of the host side."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
