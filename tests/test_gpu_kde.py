@@ -262,7 +262,9 @@ def _random_value_net(rng, d, da, h1, h2, layer_norm, last_tanh, norms):
 
 @pytest.mark.parametrize("cfg", [(3, 1, 64, 32, False, True, False),      # the example's DDPG nets
                                  (2, 1, 64, 64, True, False, True), (4, 2, 200, 100, True, True, True),
-                                 (3, 1, 64, 32, False, True, "clip_only")])
+                                 (3, 1, 64, 32, False, True, "clip_only"),
+                                 # register-tiled kernel with widths that are not multiples of 16 and da = 2 / 5
+                                 (4, 2, 48, 40, True, True, True), (5, 5, 20, 7, False, False, False)])
 def test_value_net_matches_oracle_and_feeds_the_ucb(engine, cfg):
     """Row f4: critic(q, actor(q)) on the device vs the float32 numpy restatement, and a selection
     with values=None equals the selection fed with the host-evaluated values."""
