@@ -21,6 +21,16 @@ if os.environ.get("SS_PROFILE_CFG") == "c3":
                      penalty_mode="reference", precision="bf16_tc")
     print("mpc c3", r["best_k"], r["best_score"], eng.last_timings())
     sys.exit(0)
+if os.environ.get("SS_PROFILE_CFG") == "c1":
+    # BASELINE config 1 (the reference's own example): MountainCar, K=5000, H=4, MLP 1x32 -- the FP32 kernel
+    wl = bench.make_workload_mountaincar(1, 32)
+    eng.set_model(wl["w"], wl["b"], wl["norm"])
+    eng.set_plan(wl["plan"]["desired_states"], wl["plan"]["distances_left"], wl["plan"]["radii"])
+    for i in range(6):
+        r = eng.plan(wl["state"], 0, K=bench.C1_K, H=bench.C1_H, seed=i, act_low=wl["low"], act_high=wl["high"],
+                     penalty_mode="reference", precision="auto")
+    print("mpc c1", r["best_k"], r["best_score"], eng.last_timings())
+    sys.exit(0)
 if os.environ.get("SS_PROFILE_CFG") == "mt":
     # numpy's MT19937 stream on the device at the bench shape (K = 131072, H = 50) and at config 3's
     rs = np.random.RandomState(1)
