@@ -254,7 +254,8 @@ int ss_py_random_sample(uint32_t* mt_state, int* mt_index, int64_t first, int64_
 /* 1 when ss_mpc_set_model's shape can run on the tcgen05 kernel */
 int ss_mpc_tc_supported(ss_ctx* ctx);
 /* rollout kernel of the last ss_mpc_rollout: 0 = FP32 SIMT, 1 = tcgen05 CTA pairs (mpc_tc.cu), 2 = tcgen05
- * 4-CTA clusters with the hidden layer split over the cluster (small batches, mpc_tc_quad.cu); -1 = none */
+ * 4-CTA clusters with the hidden layer split over the cluster (small batches, mpc_tc_quad.cu), 3 = FP32 thread per
+ * sequence (one hidden layer of <= 64 units, the reference's default 1 x 32 model); -1 = none */
 int ss_mpc_last_kernel(ss_ctx* ctx);
 
 /* ---- dynamics-model training on the device ------------------------------

@@ -354,7 +354,7 @@ extern "C" int ss_mpc_rollout(ss_ctx* c, const double* state, int wp_index, int6
     } else {
         rc = mpc_simt_launch(c, a, &grid);
         if (rc) return rc;
-        r.kernel = 0;
+        r.kernel = mpc_simt_is_thread_kernel(a) ? 3 : 0;
     }
     timer_mark(c, "mpc_rollout");
     r.sum_cols = nullptr;

@@ -30,6 +30,7 @@ struct RolloutArgs {
 // fp32 SIMT rollout (mpc_simt.cu)
 int mpc_simt_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out);
 int mpc_simt_grid(const RolloutArgs& a);
+bool mpc_simt_is_thread_kernel(const RolloutArgs& a);   // small single-hidden-layer nets: one thread per sequence
 
 // tcgen05 rollout (mpc_tc.cu)
 bool mpc_tc_shape_supported(const ss_ctx* c);

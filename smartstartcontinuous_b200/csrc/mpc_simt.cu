@@ -212,6 +212,114 @@ __global__ void __launch_bounds__(ST) mpc_rollout_simt_kernel(const RolloutArgs 
     if (live && a.scores_out) a.scores_out[k_local] = sc.score;
 }
 
+// ---- small single-hidden-layer networks (the reference's default NND_MB model: 1 x 32) -----------------
+// The CTA kernel above gives 32 sequences to 256 threads and runs the MLP as tiled GEMMs between block barriers;
+// for a 160-MAC network that is all barrier and the owner warp's serial chain (score -> sample -> normalise ->
+// update): ncu on config 1 (K = 5000, H = 4) shows 8 warps stalled on the barrier per issued instruction and 22 us
+// for 20 000 rollout steps.  Here a THREAD rolls its own sequence: weights in shared memory (broadcast reads), one
+// layer of activations in registers, no barrier after the staging; a warp is still one column of the
+// projection-sum table (32 consecutive sequences), so the tail and the multi-GPU exchange see the same layout.
+constexpr int TT = 128;                    // threads = sequences per CTA (4 warps = 4 table columns)
+
+template <int DT, int HP>                  // d <= DT, h_pad <= HP
+__global__ void __launch_bounds__(TT) mpc_rollout_thread_kernel(const RolloutArgs a) {
+    pdl_trigger();
+    extern __shared__ __align__(16) float sm[];
+    float* W0 = sm;                                // [din_pad][h_pad]
+    float* W1 = W0 + a.din_pad * a.h_pad;          // [h_pad][dout_pad]
+    float* B0 = W1 + a.h_pad * a.dout_pad;         // [h_pad]
+    float* B1 = B0 + a.h_pad;                      // [dout_pad]
+    const int tid = threadIdx.x;
+    for (int v = tid; v < a.din_pad * a.h_pad / 4; v += TT)
+        reinterpret_cast<float4*>(W0)[v] = __ldg(reinterpret_cast<const float4*>(a.w[0]) + v);
+    for (int v = tid; v < a.h_pad * a.dout_pad / 4; v += TT)
+        reinterpret_cast<float4*>(W1)[v] = __ldg(reinterpret_cast<const float4*>(a.w[1]) + v);
+    for (int v = tid; v < a.h_pad; v += TT) B0[v] = __ldg(a.b[0] + v);
+    for (int v = tid; v < a.dout_pad; v += TT) B1[v] = v < a.d ? __ldg(a.b[1] + v) : 0.f;
+    __syncthreads();
+
+    const int lane = tid & 31;
+    const long long n_qcols = (a.K_local + 31) / 32;
+    const long long qcol = (long long)blockIdx.x * (TT / 32) + (tid >> 5);
+    if (qcol >= n_qcols) return;                   // (no barrier below)
+    const long long k_local = (long long)blockIdx.x * TT + tid;
+    const bool live = k_local < a.K_local;
+    const int T = a.H + 1;
+    const int nq = a.h_pad >> 2;                   // float4 pieces of a hidden row
+
+    ScoreAcc sc;
+    float x[DT];
+#pragma unroll
+    for (int j = 0; j < DT; ++j) x[j] = j < a.d ? a.state0[j] : 0.f;
+    score_init<DT>(a.plan, a.wp_index, x, sc);
+
+    for (int t = 0; t < T; ++t) {
+        tc::score_row<DT>(a, t, x, sc, live, k_local, qcol, n_qcols, lane);
+        if (t == a.H) break;
+        // ---- hidden layer: h[u] = relu(b0[u] + sum_k in[k] W0[k][u]), inputs = normalised state, then action
+        float h[HP];
+#pragma unroll
+        for (int q = 0; q < HP / 4; ++q) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (q < nq) b = reinterpret_cast<const float4*>(B0)[q];
+            h[4 * q] = b.x; h[4 * q + 1] = b.y; h[4 * q + 2] = b.z; h[4 * q + 3] = b.w;
+        }
+#pragma unroll
+        for (int k = 0; k < DT + SS_MAX_DA; ++k) {
+            if (k < a.d + a.da) {
+                float in;
+                if (k < a.d) in = (x[k < DT ? k : 0] - a.norm.mean_x[k]) * a.norm.inv_std_x[k];
+                else {
+                    const int j = k - a.d;
+                    const float act = live ? fetch_action(a.act, k_local, a.k_offset + k_local, t, j) : 0.f;
+                    in = (act - a.norm.mean_y[j]) * a.norm.inv_std_y[j];
+                }
+                const float4* wr = reinterpret_cast<const float4*>(W0 + k * a.h_pad);
+#pragma unroll
+                for (int q = 0; q < HP / 4; ++q) {
+                    if (q < nq) {
+                        const float4 w = wr[q];
+                        h[4 * q] = fmaf(in, w.x, h[4 * q]); h[4 * q + 1] = fmaf(in, w.y, h[4 * q + 1]);
+                        h[4 * q + 2] = fmaf(in, w.z, h[4 * q + 2]); h[4 * q + 3] = fmaf(in, w.w, h[4 * q + 3]);
+                    }
+                }
+            }
+        }
+        // ---- output layer: z[j] = b1[j] + sum_u relu(h[u]) W1[u][j]
+        float z[DT];
+#pragma unroll
+        for (int j = 0; j < DT; ++j) z[j] = B1[j < 8 ? j : 0];
+#pragma unroll
+        for (int u = 0; u < HP; ++u) {
+            if (u < a.h_pad) {
+                const float hu = fmaxf(h[u], 0.f);
+                const float4* wr = reinterpret_cast<const float4*>(W1 + u * a.dout_pad);
+                const float4 w0 = wr[0];
+                z[0] = fmaf(hu, w0.x, z[0]);
+                if (DT > 1) z[1] = fmaf(hu, w0.y, z[1]);
+                if (DT > 2) z[2] = fmaf(hu, w0.z, z[2]);
+                if (DT > 3) z[3] = fmaf(hu, w0.w, z[3]);
+                if (DT > 4) {
+                    const float4 w1 = wr[1];
+                    z[4 % DT] = fmaf(hu, w1.x, z[4 % DT]);
+                    z[5 % DT] = fmaf(hu, w1.y, z[5 % DT]);
+                    z[6 % DT] = fmaf(hu, w1.z, z[6 % DT]);
+                    z[7 % DT] = fmaf(hu, w1.w, z[7 % DT]);
+                }
+            }
+        }
+        // ---- state update (dynamics_model.py:234-237)
+#pragma unroll
+        for (int j = 0; j < DT; ++j)
+            if (j < a.d) x[j] = x[j] + fmaf(z[j], a.norm.std_z[j], a.norm.mean_z[j]);
+    }
+    if (live && a.scores_out) a.scores_out[k_local] = sc.score;
+}
+
+bool simt_thread_variant(const RolloutArgs& a) {
+    return a.L == 1 && a.h_pad <= 64 && a.d <= 8 && a.dout_pad == 8 && !getenv("SS_SIMT_GENERAL");
+}
+
 size_t simt_smem_bytes(const RolloutArgs& a) {
     const int act_elems = (a.h_pad > a.din_pad ? a.h_pad : a.din_pad) * SR;
     return sizeof(float) * ((size_t)2 * act_elems + 2 * KT * UT + 2 * SS_MAX_D * SR + 8 * SS_MAX_D * SR);
@@ -221,7 +329,26 @@ size_t simt_smem_bytes(const RolloutArgs& a) {
 
 int mpc_simt_grid(const RolloutArgs& a) { return (int)((a.K_local + SR - 1) / SR); }
 
+bool mpc_simt_is_thread_kernel(const RolloutArgs& a) { return simt_thread_variant(a); }
+
+template <int DT, int HP>
+static cudaError_t launch_thread_kernel(ss_ctx* c, const RolloutArgs& a, int grid, size_t smem) {
+    mpc_rollout_thread_kernel<DT, HP><<<grid, TT, smem, c->stream>>>(a);
+    return cudaGetLastError();
+}
+
 int mpc_simt_launch(ss_ctx* c, const RolloutArgs& a, int* grid_blocks_out) {
+    if (simt_thread_variant(a)) {
+        const int grid = (int)((a.K_local + TT - 1) / TT);
+        if (grid_blocks_out) *grid_blocks_out = grid;
+        const size_t smem = sizeof(float) * ((size_t)a.din_pad * a.h_pad + (size_t)a.h_pad * a.dout_pad + a.h_pad + a.dout_pad);
+        cudaError_t e;
+        if (a.d <= 4) e = a.h_pad <= 32 ? launch_thread_kernel<4, 32>(c, a, grid, smem) : launch_thread_kernel<4, 64>(c, a, grid, smem);
+        else e = a.h_pad <= 32 ? launch_thread_kernel<8, 32>(c, a, grid, smem) : launch_thread_kernel<8, 64>(c, a, grid, smem);
+        c->launches++;
+        SS_CUDA_CHECK(c, e);
+        return SS_OK;
+    }
     const size_t smem = simt_smem_bytes(a);
     if (smem > 227 * 1024)
         SS_FAIL(c, SS_EUNSUPPORTED, "mpc: depth_fc_layers too large for the FP32 kernel's shared memory");

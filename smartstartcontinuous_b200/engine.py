@@ -432,7 +432,8 @@ class Engine:
 
     def last_rollout_kernel(self):
         """Name of the rollout kernel the last decision ran on."""
-        return {0: "mpc_rollout_simt_kernel", 1: "mpc_rollout_tc_kernel", 2: "mpc_rollout_tc_quad_kernel"}.get(
+        return {0: "mpc_rollout_simt_kernel", 1: "mpc_rollout_tc_kernel", 2: "mpc_rollout_tc_quad_kernel",
+                3: "mpc_rollout_thread_kernel"}.get(
             int(self._lib.ss_mpc_last_kernel(self._h)))
 
     def set_plan(self, desired_states, distances_left, radii):

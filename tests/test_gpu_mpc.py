@@ -629,3 +629,56 @@ def test_tc_quad_kernel_vs_oracle_and_pair_kernel(engine, env_name, d):
     # repeatable bit for bit
     again = engine.plan(start, 0, actions=acts, penalty_mode="per_sample", precision="bf16_tc", want_scores=True)
     np.testing.assert_array_equal(again["scores"], whole["scores"])
+
+
+@pytest.mark.parametrize("env_name,h", [("mountaincar", 32), ("pendulum", 48), ("pendulum", 64)])
+def test_thread_kernel_small_single_layer_networks(engine, env_name, h):
+    """mpc_rollout_thread_kernel (one thread per sequence: the reference's default 1 x 32 dynamics model,
+    csrc/mpc_simt.cu) against the float64 oracle and against the general FP32 kernel (SS_SIMT_GENERAL=1) on the
+    same batches: ragged K (a last warp that is partly / entirely empty), both penalty modes, host samples and
+    the Philox sampler, shards = whole batch."""
+    rng = np.random.default_rng(60 + h)
+    if env_name == "mountaincar":
+        roll = [syn.mountaincar_rollout(rng, 200) for _ in range(6)]
+        states = np.concatenate([r[0] for r in roll])
+        acts_all = np.concatenate([np.concatenate([r[1], r[1][-1:]]) for r in roll])
+        path, lo, hi, start, d = list(roll[0][0][:50]), -1.0, 1.0, roll[0][0][0], 2
+    else:
+        obs, act = syn.pendulum_rollouts(rng, 6, 200)
+        states = obs.reshape(-1, 3)
+        acts_all = np.concatenate([act, act[:, -1:]], axis=1).reshape(-1, 1)
+        path, lo, hi, start, d = list(obs[0, :50]), -2.0, 2.0, obs[0, 0], 3
+    norm = syn.normalisation_stats(states, acts_all)
+    w, b = syn.xavier_mlp(rng, d, 1, 1, h, scale=0.5)
+    from smartstartcontinuous_b200.nnd_mb_agent import plan_from_path
+    plan = plan_from_path(path, mean_per_stepsize=1, std_per_stepsize=1, stepsizes_in_waypoint_radii=1,
+                          path_shortcutting=True, theta=1, steps_per_waypoint=1)
+    engine.set_model(w, b, norm)
+    engine.set_plan(plan["desired_states"], plan["distances_left"], plan["radii"])
+    for K, H in ((5000, 4), (97, 11), (129, 3)):
+        acts = np.random.RandomState(K).uniform(lo, hi, (K, H, 1))
+        for mode in ("reference", "per_sample"):
+            res = engine.plan(start, 0, actions=acts, penalty_mode=mode, precision="fp32", want_scores=True)
+            assert engine.last_rollout_kernel() == "mpc_rollout_thread_kernel"
+            o = mpc_oracle.plan(start, acts, w, b, norm, plan["desired_states"], plan["distances_left"], plan["radii"],
+                                0, .75, .5, penalty_mode=0 if mode == "reference" else 1)
+            _score_close(res["scores"], o["scores"], SCORE_TOL)
+            _check_best(res["best_k"], o["scores"], SCORE_TOL)
+            np.testing.assert_array_equal(res["best_sequence"], acts[res["best_k"]])
+            np.testing.assert_allclose(res["best_path"], o["states"][:, res["best_k"]], rtol=STATE_RTOL,
+                                       atol=STATE_RTOL * np.abs(o["states"]).max())
+            general = _with_env("SS_SIMT_GENERAL", "1", lambda: engine.plan(start, 0, actions=acts, penalty_mode=mode,
+                                                                           precision="fp32", want_scores=True))
+            assert engine.last_rollout_kernel() == "mpc_rollout_simt_kernel"
+            _score_close(res["scores"], general["scores"], SCORE_TOL)
+    # Philox samples: same decision as the oracle on the same samples; shards reproduce the whole batch bit for bit
+    K, H, seed = 3000, 7, 99
+    kw = dict(seed=seed, act_low=[lo], act_high=[hi], precision="fp32")
+    whole = engine.plan(start, 0, K=K, H=H, penalty_mode="per_sample", want_scores=True, **kw)
+    acts = philox.sample_actions(K, H, 1, seed, [lo], [hi])
+    o = mpc_oracle.plan(start, acts, w, b, norm, plan["desired_states"], plan["distances_left"], plan["radii"],
+                        0, .75, .5, penalty_mode=1)
+    _score_close(whole["scores"], o["scores"], SCORE_TOL)
+    parts = [engine.plan(start, 0, K=k1 - k0, H=H, penalty_mode="per_sample", want_scores=True, k_offset=k0,
+                         K_global=K, **kw)["scores"] for k0, k1 in ((0, 1111), (1111, 3000))]
+    np.testing.assert_array_equal(np.concatenate(parts), whole["scores"])
