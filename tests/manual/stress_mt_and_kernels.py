@@ -47,4 +47,26 @@ while time.time() - t0 < budget:
         b = eng.select_start(kw["all_states"], kw["queries"], kw["values"], kw["n"], kw["volume"])
         assert a[0] == b[0] and a[1] == b[1]
     n += 1
-print("stress ok: %d decisions in %.0f s, kernels %s" % (n, time.time() - t0, kernels))
+# ---- results through the tagged host slots: back-to-back small decisions without any stream synchronisation in
+# between (no scores requested); a stale or torn package would differ from the decision recomputed with the scores
+t1, m = time.time(), 0
+wl = models["2x500"]
+eng.set_model(wl["w"], wl["b"], wl["norm"])
+eng.set_plan(wl["plan"]["desired_states"], wl["plan"]["distances_left"], wl["plan"]["radii"])
+while time.time() - t1 < budget / 3:
+    K = int(rng.choice([64, 300, 1000, 4096]))
+    H = int(rng.choice([3, 8, 20, 50]))
+    seeds = [int(s) for s in rng.integers(1 << 40, size=40)]
+    fast = [eng.plan(wl["state"], 0, K=K, H=H, seed=s, act_low=wl["low"], act_high=wl["high"]) for s in seeds]
+    sel = [eng.select_start(kw["all_states"], kw["queries"][:256 + 8 * i], kw["values"][:256 + 8 * i], kw["n"], kw["volume"])
+           for i in range(8)]
+    for s, f in zip(seeds[::8], fast[::8]):
+        full = eng.plan(wl["state"], 0, K=K, H=H, seed=s, act_low=wl["low"], act_high=wl["high"], want_scores=True)
+        assert f["best_k"] == full["best_k"] == int(np.argmax(full["scores"])) and f["best_score"] == full["best_score"]
+        assert np.array_equal(f["best_sequence"], full["best_sequence"]) and np.array_equal(f["best_path"], full["best_path"])
+    for i, r in enumerate(sel[::4]):
+        again = eng.select_start(kw["all_states"], kw["queries"][:256 + 32 * i], kw["values"][:256 + 32 * i], kw["n"], kw["volume"])
+        assert r[0] == again[0] and r[1] == again[1]
+    m += len(seeds) + len(sel)
+print("stress ok: %d decisions in %.0f s, kernels %s; %d back-to-back results through the host slots" %
+      (n, time.time() - t0, kernels, m))
